@@ -1,0 +1,205 @@
+// C-ABI entry points that are compositions of kernels: library info, hicom_linear, and the global
+// compressor ops.  See include/hicom_b200.h for the contract of each.
+#include <stdarg.h>
+
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace hicom {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+int launch_posadd(const void* X, void* Y, const float* pt, const float* ph, const float* pw, int B, int T_,
+                  int H, int W, int d, int dtype, cudaStream_t stream);
+int launch_col_softmax(float* S, float* m, float* l, int B, int N, int J, int splits, int rows_per_split,
+                       cudaStream_t stream);
+
+static GemmParams plain_gemm() {
+  GemmParams g{};
+  g.nb1 = g.nb2 = 1;
+  g.alpha = 1.f;
+  g.act = HICOM_ACT_NONE;
+  g.rows_per_group = 1 << 30;
+  g.group_stride_rows = 0;
+  return g;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace hicom
+
+using namespace hicom;
+
+extern "C" int hicom_abi_version(void) { return HICOM_ABI_VERSION; }
+extern "C" const char* hicom_last_error(void) { return g_err; }
+
+extern "C" int hicom_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  HICOM_REQUIRE(e == cudaSuccess, "device_info: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  HICOM_REQUIRE(e == cudaSuccess, "device_info: %s", cudaGetErrorString(e));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  HICOM_REQUIRE(prop.major == 10, "hicom_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+  return 0;
+}
+
+extern "C" int hicom_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                            const void* R, int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int act,
+                            int in_dtype, int out_dtype, int rows_per_group, int64_t group_stride_rows,
+                            int impl, void* stream) {
+  HICOM_REQUIRE(A && W && C, "linear: null pointer");
+  HICOM_REQUIRE(M >= 0 && N > 0 && K > 0, "linear: bad shape M=%d N=%d K=%d", M, N, K);
+  HICOM_REQUIRE(lda >= K && ldw >= K && ldc >= N, "linear: leading dimension too small");
+  HICOM_REQUIRE(rows_per_group > 0, "linear: rows_per_group must be positive");
+  HICOM_REQUIRE(act == HICOM_ACT_NONE || act == HICOM_ACT_GELU, "linear: bad activation %d", act);
+  if (M == 0) return 0;
+  const bool tc_ok = tc_linear_supported(in_dtype, out_dtype, M, N, K, lda, ldw, ldc, A, W, C);
+  if (impl == HICOM_IMPL_TCGEN05) HICOM_REQUIRE(tc_ok, "linear: tcgen05 path does not support this problem");
+  if (impl == HICOM_IMPL_TCGEN05 || (impl == HICOM_IMPL_AUTO && tc_ok && M >= 64)) {
+    TcLinearParams t{};
+    t.A = A; t.W = W; t.bias = bias; t.R = R; t.C = C;
+    t.lda = lda; t.ldw = ldw; t.ldr = ldr; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.act = act;
+    t.out_dtype = out_dtype; t.rows_per_group = rows_per_group; t.group_stride_rows = group_stride_rows;
+    return launch_tc_linear(t, as_stream(stream));
+  }
+  GemmParams g = plain_gemm();
+  g.A = A; g.B = W; g.bias = bias; g.R = R; g.C = C;
+  g.M = M; g.N = N; g.K = K;
+  g.sAm = lda; g.sAk = 1;
+  g.sBk = 1; g.sBn = ldw;
+  g.ldc = ldc; g.ldr = ldr;
+  g.act = act; g.rows_per_group = rows_per_group; g.group_stride_rows = group_stride_rows;
+  cudaStream_t s = as_stream(stream);
+  if (in_dtype == HICOM_F32 && out_dtype == HICOM_F32) return launch_gemm_simt<float, float, float>(g, s);
+  if (in_dtype == HICOM_BF16 && out_dtype == HICOM_BF16) return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(g, s);
+  if (in_dtype == HICOM_BF16 && out_dtype == HICOM_F32) return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, float>(g, s);
+  if (in_dtype == HICOM_F32 && out_dtype == HICOM_BF16) return launch_gemm_simt<float, float, __nv_bfloat16>(g, s);
+  set_error("linear: bad dtype codes %d/%d", in_dtype, out_dtype);
+  return 1;
+}
+
+extern "C" int hicom_global_fold_query(const void* q, const void* Wk, void* qfold, int B, int Q, int d,
+                                       int heads, float alpha, int dtype, void* stream) {
+  HICOM_REQUIRE(q && Wk && qfold, "global_fold_query: null pointer");
+  HICOM_REQUIRE(B >= 0 && Q > 0 && heads > 0 && d % heads == 0, "global_fold_query: bad shape");
+  if (B == 0) return 0;
+  const int hd = d / heads;
+  GemmParams g = plain_gemm();
+  g.A = q; g.B = Wk; g.C = qfold;
+  g.M = Q; g.N = d; g.K = hd;
+  g.sAm = d; g.sAk = 1; g.sAb1 = (long long)Q * d; g.sAb2 = hd;
+  g.sBk = d; g.sBn = 1; g.sBb1 = 0; g.sBb2 = (long long)hd * d;
+  g.ldc = d; g.sCb1 = (long long)heads * Q * d; g.sCb2 = (long long)Q * d;
+  g.nb1 = B; g.nb2 = heads; g.alpha = alpha;
+  cudaStream_t s = as_stream(stream);
+  if (dtype == HICOM_F32) return launch_gemm_simt<float, float, float>(g, s);
+  if (dtype == HICOM_BF16) return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(g, s);
+  set_error("global_fold_query: bad dtype %d", dtype);
+  return 1;
+}
+
+extern "C" int hicom_global_value_proj(const void* pooled, const void* Wv, const void* bv, void* attn, int B,
+                                       int Q, int d, int heads, int dtype, void* stream) {
+  HICOM_REQUIRE(pooled && Wv && attn, "global_value_proj: null pointer");
+  HICOM_REQUIRE(B >= 0 && Q > 0 && heads > 0 && d % heads == 0, "global_value_proj: bad shape");
+  if (B == 0) return 0;
+  const int hd = d / heads;
+  GemmParams g = plain_gemm();
+  g.A = pooled; g.B = Wv; g.bias = bv; g.C = attn;
+  g.M = Q; g.N = hd; g.K = d;
+  g.sAm = d; g.sAk = 1; g.sAb1 = (long long)heads * Q * d; g.sAb2 = (long long)Q * d;
+  g.sBk = 1; g.sBn = d; g.sBb1 = 0; g.sBb2 = (long long)hd * d;
+  g.ldc = d; g.sCb1 = (long long)Q * d; g.sCb2 = hd;
+  g.sBiasb2 = hd;
+  g.nb1 = B; g.nb2 = heads;
+  cudaStream_t s = as_stream(stream);
+  if (dtype == HICOM_F32) return launch_gemm_simt<float, float, float>(g, s);
+  if (dtype == HICOM_BF16) return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(g, s);
+  set_error("global_value_proj: bad dtype %d", dtype);
+  return 1;
+}
+
+// ---- global attention partials --------------------------------------------------------------------
+// SIMT pipeline (fp32 mode, and the cross-check for the tensor path):
+//   posadd -> S = X'·qfoldᵀ (fp32) -> per-split column softmax stats, P in place -> O = Pᵀ·X' per split.
+static size_t elem_size(int dtype) { return dtype == HICOM_BF16 ? 2 : 4; }
+
+extern "C" size_t hicom_global_attend_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits,
+                                                      int dtype, int impl) {
+  (void)splits;
+  const size_t N = (size_t)T * H * W;
+  if (tc_global_selected(dtype, impl, d, J)) return tc_global_workspace_bytes(B, T, H, W, d, J, splits);
+  return align256((size_t)B * N * d * elem_size(dtype)) + align256((size_t)B * N * J * sizeof(float));
+}
+
+extern "C" int hicom_global_attend_partial(const void* X, const float* pos_t, const float* pos_h,
+                                           const float* pos_w, const void* qfold, float* m, float* l, float* o,
+                                           int B, int T, int H, int W, int d, int J, int splits, int dtype,
+                                           void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  HICOM_REQUIRE(X && qfold && m && l && o && workspace, "global_attend_partial: null pointer");
+  HICOM_REQUIRE(pos_t && pos_h && pos_w, "global_attend_partial: position tables required");
+  HICOM_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && d > 0 && d % 128 == 0 && J > 0 && splits > 0,
+                "global_attend_partial: bad shape");
+  HICOM_REQUIRE(dtype == HICOM_F32 || dtype == HICOM_BF16, "global_attend_partial: bad dtype %d", dtype);
+  HICOM_REQUIRE(workspace_bytes >= hicom_global_attend_workspace_bytes(B, T, H, W, d, J, splits, dtype, impl),
+                "global_attend_partial: workspace too small");
+  HICOM_REQUIRE(((uintptr_t)workspace & 255) == 0, "global_attend_partial: workspace must be 256-byte aligned");
+  if (B == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  const int N = T * H * W;
+  if (impl == HICOM_IMPL_TCGEN05)
+    HICOM_REQUIRE(tc_global_selected(dtype, impl, d, J), "global_attend_partial: tcgen05 path needs bf16, d%%128==0");
+  if (tc_global_selected(dtype, impl, d, J))
+    return launch_tc_global(X, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace, s);
+
+  const int rows_per_split = (N + splits - 1) / splits;
+  char* ws = static_cast<char*>(workspace);
+  void* Xp = ws;
+  float* S = reinterpret_cast<float*>(ws + align256((size_t)B * N * d * elem_size(dtype)));
+  if (launch_posadd(X, Xp, pos_t, pos_h, pos_w, B, T, H, W, d, dtype, s)) return 1;
+  {  // S[b] (N,J) = X'[b] (N,d) · qfold[b]ᵀ (d,J)
+    GemmParams g = plain_gemm();
+    g.A = Xp; g.B = qfold; g.C = S;
+    g.M = N; g.N = J; g.K = d;
+    g.sAm = d; g.sAk = 1; g.sAb1 = (long long)N * d;
+    g.sBk = 1; g.sBn = d; g.sBb1 = (long long)J * d;
+    g.ldc = J; g.sCb1 = (long long)N * J;
+    g.nb1 = B; g.nb2 = 1;
+    int rc = dtype == HICOM_F32 ? launch_gemm_simt<float, float, float>(g, s) : launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, float>(g, s);
+    if (rc) return rc;
+  }
+  if (launch_col_softmax(S, m, l, B, N, J, splits, rows_per_split, s)) return 1;
+  // O[b,s] (J,d) = P[b, rows of s]ᵀ (J,n) · X'[b, rows of s] (n,d).  A is fp32 (P), B is X' in `dtype`.
+  {
+    GemmParams g = plain_gemm();
+    g.A = S; g.B = Xp; g.C = o;
+    g.M = J; g.N = d; g.K = rows_per_split; g.k_total2 = N;
+    g.sAm = 1; g.sAk = J; g.sAb1 = (long long)N * J; g.sAb2 = (long long)rows_per_split * J;
+    g.sBk = d; g.sBn = 1; g.sBb1 = (long long)N * d; g.sBb2 = (long long)rows_per_split * d;
+    g.ldc = d; g.sCb1 = (long long)splits * J * d; g.sCb2 = (long long)J * d;
+    g.nb1 = B; g.nb2 = splits;
+    int rc = dtype == HICOM_F32 ? launch_gemm_simt<float, float, float>(g, s) : launch_gemm_simt<float, __nv_bfloat16, float>(g, s);
+    if (rc) return rc;
+  }
+  return 0;
+}

@@ -1,0 +1,24 @@
+// tcgen05 / TMEM / TMA tensor-core paths (bf16 in, fp32 accumulate).
+#pragma once
+#include "common.cuh"
+
+namespace hicom {
+
+struct TcLinearParams {
+  const void* A; const void* W; const void* bias; const void* R; void* C;
+  long long lda, ldw, ldr, ldc;
+  int M, N, K, act, out_dtype;
+  int rows_per_group; long long group_stride_rows;
+};
+
+bool tc_linear_supported(int in_dtype, int out_dtype, int M, int N, int K, long long lda, long long ldw,
+                         long long ldc, const void* A, const void* W, const void* C);
+int launch_tc_linear(const TcLinearParams& p, cudaStream_t stream);
+
+bool tc_global_selected(int dtype, int impl, int d, int J);
+size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits);
+int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, const float* pos_w,
+                     const void* qfold, float* m, float* l, float* o, int B, int T, int H, int W, int d, int J,
+                     int splits, void* workspace, cudaStream_t stream);
+
+}  // namespace hicom

@@ -1,0 +1,278 @@
+// Fused local compressor: grid-pool -> instruction injection -> window softmax -> A·V.
+//
+// Replaces, in one pass over HBM, the reference's
+//   K/V identity mixes       projector.py:533-534  (6 elementwise passes, eliminated)
+//   trilinear grid pooling   projector.py:539-540
+//   coarse/direct injection  projector.py:352-372  (the MLP itself runs once per video elsewhere)
+//   window gather x3         projector.py:473-522,544-546  (never materialised)
+//   bmm / softmax / bmm      projector.py:549-553
+//
+// HBM-bound: per window it must read kt*ks*ks key rows and as many value rows of d elements.
+// One warp owns one window; lane L owns the 4-element chunks {L, L+32, ...} of the channel axis
+// (d = 128*CPL), so every row read is a fully coalesced 256 B (bf16) / 512 B (fp32) request per
+// chunk, and all per-channel state (query, accumulator, FiLM vectors) lives in registers.
+// Softmax is the online form so arbitrary window sizes (e.g. local412: 576 members) work.
+#include "common.cuh"
+
+namespace hicom {
+
+struct LocalParams {
+  const void* K;
+  const void* V;
+  const void* P;
+  const void* q_aux;
+  const float* film;
+  const void* ln_w;
+  const void* ln_b;
+  void* out;
+  int B, T, H, W, d;
+  AxisWin wt, wh, ww;
+  int qmode;
+  float scale_log2;  // logit scale * log2(e)
+  int k_l2norm;
+  int same_kv;    // K and V alias: load each row once
+  int pool_only;  // write the pooled query and stop (hicom_grid_pool)
+};
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) local_attend_kernel(const LocalParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long nwin_video = (long long)p.wt.count * p.wh.count * p.ww.count;
+  const long long total = nwin_video * p.B;
+  const int d = p.d;
+  const T* __restrict__ Kp = static_cast<const T*>(p.K);
+  const T* __restrict__ Vp = static_cast<const T*>(p.V);
+  const T* __restrict__ Pp = static_cast<const T*>(p.P);
+  T* __restrict__ outp = static_cast<T*>(p.out);
+
+  for (long long wi = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); wi < total;
+       wi += (long long)gridDim.x * warps_per_block) {
+    const int b = (int)(wi / nwin_video);
+    const int r = (int)(wi % nwin_video);
+    const int t1 = r / (p.wh.count * p.ww.count);
+    const int h1 = (r / p.ww.count) % p.wh.count;
+    const int w1 = r % p.ww.count;
+    const size_t video_off = (size_t)b * p.T * p.H * p.W * d;
+
+    float q[CPL][4];
+
+    // ---- query ------------------------------------------------------------------------------
+    if (p.qmode == HICOM_Q_POOLED || p.qmode == HICOM_Q_FILM_LN) {
+      // trilinear taps, nested exactly like upsample_trilinear3d: t(h(w))
+      const Tap tt = linear_tap(t1, p.T, p.wt.count);
+      const Tap th = linear_tap(h1, p.H, p.wh.count);
+      const Tap tw = linear_tap(w1, p.W, p.ww.count);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[c][e] = 0.f;
+      const int ti[2] = {tt.i0, tt.i1}; const float tw_[2] = {tt.w0, tt.w1};
+      const int hi[2] = {th.i0, th.i1}; const float hw_[2] = {th.w0, th.w1};
+      const int wi_[2] = {tw.i0, tw.i1}; const float ww_[2] = {tw.w0, tw.w1};
+      for (int a = 0; a < 2; ++a) {
+        if (tw_[a] == 0.f) continue;
+        for (int bb = 0; bb < 2; ++bb) {
+          if (hw_[bb] == 0.f) continue;
+          for (int cc = 0; cc < 2; ++cc) {
+            if (ww_[cc] == 0.f) continue;
+            const float wgt = tw_[a] * (hw_[bb] * ww_[cc]);
+            const T* row = Pp + video_off + ((size_t)(ti[a] * p.H + hi[bb]) * p.W + wi_[cc]) * d;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+              float x[4];
+              Vec4<T>::load(row + (lane + 32 * c) * 4, x);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) q[c][e] = fmaf(wgt, x[e], q[c][e]);
+            }
+          }
+        }
+      }
+      if (p.pool_only) {
+        T* orow = outp + (size_t)wi * d;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) Vec4<T>::store(orow + (lane + 32 * c) * 4, q[c]);
+        continue;
+      }
+      if (p.qmode == HICOM_Q_FILM_LN) {
+        const float* sc = p.film + (size_t)b * 2 * d;
+        const float* sh = sc + d;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          float s4[4], h4[4];
+          Vec4<float>::load(sc + (lane + 32 * c) * 4, s4);
+          Vec4<float>::load(sh + (lane + 32 * c) * 4, h4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            q[c][e] = fmaf(q[c][e], 1.f + s4[e], h4[e]);
+            sum += q[c][e];
+          }
+        }
+        const float mean = warp_sum(sum) / (float)d;
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float dv = q[c][e] - mean;
+            var = fmaf(dv, dv, var);
+          }
+        const float rstd = rsqrtf(warp_sum(var) / (float)d + kLnEps);
+        const T* gw = static_cast<const T*>(p.ln_w);
+        const T* gb = static_cast<const T*>(p.ln_b);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          float g4[4], b4[4];
+          Vec4<T>::load(gw + (lane + 32 * c) * 4, g4);
+          Vec4<T>::load(gb + (lane + 32 * c) * 4, b4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) q[c][e] = fmaf((q[c][e] - mean) * rstd, g4[e], b4[e]);
+        }
+      }
+    } else {
+      const T* qrow = static_cast<const T*>(p.q_aux) +
+                      (p.qmode == HICOM_Q_VECTOR ? (size_t)b * d : (size_t)wi * d);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) Vec4<T>::load(qrow + (lane + 32 * c) * 4, q[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) q[c][e] *= p.scale_log2;
+
+    // ---- window members: online softmax over (t2,h2,w2) ----------------------------------------
+    const int t0 = axis_win_start(p.wt, t1), h0 = axis_win_start(p.wh, h1), w0 = axis_win_start(p.ww, w1);
+    const int Lt = p.wt.len, Lh = p.wh.len, Lw = p.ww.len;
+    const int members = Lt * Lh * Lw;
+    float acc[CPL][4];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[c][e] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int mi = 0; mi < members; mi += 2) {
+      const bool two = (mi + 1) < members;
+      size_t off[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int mj = two ? mi + j : mi;
+        const int t2 = mj / (Lh * Lw), h2 = (mj / Lw) % Lh, w2 = mj % Lw;
+        off[j] = video_off + ((size_t)((t0 + t2) * p.H + h0 + h2) * p.W + w0 + w2) * d;
+      }
+      float kv[2][CPL][4];
+      float dot[2] = {0.f, 0.f}, kk[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) Vec4<T>::load_stream(Kp + off[j] + (lane + 32 * c) * 4, kv[j][c]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            dot[j] = fmaf(q[c][e], kv[j][c][e], dot[j]);
+            if (p.k_l2norm) kk[j] = fmaf(kv[j][c][e], kv[j][c][e], kk[j]);
+          }
+      if (!p.same_kv) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) Vec4<T>::load_stream(Vp + off[j] + (lane + 32 * c) * 4, kv[j][c]);
+      }
+      float s0 = warp_sum(dot[0]), s1 = warp_sum(dot[1]);
+      if (p.k_l2norm) {
+        s0 *= rsqrtf(warp_sum(kk[0]));
+        s1 *= rsqrtf(warp_sum(kk[1]));
+      }
+      if (!two) s1 = -INFINITY;
+      const float m_new = fmaxf(m_run, fmaxf(s0, s1));
+      const float corr = exp2f(m_run - m_new);
+      const float p0 = exp2f(s0 - m_new), p1 = exp2f(s1 - m_new);
+      l_run = fmaf(l_run, corr, p0 + p1);
+      m_run = m_new;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          acc[c][e] = fmaf(acc[c][e], corr, fmaf(p0, kv[0][c][e], p1 * kv[1][c][e]));
+    }
+    const float inv = 1.f / l_run;
+    T* orow = outp + (size_t)wi * d;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[c][e] *= inv;
+      Vec4<T>::store(orow + (lane + 32 * c) * 4, acc[c]);
+    }
+  }
+}
+
+template <typename T>
+static int launch_local(const LocalParams& p, cudaStream_t stream) {
+  const long long total = (long long)p.wt.count * p.wh.count * p.ww.count * p.B;
+  if (total == 0) return 0;
+  const int warps_per_block = 8;
+  long long blocks = (total + warps_per_block - 1) / warps_per_block;
+  if (blocks > (1 << 20)) blocks = 1 << 20;
+  const int cpl = p.d / 128;
+  switch (cpl) {
+    case 9: local_attend_kernel<T, 9><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(p); break;
+    case 6: local_attend_kernel<T, 6><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(p); break;
+    case 8: local_attend_kernel<T, 8><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(p); break;
+    case 1: local_attend_kernel<T, 1><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(p); break;
+    default:
+      set_error("local_attend: d=%d unsupported (need d in {128,768,1024,1152})", p.d);
+      return 1;
+  }
+  return check_launch("local_attend_kernel");
+}
+
+static int fill_geometry(LocalParams& p, int T, int H, int W, int kt, int ks) {
+  HICOM_REQUIRE(kt >= 1 && ks >= 1, "local_attend: kernel sizes must be >= 1 (kt=%d ks=%d)", kt, ks);
+  HICOM_REQUIRE(make_axis_win(T, kt, &p.wt),
+                "local_attend: T=%d with temporal kernel %d gives unequal windows (the reference's "
+                "torch.stack raises here, projector.py:520)", T, kt);
+  HICOM_REQUIRE(make_axis_win(H, ks, &p.wh), "local_attend: H=%d with kernel %d gives unequal windows", H, ks);
+  HICOM_REQUIRE(make_axis_win(W, ks, &p.ww), "local_attend: W=%d with kernel %d gives unequal windows", W, ks);
+  return 0;
+}
+
+}  // namespace hicom
+
+using namespace hicom;
+
+extern "C" int hicom_grid_pool(const void* X, void* Q, int B, int T, int H, int W, int d, int kt, int ks,
+                               int dtype, void* stream) {
+  HICOM_REQUIRE(X && Q, "grid_pool: null pointer");
+  HICOM_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && d > 0 && d % 128 == 0, "grid_pool: bad shape");
+  LocalParams p{};
+  p.K = p.V = p.P = X; p.out = Q;
+  p.B = B; p.T = T; p.H = H; p.W = W; p.d = d;
+  p.qmode = HICOM_Q_POOLED; p.pool_only = 1; p.scale_log2 = 1.f;
+  // pooling only needs the window COUNTS (ceil(n/k)); geometry validity is irrelevant here
+  p.wt.n = T; p.wt.k = kt; p.wt.count = ceil_div(T, kt); p.wt.keep = p.wt.count; p.wt.len = 1;
+  p.wh.n = H; p.wh.k = ks; p.wh.count = ceil_div(H, ks); p.wh.keep = p.wh.count; p.wh.len = 1;
+  p.ww.n = W; p.ww.k = ks; p.ww.count = ceil_div(W, ks); p.ww.keep = p.ww.count; p.ww.len = 1;
+  HICOM_DISPATCH_DTYPE(dtype, T_, return launch_local<T_>(p, as_stream(stream)));
+}
+
+extern "C" int hicom_local_attend(const void* Ksrc, const void* Vsrc, const void* Psrc, const void* q_aux,
+                                  const float* film, const void* ln_w, const void* ln_b, void* out, int B,
+                                  int T, int H, int W, int d, int kt, int ks, int qmode, float logit_scale,
+                                  int k_l2norm, int dtype, void* stream) {
+  HICOM_REQUIRE(Ksrc && Vsrc && out, "local_attend: null pointer");
+  HICOM_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && d > 0 && d % 128 == 0, "local_attend: bad shape");
+  HICOM_REQUIRE(qmode >= HICOM_Q_POOLED && qmode <= HICOM_Q_EXPLICIT, "local_attend: bad qmode %d", qmode);
+  if (qmode == HICOM_Q_POOLED || qmode == HICOM_Q_FILM_LN) HICOM_REQUIRE(Psrc, "local_attend: Psrc required");
+  if (qmode == HICOM_Q_FILM_LN) HICOM_REQUIRE(film && ln_w && ln_b, "local_attend: film/ln required");
+  if (qmode == HICOM_Q_VECTOR || qmode == HICOM_Q_EXPLICIT) HICOM_REQUIRE(q_aux, "local_attend: q_aux required");
+  LocalParams p{};
+  p.K = Ksrc; p.V = Vsrc; p.P = Psrc; p.q_aux = q_aux; p.film = film; p.ln_w = ln_w; p.ln_b = ln_b;
+  p.out = out; p.B = B; p.T = T; p.H = H; p.W = W; p.d = d; p.qmode = qmode;
+  p.scale_log2 = logit_scale * kLog2e; p.k_l2norm = k_l2norm; p.same_kv = (Ksrc == Vsrc);
+  if (fill_geometry(p, T, H, W, kt, ks)) return 1;
+  HICOM_DISPATCH_DTYPE(dtype, T_, return launch_local<T_>(p, as_stream(stream)));
+}

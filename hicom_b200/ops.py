@@ -1,0 +1,341 @@
+"""Thin torch custom-op layer over the C ABI (include/hicom_b200.h).
+
+Each op validates its tensors, allocates the result with torch's caching allocator, and passes raw
+device pointers plus the CURRENT CUDA stream to ``libhicom_b200.so`` — nothing here computes.  The ops
+are registered as ``torch.ops.hicom_b200.*`` (forward only: no autograd formula is registered, so a
+backward through them raises instead of silently dropping gradients).  There is no CPU or PyTorch
+fallback: CPU tensors raise, a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+from ._cabi import ACT_GELU, ACT_NONE, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05  # noqa: F401 (re-exported)
+from ._cabi import Q_EXPLICIT, Q_FILM_LN, Q_POOLED, Q_VECTOR  # noqa: F401
+
+_DT = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+
+
+def _dt(t: Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"hicom_b200 supports float32 and bfloat16 tensors, got {t.dtype}") from None
+
+
+def _need_cuda(*ts: Optional[Tensor]):
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("hicom_b200 ops run on CUDA tensors only (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _c(t: Optional[Tensor]) -> Optional[Tensor]:
+    return None if t is None else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# local compressor
+# ------------------------------------------------------------------------------------------
+def num_windows(T: int, H: int, W: int, kt: int, ks: int) -> int:
+    return math.ceil(T / kt) * math.ceil(H / ks) * math.ceil(W / ks)
+
+
+@torch.library.custom_op("hicom_b200::grid_pool", mutates_args=(), device_types="cuda")
+def grid_pool(X: Tensor, kt: int, ks: int) -> Tensor:
+    """(B,T,H,W,d) -> (B,Nw,d) trilinear grid pooling — projector.py:536-540."""
+    dev = _need_cuda(X)
+    X = X.contiguous()
+    B, T, H, W, d = X.shape
+    out = torch.empty((B, num_windows(T, H, W, kt, ks), d), dtype=X.dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_grid_pool(_ptr(X), _ptr(out), B, T, H, W, d, kt, ks, _dt(X), _stream(dev))
+    _cabi.check(rc, "hicom_grid_pool")
+    return out
+
+
+@torch.library.custom_op("hicom_b200::local_attend", mutates_args=(), device_types="cuda")
+def local_attend(K: Tensor, V: Tensor, P: Tensor, q_aux: Optional[Tensor], film: Optional[Tensor],
+                 ln_w: Optional[Tensor], ln_b: Optional[Tensor], kt: int, ks: int, qmode: int,
+                 logit_scale: float, k_l2norm: bool) -> Tensor:
+    """Fused pool -> inject -> window softmax -> A·V — projector.py:536-558.  Returns (B,Nw,d)."""
+    dev = _need_cuda(K, V, P, q_aux, film, ln_w, ln_b)
+    same_kv = K.data_ptr() == V.data_ptr()
+    same_pv = P.data_ptr() == V.data_ptr()
+    V = V.contiguous()
+    K = V if same_kv else K.contiguous()
+    P = V if same_pv else P.contiguous()
+    if not (K.shape == V.shape == P.shape) or V.dim() != 5:
+        raise ValueError(f"local_attend: K/V/P must share a (B,T,H,W,d) shape, got {K.shape} {V.shape} {P.shape}")
+    if not (K.dtype == V.dtype == P.dtype):
+        raise TypeError("local_attend: K/V/P dtypes differ")
+    B, T, H, W, d = V.shape
+    nw = num_windows(T, H, W, kt, ks)
+    q_aux, ln_w, ln_b = _c(q_aux), _c(ln_w), _c(ln_b)
+    if film is not None:
+        film = film.contiguous()
+        if film.dtype != torch.float32 or film.shape != (B, 2 * d):
+            raise ValueError("local_attend: film must be fp32 (B, 2d)")
+    for t in (q_aux, ln_w, ln_b):
+        if t is not None and t.dtype != V.dtype:
+            raise TypeError("local_attend: q_aux / ln params must have the feature dtype")
+    if qmode == Q_VECTOR and (q_aux is None or q_aux.shape != (B, d)):
+        raise ValueError("local_attend: Q_VECTOR needs q_aux (B,d)")
+    if qmode == Q_EXPLICIT and (q_aux is None or q_aux.shape != (B, nw, d)):
+        raise ValueError(f"local_attend: Q_EXPLICIT needs q_aux (B,{nw},{d})")
+    out = torch.empty((B, nw, d), dtype=V.dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_local_attend(_ptr(K), _ptr(V), _ptr(P), _ptr(q_aux), _ptr(film), _ptr(ln_w),
+                                             _ptr(ln_b), _ptr(out), B, T, H, W, d, kt, ks, qmode,
+                                             float(logit_scale), int(k_l2norm), _dt(V), _stream(dev))
+    _cabi.check(rc, "hicom_local_attend")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# dense layers
+# ------------------------------------------------------------------------------------------
+def _rows2d(t: Tensor) -> Tensor:
+    t2 = t.reshape(-1, t.shape[-1])
+    if t2.stride(-1) != 1:
+        t2 = t2.contiguous()
+    return t2
+
+
+def _linear_call(A2, W, bias, R2, C, ldc, M, N, K, act, out_dtype_code, rpg, gstride, impl, dev):
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_linear(_ptr(A2), A2.stride(0), _ptr(W), W.stride(0), _ptr(bias), _ptr(R2),
+                                       0 if R2 is None else R2.stride(0), _ptr(C), ldc, M, N, K, act,
+                                       _dt(A2), out_dtype_code, rpg, gstride, impl, _stream(dev))
+    _cabi.check(rc, "hicom_linear")
+
+
+def _check_linear(A, W, bias, residual):
+    dev = _need_cuda(A, W, bias, residual)
+    if W.dim() != 2 or A.shape[-1] != W.shape[1]:
+        raise ValueError(f"linear: A (...,{A.shape[-1]}) does not match W {tuple(W.shape)}")
+    if W.dtype != A.dtype or (bias is not None and bias.dtype != A.dtype):
+        raise TypeError("linear: A, W, bias must share a dtype")
+    if W.stride(1) != 1:
+        W = W.contiguous()
+    return dev, W
+
+
+@torch.library.custom_op("hicom_b200::linear", mutates_args=(), device_types="cuda")
+def linear(A: Tensor, W: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], act: int,
+           out_fp32: bool, impl: int) -> Tensor:
+    """act(A·Wᵀ + bias) [+ residual] — nn.Linear / build_mlp stage (projector.py:180-182,226,307-312)."""
+    dev, W = _check_linear(A, W, bias, residual)
+    A2 = _rows2d(A)
+    M, K = A2.shape
+    N = W.shape[0]
+    R2 = None
+    if residual is not None:
+        if residual.dtype != A.dtype:
+            raise TypeError("linear: residual dtype differs")
+        R2 = _rows2d(residual)
+        if R2.shape != (M, N):
+            raise ValueError("linear: residual shape mismatch")
+    odt = torch.float32 if out_fp32 else A.dtype
+    C = torch.empty((M, N), dtype=odt, device=dev)
+    _linear_call(A2, W, _c(bias), R2, C, N, M, N, K, act, _DT[odt], max(M, 1), 0, impl, dev)
+    return C.reshape(*A.shape[:-1], N)
+
+
+@torch.library.custom_op("hicom_b200::linear_into", mutates_args=("out",), device_types="cuda")
+def linear_into(A: Tensor, W: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], act: int,
+                out: Tensor, row_offset: int, rows_per_group: int, group_stride_rows: int, impl: int) -> None:
+    """Same as ``linear`` but writes row r to ``out[(r // rows_per_group) * group_stride_rows +
+    r % rows_per_group + row_offset]`` — the readouts write straight into the concatenated token block
+    of every video (projector.py:707), no ``cat``."""
+    dev, W = _check_linear(A, W, bias, residual)
+    _need_cuda(out)
+    A2 = _rows2d(A)
+    M, K = A2.shape
+    N = W.shape[0]
+    if out.dim() != 2 or out.shape[1] != N or out.stride(1) != 1:
+        raise ValueError("linear_into: out must be (rows, N) with unit inner stride")
+    if M > 0:
+        last = ((M - 1) // rows_per_group) * group_stride_rows + (M - 1) % rows_per_group + row_offset
+        if last >= out.shape[0] or row_offset < 0:
+            raise ValueError("linear_into: destination rows out of range")
+    R2 = _rows2d(residual) if residual is not None else None
+    Cview = out[row_offset:]
+    _linear_call(A2, W, _c(bias), R2, Cview, out.stride(0), M, N, K, act, _dt(out), rows_per_group,
+                 group_stride_rows, impl, dev)
+
+
+@torch.library.custom_op("hicom_b200::film_layernorm", mutates_args=(), device_types="cuda")
+def film_layernorm(x: Tensor, film: Tensor, ln_w: Tensor, ln_b: Tensor, rows_per_group: int) -> Tensor:
+    """LN(x*(1+scale)+shift), film (G,2d) fp32 — coarse injector on explicit rows (projector.py:369-372)."""
+    dev = _need_cuda(x, film, ln_w, ln_b)
+    x = x.contiguous()
+    d = x.shape[-1]
+    rows = x.numel() // d
+    film = film.contiguous()
+    if film.dtype != torch.float32 or film.shape[-1] != 2 * d:
+        raise ValueError("film_layernorm: film must be fp32 (G, 2d)")
+    if rows > film.shape[0] * rows_per_group:
+        raise ValueError("film_layernorm: not enough film rows")
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_film_layernorm(_ptr(x), _ptr(film), _ptr(_c(ln_w)), _ptr(_c(ln_b)), _ptr(out),
+                                               rows, d, rows_per_group, _dt(x), _stream(dev))
+    _cabi.check(rc, "hicom_film_layernorm")
+    return out
+
+
+@torch.library.custom_op("hicom_b200::add_layernorm", mutates_args=(), device_types="cuda")
+def add_layernorm(a: Tensor, b: Tensor, ln_w: Tensor, ln_b: Tensor) -> Tensor:
+    """LN(a + b) — fine injector residual (projector.py:392)."""
+    dev = _need_cuda(a, b, ln_w, ln_b)
+    a, b = a.contiguous(), b.contiguous()
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("add_layernorm: operands differ")
+    d = a.shape[-1]
+    out = torch.empty_like(a)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_add_layernorm(_ptr(a), _ptr(b), _ptr(_c(ln_w)), _ptr(_c(ln_b)), _ptr(out),
+                                              a.numel() // d, d, _dt(a), _stream(dev))
+    _cabi.check(rc, "hicom_add_layernorm")
+    return out
+
+
+@torch.library.custom_op("hicom_b200::mix_layernorm", mutates_args=(), device_types="cuda")
+def mix_layernorm(x: Tensor, y: Tensor, ln_w: Tensor, ln_b: Tensor, alpha: Tensor) -> Tensor:
+    """(1-alpha)*x + alpha*LN(y) — adapter mixes (projector.py:365,533-534,541)."""
+    dev = _need_cuda(x, y, ln_w, ln_b, alpha)
+    x, y = x.contiguous(), y.contiguous()
+    if x.shape != y.shape or x.dtype != y.dtype or alpha.dtype != x.dtype:
+        raise ValueError("mix_layernorm: operands differ")
+    d = x.shape[-1]
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_mix_layernorm(_ptr(x), _ptr(y), _ptr(_c(ln_w)), _ptr(_c(ln_b)),
+                                              _ptr(alpha.contiguous()), _ptr(out), x.numel() // d, d, _dt(x),
+                                              _stream(dev))
+    _cabi.check(rc, "hicom_mix_layernorm")
+    return out
+
+
+@torch.library.custom_op("hicom_b200::guide_attend", mutates_args=(), device_types="cuda")
+def guide_attend(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
+    """MHA of (G,Mq,d) queries over (G,L,d) instruction tokens — projector.py:391 -> :193-224."""
+    dev = _need_cuda(q, k, v)
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    G, Mq, d = q.shape
+    if k.shape != v.shape or k.shape[0] != G or k.shape[2] != d:
+        raise ValueError("guide_attend: shape mismatch")
+    out = torch.empty_like(q)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_guide_attend(_ptr(q), _ptr(k), _ptr(v), _ptr(out), G, Mq, k.shape[1], d, heads,
+                                             float(scale), _dt(q), _stream(dev))
+    _cabi.check(rc, "hicom_guide_attend")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# global compressor
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("hicom_b200::global_fold_query", mutates_args=(), device_types="cuda")
+def global_fold_query(q: Tensor, Wk: Tensor, heads: int, alpha: float) -> Tensor:
+    """qfold[b,h*Q+i,:] = alpha * q[b,i,head h] · Wk[head h rows, :] — folds k_proj (:181) and the scale (:197)."""
+    dev = _need_cuda(q, Wk)
+    q, Wk = q.contiguous(), Wk.contiguous()
+    B, Q, d = q.shape
+    out = torch.empty((B, heads * Q, d), dtype=q.dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_global_fold_query(_ptr(q), _ptr(Wk), _ptr(out), B, Q, d, heads, float(alpha),
+                                                  _dt(q), _stream(dev))
+    _cabi.check(rc, "hicom_global_fold_query")
+    return out
+
+
+@torch.library.custom_op("hicom_b200::global_attend_partial", mutates_args=(), device_types="cuda")
+def global_attend_partial(X: Tensor, pos_t: Tensor, pos_h: Tensor, pos_w: Tensor, qfold: Tensor, splits: int,
+                          impl: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Split-softmax partials (m,l,o) of the global attention over X's frames — projector.py:636-640,197,213,215."""
+    dev = _need_cuda(X, pos_t, pos_h, pos_w, qfold)
+    X, qfold = X.contiguous(), qfold.contiguous()
+    B, T, H, W, d = X.shape
+    J = qfold.shape[1]
+    for name, tab, n in (("pos_t", pos_t, T), ("pos_h", pos_h, H), ("pos_w", pos_w, W)):
+        if tab.dtype != torch.float32 or tab.shape != (n, d) or not tab.is_contiguous():
+            raise ValueError(f"global_attend_partial: {name} must be contiguous fp32 ({n},{d})")
+    if qfold.shape != (B, J, d) or qfold.dtype != X.dtype:
+        raise ValueError("global_attend_partial: qfold must be (B,J,d) in the feature dtype")
+    lib = _cabi.load()
+    ws_bytes = lib.hicom_global_attend_workspace_bytes(B, T, H, W, d, J, splits, _dt(X), impl)
+    ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
+    m = torch.empty((B, splits, J), dtype=torch.float32, device=dev)
+    l = torch.empty((B, splits, J), dtype=torch.float32, device=dev)
+    o = torch.empty((B, splits, J, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.hicom_global_attend_partial(_ptr(X), _ptr(pos_t), _ptr(pos_h), _ptr(pos_w), _ptr(qfold), _ptr(m),
+                                             _ptr(l), _ptr(o), B, T, H, W, d, J, splits, _dt(X), _ptr(ws),
+                                             ws.numel(), impl, _stream(dev))
+    _cabi.check(rc, "hicom_global_attend_partial")
+    return m, l, o
+
+
+@torch.library.custom_op("hicom_b200::softmax_merge", mutates_args=(), device_types="cuda")
+def softmax_merge(m: Tensor, l: Tensor, o: Tensor, out_bf16: bool) -> Tensor:
+    """Combine (m,l,o) partials over dim 1 (token splits and/or frame shards) -> pooled (B,J,d)."""
+    dev = _need_cuda(m, l, o)
+    m, l, o = m.contiguous(), l.contiguous(), o.contiguous()
+    B, P, J, d = o.shape
+    if m.shape != (B, P, J) or l.shape != (B, P, J) or o.dtype != torch.float32:
+        raise ValueError("softmax_merge: shape mismatch")
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+    out = torch.empty((B, J, d), dtype=odt, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_softmax_merge(_ptr(m), _ptr(l), _ptr(o), B, P, J, d, _ptr(out), _DT[odt],
+                                              _stream(dev))
+    _cabi.check(rc, "hicom_softmax_merge")
+    return out
+
+
+@torch.library.custom_op("hicom_b200::global_value_proj", mutates_args=(), device_types="cuda")
+def global_value_proj(pooled: Tensor, Wv: Tensor, bv: Optional[Tensor], Q: int, heads: int) -> Tensor:
+    """attn[b,i,head h] = Wv[head h rows] · pooled[b,h*Q+i] + bv — v_proj (:182) after pooling + head merge (:223-224)."""
+    dev = _need_cuda(pooled, Wv, bv)
+    pooled, Wv = pooled.contiguous(), Wv.contiguous()
+    B, J, d = pooled.shape
+    if J != Q * heads:
+        raise ValueError("global_value_proj: J != Q*heads")
+    out = torch.empty((B, Q, d), dtype=pooled.dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_global_value_proj(_ptr(pooled), _ptr(Wv), _ptr(_c(bv)), _ptr(out), B, Q, d, heads,
+                                                  _dt(pooled), _stream(dev))
+    _cabi.check(rc, "hicom_global_value_proj")
+    return out
+
+
+def device_info(device=None):
+    """(sm_count, cc_major, cc_minor) of the current CUDA device; raises unless it is sm_100."""
+    sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    with torch.cuda.device(device):
+        rc = _cabi.load().hicom_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi))
+    _cabi.check(rc, "hicom_device_info")
+    return sm.value, ma.value, mi.value

@@ -1,0 +1,155 @@
+/*
+ * hicom_b200 — C ABI of the B200-native HICom compressor kernels (sm_100a).
+ *
+ * The reference (lntzm/HICom) is 100 % Python and defines no FFI; its hot path is
+ * `HIComProjector.forward` (hicom/model/projector.py:676-708).  This header is the seam a
+ * maintainer binds instead of the ATen calls on that path.  Every entry point names the reference
+ * lines it replaces.  All pointers are DEVICE pointers (plain `void*`, no torch types), tensors are
+ * dense row-major unless a leading dimension is given, `stream` is a `cudaStream_t` passed as
+ * `void*`; nothing here synchronises the device.  Functions return 0 on success and a non-zero
+ * code otherwise — `hicom_last_error()` then holds a message (thread-local).  Nothing aborts.
+ *
+ * dtype codes: HICOM_F32 tensors are float, HICOM_BF16 tensors are __nv_bfloat16; accumulation is
+ * always fp32, softmax statistics are fp32.
+ */
+#ifndef HICOM_B200_H
+#define HICOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HICOM_ABI_VERSION 1
+
+enum { HICOM_F32 = 0, HICOM_BF16 = 1 };
+enum { HICOM_ACT_NONE = 0, HICOM_ACT_GELU = 1 }; /* GELU = exact erf form (nn.GELU(), projector.py:310) */
+enum {
+  HICOM_Q_POOLED = 0,   /* query = grid-pooled feature                 (use_guide None/off)        */
+  HICOM_Q_FILM_LN = 1,  /* query = LN(pooled*(1+scale)+shift)           (coarse, projector.py:369-372) */
+  HICOM_Q_VECTOR = 2,   /* query = per-video vector, pooled discarded  (direct, projector.py:367-368) */
+  HICOM_Q_EXPLICIT = 3  /* query rows supplied by the caller           (fine / adapt_q paths)       */
+};
+enum { HICOM_IMPL_AUTO = 0, HICOM_IMPL_SIMT = 1, HICOM_IMPL_TCGEN05 = 2 };
+
+/* ---- library ---------------------------------------------------------------------------- */
+int hicom_abi_version(void);
+const char* hicom_last_error(void);
+/* Fills SM count / compute capability of the current device; fails if it is not sm_100. */
+int hicom_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- local compressor -------------------------------------------------------------------
+ * hicom_grid_pool: the trilinear grid pooling `F.interpolate(..., mode='trilinear')`
+ *   (projector.py:536-540).  X (B,T,H,W,d) -> Q (B, Nw, d), Nw = ceil(T/kt)*ceil(H/ks)*ceil(W/ks),
+ *   align_corners=False taps, rows in (t1,h1,w1) raster order.  Needed on its own only when the
+ *   pooled query goes through GEMMs before the attention (adapt_q, fine).
+ */
+int hicom_grid_pool(const void* X, void* Q, int B, int T, int H, int W, int d, int kt, int ks,
+                    int dtype, void* stream);
+
+/* hicom_local_attend: fused grid-pool -> instruction injection -> window gather -> softmax -> A·V
+ *   (projector.py:536-558 with GuideInjector.forward_direct_and_coarse :352-372 and
+ *   divide_feature/balance_divide_feature :473-522).
+ *   Ksrc  (B,T,H,W,d)  keys   (frames_embed, or frames_feature when that is None, :532-533)
+ *   Vsrc  (B,T,H,W,d)  values (frames_feature, :534)
+ *   Psrc  (B,T,H,W,d)  pooling source (raw frames_feature, :539); may alias Vsrc
+ *   qmode HICOM_Q_*; q_aux: (B,d) vector for Q_VECTOR, (B,Nw,d) rows for Q_EXPLICIT, else NULL
+ *   film  (B,2d) fp32 [scale | shift] for Q_FILM_LN (the coarse_proj MLP output, :370-371)
+ *   ln_w, ln_b (d) in `dtype` for Q_FILM_LN (coarse_norm, eps 1e-6)
+ *   score = (q·k) * logit_scale   (1/sqrt(qk_dim) :551, or exp(logit_scale) :549; the additive
+ *   logit_bias is constant over a window and cancels in the softmax).  k_l2norm != 0 divides each
+ *   key by its L2 norm first (:528).  Windows follow the reference's balanced overlapping rule
+ *   when a dimension is not divisible; kt/ks are the EFFECTIVE kernel (caller passes kt=1 for
+ *   images / T==1, :536).  Shapes the reference cannot stack (e.g. T in {5,6,9}, kt=4) fail.
+ *   out (B,Nw,d) in `dtype`.
+ */
+int hicom_local_attend(const void* Ksrc, const void* Vsrc, const void* Psrc, const void* q_aux,
+                       const float* film, const void* ln_w, const void* ln_b, void* out, int B,
+                       int T, int H, int W, int d, int kt, int ks, int qmode, float logit_scale,
+                       int k_l2norm, int dtype, void* stream);
+
+/* ---- dense layers -----------------------------------------------------------------------
+ * hicom_linear: C = act(A · Wᵀ + bias) [+ R]   — nn.Linear / build_mlp stages
+ *   (projector.py:180-182,226,307-312,559,646).
+ *   A (M,K) lda; W (N,K) ldw (torch Linear layout); bias (N) or NULL; R (M,N) ldr residual or NULL
+ *   (added after the activation); C (·,N) ldc.  Output row r is written to row
+ *   (r / rows_per_group) * group_stride_rows + (r % rows_per_group) of C — this is how the local
+ *   and global readouts write straight into the concatenated (Nw+Q, Dh) token block of each video
+ *   (projector.py:707); pass rows_per_group = M, group_stride_rows = 0 for a plain GEMM.
+ *   in_dtype covers A, W, bias, R; out_dtype covers C.  impl: HICOM_IMPL_*.
+ */
+int hicom_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                 const void* R, int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int act,
+                 int in_dtype, int out_dtype, int rows_per_group, int64_t group_stride_rows,
+                 int impl, void* stream);
+
+/* Row-wise LayerNorm family over rows of length d (eps 1e-6), all tensors in `dtype`:
+ *   film_layernorm : out = LN(x*(1+scale)+shift)     coarse injector on explicit rows (:369-372);
+ *                    film (G,2d) fp32, row r uses film[r / rows_per_group]
+ *   add_layernorm  : out = LN(a + b)                 fine injector residual (:392)
+ *   mix_layernorm  : out = (1-alpha)*x + alpha*LN(y) adapters (:365,533-534,541); alpha read from device
+ */
+int hicom_film_layernorm(const void* x, const float* film, const void* ln_w, const void* ln_b,
+                         void* out, int rows, int d, int rows_per_group, int dtype, void* stream);
+int hicom_add_layernorm(const void* a, const void* b, const void* ln_w, const void* ln_b, void* out,
+                        int rows, int d, int dtype, void* stream);
+int hicom_mix_layernorm(const void* x, const void* y, const void* ln_w, const void* ln_b,
+                        const void* alpha, void* out, int64_t rows, int d, int dtype, void* stream);
+
+/* hicom_guide_attend: multi-head attention of query rows over a SHORT key/value list — the `fine`
+ *   injector's MHA over the L instruction tokens (projector.py:391 -> :193-224).  q (G,Mq,d),
+ *   k,v (G,L,d) already projected; out (G,Mq,d); heads = d/128; score = q·k*scale; fp32 softmax.
+ */
+int hicom_guide_attend(const void* q, const void* k, const void* v, void* out, int G, int Mq, int L,
+                       int d, int heads, float scale, int dtype, void* stream);
+
+/* ---- global compressor ------------------------------------------------------------------
+ * The global cross-attention (projector.py:634-646 -> MultiheadAttention.forward :166-228) is
+ * evaluated in the reassociated form: with q = Wq·Qg+bq,
+ *     S[n,(h,i)] = scale * q[i,h]·(Wk_h x'_n + bk_h)  =  x'_n · qfold[(h,i)]  + const(h,i)
+ *     O[i,h]     = Wv_h (sum_n softmax_n(S)[n,(h,i)] x'_n) + bv_h
+ * where x' = x + pos_embed.  The constant drops out of the softmax.  J = heads*Q columns.
+ *
+ * hicom_global_fold_query: qfold[b,h*Q+i,:] = alpha * sum_c q[b,i,h*hd+c] * Wk[h*hd+c,:]
+ *   (replaces k_proj :181 together with the scale of :197).  q (B,Q,d), Wk (d,d), qfold (B,J,d).
+ */
+int hicom_global_fold_query(const void* q, const void* Wk, void* qfold, int B, int Q, int d,
+                            int heads, float alpha, int dtype, void* stream);
+
+/* hicom_global_attend_partial: split-softmax partials of the global attention over a block of
+ *   frames (:636-640 pos-embed add, :197 scores, :213 softmax, :215 P·V).
+ *   X (B,T,H,W,d); pos_t (T,d), pos_h (H,d), pos_w (W,d) fp32 per-axis sincos tables
+ *   (projector.py:57-101 is separable: PE[t,h,w] = f(t)+f(h)+f(w); the caller builds the tables in
+ *   float64 like the reference, rounds each once, and offsets pos_t to the shard's first global
+ *   frame); qfold (B,J,d).
+ *   Tokens of each video are cut into `splits` contiguous ranges; for range s and column j:
+ *     m[b,s,j] = max_n S,   l[b,s,j] = sum_n exp(S-m),   o[b,s,j,:] = sum_n exp(S-m) x'_n  (fp32)
+ *   workspace: at least hicom_global_attend_workspace_bytes(...) bytes, 256-byte aligned.
+ */
+size_t hicom_global_attend_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits,
+                                           int dtype, int impl);
+int hicom_global_attend_partial(const void* X, const float* pos_t, const float* pos_h,
+                                const float* pos_w, const void* qfold, float* m, float* l, float* o,
+                                int B, int T, int H, int W, int d, int J, int splits, int dtype,
+                                void* workspace, size_t workspace_bytes, int impl, void* stream);
+
+/* hicom_softmax_merge: combine P partials per (video, column) — across token splits and, after an
+ *   all-gather, across frame shards on other GPUs:
+ *     M = max_p m_p;  L = sum_p l_p e^{m_p-M};  pooled = sum_p o_p e^{m_p-M} / L
+ *   m,l (B,P,J) o (B,P,J,d) fp32; pooled (B,J,d) in out_dtype.
+ */
+int hicom_softmax_merge(const float* m, const float* l, const float* o, int B, int P, int J, int d,
+                        void* pooled, int out_dtype, void* stream);
+
+/* hicom_global_value_proj: attn[b,i,h*hd+c] = sum_k Wv[h*hd+c,k] * pooled[b,h*Q+i,k] + bv[h*hd+c]
+ *   (v_proj :182 applied after the pooling, and the head merge :223-224).
+ */
+int hicom_global_value_proj(const void* pooled, const void* Wv, const void* bv, void* attn, int B,
+                            int Q, int d, int heads, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HICOM_B200_H */

@@ -1,0 +1,106 @@
+"""CPU: the drop-in boundary — factory grammar, state_dict contract, C-ABI exports, loud failures."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import hicom_oracle as O
+
+from util import Cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("ptype", ["local43_global32", "local43_global32_coarse", "local412_global8",
+                                   "local43_adaptqkvg_global32_adaptg", "local43guidefine_global32guidedirect",
+                                   "global16", "local22"])
+@pytest.mark.parametrize("use_guide", [None, "off", "direct", "coarse", "fine"])
+def test_state_dict_contract(ptype, use_guide):
+    import hicom_b200
+    m = hicom_b200.build_vision_projector(Cfg(mm_projector_type=ptype, use_guide=use_guide, hidden_size=64))
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == O.param_shapes(ptype, use_guide, 64)
+    assert "global_compressor.pos_embed" not in got  # non-persistent in the reference (projector.py:607)
+    sd = O.synth_state_dict(ptype, use_guide, 64, seed=3)
+    m.load_state_dict(sd, strict=True)
+    m.to(torch.bfloat16)
+    assert all(v.dtype == torch.bfloat16 for v in m.state_dict().values())
+
+
+def test_factory_grammar():
+    import hicom_b200
+    from hicom_b200 import projector as P
+    m = hicom_b200.build_vision_projector(Cfg(mm_projector_type="local43_global32_coarse", use_guide="direct"))
+    assert isinstance(m, P.HIComProjector)
+    # the _coarse suffix is ignored: guide mode comes from config.use_guide (SURVEY finding 1)
+    assert m.local_compressor.use_guide == "direct" and m.global_compressor.use_guide == "direct"
+    assert (m.local_compressor.temporal_kernel_size, m.local_compressor.spatial_kernel_size) == (4, 3)
+    assert m.global_compressor.query.shape == (32, 1152)
+    assert float(m.global_compressor.query.detach().abs().max()) == 0.0  # zero-init (projector.py:583)
+    m = hicom_b200.build_vision_projector(Cfg(mm_projector_type="local412_global8"))
+    assert m.local_compressor.spatial_kernel_size == 12 and m.global_compressor.query.shape[0] == 8
+    m = hicom_b200.build_vision_projector(Cfg(mm_projector_type="local43guidecoarse_global32guidedirect"))
+    assert m.local_compressor.use_guide == "coarse" and m.global_compressor.use_guide == "direct"
+    assert isinstance(hicom_b200.build_vision_projector(Cfg(mm_projector_type="linear")), torch.nn.Linear)
+    seq = hicom_b200.build_vision_projector(Cfg(mm_projector_type="mlp2x_gelu"))
+    assert isinstance(seq, torch.nn.Sequential) and len(seq) == 3
+    with pytest.raises(NotImplementedError):
+        hicom_b200.build_vision_projector(Cfg(mm_vision_tower="openai/other"))
+    with pytest.raises(AssertionError):
+        P.HIComProjector(Cfg(), None, None)
+    clip = hicom_b200.build_vision_projector(Cfg(mm_vision_tower="openai/clip-vit-large-patch14-336",
+                                                 mm_hidden_size=768, hidden_size=64))
+    assert clip.local_compressor.qk_dim == 768 and clip.global_compressor.attn_layer.num_heads == 6
+
+
+def test_parser_matches_oracle_parser():
+    import hicom_b200
+    for ptype in ["local43_global32", "local412_global8_adaptg", "local43_adaptkv_global32", "local22guideoff_global4"]:
+        spec = O.parse_projector_type(ptype)
+        m = hicom_b200.build_vision_projector(Cfg(mm_projector_type=ptype, use_guide="coarse", hidden_size=32))
+        lc, gc = m.local_compressor, m.global_compressor
+        assert (lc.temporal_kernel_size, lc.spatial_kernel_size) == (spec.local.temporal_kernel, spec.local.spatial_kernel)
+        assert isinstance(lc.k_alpha, torch.Tensor) == spec.local.adapt_k
+        assert isinstance(lc.v_alpha, torch.Tensor) == spec.local.adapt_v
+        assert gc.query.shape[0] == spec.global_.num_queries
+
+
+def test_position_table_matches_reference_formula():
+    import hicom_b200
+    from hicom_b200.projector import _axis_table
+    dense = hicom_b200.get_3d_position_embedding(5, 4, 3, 1152)
+    assert torch.equal(torch.from_numpy(dense).float(), O.pos_embed_3d(5, 4, 3, 1152))
+    sep = (torch.from_numpy(_axis_table(5, 1152)).float()[:, None, None] +
+           torch.from_numpy(_axis_table(4, 1152)).float()[None, :, None] +
+           torch.from_numpy(_axis_table(3, 1152)).float()[None, None, :])
+    assert float((sep - O.pos_embed_3d(5, 4, 3, 1152)).abs().max()) < 5e-7
+
+
+def test_cabi_exports_every_declared_symbol(built_library):
+    header = open(os.path.join(ROOT, "include", "hicom_b200.h")).read()
+    declared = set(re.findall(r"\b(hicom_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(built_library)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/hicom_b200.h but not exported"
+    from hicom_b200 import _cabi
+    assert set(_cabi.PROTOTYPES) == declared
+    assert _cabi.load().hicom_abi_version() == 1
+
+
+def test_no_cpu_fallback(built_library):
+    import hicom_b200
+    m = hicom_b200.build_vision_projector(Cfg(hidden_size=64))
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        m(torch.randn(4, 6, 6, 1152), None, None, "video")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "hicom_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"

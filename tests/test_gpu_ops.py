@@ -1,0 +1,178 @@
+"""GPU: each C-ABI op against the matching oracle piece (small shapes), SIMT and tensor paths."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hicom_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(*shape, seed=0, std=0.5, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (std * torch.randn(*shape, generator=g)).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(8, 9, 9, 4, 3), (7, 7, 8, 4, 3), (1, 6, 6, 1, 3), (2, 6, 6, 4, 3), (8, 8, 8, 4, 2)])
+def test_grid_pool(shape, dtype, built_library):
+    from hicom_b200 import ops
+    T, H, W, kt, ks = shape
+    X = _rand(2, T, H, W, 1152, dtype=dtype)
+    got = ops.grid_pool(X.cuda(), kt, ks).float().cpu()
+    ds = (math.ceil(T / kt), math.ceil(H / ks), math.ceil(W / ks))
+    want = torch.stack([F.interpolate(x.float().permute(3, 0, 1, 2)[None], size=ds, mode="trilinear")[0]
+                        .permute(1, 2, 3, 0).reshape(-1, 1152) for x in X])
+    assert O.rel_err(got, want) <= (1e-6 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(1, 2304, 1152), (33, 64, 1152), (324, 896, 1152), (700, 1152, 1152), (64, 3584, 3584)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_linear(M, N, K, act, dtype, built_library):
+    from hicom_b200 import ops
+    A, Wt, b, R = _rand(M, K, seed=1, dtype=dtype), _rand(N, K, seed=2, std=0.02, dtype=dtype), \
+        _rand(N, seed=3, std=0.02, dtype=dtype), _rand(M, N, seed=4, dtype=dtype)
+    want = F.linear(A.float(), Wt.float(), b.float())
+    if act:
+        want = F.gelu(want)
+    want = want + R.float()
+    for impl in (ops.IMPL_SIMT, ops.IMPL_AUTO):
+        got = ops.linear(A.cuda(), Wt.cuda(), b.cuda(), R.cuda(), act, False, impl).float().cpu()
+        assert O.rel_err(got, want) <= (2e-5 if dtype == torch.float32 else 6e-3), impl
+    # row-remapped destination
+    rpg, stride, off = 5, 9, 2
+    groups = (M + rpg - 1) // rpg
+    out = torch.zeros(groups * stride + off, N, dtype=dtype, device="cuda")
+    ops.linear_into(A.cuda(), Wt.cuda(), b.cuda(), None, act, out, off, rpg, stride, ops.IMPL_AUTO)
+    ref = F.linear(A.float(), Wt.float(), b.float())
+    if act:
+        ref = F.gelu(ref)
+    rows = torch.tensor([(r // rpg) * stride + r % rpg + off for r in range(M)])
+    assert O.rel_err(out.float().cpu()[rows], ref) <= (2e-5 if dtype == torch.float32 else 6e-3)
+    mask = torch.ones(out.shape[0], dtype=torch.bool); mask[rows] = False
+    assert float(out.float().cpu()[mask].abs().max() if mask.any() else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_family(dtype, built_library):
+    from hicom_b200 import ops
+    d = 1152
+    x, y = _rand(37, d, seed=1, dtype=dtype), _rand(37, d, seed=2, dtype=dtype)
+    w, b = (1 + _rand(d, seed=3, std=0.1)).to(dtype), _rand(d, seed=4, std=0.1, dtype=dtype)
+    film = _rand(4, 2 * d, seed=5, std=0.3)
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    ln = lambda t: F.layer_norm(t, (d,), w.float(), b.float(), 1e-6)
+    got = ops.film_layernorm(x.cuda(), film.cuda(), w.cuda(), b.cuda(), 10).float().cpu()
+    grp = torch.arange(37) // 10
+    want = ln(x.float() * (1 + film[grp, :d]) + film[grp, d:])
+    assert O.rel_err(got, want) <= tol
+    got = ops.add_layernorm(x.cuda(), y.cuda(), w.cuda(), b.cuda()).float().cpu()
+    assert O.rel_err(got, ln(x.float() + y.float())) <= tol
+    alpha = torch.tensor([0.3]).to(dtype)
+    got = ops.mix_layernorm(x.cuda(), y.cuda(), w.cuda(), b.cuda(), alpha.cuda()).float().cpu()
+    a = alpha.float()
+    assert O.rel_err(got, (1 - a) * x.float() + a * ln(y.float())) <= tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_guide_attend(dtype, built_library):
+    from hicom_b200 import ops
+    G, Mq, L, d, heads = 2, 19, 32, 1152, 9
+    q, k, v = _rand(G, Mq, d, seed=1, dtype=dtype), _rand(G, L, d, seed=2, dtype=dtype), _rand(G, L, d, seed=3, dtype=dtype)
+    got = ops.guide_attend(q.cuda(), k.cuda(), v.cuda(), heads, 128 ** -0.5).float().cpu()
+    qh = q.float().view(G, Mq, heads, 128).transpose(1, 2)
+    kh = k.float().view(G, L, heads, 128).transpose(1, 2)
+    vh = v.float().view(G, L, heads, 128).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(2, 3) * 128 ** -0.5, -1)
+    want = (p @ vh).transpose(1, 2).reshape(G, Mq, d)
+    assert O.rel_err(got, want) <= (1e-5 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["pooled", "film", "vector", "explicit"])
+@pytest.mark.parametrize("geom", [(8, 9, 9, 4, 3), (7, 7, 8, 4, 3), (1, 6, 6, 1, 3), (2, 6, 6, 4, 3), (4, 24, 24, 4, 12)])
+def test_local_attend(geom, mode, dtype, built_library):
+    from hicom_b200 import ops
+    T, H, W, kt, ks = geom
+    d, B = 1152, 2
+    X, E = _rand(B, T, H, W, d, seed=1, dtype=dtype), _rand(B, T, H, W, d, seed=2, dtype=dtype)
+    nw = ops.num_windows(T, H, W, kt, ks)
+    film = _rand(B, 2 * d, seed=3, std=0.3)
+    w, b = (1 + _rand(d, seed=4, std=0.1)).to(dtype), _rand(d, seed=5, std=0.1, dtype=dtype)
+    gvec, qexp = _rand(B, d, seed=6, dtype=dtype), _rand(B, nw, d, seed=7, dtype=dtype)
+    ds = (math.ceil(T / kt), math.ceil(H / ks), math.ceil(W / ks))
+    qmode = {"pooled": ops.Q_POOLED, "film": ops.Q_FILM_LN, "vector": ops.Q_VECTOR, "explicit": ops.Q_EXPLICIT}[mode]
+    q_aux = {"vector": gvec, "explicit": qexp}.get(mode)
+    got = ops.local_attend(E.cuda(), X.cuda(), X.cuda(), None if q_aux is None else q_aux.cuda(),
+                           film.cuda() if mode == "film" else None, w.cuda() if mode == "film" else None,
+                           b.cuda() if mode == "film" else None, kt, ks, qmode, 1 / math.sqrt(d), False).float().cpu()
+    for i in range(B):
+        x, e = X[i].float(), E[i].float()
+        q0 = F.interpolate(x.permute(3, 0, 1, 2)[None], size=ds, mode="trilinear")[0].permute(1, 2, 3, 0).reshape(-1, d)
+        if mode == "pooled":
+            q = q0
+        elif mode == "film":
+            q = F.layer_norm(q0 * (1 + film[i, :d]) + film[i, d:], (d,), w.float(), b.float(), 1e-6)
+        elif mode == "vector":
+            q = gvec[i].float()[None].expand(nw, d)
+        else:
+            q = qexp[i].float()
+        rk, rv = O.window_gather(e, (kt, ks, ks)), O.window_gather(x, (kt, ks, ks))
+        a = torch.softmax(torch.bmm(q[:, None], rk.transpose(1, 2)) / math.sqrt(d), -1)
+        want = torch.bmm(a, rv)[:, 0]
+        assert O.rel_err(got[i], want) <= (2e-5 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("impl_name", ["simt", "auto"])
+def test_global_partial_merge(dtype, impl_name, built_library):
+    """fold -> partial -> merge -> value_proj against the reference-form attention (projector.py:180-224)."""
+    from hicom_b200 import ops
+    from hicom_b200.projector import _axis_table
+    impl = ops.IMPL_SIMT if impl_name == "simt" else ops.IMPL_AUTO
+    B, T, H, W, d, Q, heads = 2, 4, 9, 9, 1152, 32, 9
+    X = _rand(B, T, H, W, d, seed=1, dtype=dtype)
+    Qg = _rand(B, Q, d, seed=2, dtype=dtype)
+    Wq, Wk, Wv = (_rand(d, d, seed=s, std=0.02, dtype=dtype) for s in (3, 4, 5))
+    bq, bk, bv = (_rand(d, seed=s, std=0.02, dtype=dtype) for s in (6, 7, 8))
+    t0 = 3
+    tabs = [torch.from_numpy(_axis_table(n, d)).float() for n in (t0 + T, H, W)]
+    pt, ph, pw = tabs[0][t0:].contiguous(), tabs[1], tabs[2]
+    q = ops.linear(Qg.cuda(), Wq.cuda(), bq.cuda(), None, 0, False, impl)
+    qf = ops.global_fold_query(q, Wk.cuda(), heads, 128 ** -0.5)
+    for splits in (1, 3):
+        m, l, o = ops.global_attend_partial(X.cuda(), pt.cuda(), ph.cuda(), pw.cuda(), qf, splits, impl)
+        pooled = ops.softmax_merge(m, l, o, dtype == torch.bfloat16)
+        got = ops.global_value_proj(pooled, Wv.cuda(), bv.cuda(), Q, heads).float().cpu()
+        for i in range(B):
+            xp = (X[i].float() + O.pos_embed_3d(t0 + T, H, W, d)[t0:]).reshape(-1, d)
+            qq = F.linear(Qg[i].float(), Wq.float(), bq.float()).view(Q, heads, 128).transpose(0, 1)
+            kk = F.linear(xp, Wk.float(), bk.float()).view(-1, heads, 128).transpose(0, 1)
+            vv = F.linear(xp, Wv.float(), bv.float()).view(-1, heads, 128).transpose(0, 1)
+            p = torch.softmax(qq @ kk.transpose(1, 2) * 128 ** -0.5, -1)
+            want = (p @ vv).transpose(0, 1).reshape(Q, d)
+            assert O.rel_err(got[i], want) <= (2e-5 if dtype == torch.float32 else 8e-3), (splits, i)
+
+
+def test_softmax_merge_handles_empty_and_extreme(built_library):
+    from hicom_b200 import ops
+    B, P, J, d = 1, 3, 4, 128
+    m = torch.tensor([[[0.0, 50.0, -80.0, 3.0], [float("-inf")] * 4, [1.0, -50.0, 80.0, 3.0]]])
+    l = torch.tensor([[[2.0, 1.0, 1.0, 4.0], [0.0] * 4, [3.0, 1.0, 1.0, 4.0]]])
+    o = _rand(B, P, J, d, seed=1).abs()
+    got = ops.softmax_merge(m.cuda(), l.cuda(), o.cuda(), False).cpu()
+    M = m.max(1).values
+    w = (m - M[:, None]).exp()
+    L = (l * w).sum(1)
+    want = (o * w[..., None]).sum(1) / L[..., None]
+    assert torch.isfinite(got).all()
+    assert O.rel_err(got, want) <= 1e-5
+
+
+def test_device_info(built_library):
+    from hicom_b200 import ops
+    sm, major, minor = ops.device_info()
+    assert major == 10 and sm >= 100

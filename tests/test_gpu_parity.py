@@ -1,0 +1,138 @@
+"""GPU: the CUDA path (through the torch custom ops -> C ABI) against the golden reference outputs and the oracle.
+
+Tolerances (BASELINE.json north_star / SURVEY §8c):
+  fp32 : max|a-b| / max|b| <= 1e-4 vs the reference's fp32 output (stored golden)
+  bf16 : vs the fp32 oracle on the bf16-rounded weights/inputs: cosine >= 0.999 and max|a-b|/max|b| <= 1e-2
+Token order/layout is checked by the same comparison (a permuted row fails the tolerance) plus shape equality.
+"""
+import pytest
+import torch
+
+from oracle import hicom_oracle as O
+from oracle.cases import CASES, CASES_BY_NAME, materialise
+
+from util import cuda_module_for, oracle_for, to_dev, truth_fp32
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_REL, BF16_COS = 1e-2, 0.999
+
+
+def run_cuda(case, batched=False):
+    sd, X, E, g, nl = materialise(case)
+    m = cuda_module_for(case, sd)
+    with torch.no_grad():
+        out = m(to_dev(X), to_dev(E), to_dev(g), case.modal, to_dev(nl))
+    torch.cuda.synchronize()
+    return out.float().cpu()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+def test_forward_matches_reference(case, golden, built_library):
+    out = run_cuda(case)
+    ref = golden[case.name]
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert torch.isfinite(out).all()
+    if case.dtype == "float32":
+        assert O.rel_err(out, ref) <= FP32_TOL
+    else:
+        truth = truth_fp32(case)
+        assert O.cosine(out, truth) >= BF16_COS
+        assert O.rel_err(out, truth) <= BF16_REL
+        # informational: how far the reference's own bf16 forward is from the same truth
+        print(f"{case.name}: ours vs truth {O.rel_err(out, truth):.2e}; reference-bf16 vs truth "
+              f"{O.rel_err(ref, truth):.2e}")
+
+
+@pytest.mark.parametrize("name", ["coarse_T8", "none_T8", "direct_T8", "fine_T8", "adaptkv_coarse_T8"])
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_forward_batched_equals_loop(name, dtype, built_library):
+    """forward_batched == stacking forward over the batch (hicom_arch.py:167-178)."""
+    import dataclasses
+    case = dataclasses.replace(CASES_BY_NAME[name], dtype=dtype)
+    sd, _, _, _, _ = materialise(case)
+    m = cuda_module_for(case, sd)
+    kind = O.guide_kind_for(case.use_guide)
+    dt = getattr(torch, dtype)
+    xs, es, gs = [], [], []
+    for b in range(3):
+        X, E, g = O.synth_inputs(case.T, case.H, case.W, kind, seed=100 + b, dtype=dt)
+        xs.append(X); es.append(E); gs.append(g)
+    Xb = torch.stack(xs).cuda()
+    Eb = torch.stack(es).cuda() if kind else None
+    Gb = torch.stack(gs).cuda() if kind else None
+    with torch.no_grad():
+        got = m.forward_batched(Xb, Eb, Gb, "video")
+        want = torch.stack([m(Xb[b], None if Eb is None else Eb[b], None if Gb is None else Gb[b], "video")
+                            for b in range(3)])
+    assert got.shape == want.shape
+    assert O.rel_err(got.float().cpu(), want.float().cpu()) <= (1e-5 if dtype == "float32" else 4e-3)
+    # and each video matches the oracle truth
+    orc = oracle_for(case, sd, torch.float32)
+    for b in range(3):
+        f = lambda t: None if t is None else t.float()
+        truth = orc.forward(f(xs[b]), f(es[b]), f(gs[b]), "video")
+        err = O.rel_err(got[b].float().cpu(), truth)
+        assert err <= (FP32_TOL if dtype == "float32" else BF16_REL)
+
+
+def test_anyres_dict_branch(built_library):
+    """any-res image dict input (projector.py:679-698): base -> local only, patch -> local + global."""
+    case = CASES_BY_NAME["image_T1_newline"]
+    sd, X, E, g, nl = materialise(case)
+    gen = torch.Generator().manual_seed(3)
+    patch = 0.5 * torch.randn(12, 6, 1152, generator=gen)
+    patch_e = 0.5 * torch.randn(12, 6, 1152, generator=gen)
+    want = oracle_for(case, sd).forward({"base": X[0], "patch": patch}, {"base": E[0], "patch": patch_e}, g,
+                                        "image", nl)
+    m = cuda_module_for(case, sd)
+    with torch.no_grad():
+        got = m({"base": X[0].cuda(), "patch": patch.cuda()}, {"base": E[0].cuda(), "patch": patch_e.cuda()},
+                g.cuda(), "image", nl.cuda())
+    assert got.shape == want.shape
+    assert O.rel_err(got.float().cpu(), want) <= FP32_TOL
+
+
+def test_reference_failures_are_loud(built_library):
+    """T in {5,6,9} with temporal kernel 4 raise (the reference's torch.stack fails); bad guide rank raises."""
+    case = CASES_BY_NAME["coarse_T8"]
+    sd, X, E, g, nl = materialise(case)
+    m = cuda_module_for(case, sd)
+    for T in (5, 6, 9):
+        x = torch.randn(T, 6, 6, 1152, device="cuda")
+        with pytest.raises(RuntimeError):
+            m(x, x, g.cuda(), "video")
+    with pytest.raises(ValueError):
+        m(X.cuda(), E.cuda(), torch.randn(4, 1152, device="cuda"), "video")  # coarse wants a (d,) vector
+    with pytest.raises(ValueError):
+        m(X.cuda(), E.cuda(), None, "video")
+
+
+def test_full_size_properties_bf16(built_library):
+    """BASELINE config c2 shape (width 3584, 16 frames, bf16), one video: size-independent properties.
+    direct mode => 32 identical global rows; frame-sharded partial merge == unsharded; row count."""
+    import dataclasses
+    base = dataclasses.replace(CASES_BY_NAME["c1_direct_896_T16"], hidden=3584, dtype="bfloat16")
+    sd, X, E, g, nl = materialise(base)
+    m = cuda_module_for(base, sd)
+    with torch.no_grad():
+        out = m(X.cuda(), E.cuda(), g.cuda(), "video")
+    assert out.shape == (4 * 81 + 32, 3584) and out.dtype == torch.bfloat16
+    glob = out[-32:].float()
+    assert float((glob - glob[0]).abs().max()) == 0.0
+    # split-softmax: 2 frame shards merged == whole video
+    gc = m.global_compressor
+    Xd, gd = X.cuda().unsqueeze(0), g.cuda().unsqueeze(0)
+    with torch.no_grad():
+        Qg = gc.injected_query(gd, 1, Xd.dtype)
+        qf = gc.fold(Qg)
+        whole = torch.empty(32, 3584, dtype=Xd.dtype, device="cuda")
+        gc.finish(Qg, *gc.partials(Xd, qf), whole, 0, 0)
+        parts = [gc.partials(Xd[:, t0:t0 + 8].contiguous(), qf, t0=t0) for t0 in (0, 8)]
+        mm = torch.cat([p[0] for p in parts], 1); ll = torch.cat([p[1] for p in parts], 1)
+        oo = torch.cat([p[2] for p in parts], 1)
+        merged = torch.empty_like(whole)
+        gc.finish(Qg, mm, ll, oo, merged, 0, 0)
+    assert O.rel_err(merged.float().cpu(), whole.float().cpu()) <= 4e-3
+    assert O.rel_err(whole.float().cpu(), out[-32:].float().cpu()) <= 4e-3

@@ -1,0 +1,60 @@
+"""CPU, authoring container only: the oracle against the live reference module (skipped without /root/reference)."""
+import pytest
+import torch
+
+from oracle import hicom_oracle as O
+from oracle.cases import CASES, materialise
+from oracle.ref_shim import load_reference, reference_available
+
+from util import cfg_for, oracle_for
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+
+SMALL = [c for c in CASES if c.H <= 9]
+
+
+@pytest.mark.parametrize("case", SMALL, ids=[c.name for c in SMALL])
+def test_live_reference(case):
+    ref = load_reference()
+    sd, X, E, g, nl = materialise(case)
+    m = ref.build_vision_projector(cfg_for(case))
+    m.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+    m = m.to(getattr(torch, case.dtype)).eval()
+    with torch.no_grad():
+        want = m(X, E, g, case.modal, nl)
+        got = oracle_for(case, sd).forward(X, E, g, case.modal, nl)
+    assert got.shape == want.shape
+    assert O.rel_err(got.float(), want.float()) <= (2e-6 if case.dtype == "float32" else 8e-3)
+
+
+@pytest.mark.parametrize("ptype", ["local43_global32_coarse", "local412_global8", "local43_adaptqk_global32_adaptg",
+                                   "local43guidefine_global32", "global16", "local22", "mlp2x_gelu", "linear"])
+@pytest.mark.parametrize("use_guide", [None, "direct", "coarse", "fine"])
+def test_parser_and_state_dict_names(ptype, use_guide):
+    from util import Cfg
+    ref = load_reference()
+    m = ref.build_vision_projector(Cfg(mm_projector_type=ptype, use_guide=use_guide, hidden_size=64, max_num_frames=2))
+    if ptype in ("mlp2x_gelu", "linear"):
+        assert O.parse_projector_type(ptype).kind in ("mlp", "linear")
+        return
+    want = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert O.param_shapes(ptype, use_guide, 64) == want
+
+
+def test_reference_dict_branch_anyres():
+    """any-res image dict input (projector.py:679-698)."""
+    from oracle.cases import CASES_BY_NAME
+    ref = load_reference()
+    case = CASES_BY_NAME["image_T1_newline"]
+    sd, X, E, g, nl = materialise(case)
+    m = ref.build_vision_projector(cfg_for(case))
+    m.load_state_dict(sd, strict=True)
+    gen = torch.Generator().manual_seed(3)
+    patch = 0.5 * torch.randn(12, 6, 1152, generator=gen)
+    patch_e = 0.5 * torch.randn(12, 6, 1152, generator=gen)
+    feats = {"base": X[0], "patch": patch}
+    embeds = {"base": E[0], "patch": patch_e}
+    with torch.no_grad():
+        want = m(feats, embeds, g, "image", nl)
+        got = oracle_for(case, sd).forward(feats, embeds, g, "image", nl)
+    assert torch.equal(got, want)
