@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — frames/s through the HICom compressor (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5|c4]
+
+One "step" = one pass of the hot path (``HIComProjector.forward_batched``) over one batch of synthetic
+videos per GPU.  N=1 default workload = BASELINE.json configs[1] (c2: Qwen2.5-7B width 3584, 16 frames,
+bf16, batch 32).  N>1 shards by video (no data-path collective, weak scaling: every rank runs the same
+per-GPU batch); ``--workload c4`` is the frame-sharded long video (split-softmax merge over NCCL).
+``--impl reference`` times the CPU oracle port of the reference projector on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (hidden, T, per-GPU batch, description)
+    "c2": (3584, 16, 32, "c2: Qwen2.5-7B width 3584, 16 frames x 729 x 1152, bf16, batch 32 per GPU"),
+    "c3": (3584, 64, 8, "c3: width 3584, 64 frames, bf16, batch 64 video-parallel over 8 GPUs (8 per GPU)"),
+    "c5": (1536, 32, 64, "c5: Qwen2.5-1.5B width 1536, 32 frames, bf16, batch 512 over 8 GPUs (64 per GPU)"),
+    "c4": (3584, 512, 1, "c4: width 3584, one 512-frame video, frame-sharded over the GPUs (split-softmax merge)"),
+}
+PTYPE, USE_GUIDE = "local43_global32", "coarse"  # headline mode
+H = W = 27
+D = 1152
+Q, HEADS = 32, 9
+
+
+class Cfg:
+    def __init__(self, hidden):
+        self.mm_vision_tower = "google/siglip-so400m-patch14-384"
+        self.mm_hidden_size = D
+        self.hidden_size = hidden
+        self.mm_projector_type = PTYPE
+        self.use_guide = USE_GUIDE
+        self.max_num_frames = 64
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"],
+                "tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work per step (SURVEY §8d / BASELINE.md §4)
+# ---------------------------------------------------------------------------------------------
+def work_per_video(hidden, T):
+    N = T * H * W
+    Nw = (T // 4) * 81
+    J = Q * HEADS
+    return {
+        "N": N, "Nw": Nw, "tokens_out": Nw + Q,
+        # reference formulation (K/V projected for every token) — for context only
+        "flops_reference": 4 * N * D * D + 4 * Q * N * D + 4 * N * D + 2 * Nw * (D * hidden + hidden * hidden)
+                           + 4 * Q * D * D + 2 * Q * (D * hidden + hidden * hidden),
+        # what this implementation executes on the tensor pipe (reassociated global path)
+        "flops_scores": 2 * N * J * D, "flops_pool": 2 * N * J * D,
+        "flops_local_readout": 2 * Nw * (D * hidden + hidden * hidden),
+        "bytes_local": (2 * N * D + Nw * D) * 2,  # read X and E once, write attended windows (bf16)
+        "bytes_in": 2 * N * D * 2, "bytes_out": (Nw + Q) * hidden * 2,
+    }
+
+
+def op_work(name, B, hidden, T):
+    """(kind, amount) for the op-timer label: algorithmic FLOPs or bytes of ONE call."""
+    w = work_per_video(hidden, T)
+    if name == "local_attend":
+        return "hbm", B * w["bytes_local"]
+    if name == "global_attend_partial":
+        return "tensor", B * (w["flops_scores"] + w["flops_pool"])
+    if name.startswith("linear "):
+        f = dict(kv.split("=") for kv in name.split()[1:])
+        return "tensor", 2 * int(f["M"]) * int(f["N"]) * int(f["K"])
+    return None, 0
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference projector on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(hidden, T, videos, steps, warmup):
+    """frames/s of the reference algorithm (oracle port, fp32) over `videos` videos per step, looped per
+    video exactly like hicom_arch.py:167-178."""
+    from oracle import hicom_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.synth_state_dict(PTYPE, USE_GUIDE, hidden, seed=0)
+    orc = O.OracleProjector(PTYPE, USE_GUIDE, "flat", "one_token", sd)
+    inputs = [O.synth_inputs(T, H, W, "vec", seed=1234 + i) for i in range(videos)]
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            for X, E, g in inputs:
+                orc.forward(X, E, g, "video")
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return videos * T / sec, sec * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    hidden, T, B, desc = WORKLOADS[args.workload]
+    videos = 2 if T <= 16 else 1
+    if args.workload == "c4":
+        T, videos = 64, 1  # bounded sample: one 64-frame shard of the 512-frame video
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    fps, ms, cores = cpu_reference(hidden, T, videos, steps, warmup)
+    w = work_per_video(hidden, T)
+    sample = f"{videos} video(s) of {T} frames per step, fp32, torch CPU oracle port of projector.py:676-708"
+    line = {
+        "impl": "reference", "metric": "frames/s through the HICom compressor", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "projector_type": PTYPE, "use_guide": USE_GUIDE},
+        "tokens_per_s": fps / T * w["tokens_out"],
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def build_projector(hidden, device):
+    import hicom_b200
+    torch.manual_seed(0)
+    m = hicom_b200.build_vision_projector(Cfg(hidden))
+    with torch.no_grad():
+        m.global_compressor.query.normal_(0, 0.02)  # zero-init in the reference (projector.py:583)
+    return m.to(torch.bfloat16).to(device).eval()
+
+
+def synth_batch(B, T, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    mk = lambda *s: (0.5 * torch.randn(*s, generator=g, device=device, dtype=torch.float32)).to(torch.bfloat16)
+    return mk(B, T, H, W, D), mk(B, T, H, W, D), mk(B, D)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from hicom_b200 import ops
+    from hicom_b200.pipeline import compress_from_host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    hidden, T, B, desc = WORKLOADS[args.workload]
+    frame_sharded = args.workload == "c4"
+    if frame_sharded:
+        from hicom_b200 import dist as hdist
+        assert T % (4 * world) == 0
+        T_local = T // world
+    else:
+        T_local = T
+
+    from __graft_entry__ import build
+    if local_rank == 0:
+        build()
+    if world > 1:
+        dist.barrier()
+    proj = build_projector(hidden, device)
+    X, E, G = synth_batch(B, T_local, device, 1234 + rank)
+    if frame_sharded:  # every rank must see the same instruction vector
+        G = synth_batch(1, 4, device, 99)[2]
+
+    def step():
+        if frame_sharded:
+            return hdist.forward_frame_sharded(proj, X, E, G, t0=rank * T_local)
+        return proj.forward_batched(X, E, G, "video")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = step()
+        barrier()
+        launches0 = ops.kernel_launch_count()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            with ops.OpTimer() as timer:
+                start.record()
+                for _ in range(args.steps):
+                    out = step()
+                end.record()
+            barrier()
+        ms_total = start.elapsed_time(end)
+        launches = ops.kernel_launch_count() - launches0
+        op_times = timer.summary()
+    ms_t = torch.tensor([ms_total], device=device)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_t) / args.steps
+    frames_per_step = (T if frame_sharded else B * T * world)
+    value = frames_per_step / (ms_step * 1e-3)
+    w = work_per_video(hidden, T)
+    videos_per_step = 1 if frame_sharded else B * world
+
+    # ---- end-to-end through the public host API (rank-local; copies inside the timed region) -------
+    e2e = None
+    if not frame_sharded:
+        Xh, Eh, Gh = (t.cpu().pin_memory() for t in (X, E, G))
+        n_tok = out.shape[1]
+        out_h = torch.empty((B, n_tok, hidden), dtype=torch.bfloat16).pin_memory()
+        for _ in range(2):
+            compress_from_host(proj, Xh, Eh, Gh, "video", out=out_h, device=device)
+        barrier()
+        e_steps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es.record()
+        for _ in range(e_steps):
+            compress_from_host(proj, Xh, Eh, Gh, "video", out=out_h, device=device)
+        ee.record()
+        barrier()
+        e_ms = torch.tensor([es.elapsed_time(ee) / e_steps], device=device)
+        if world > 1:
+            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * T * world / (float(e_ms) * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": int(Xh.numel() * 2 + Eh.numel() * 2 + Gh.numel() * 2) * world,
+               "d2h_bytes_per_step": int(out_h.numel() * 2) * world, "ms_per_step": float(e_ms),
+               "api": "hicom_b200.pipeline.compress_from_host (pinned host buffers, 2-stream chunked overlap)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA events around each op inside the timed region) ------
+    pk = peaks()
+    total_op_ms = sum(ms for _, ms in op_times.values())
+    dom = max(op_times.items(), key=lambda kv: kv[1][1])
+    dname, (dcalls, dms) = dom
+    kind, amount = op_work(dname, B, hidden, T_local)
+    per_launch_ms = dms / dcalls
+    roof = {"kernel": dname, "share_of_step": dms / total_op_ms, "ms_per_launch": per_launch_ms}
+    if kind == "hbm":
+        ach = amount / (per_launch_ms * 1e-3) / 1e9
+        roof.update(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"])
+    else:
+        ach = amount / (per_launch_ms * 1e-3) / 1e12
+        peak = pk["tflops_sustained"]
+        roof.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak)
+    roof["peak_source"] = pk["source"] + (" (sustained bf16)" if kind != "hbm" else " (copy)")
+    roof["traffic"] = None
+    exec_flops = videos_per_step * (w["flops_scores"] + w["flops_pool"] + w["flops_local_readout"])
+    ops_table = {k: {"calls": c, "ms_per_step": ms / args.steps} for k, (c, ms) in
+                 sorted(op_times.items(), key=lambda kv: -kv[1][1])}
+
+    # ---- CPU baseline beside it (bounded sample, rank 0, N=1 only) -----------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        Tc = min(T_local, 16)
+        fps, ms, cores = cpu_reference(hidden, Tc, 2, 3, 1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"2 videos of {Tc} frames per step x 3 steps, fp32, torch CPU oracle port of "
+                         "projector.py:676-708 (the reference has no native code to compile)"}
+
+    line = {
+        "metric": "frames/s through the HICom compressor", "value": value, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong" if frame_sharded else "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": desc, "projector_type": PTYPE, "use_guide": USE_GUIDE,
+                   "per_gpu_batch": B, "frames_per_video": T, "sharding": "frame" if frame_sharded else "video",
+                   "l2": f"inputs are {2 * B * w['N'] * D * 2 / 1e9:.2f} GB per GPU per step (> 126 MB L2), "
+                         "re-read from HBM every step"},
+        "tokens_per_s": value / T * w["tokens_out"],
+        "executed_tflops": exec_flops / (ms_step * 1e-3) / 1e12,
+        "reference_equivalent_tflops": videos_per_step * w["flops_reference"] / (ms_step * 1e-3) / 1e12,
+        "clocks": clk.summary(),
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "ops": ops_table,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -8,6 +8,7 @@
 namespace hicom {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;  // kernels enqueued by this library (all threads)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -17,6 +18,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int check_launch(const char* what) {
+  __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -48,6 +50,7 @@ using namespace hicom;
 
 extern "C" int hicom_abi_version(void) { return HICOM_ABI_VERSION; }
 extern "C" const char* hicom_last_error(void) { return g_err; }
+extern "C" uint64_t hicom_kernel_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int hicom_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

@@ -1,0 +1,93 @@
+"""Multi-GPU partitioning of the compressor across one 8xB200 box.
+
+Two ways the path shards, one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch):
+
+* by VIDEO — videos are independent (the reference loops over them, hicom_arch.py:167-178):
+  ``video_shard`` gives each rank a contiguous block; no data-path collective at all.
+* by FRAME for one long video — rank r holds frames [t0, t0+Ts), Ts % temporal_kernel == 0.
+  Local path: windows never cross a 4-frame boundary and the grid-pool taps stay inside the window,
+  so there is no halo and no communication.  Global path: every rank computes split-softmax partials
+  (m, l, o) over its frames (position rows offset by t0), ONE all-gather exchanges them
+  (J*(d+2) fp32 per split), and every rank merges them with ``softmax_merge`` and finishes the 32 query
+  rows (replicated — cheaper than a second exchange).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def video_shard(num_videos: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) block of videos for ``rank`` (sizes differ by at most one)."""
+    base, extra = divmod(num_videos, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def frame_shard(num_frames: int, world: int, rank: int, temporal_kernel: int = 4) -> Tuple[int, int]:
+    """Contiguous [t0, t1) block of frames for ``rank``; blocks are multiples of the temporal kernel so
+    local windows never straddle ranks.  Raises if the video cannot be cut that way."""
+    if num_frames % temporal_kernel:
+        raise ValueError(f"{num_frames} frames are not a multiple of the temporal kernel {temporal_kernel}")
+    groups = num_frames // temporal_kernel
+    b, e = video_shard(groups, world, rank)
+    return b * temporal_kernel, e * temporal_kernel
+
+
+def pack_partials(m: torch.Tensor, l: torch.Tensor, o: torch.Tensor) -> torch.Tensor:
+    """(B,S,J),(B,S,J),(B,S,J,d) -> one (B,S,J,d+2) fp32 message [o | m | l]."""
+    return torch.cat([o, m.unsqueeze(-1), l.unsqueeze(-1)], dim=-1).contiguous()
+
+
+def unpack_partials(buf: torch.Tensor):
+    d = buf.shape[-1] - 2
+    return buf[..., d].contiguous(), buf[..., d + 1].contiguous(), buf[..., :d].contiguous()
+
+
+def gather_partials(m: torch.Tensor, l: torch.Tensor, o: torch.Tensor, group=None):
+    """All-gather the split-softmax partials of every rank; returns (m,l,o) with the split axis grown to
+    world*S, rank-major (any order would do: the merge is order-independent up to fp32 rounding)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return m, l, o
+    msg = pack_partials(m, l, o)
+    B, S, J, d2 = msg.shape
+    out = torch.empty((world * B, S, J, d2), dtype=msg.dtype, device=msg.device)  # concatenated along dim 0
+    dist.all_gather_into_tensor(out, msg, group=group)
+    out = out.view(world, B, S, J, d2).permute(1, 0, 2, 3, 4).reshape(B, world * S, J, d2)
+    return unpack_partials(out)
+
+
+@torch.no_grad()
+def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, t0: int, group=None,
+                          modal: str = "video"):
+    """One long video cut by frames: ``frames_feature`` (B,Ts,H,W,d) is THIS rank's block starting at global
+    frame ``t0``.  Returns (local tokens of this block (B, Nw_block, Dh) | None, global tokens (B,Q,Dh) | None).
+    Concatenating the local blocks in rank order and appending the global tokens reproduces
+    ``forward_batched`` on the whole video (newline layouts other than flat/no_token are not sharded)."""
+    X = frames_feature
+    B, Ts, H, W, d = X.shape
+    lc, gc = projector.local_compressor, projector.global_compressor
+    local_tokens = global_tokens = None
+    if lc is not None:
+        if Ts % lc.temporal_kernel_size:
+            raise ValueError("frame shard must be a multiple of the temporal kernel")
+        att = lc.attend(X, frames_embed, guide_embed, modal, projector.local_logit_scale,
+                        projector.local_logit_bias)
+        Dh = lc.readout[-1].out_features
+        local_tokens = torch.empty((B * att.shape[1], Dh), dtype=X.dtype, device=X.device)
+        from .projector import _mlp_into
+        _mlp_into(lc.readout, att, local_tokens, 0, att.shape[1], att.shape[1])
+        local_tokens = local_tokens.view(B, att.shape[1], Dh)
+    if gc is not None:
+        Qg = gc.injected_query(guide_embed, B, X.dtype)
+        m, l, o = gc.partials(X, gc.fold(Qg, projector.global_logit_scale), t0=t0)
+        if dist.is_available() and dist.is_initialized():
+            m, l, o = gather_partials(m, l, o, group)
+        Dh = gc.readout[-1].out_features
+        global_tokens = torch.empty((B * Qg.shape[1], Dh), dtype=X.dtype, device=X.device)
+        gc.finish(Qg, m, l, o, global_tokens, 0, Qg.shape[1])
+        global_tokens = global_tokens.view(B, Qg.shape[1], Dh)
+    return local_tokens, global_tokens

@@ -332,6 +332,63 @@ def global_value_proj(pooled: Tensor, Wv: Tensor, bv: Optional[Tensor], Q: int, 
     return out
 
 
+def kernel_launch_count() -> int:
+    """Kernels enqueued by libhicom_b200 since load (bench.py's ``gpu_launches``)."""
+    return int(_cabi.load().hicom_kernel_launch_count())
+
+
+class OpTimer:
+    """Times every hicom_b200 op with CUDA events on the launching stream (no synchronisation while
+    recording).  ``with OpTimer() as t: ...; t.summary()`` -> {op: (calls, total_ms)}."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _ACTIVE_TIMER
+        _ACTIVE_TIMER = self
+        return self
+
+    def __exit__(self, *exc):
+        global _ACTIVE_TIMER
+        _ACTIVE_TIMER = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.records:
+            calls, ms = out.get(name, (0, 0.0))
+            out[name] = (calls + 1, ms + a.elapsed_time(b))
+        return out
+
+
+_ACTIVE_TIMER = None
+
+
+def timed(name: str):
+    """Context manager used by the modules around each op call; free when no OpTimer is active."""
+    return _Timed(name)
+
+
+class _Timed:
+    __slots__ = ("name", "start")
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _ACTIVE_TIMER is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _ACTIVE_TIMER is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _ACTIVE_TIMER.records.append((self.name, self.start, end))
+
+
 def device_info(device=None):
     """(sm_count, cc_major, cc_minor) of the current CUDA device; raises unless it is sm_100."""
     sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -339,3 +396,36 @@ def device_info(device=None):
         rc = _cabi.load().hicom_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi))
     _cabi.check(rc, "hicom_device_info")
     return sm.value, ma.value, mi.value
+
+
+# ------------------------------------------------------------------------------------------
+# op-level timing hooks: wrap the registered ops so an active OpTimer sees every call
+# ------------------------------------------------------------------------------------------
+def _wrap(op, label):
+    def call(*args):
+        if _ACTIVE_TIMER is None:
+            return op(*args)
+        with _Timed(label(*args)):
+            return op(*args)
+    call.__name__ = getattr(op, "__name__", "op")
+    call.__doc__ = op.__doc__
+    call.op = op
+    return call
+
+
+def _rows(t):
+    return t.numel() // t.shape[-1]
+
+
+grid_pool = _wrap(grid_pool, lambda X, *a: "grid_pool")
+local_attend = _wrap(local_attend, lambda *a: "local_attend")
+linear = _wrap(linear, lambda A, W, *a: f"linear M={_rows(A)} N={W.shape[0]} K={W.shape[1]}")
+linear_into = _wrap(linear_into, lambda A, W, *a: f"linear M={_rows(A)} N={W.shape[0]} K={W.shape[1]}")
+film_layernorm = _wrap(film_layernorm, lambda *a: "film_layernorm")
+add_layernorm = _wrap(add_layernorm, lambda *a: "add_layernorm")
+mix_layernorm = _wrap(mix_layernorm, lambda *a: "mix_layernorm")
+guide_attend = _wrap(guide_attend, lambda *a: "guide_attend")
+global_fold_query = _wrap(global_fold_query, lambda *a: "global_fold_query")
+global_attend_partial = _wrap(global_attend_partial, lambda *a: "global_attend_partial")
+softmax_merge = _wrap(softmax_merge, lambda *a: "softmax_merge")
+global_value_proj = _wrap(global_value_proj, lambda *a: "global_value_proj")

@@ -1,0 +1,42 @@
+"""Host-buffer entry: run the compressor on videos that live in (pinned) host memory.
+
+``compress_from_host`` is the end-to-end call a serving process makes when the features arrive on the
+host: it cuts the batch into chunks, and double-buffers host->device copies, the compressor, and the
+device->host copy of the tokens on two CUDA streams so PCIe transfers overlap the kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+@torch.no_grad()
+def compress_from_host(projector, frames_feature: torch.Tensor, frames_embed: Optional[torch.Tensor],
+                       guide_embed: Optional[torch.Tensor], modal: str = "video", out: Optional[torch.Tensor] = None,
+                       chunk: int = 8, device=None) -> torch.Tensor:
+    """``frames_feature`` (B,T,H,W,d) [+ ``frames_embed``] and ``guide_embed`` (B,…) on the HOST (pinned for
+    async copies) -> tokens (B, n_tokens, Dh) on the host (``out`` if given, else a new pinned tensor)."""
+    device = torch.device(device if device is not None else torch.cuda.current_device())
+    B = frames_feature.shape[0]
+    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+    main = torch.cuda.current_stream(device)
+    for s in streams:
+        s.wait_stream(main)
+    pending = []
+    for i, b0 in enumerate(range(0, B, chunk)):
+        b1 = min(B, b0 + chunk)
+        s = streams[i % 2]
+        with torch.cuda.stream(s):
+            x = frames_feature[b0:b1].to(device, non_blocking=True)
+            e = None if frames_embed is None else frames_embed[b0:b1].to(device, non_blocking=True)
+            g = None if guide_embed is None else guide_embed[b0:b1].to(device, non_blocking=True)
+            tok = projector.forward_batched(x, e, g, modal)
+            if out is None:
+                out = torch.empty((B,) + tuple(tok.shape[1:]), dtype=tok.dtype).pin_memory()
+            out[b0:b1].copy_(tok, non_blocking=True)
+            pending.append((x, e, g, tok))  # keep device buffers alive until the stream drains
+    for s in streams:
+        main.wait_stream(s)
+    main.synchronize()
+    return out

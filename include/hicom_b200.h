@@ -37,6 +37,8 @@ enum { HICOM_IMPL_AUTO = 0, HICOM_IMPL_SIMT = 1, HICOM_IMPL_TCGEN05 = 2 };
 /* ---- library ---------------------------------------------------------------------------- */
 int hicom_abi_version(void);
 const char* hicom_last_error(void);
+/* Number of CUDA kernels this library has enqueued since load (monotonic; for launch accounting). */
+uint64_t hicom_kernel_launch_count(void);
 /* Fills SM count / compute capability of the current device; fails if it is not sm_100. */
 int hicom_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
