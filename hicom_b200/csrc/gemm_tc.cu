@@ -1,9 +1,551 @@
-// placeholder until the tcgen05 kernels land: everything routes to the SIMT path
+// tcgen05 / TMEM / TMA GEMM family for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+// One warp-specialised kernel template, one 128 x BN output tile per CTA:
+//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B boxes) into a STAGES-deep smem ring
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma (M=128, N<=256, K=16) per 32-byte K slice,
+//                              tcgen05.commit releases smem stages and finally publishes the accumulator
+//   warps 2..5  epilogue       tcgen05.ld of the 128 x BN fp32 accumulator (one TMEM lane = one output row
+//                              per thread), fused epilogue, stores
+// Uses:
+//   EPI_LINEAR  C = act(A·Wᵀ + bias) + R                 nn.Linear stages / readouts   (projector.py:307-312)
+//   EPI_MAX     column max of S = qfold·X'ᵀ               global scores, pass 1         (projector.py:197,213)
+//   EPI_PROB    P = exp(S - max) (bf16) and its row sums  global scores, pass 2
+//   EPI_POOL    O = X'ᵀ·P (A operand MN-major)            global P·V in reassociated form (projector.py:215)
+#include <cuda.h>
+
 #include "gemm_tc.cuh"
+
 namespace hicom {
-bool tc_linear_supported(int, int, int, int, int, long long, long long, long long, const void*, const void*, const void*) { return false; }
-int launch_tc_linear(const TcLinearParams&, cudaStream_t) { set_error("tcgen05 linear not built"); return 1; }
-bool tc_global_selected(int, int, int, int) { return false; }
-size_t tc_global_workspace_bytes(int, int, int, int, int, int, int) { return 0; }
-int launch_tc_global(const void*, const float*, const float*, const float*, const void*, float*, float*, float*, int, int, int, int, int, int, int, void*, cudaStream_t) { set_error("tcgen05 global not built"); return 1; }
+int launch_posadd(const void* X, void* Y, const float* pt, const float* ph, const float* pw, int B, int T_,
+                  int H, int W, int d, int dtype, cudaStream_t stream);
+
+namespace tc {
+
+constexpr int BM = 128;  // UMMA M (rows of the accumulator = TMEM lanes)
+constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int UK = 16;   // K per tcgen05.mma for 16-bit inputs
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192;
+
+enum { EPI_LINEAR = 0, EPI_MAX = 1, EPI_PROB = 2, EPI_POOL = 3 };
+
+struct Params {
+  int M, N, K;       // valid rows of A / rows of B / reduction length (per batch)
+  int k_chunk;       // K range per blockIdx.x for EPI_POOL (multiple of BK); else K
+  int b_box_rows;    // rows per TMA box of the B tile
+  // EPI_LINEAR
+  const __nv_bfloat16* bias; const __nv_bfloat16* R; long long ldr;
+  void* C; long long ldc; int out_dtype; int act; int rows_per_group; long long group_stride_rows;
+  // EPI_MAX / EPI_PROB / EPI_POOL
+  float* mg; float* lg;            // (B, J) running max / sum of probabilities
+  __nv_bfloat16* Pt; long long pt_ld;  // (B, J, pt_ld) transposed probabilities
+  float* o; int splits;            // (B, splits, J, d) pooled partials
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane_base+i), columns col..col+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= 2ull << 61;  // layout type SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: bf16 x bf16 -> fp32, M=128.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg {
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = BN <= 256 ? 256 : 512;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int batch = blockIdx.z;
+  const int m_tile = blockIdx.y;
+  // EPI_POOL: blockIdx.x = K split, single N tile.  Otherwise blockIdx.x = N tile, full K.
+  const int n_tile = (EPI == EPI_POOL) ? 0 : blockIdx.x;
+  const int split = (EPI == EPI_POOL) ? blockIdx.x : 0;
+  const int k_begin = split * p.k_chunk;
+  int k_end = k_begin + p.k_chunk;
+  if (k_end > p.K) k_end = p.K;
+  const int nkb = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * C::STAGE_BYTES;
+        uint8_t* sb = sa + C::A_BYTES;
+        mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+        const int k0 = k_begin + kb * BK;
+        if (A_MN) {
+          // A[m, k] stored (k rows, m contiguous): two 64-wide M blocks of (BK rows x 128 B)
+          tma_load_3d(sa, &tmA, &full_bar[s], m_tile * BM, k0, batch);
+          tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], m_tile * BM + 64, k0, batch);
+        } else {
+          tma_load_3d(sa, &tmA, &full_bar[s], k0, m_tile * BM, batch);
+        }
+        for (int r = 0; r < BN; r += p.b_box_rows)
+          tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0, n_tile * BN + r, batch);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_main = make_idesc(BN > 256 ? 256 : BN, A_MN, false);
+      constexpr uint32_t idesc_tail = make_idesc(BN > 256 ? BN - 256 : 8, A_MN, false);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+        const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / UK; ++kk) {
+          // K-major: +32 B per 16-element K slice inside the 128 B swizzle row (SBO = 8 rows x 128 B).
+          // MN-major A: 16 k-rows = two 1024 B swizzle atoms per slice; LBO = stride between 64-wide M blocks.
+          const uint64_t adesc = A_MN ? make_smem_desc(sa + kk * 2048, BK * 128, 1024)
+                                      : make_smem_desc(sa + kk * 32, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sb + kk * 32, 16, 1024);
+          const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+          umma_bf16(tmem_base, adesc, bdesc, idesc_main, acc);
+          if (BN > 256) {
+            const uint64_t bdesc2 = make_smem_desc(sb + 256 * 128 + kk * 32, 16, 1024);
+            umma_bf16(tmem_base + 256, adesc, bdesc2, idesc_tail, acc);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int row = m_tile * BM + q * 32 + lane;  // output row of this thread
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (nkb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    float v[32];
+
+    if (EPI == EPI_LINEAR) {
+      const bool row_ok = row < p.M;
+      const long long orow = row_ok ? (long long)(row / p.rows_per_group) * p.group_stride_rows +
+                                          (row % p.rows_per_group) : 0;
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_tile * BN + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        tmem_ld32(taddr + c * 32, v);
+        if (!row_ok) continue;
+        const int nvalid = p.N - n0 < 32 ? p.N - n0 : 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < nvalid) {
+            float x = v[i];
+            if (p.bias) x += __bfloat162float(p.bias[n0 + i]);
+            if (p.act == HICOM_ACT_GELU) x = gelu_erf(x);
+            if (p.R) x += __bfloat162float(p.R[(long long)row * p.ldr + n0 + i]);
+            v[i] = x;
+          }
+        }
+        if (p.out_dtype == HICOM_BF16) {
+          __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n0;
+          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 pk;
+              pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+              pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+              pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+              pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+              reinterpret_cast<uint4*>(dst)[g] = pk;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) dst[i] = __float2bfloat16_rn(v[i]);
+          }
+        } else {
+          float* dst = static_cast<float*>(p.C) + orow * p.ldc + n0;
+          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              reinterpret_cast<float4*>(dst)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvalid) dst[i] = v[i];
+          }
+        }
+      }
+    } else if (EPI == EPI_MAX) {
+      // rows = score columns j (M = J), columns = tokens of this tile
+      float mx = -INFINITY;
+      for (int c = 0; c < BN / 32; ++c) {
+        const int t0 = n_tile * BN + c * 32;
+        if (t0 >= p.N) break;
+        tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (t0 + i < p.N) mx = fmaxf(mx, v[i]);
+      }
+      if (row < p.M) atomic_max_float(p.mg + (size_t)batch * p.M + row, mx);
+    } else if (EPI == EPI_PROB) {
+      const bool row_ok = row < p.M;
+      const float pre = row_ok ? p.mg[(size_t)batch * p.M + row] * kLog2e : 0.f;
+      float sum = 0.f;
+      __nv_bfloat16* prow = p.Pt + ((size_t)batch * p.M + (row_ok ? row : 0)) * p.pt_ld + (size_t)n_tile * BN;
+      for (int c = 0; c < BN / 32; ++c) {
+        const int t0 = n_tile * BN + c * 32;
+        const bool any = t0 < p.N;  // warp-uniform
+        if (any) tmem_ld32(taddr + c * 32, v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a = 0.f, b = 0.f;
+          if (any && t0 + i < p.N) a = exp2f(fmaf(v[i], kLog2e, -pre));
+          if (any && t0 + i + 1 < p.N) b = exp2f(fmaf(v[i + 1], kLog2e, -pre));
+          __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+          sum += __low2float(t) + __high2float(t);  // sum what P·V will actually multiply
+          pk[i / 2] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(prow + c * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+        }
+      }
+      if (row_ok) atomicAdd(p.lg + (size_t)batch * p.M + row, sum);
+    } else {  // EPI_POOL: rows = channels d (M), columns = score columns j (N = J)
+      float* obase = p.o + (((size_t)batch * p.splits + split) * p.N) * p.M + row;
+      for (int c = 0; c < (BN + 31) / 32; ++c) {
+        if (nkb > 0) tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int j = c * 32 + i;
+          if (j < p.N && row < p.M) obase[(size_t)j * p.M] = nkb > 0 ? v[i] : 0.f;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helpers for the global pipeline
+// ---------------------------------------------------------------------------------------------
+__global__ void init_stats_kernel(float* mg, float* lg, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { mg[i] = -INFINITY; lg[i] = 0.f; }
+}
+// m[b,s,j] = mg[b,j] for every split; l[b,0,j] = lg[b,j], 0 for the other splits (they share the same max).
+__global__ void spread_stats_kernel(const float* mg, const float* lg, float* m, float* l, int B, int S, int J) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * S * J) return;
+  const int j = i % J, s = (i / J) % S, b = i / (J * S);
+  m[i] = mg[b * J + j];
+  l[i] = s == 0 ? lg[b * J + j] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+    set_error("cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// bf16 tensor viewed as (batch, rows, inner) with row pitch `ld` elements and batch pitch `batch_stride` elements;
+// box = (64 inner, box_rows, 1), SWIZZLE_128B, out-of-range elements read as zero.
+static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t ld,
+                    uint64_t batch_stride, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return 1;
+  HICOM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tcgen05 path: operand not 16-byte aligned");
+  HICOM_REQUIRE(ld % 8 == 0 && (batch <= 1 || batch_stride % 8 == 0), "tcgen05 path: pitch must be a multiple of 8 elements");
+  cuuint64_t dims[3] = {inner, rows, batch ? batch : 1};
+  cuuint64_t strides[2] = {ld * 2, (batch_stride ? batch_stride : rows * ld) * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HICOM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  return 0;
+}
+
+template <int BN, bool A_MN, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = tc_gemm_kernel<BN, A_MN, EPI>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM_BYTES);
+    HICOM_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+  return check_launch("tc_gemm_kernel");
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// linear
+// ---------------------------------------------------------------------------------------------
+bool tc_linear_supported(int in_dtype, int out_dtype, int M, int N, int K, long long lda, long long ldw,
+                         long long ldc, const void* A, const void* W, const void* C) {
+  (void)ldc; (void)C; (void)N;
+  if (in_dtype != HICOM_BF16) return false;
+  if (out_dtype != HICOM_BF16 && out_dtype != HICOM_F32) return false;
+  if (M <= 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return false;
+  return true;
+}
+
+int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
+  using namespace tc;
+  CUtensorMap ta, tb;
+  if (make_map(&ta, q.A, q.K, q.M, 1, q.lda, 0, BM)) return 1;
+  if (make_map(&tb, q.W, q.K, q.N, 1, q.ldw, 0, 256)) return 1;
+  Params p{};
+  p.M = q.M; p.N = q.N; p.K = q.K; p.k_chunk = q.K; p.b_box_rows = 256;
+  p.bias = static_cast<const __nv_bfloat16*>(q.bias);
+  p.R = static_cast<const __nv_bfloat16*>(q.R); p.ldr = q.ldr;
+  p.C = q.C; p.ldc = q.ldc; p.out_dtype = q.out_dtype; p.act = q.act;
+  p.rows_per_group = q.rows_per_group; p.group_stride_rows = q.group_stride_rows;
+  dim3 grid((q.N + 255) / 256, (q.M + BM - 1) / BM, 1);
+  HICOM_REQUIRE(grid.y <= 65535, "tcgen05 linear: too many row tiles");
+  return launch<256, false, EPI_LINEAR>(ta, tb, p, grid, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// global attention partials
+// ---------------------------------------------------------------------------------------------
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+bool tc_global_selected(int dtype, int impl, int d, int J) {
+  if (impl == HICOM_IMPL_SIMT) return false;
+  return dtype == HICOM_BF16 && d % 128 == 0 && J == 288;
+}
+
+struct GlobalWs {
+  size_t xp, pt, mg, lg, total;
+  long long pt_ld;
+};
+static GlobalWs global_ws(int B, int T, int H, int W, int d, int J) {
+  const size_t N = (size_t)T * H * W;
+  GlobalWs w;
+  w.pt_ld = (long long)((N + 255) / 256) * 256;
+  w.xp = 0;
+  w.pt = al256((size_t)B * N * d * 2);
+  w.mg = w.pt + al256((size_t)B * J * w.pt_ld * 2);
+  w.lg = w.mg + al256((size_t)B * J * 4);
+  w.total = w.lg + al256((size_t)B * J * 4);
+  return w;
+}
+
+size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits) {
+  (void)splits;
+  return global_ws(B, T, H, W, d, J).total;
+}
+
+int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, const float* pos_w, const void* qfold,
+                     float* m, float* l, float* o, int B, int T, int H, int W, int d, int J, int splits,
+                     void* workspace, cudaStream_t stream) {
+  using namespace tc;
+  HICOM_REQUIRE(B <= 65535, "global_attend_partial: batch too large for one launch");
+  const int N = T * H * W;
+  const GlobalWs w = global_ws(B, T, H, W, d, J);
+  char* ws = static_cast<char*>(workspace);
+  __nv_bfloat16* Xp = reinterpret_cast<__nv_bfloat16*>(ws + w.xp);
+  __nv_bfloat16* Pt = reinterpret_cast<__nv_bfloat16*>(ws + w.pt);
+  float* mg = reinterpret_cast<float*>(ws + w.mg);
+  float* lg = reinterpret_cast<float*>(ws + w.lg);
+
+  if (launch_posadd(X, Xp, pos_t, pos_h, pos_w, B, T, H, W, d, HICOM_BF16, stream)) return 1;
+  init_stats_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, lg, B * J);
+  if (check_launch("init_stats_kernel")) return 1;
+
+  // scores: S[b] (J x N) = qfold[b] (J x d) · X'[b]ᵀ  — A = qfold (rows j), "W" = X' (rows = tokens)
+  CUtensorMap tq, tx;
+  if (make_map(&tq, qfold, d, J, B, d, (uint64_t)J * d, BM)) return 1;
+  if (make_map(&tx, Xp, d, N, B, d, (uint64_t)N * d, 256)) return 1;
+  Params p{};
+  p.M = J; p.N = N; p.K = d; p.k_chunk = d; p.b_box_rows = 256;
+  p.mg = mg; p.lg = lg; p.Pt = Pt; p.pt_ld = w.pt_ld;
+  dim3 gs((N + 255) / 256, (J + BM - 1) / BM, B);
+  if (launch<256, false, EPI_MAX>(tq, tx, p, gs, stream)) return 1;
+  if (launch<256, false, EPI_PROB>(tq, tx, p, gs, stream)) return 1;
+
+  // pooling: O[b,s] (d x J) = X'[b, tokens of s]ᵀ · P[b, tokens of s]  — A = X' read MN-major, B = Ptᵀ rows j
+  CUtensorMap txa, tp;
+  if (make_map(&txa, Xp, d, N, B, d, (uint64_t)N * d, 64)) return 1;
+  if (make_map(&tp, Pt, w.pt_ld, J, B, w.pt_ld, (uint64_t)J * w.pt_ld, 96)) return 1;
+  Params g{};
+  g.M = d; g.N = J; g.K = N;
+  int chunk = (N + splits - 1) / splits;
+  chunk = (chunk + BK - 1) / BK * BK;
+  g.k_chunk = chunk; g.b_box_rows = 96;
+  g.o = o; g.splits = splits;
+  dim3 gp(splits, d / BM, B);
+  if (launch<288, true, EPI_POOL>(txa, tp, g, gp, stream)) return 1;
+
+  spread_stats_kernel<<<(B * splits * J + 255) / 256, 256, 0, stream>>>(mg, lg, m, l, B, splits, J);
+  return check_launch("spread_stats_kernel");
+}
+
 }  // namespace hicom
