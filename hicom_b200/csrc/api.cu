@@ -78,7 +78,7 @@ extern "C" int hicom_linear(const void* A, int64_t lda, const void* W, int64_t l
   if (M == 0) return 0;
   const bool tc_ok = tc_linear_supported(in_dtype, out_dtype, M, N, K, lda, ldw, ldc, A, W, C);
   if (impl == HICOM_IMPL_TCGEN05) HICOM_REQUIRE(tc_ok, "linear: tcgen05 path does not support this problem");
-  if (impl == HICOM_IMPL_TCGEN05 || (impl == HICOM_IMPL_AUTO && tc_ok && M >= 64)) {
+  if (impl == HICOM_IMPL_TCGEN05 || (impl == HICOM_IMPL_AUTO && tc_ok)) {
     TcLinearParams t{};
     t.A = A; t.W = W; t.bias = bias; t.R = R; t.C = C;
     t.lda = lda; t.ldw = ldw; t.ldr = ldr; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.act = act;
@@ -107,6 +107,17 @@ extern "C" int hicom_global_fold_query(const void* q, const void* Wk, void* qfol
   HICOM_REQUIRE(B >= 0 && Q > 0 && heads > 0 && d % heads == 0, "global_fold_query: bad shape");
   if (B == 0) return 0;
   const int hd = d / heads;
+  if (dtype == HICOM_BF16 && hd % 64 == 0 && d % 8 == 0 && !((uintptr_t)q & 15) && !((uintptr_t)Wk & 15)) {
+    // one tcgen05 launch, blockIdx.z = head: A = q (B*Q, d) K-slice of the head, B operand = Wk (k rows, n
+    // contiguous -> MN-major), rows (b,i) land at qfold row b*J + h*Q + i
+    TcLinearParams t{};
+    t.A = q; t.W = Wk; t.C = qfold;
+    t.lda = d; t.ldw = d; t.ldc = d; t.M = B * Q; t.N = d; t.K = hd; t.act = HICOM_ACT_NONE;
+    t.out_dtype = HICOM_BF16; t.rows_per_group = Q; t.group_stride_rows = (long long)heads * Q;
+    t.alpha = alpha; t.w_is_kn = 1;
+    t.z_slices = heads; t.z_a_k = hd; t.z_b_k = hd; t.z_c_rows = Q;
+    return launch_tc_linear(t, as_stream(stream));
+  }
   GemmParams g = plain_gemm();
   g.A = q; g.B = Wk; g.C = qfold;
   g.M = Q; g.N = d; g.K = hd;
@@ -127,6 +138,16 @@ extern "C" int hicom_global_value_proj(const void* pooled, const void* Wv, const
   HICOM_REQUIRE(B >= 0 && Q > 0 && heads > 0 && d % heads == 0, "global_value_proj: bad shape");
   if (B == 0) return 0;
   const int hd = d / heads;
+  if (dtype == HICOM_BF16 && hd % 32 == 0 && d % 8 == 0 && !((uintptr_t)pooled & 15) && !((uintptr_t)Wv & 15)) {
+    // one dense tcgen05 GEMM (B*J, d) x Wvᵀ whose epilogue keeps only the diagonal head blocks: the 9x redundant
+    // flops (tens of GFLOP) are cheaper than nine launch-bound per-head GEMMs.
+    TcLinearParams t{};
+    t.A = pooled; t.W = Wv; t.bias = bv; t.C = attn;
+    t.lda = d; t.ldw = d; t.ldc = d; t.M = B * heads * Q; t.N = d; t.K = d; t.act = HICOM_ACT_NONE;
+    t.out_dtype = HICOM_BF16; t.rows_per_group = 1 << 30; t.group_stride_rows = 0;
+    t.diag_heads = heads; t.diag_rows = Q; t.diag_cols = hd;
+    return launch_tc_linear(t, as_stream(stream));
+  }
   GemmParams g = plain_gemm();
   g.A = pooled; g.B = Wv; g.bias = bv; g.C = attn;
   g.M = Q; g.N = hd; g.K = d;

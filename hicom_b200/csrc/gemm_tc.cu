@@ -36,6 +36,11 @@ struct Params {
   // EPI_LINEAR
   const __nv_bfloat16* bias; const __nv_bfloat16* R; long long ldr;
   void* C; long long ldc; int out_dtype; int act; int rows_per_group; long long group_stride_rows;
+  float alpha;                     // accumulator scale applied before the bias
+  int diag_heads, diag_rows, diag_cols;  // >0: row r=(g,h,i) keeps only columns of head h, written to row g*diag_rows+i
+  int z_slices;                    // >0: blockIdx.z is not a tensor batch but a K-slice (one head) of the SAME A/B:
+  int z_a_k, z_b_k;                //     A / B reduction coordinates start at z*z_a_k / z*z_b_k
+  long long z_c_rows;              //     and output rows are shifted by z*z_c_rows
   // EPI_MAX / EPI_PROB / EPI_POOL
   float* mg; float* lg;            // (B, J) running max / sum of probabilities
   __nv_bfloat16* Pt; long long pt_ld;  // (B, J, pt_ld) transposed probabilities
@@ -164,7 +169,7 @@ struct Cfg {
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   using C = Cfg<BN>;
@@ -176,7 +181,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int batch = blockIdx.z;
+  const int zslice = p.z_slices > 0 ? blockIdx.z : 0;
+  const int batch = p.z_slices > 0 ? 0 : blockIdx.z;
   const int m_tile = blockIdx.y;
   // EPI_POOL: blockIdx.x = K split, single N tile.  Otherwise blockIdx.x = N tile, full K.
   const int n_tile = (EPI == EPI_POOL) ? 0 : blockIdx.x;
@@ -219,17 +225,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_3d(sa, &tmA, &full_bar[s], m_tile * BM, k0, batch);
           tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], m_tile * BM + 64, k0, batch);
         } else {
-          tma_load_3d(sa, &tmA, &full_bar[s], k0, m_tile * BM, batch);
+          tma_load_3d(sa, &tmA, &full_bar[s], k0 + zslice * p.z_a_k, m_tile * BM, batch);
         }
-        for (int r = 0; r < BN; r += p.b_box_rows)
-          tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0, n_tile * BN + r, batch);
+        if (B_MN) {
+          // B[k, n] stored (k rows, n contiguous): BN/64 blocks of (BK rows x 128 B)
+          for (int r = 0; r < BN; r += 64)
+            tma_load_3d(sb + (r / 64) * (BK * 128), &tmB, &full_bar[s], n_tile * BN + r, k0 + zslice * p.z_b_k, batch);
+        } else {
+          for (int r = 0; r < BN; r += p.b_box_rows)
+            tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0 + zslice * p.z_b_k, n_tile * BN + r, batch);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc_main = make_idesc(BN > 256 ? 256 : BN, A_MN, false);
-      constexpr uint32_t idesc_tail = make_idesc(BN > 256 ? BN - 256 : 8, A_MN, false);
+      static_assert(!(B_MN && BN > 256), "MN-major B is only wired for a single N<=256 instruction");
+      constexpr uint32_t idesc_main = make_idesc(BN > 256 ? 256 : BN, A_MN, B_MN);
+      constexpr uint32_t idesc_tail = make_idesc(BN > 256 ? BN - 256 : 8, A_MN, B_MN);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -243,7 +256,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // MN-major A: 16 k-rows = two 1024 B swizzle atoms per slice; LBO = stride between 64-wide M blocks.
           const uint64_t adesc = A_MN ? make_smem_desc(sa + kk * 2048, BK * 128, 1024)
                                       : make_smem_desc(sa + kk * 32, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(sb + kk * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc(sb + kk * 2048, BK * 128, 1024)
+                                      : make_smem_desc(sb + kk * 32, 16, 1024);
           const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
           umma_bf16(tmem_base, adesc, bdesc, idesc_main, acc);
           if (BN > 256) {
@@ -268,18 +282,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (EPI == EPI_LINEAR) {
       const bool row_ok = row < p.M;
-      const long long orow = row_ok ? (long long)(row / p.rows_per_group) * p.group_stride_rows +
-                                          (row % p.rows_per_group) : 0;
+      long long orow = row_ok ? (long long)(row / p.rows_per_group) * p.group_stride_rows +
+                                    (row % p.rows_per_group) : 0;
+      int my_head = -1;
+      if (p.diag_heads > 0 && row_ok) {
+        my_head = (row / p.diag_rows) % p.diag_heads;
+        orow = (long long)(row / (p.diag_rows * p.diag_heads)) * p.diag_rows + row % p.diag_rows;
+      }
+      orow += (long long)zslice * p.z_c_rows;
       for (int c = 0; c < BN / 32; ++c) {
         const int n0 = n_tile * BN + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
         tmem_ld32(taddr + c * 32, v);
         if (!row_ok) continue;
+        if (p.diag_heads > 0 && n0 / p.diag_cols != my_head) continue;  // off-diagonal head block: discard
         const int nvalid = p.N - n0 < 32 ? p.N - n0 : 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (i < nvalid) {
-            float x = v[i];
+            float x = v[i] * p.alpha;
             if (p.bias) x += __bfloat162float(p.bias[n0 + i]);
             if (p.act == HICOM_ACT_GELU) x = gelu_erf(x);
             if (p.R) x += __bfloat162float(p.R[(long long)row * p.ldr + n0 + i]);
@@ -428,10 +449,10 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   return 0;
 }
 
-template <int BN, bool A_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t stream) {
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BN, A_MN, EPI>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM_BYTES);
     HICOM_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -459,17 +480,25 @@ bool tc_linear_supported(int in_dtype, int out_dtype, int M, int N, int K, long 
 int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   using namespace tc;
   CUtensorMap ta, tb;
-  if (make_map(&ta, q.A, q.K, q.M, 1, q.lda, 0, BM)) return 1;
-  if (make_map(&tb, q.W, q.K, q.N, 1, q.ldw, 0, 256)) return 1;
+  const uint64_t kext = (uint64_t)q.K * (q.z_slices > 0 ? q.z_slices : 1);  // full reduction extent in memory
+  if (make_map(&ta, q.A, kext, q.M, 1, q.lda, 0, BM)) return 1;
+  if (q.w_is_kn) {  // W given as (K, N) row-major: MN-major B operand, boxes of 64 n x 64 k
+    if (make_map(&tb, q.W, q.N, kext, 1, q.ldw, 0, 64)) return 1;
+  } else {
+    if (make_map(&tb, q.W, kext, q.N, 1, q.ldw, 0, 256)) return 1;
+  }
   Params p{};
+  p.alpha = q.alpha; p.diag_heads = q.diag_heads; p.diag_rows = q.diag_rows; p.diag_cols = q.diag_cols;
+  p.z_slices = q.z_slices; p.z_a_k = q.z_a_k; p.z_b_k = q.z_b_k; p.z_c_rows = q.z_c_rows;
   p.M = q.M; p.N = q.N; p.K = q.K; p.k_chunk = q.K; p.b_box_rows = 256;
   p.bias = static_cast<const __nv_bfloat16*>(q.bias);
   p.R = static_cast<const __nv_bfloat16*>(q.R); p.ldr = q.ldr;
   p.C = q.C; p.ldc = q.ldc; p.out_dtype = q.out_dtype; p.act = q.act;
   p.rows_per_group = q.rows_per_group; p.group_stride_rows = q.group_stride_rows;
-  dim3 grid((q.N + 255) / 256, (q.M + BM - 1) / BM, 1);
+  dim3 grid((q.N + 255) / 256, (q.M + BM - 1) / BM, q.z_slices > 0 ? q.z_slices : 1);
   HICOM_REQUIRE(grid.y <= 65535, "tcgen05 linear: too many row tiles");
-  return launch<256, false, EPI_LINEAR>(ta, tb, p, grid, stream);
+  if (q.w_is_kn) return launch<256, false, true, EPI_LINEAR>(ta, tb, p, grid, stream);
+  return launch<256, false, false, EPI_LINEAR>(ta, tb, p, grid, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -528,8 +557,8 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   p.M = J; p.N = N; p.K = d; p.k_chunk = d; p.b_box_rows = 256;
   p.mg = mg; p.lg = lg; p.Pt = Pt; p.pt_ld = w.pt_ld;
   dim3 gs((N + 255) / 256, (J + BM - 1) / BM, B);
-  if (launch<256, false, EPI_MAX>(tq, tx, p, gs, stream)) return 1;
-  if (launch<256, false, EPI_PROB>(tq, tx, p, gs, stream)) return 1;
+  if (launch<256, false, false, EPI_MAX>(tq, tx, p, gs, stream)) return 1;
+  if (launch<256, false, false, EPI_PROB>(tq, tx, p, gs, stream)) return 1;
 
   // pooling: O[b,s] (d x J) = X'[b, tokens of s]ᵀ · P[b, tokens of s]  — A = X' read MN-major, B = Ptᵀ rows j
   CUtensorMap txa, tp;
@@ -542,7 +571,7 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   g.k_chunk = chunk; g.b_box_rows = 96;
   g.o = o; g.splits = splits;
   dim3 gp(splits, d / BM, B);
-  if (launch<288, true, EPI_POOL>(txa, tp, g, gp, stream)) return 1;
+  if (launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream)) return 1;
 
   spread_stats_kernel<<<(B * splits * J + 255) / 256, 256, 0, stream>>>(mg, lg, m, l, B, splits, J);
   return check_launch("spread_stats_kernel");

@@ -9,6 +9,10 @@ struct TcLinearParams {
   long long lda, ldw, ldr, ldc;
   int M, N, K, act, out_dtype;
   int rows_per_group; long long group_stride_rows;
+  float alpha = 1.f;        // C = act(alpha * A·op(W) + bias) + R
+  int w_is_kn = 0;          // W stored (K, N) row-major instead of torch's (N, K)
+  int diag_heads = 0, diag_rows = 0, diag_cols = 0;  // block-diagonal store (see gemm_tc.cu)
+  int z_slices = 0, z_a_k = 0, z_b_k = 0; long long z_c_rows = 0;  // per-head K slices on blockIdx.z
 };
 
 bool tc_linear_supported(int in_dtype, int out_dtype, int M, int N, int K, long long lda, long long ldw,

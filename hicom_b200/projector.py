@@ -384,7 +384,7 @@ class GlobalCompressor(nn.Module):
             raise NotImplementedError("use_pos_emb=False is never built by the reference parser (:293)")
         pt, ph, pw = self.pos_tables(t0, T, H, W, X.device)
         if splits is None:
-            splits = default_splits(B, T * H * W)
+            splits = default_splits(B, T * H * W, d)
         return ops.global_attend_partial(X, pt, ph, pw, qfold, splits, _IMPL)
 
     def finish(self, Qg, m, l, o, out, row_offset, group_stride):
@@ -415,9 +415,11 @@ class GlobalCompressor(nn.Module):
         return out
 
 
-def default_splits(B: int, N: int) -> int:
-    """Token ranges per video for the split-softmax: enough independent work for 148 SMs, >= 512 tokens each."""
-    want = max(1, -(-296 // max(B, 1)))
+def default_splits(B: int, N: int, d: int = 1152) -> int:
+    """Token ranges per video for the pooling GEMM's split-K: (d/128) row tiles x B videos x splits CTAs should
+    cover the 148 SMs about twice; each range keeps >= 512 tokens.  Fewer splits = fewer fp32 partials to merge."""
+    tiles = max(1, d // 128) * max(B, 1)
+    want = max(1, -(-296 // tiles))
     return max(1, min(want, N // 512 if N >= 512 else 1))
 
 

@@ -67,7 +67,7 @@ def test_forward_batched_equals_loop(name, dtype, built_library):
         want = torch.stack([m(Xb[b], None if Eb is None else Eb[b], None if Gb is None else Gb[b], "video")
                             for b in range(3)])
     assert got.shape == want.shape
-    assert O.rel_err(got.float().cpu(), want.float().cpu()) <= (1e-5 if dtype == "float32" else 4e-3)
+    assert O.rel_err(got.float().cpu(), want.float().cpu()) <= (1e-5 if dtype == "float32" else 1e-2)
     # and each video matches the oracle truth
     orc = oracle_for(case, sd, torch.float32)
     for b in range(3):
