@@ -134,5 +134,29 @@ def test_full_size_properties_bf16(built_library):
         oo = torch.cat([p[2] for p in parts], 1)
         merged = torch.empty_like(whole)
         gc.finish(Qg, mm, ll, oo, merged, 0, 0)
-    assert O.rel_err(merged.float().cpu(), whole.float().cpu()) <= 4e-3
-    assert O.rel_err(whole.float().cpu(), out[-32:].float().cpu()) <= 4e-3
+    # two valid bf16 evaluations (different softmax stabilisers round P differently): within two bf16 ulps of the
+    # largest output; the fp32 version of this identity is checked to 1e-5 in test_frame_shard_merge_fp32
+    assert O.rel_err(merged.float().cpu(), whole.float().cpu()) <= 8e-3
+    assert O.rel_err(whole.float().cpu(), out[-32:].float().cpu()) <= 8e-3
+
+
+def test_frame_shard_merge_fp32(built_library):
+    """fp32: partials of 4 frame shards (position rows offset by t0) merged == unsharded, to rounding noise."""
+    case = CASES_BY_NAME["coarse_27x27_T4"]
+    import dataclasses
+    case = dataclasses.replace(case, T=16, H=9, W=9)
+    sd, X, E, g, nl = materialise(case)
+    m = cuda_module_for(case, sd)
+    gc = m.global_compressor
+    Xd, gd = X.cuda().unsqueeze(0), g.cuda().unsqueeze(0)
+    with torch.no_grad():
+        Qg = gc.injected_query(gd, 1, Xd.dtype)
+        qf = gc.fold(Qg)
+        whole = torch.empty(32, case.hidden, dtype=Xd.dtype, device="cuda")
+        gc.finish(Qg, *gc.partials(Xd, qf, splits=3), whole, 0, 0)
+        parts = [gc.partials(Xd[:, t0:t0 + 4].contiguous(), qf, t0=t0, splits=2) for t0 in (0, 4, 8, 12)]
+        merged = torch.empty_like(whole)
+        gc.finish(Qg, *(torch.cat([p[i] for p in parts], 1) for i in range(3)), merged, 0, 0)
+    assert O.rel_err(merged.cpu(), whole.cpu()) <= 1e-5
+    truth = oracle_for(case, sd)._global(X, g)
+    assert O.rel_err(whole.cpu(), truth) <= FP32_TOL
