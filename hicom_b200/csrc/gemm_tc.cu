@@ -152,6 +152,20 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// GELU(x) = 0.5 x (1 + erf(x/sqrt2)) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, branch-free,
+// two MUFU ops).  Only used where the result is rounded to bf16 (eps 4e-3); the fp32 path keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = 1.0f - poly * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -169,7 +183,8 @@ struct Cfg {
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+// FLAGS (EPI_LINEAR only): bit 0 = GELU, bit 1 = fp32 output
+template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   using C = Cfg<BN>;
@@ -281,6 +296,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float v[32];
 
     if (EPI == EPI_LINEAR) {
+      constexpr bool kGelu = (FLAGS & 1) != 0;
+      constexpr bool kOutF32 = (FLAGS & 2) != 0;
       const bool row_ok = row < p.M;
       long long orow = row_ok ? (long long)(row / p.rows_per_group) * p.group_stride_rows +
                                     (row % p.rows_per_group) : 0;
@@ -290,50 +307,87 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         orow = (long long)(row / (p.diag_rows * p.diag_heads)) * p.diag_rows + row % p.diag_rows;
       }
       orow += (long long)zslice * p.z_c_rows;
-      for (int c = 0; c < BN / 32; ++c) {
+      const bool has_bias = p.bias != nullptr, has_res = p.R != nullptr;
+      const int n_chunks = (p.N - n_tile * BN + 31) / 32 < BN / 32 ? (p.N - n_tile * BN + 31) / 32 : BN / 32;
+      for (int c = 0; c < n_chunks; ++c) {  // warp-uniform trip count: tcgen05.ld needs the whole warp
         const int n0 = n_tile * BN + c * 32;
-        if (n0 >= p.N) break;  // warp-uniform
         tmem_ld32(taddr + c * 32, v);
-        if (!row_ok) continue;
-        if (p.diag_heads > 0 && n0 / p.diag_cols != my_head) continue;  // off-diagonal head block: discard
-        const int nvalid = p.N - n0 < 32 ? p.N - n0 : 32;
+        const bool keep = row_ok && (p.diag_heads == 0 || n0 / p.diag_cols == my_head);
+        if (keep) {
+          const int nvalid = p.N - n0 < 32 ? p.N - n0 : 32;
+          const bool full = nvalid == 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < nvalid) {
-            float x = v[i] * p.alpha;
-            if (p.bias) x += __bfloat162float(p.bias[n0 + i]);
-            if (p.act == HICOM_ACT_GELU) x = gelu_erf(x);
-            if (p.R) x += __bfloat162float(p.R[(long long)row * p.ldr + n0 + i]);
-            v[i] = x;
+          for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+          if (has_bias) {
+            const __nv_bfloat16* bp = p.bias + n0;
+            if (full && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(bp) + g);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[g * 8 + 2 * e] += __uint_as_float(w[e] << 16);
+                  v[g * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) v[i] += __bfloat162float(bp[i]);
+            }
           }
-        }
-        if (p.out_dtype == HICOM_BF16) {
-          __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n0;
-          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          if (kGelu) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 pk;
-              pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-              pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-              pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-              pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-              reinterpret_cast<uint4*>(dst)[g] = pk;
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          }
+          if (has_res) {
+            const __nv_bfloat16* rp = p.R + (long long)row * p.ldr + n0;
+            if (full && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + g);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[g * 8 + 2 * e] += __uint_as_float(w[e] << 16);
+                  v[g * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) v[i] += __bfloat162float(rp[i]);
+            }
+          }
+          if (!kOutF32) {
+            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n0;
+            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 pk;
+                pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                reinterpret_cast<uint4*>(dst)[g] = pk;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) dst[i] = __float2bfloat16_rn(v[i]);
             }
           } else {
+            float* dst = static_cast<float*>(p.C) + orow * p.ldc + n0;
+            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nvalid) dst[i] = __float2bfloat16_rn(v[i]);
-          }
-        } else {
-          float* dst = static_cast<float*>(p.C) + orow * p.ldc + n0;
-          if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              for (int g = 0; g < 8; ++g)
+                reinterpret_cast<float4*>(dst)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            } else {
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              reinterpret_cast<float4*>(dst)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < nvalid) dst[i] = v[i];
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) dst[i] = v[i];
+            }
           }
         }
       }
@@ -449,10 +503,10 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS = 0>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t stream) {
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI, FLAGS>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM_BYTES);
     HICOM_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -497,8 +551,19 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   p.rows_per_group = q.rows_per_group; p.group_stride_rows = q.group_stride_rows;
   dim3 grid((q.N + 255) / 256, (q.M + BM - 1) / BM, q.z_slices > 0 ? q.z_slices : 1);
   HICOM_REQUIRE(grid.y <= 65535, "tcgen05 linear: too many row tiles");
-  if (q.w_is_kn) return launch<256, false, true, EPI_LINEAR>(ta, tb, p, grid, stream);
-  return launch<256, false, false, EPI_LINEAR>(ta, tb, p, grid, stream);
+  const int flags = (q.act == HICOM_ACT_GELU ? 1 : 0) | (q.out_dtype == HICOM_F32 ? 2 : 0);
+#define HICOM_TC_LINEAR_CASE(F)                                                                  \
+  case F:                                                                                         \
+    return q.w_is_kn ? launch<256, false, true, EPI_LINEAR, F>(ta, tb, p, grid, stream)          \
+                     : launch<256, false, false, EPI_LINEAR, F>(ta, tb, p, grid, stream);
+  switch (flags) {
+    HICOM_TC_LINEAR_CASE(0)
+    HICOM_TC_LINEAR_CASE(1)
+    HICOM_TC_LINEAR_CASE(2)
+    HICOM_TC_LINEAR_CASE(3)
+  }
+#undef HICOM_TC_LINEAR_CASE
+  return 1;
 }
 
 // ---------------------------------------------------------------------------------------------

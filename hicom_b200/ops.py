@@ -62,8 +62,7 @@ def num_windows(T: int, H: int, W: int, kt: int, ks: int) -> int:
     return math.ceil(T / kt) * math.ceil(H / ks) * math.ceil(W / ks)
 
 
-@torch.library.custom_op("hicom_b200::grid_pool", mutates_args=(), device_types="cuda")
-def grid_pool(X: Tensor, kt: int, ks: int) -> Tensor:
+def _impl_grid_pool(X: Tensor, kt: int, ks: int) -> Tensor:
     """(B,T,H,W,d) -> (B,Nw,d) trilinear grid pooling — projector.py:536-540."""
     dev = _need_cuda(X)
     X = X.contiguous()
@@ -75,8 +74,7 @@ def grid_pool(X: Tensor, kt: int, ks: int) -> Tensor:
     return out
 
 
-@torch.library.custom_op("hicom_b200::local_attend", mutates_args=(), device_types="cuda")
-def local_attend(K: Tensor, V: Tensor, P: Tensor, q_aux: Optional[Tensor], film: Optional[Tensor],
+def _impl_local_attend(K: Tensor, V: Tensor, P: Tensor, q_aux: Optional[Tensor], film: Optional[Tensor],
                  ln_w: Optional[Tensor], ln_b: Optional[Tensor], kt: int, ks: int, qmode: int,
                  logit_scale: float, k_l2norm: bool) -> Tensor:
     """Fused pool -> inject -> window softmax -> A·V — projector.py:536-558.  Returns (B,Nw,d)."""
@@ -142,8 +140,7 @@ def _check_linear(A, W, bias, residual):
     return dev, W
 
 
-@torch.library.custom_op("hicom_b200::linear", mutates_args=(), device_types="cuda")
-def linear(A: Tensor, W: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], act: int,
+def _impl_linear(A: Tensor, W: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], act: int,
            out_fp32: bool, impl: int) -> Tensor:
     """act(A·Wᵀ + bias) [+ residual] — nn.Linear / build_mlp stage (projector.py:180-182,226,307-312)."""
     dev, W = _check_linear(A, W, bias, residual)
@@ -163,8 +160,7 @@ def linear(A: Tensor, W: Tensor, bias: Optional[Tensor], residual: Optional[Tens
     return C.reshape(*A.shape[:-1], N)
 
 
-@torch.library.custom_op("hicom_b200::linear_into", mutates_args=("out",), device_types="cuda")
-def linear_into(A: Tensor, W: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], act: int,
+def _impl_linear_into(A: Tensor, W: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], act: int,
                 out: Tensor, row_offset: int, rows_per_group: int, group_stride_rows: int, impl: int) -> None:
     """Same as ``linear`` but writes row r to ``out[(r // rows_per_group) * group_stride_rows +
     r % rows_per_group + row_offset]`` — the readouts write straight into the concatenated token block
@@ -186,8 +182,7 @@ def linear_into(A: Tensor, W: Tensor, bias: Optional[Tensor], residual: Optional
                  group_stride_rows, impl, dev)
 
 
-@torch.library.custom_op("hicom_b200::film_layernorm", mutates_args=(), device_types="cuda")
-def film_layernorm(x: Tensor, film: Tensor, ln_w: Tensor, ln_b: Tensor, rows_per_group: int) -> Tensor:
+def _impl_film_layernorm(x: Tensor, film: Tensor, ln_w: Tensor, ln_b: Tensor, rows_per_group: int) -> Tensor:
     """LN(x*(1+scale)+shift), film (G,2d) fp32 — coarse injector on explicit rows (projector.py:369-372)."""
     dev = _need_cuda(x, film, ln_w, ln_b)
     x = x.contiguous()
@@ -206,8 +201,7 @@ def film_layernorm(x: Tensor, film: Tensor, ln_w: Tensor, ln_b: Tensor, rows_per
     return out
 
 
-@torch.library.custom_op("hicom_b200::add_layernorm", mutates_args=(), device_types="cuda")
-def add_layernorm(a: Tensor, b: Tensor, ln_w: Tensor, ln_b: Tensor) -> Tensor:
+def _impl_add_layernorm(a: Tensor, b: Tensor, ln_w: Tensor, ln_b: Tensor) -> Tensor:
     """LN(a + b) — fine injector residual (projector.py:392)."""
     dev = _need_cuda(a, b, ln_w, ln_b)
     a, b = a.contiguous(), b.contiguous()
@@ -222,8 +216,7 @@ def add_layernorm(a: Tensor, b: Tensor, ln_w: Tensor, ln_b: Tensor) -> Tensor:
     return out
 
 
-@torch.library.custom_op("hicom_b200::mix_layernorm", mutates_args=(), device_types="cuda")
-def mix_layernorm(x: Tensor, y: Tensor, ln_w: Tensor, ln_b: Tensor, alpha: Tensor) -> Tensor:
+def _impl_mix_layernorm(x: Tensor, y: Tensor, ln_w: Tensor, ln_b: Tensor, alpha: Tensor) -> Tensor:
     """(1-alpha)*x + alpha*LN(y) — adapter mixes (projector.py:365,533-534,541)."""
     dev = _need_cuda(x, y, ln_w, ln_b, alpha)
     x, y = x.contiguous(), y.contiguous()
@@ -239,8 +232,7 @@ def mix_layernorm(x: Tensor, y: Tensor, ln_w: Tensor, ln_b: Tensor, alpha: Tenso
     return out
 
 
-@torch.library.custom_op("hicom_b200::guide_attend", mutates_args=(), device_types="cuda")
-def guide_attend(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
+def _impl_guide_attend(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> Tensor:
     """MHA of (G,Mq,d) queries over (G,L,d) instruction tokens — projector.py:391 -> :193-224."""
     dev = _need_cuda(q, k, v)
     q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
@@ -258,8 +250,7 @@ def guide_attend(q: Tensor, k: Tensor, v: Tensor, heads: int, scale: float) -> T
 # ------------------------------------------------------------------------------------------
 # global compressor
 # ------------------------------------------------------------------------------------------
-@torch.library.custom_op("hicom_b200::global_fold_query", mutates_args=(), device_types="cuda")
-def global_fold_query(q: Tensor, Wk: Tensor, heads: int, alpha: float) -> Tensor:
+def _impl_global_fold_query(q: Tensor, Wk: Tensor, heads: int, alpha: float) -> Tensor:
     """qfold[b,h*Q+i,:] = alpha * q[b,i,head h] · Wk[head h rows, :] — folds k_proj (:181) and the scale (:197)."""
     dev = _need_cuda(q, Wk)
     q, Wk = q.contiguous(), Wk.contiguous()
@@ -272,8 +263,7 @@ def global_fold_query(q: Tensor, Wk: Tensor, heads: int, alpha: float) -> Tensor
     return out
 
 
-@torch.library.custom_op("hicom_b200::global_attend_partial", mutates_args=(), device_types="cuda")
-def global_attend_partial(X: Tensor, pos_t: Tensor, pos_h: Tensor, pos_w: Tensor, qfold: Tensor, splits: int,
+def _impl_global_attend_partial(X: Tensor, pos_t: Tensor, pos_h: Tensor, pos_w: Tensor, qfold: Tensor, splits: int,
                           impl: int) -> Tuple[Tensor, Tensor, Tensor]:
     """Split-softmax partials (m,l,o) of the global attention over X's frames — projector.py:636-640,197,213,215."""
     dev = _need_cuda(X, pos_t, pos_h, pos_w, qfold)
@@ -299,8 +289,7 @@ def global_attend_partial(X: Tensor, pos_t: Tensor, pos_h: Tensor, pos_w: Tensor
     return m, l, o
 
 
-@torch.library.custom_op("hicom_b200::softmax_merge", mutates_args=(), device_types="cuda")
-def softmax_merge(m: Tensor, l: Tensor, o: Tensor, out_bf16: bool) -> Tensor:
+def _impl_softmax_merge(m: Tensor, l: Tensor, o: Tensor, out_bf16: bool) -> Tensor:
     """Combine (m,l,o) partials over dim 1 (token splits and/or frame shards) -> pooled (B,J,d)."""
     dev = _need_cuda(m, l, o)
     m, l, o = m.contiguous(), l.contiguous(), o.contiguous()
@@ -316,8 +305,7 @@ def softmax_merge(m: Tensor, l: Tensor, o: Tensor, out_bf16: bool) -> Tensor:
     return out
 
 
-@torch.library.custom_op("hicom_b200::global_value_proj", mutates_args=(), device_types="cuda")
-def global_value_proj(pooled: Tensor, Wv: Tensor, bv: Optional[Tensor], Q: int, heads: int) -> Tensor:
+def _impl_global_value_proj(pooled: Tensor, Wv: Tensor, bv: Optional[Tensor], Q: int, heads: int) -> Tensor:
     """attn[b,i,head h] = Wv[head h rows] · pooled[b,h*Q+i] + bv — v_proj (:182) after pooling + head merge (:223-224)."""
     dev = _need_cuda(pooled, Wv, bv)
     pooled, Wv = pooled.contiguous(), Wv.contiguous()
@@ -399,17 +387,38 @@ def device_info(device=None):
 
 
 # ------------------------------------------------------------------------------------------
-# op-level timing hooks: wrap the registered ops so an active OpTimer sees every call
+# registration + dispatch
+#
+# Every op is registered as ``torch.ops.hicom_b200.<name>`` (a forward-only torch custom op).  The
+# torch.library dispatcher costs ~45 us of host time per call on this stack, which is more than most of
+# these kernels take, so by default the modules call the SAME Python implementation directly; set
+# HICOM_VIA_TORCH_OPS=1 to route every call through the dispatcher instead (tests do both).
 # ------------------------------------------------------------------------------------------
-def _wrap(op, label):
+import os as _os
+
+VIA_TORCH_OPS = _os.environ.get("HICOM_VIA_TORCH_OPS", "0") == "1"
+_REGISTERED = {}
+
+
+def _register(name, fn, mutates):
+    op = torch.library.custom_op(f"hicom_b200::{name}", mutates_args=mutates, device_types="cuda")(fn)
+    _REGISTERED[name] = op
+    return op
+
+
+def _wrap(name, impl, mutates, label):
+    op = _register(name, impl, mutates)
+
     def call(*args):
+        target = op if VIA_TORCH_OPS else impl
         if _ACTIVE_TIMER is None:
-            return op(*args)
+            return target(*args)
         with _Timed(label(*args)):
-            return op(*args)
-    call.__name__ = getattr(op, "__name__", "op")
-    call.__doc__ = op.__doc__
-    call.op = op
+            return target(*args)
+
+    call.__name__ = name
+    call.__doc__ = impl.__doc__
+    call.op, call.impl = op, impl
     return call
 
 
@@ -417,15 +426,17 @@ def _rows(t):
     return t.numel() // t.shape[-1]
 
 
-grid_pool = _wrap(grid_pool, lambda X, *a: "grid_pool")
-local_attend = _wrap(local_attend, lambda *a: "local_attend")
-linear = _wrap(linear, lambda A, W, *a: f"linear M={_rows(A)} N={W.shape[0]} K={W.shape[1]}")
-linear_into = _wrap(linear_into, lambda A, W, *a: f"linear M={_rows(A)} N={W.shape[0]} K={W.shape[1]}")
-film_layernorm = _wrap(film_layernorm, lambda *a: "film_layernorm")
-add_layernorm = _wrap(add_layernorm, lambda *a: "add_layernorm")
-mix_layernorm = _wrap(mix_layernorm, lambda *a: "mix_layernorm")
-guide_attend = _wrap(guide_attend, lambda *a: "guide_attend")
-global_fold_query = _wrap(global_fold_query, lambda *a: "global_fold_query")
-global_attend_partial = _wrap(global_attend_partial, lambda *a: "global_attend_partial")
-softmax_merge = _wrap(softmax_merge, lambda *a: "softmax_merge")
-global_value_proj = _wrap(global_value_proj, lambda *a: "global_value_proj")
+_lin_label = lambda A, W, *a: f"linear M={_rows(A)} N={W.shape[0]} K={W.shape[1]}"
+grid_pool = _wrap("grid_pool", _impl_grid_pool, (), lambda *a: "grid_pool")
+local_attend = _wrap("local_attend", _impl_local_attend, (), lambda *a: "local_attend")
+linear = _wrap("linear", _impl_linear, (), _lin_label)
+linear_into = _wrap("linear_into", _impl_linear_into, ("out",), _lin_label)
+film_layernorm = _wrap("film_layernorm", _impl_film_layernorm, (), lambda *a: "film_layernorm")
+add_layernorm = _wrap("add_layernorm", _impl_add_layernorm, (), lambda *a: "add_layernorm")
+mix_layernorm = _wrap("mix_layernorm", _impl_mix_layernorm, (), lambda *a: "mix_layernorm")
+guide_attend = _wrap("guide_attend", _impl_guide_attend, (), lambda *a: "guide_attend")
+global_fold_query = _wrap("global_fold_query", _impl_global_fold_query, (), lambda *a: "global_fold_query")
+global_attend_partial = _wrap("global_attend_partial", _impl_global_attend_partial, (),
+                              lambda *a: "global_attend_partial")
+softmax_merge = _wrap("softmax_merge", _impl_softmax_merge, (), lambda *a: "softmax_merge")
+global_value_proj = _wrap("global_value_proj", _impl_global_value_proj, (), lambda *a: "global_value_proj")

@@ -106,6 +106,18 @@ def _mix(x, proj, norm, alpha):
     return ops.mix_layernorm(x, y, norm.weight, norm.bias, alpha.to(x.dtype))
 
 
+def _require_no_grad(module, *tensors):
+    """The kernels are forward-only.  Fail loudly instead of silently returning tensors cut off from autograd
+    (SURVEY §8b): run under ``torch.no_grad()`` / ``torch.inference_mode()`` (as ``mm_infer`` does,
+    hicom/__init__.py:107) or freeze the projector."""
+    if not torch.is_grad_enabled():
+        return
+    if any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in module.parameters()):
+        raise RuntimeError(
+            "hicom_b200 compressor kernels are forward-only: call under torch.no_grad()/torch.inference_mode(), "
+            "or set requires_grad_(False) on the projector and its inputs (backward is not implemented)")
+
+
 class IdentityMap(nn.Module):
     """projector.py:104-110."""
 
@@ -516,6 +528,7 @@ class HIComProjector(nn.Module):
         X = frames_feature
         if X.dim() != 5:
             raise ValueError(f"forward_batched expects (B,T,H,W,d), got {tuple(X.shape)}")
+        _require_no_grad(self, X, frames_embed, guide_embed)
         B, T, H, W, d = X.shape
         lc = self.local_compressor
         gc = self.global_compressor if with_global else None

@@ -93,7 +93,9 @@ def test_cabi_exports_every_declared_symbol(built_library):
 def test_no_cpu_fallback(built_library):
     import hicom_b200
     m = hicom_b200.build_vision_projector(Cfg(hidden_size=64))
-    with pytest.raises((RuntimeError, NotImplementedError)):
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA tensors only"):
+        m(torch.randn(4, 6, 6, 1152), None, None, "video")
+    with pytest.raises(RuntimeError, match="forward-only"):
         m(torch.randn(4, 6, 6, 1152), None, None, "video")
 
 

@@ -176,3 +176,17 @@ def test_device_info(built_library):
     from hicom_b200 import ops
     sm, major, minor = ops.device_info()
     assert major == 10 and sm >= 100
+
+
+def test_dispatcher_route_matches_direct(built_library):
+    """torch.ops.hicom_b200.* (registered custom ops) and the direct calls run the same code."""
+    from hicom_b200 import ops
+    A, W, b = _rand(70, 1152, seed=1).cuda(), _rand(96, 1152, seed=2, std=0.02).cuda(), _rand(96, seed=3).cuda()
+    direct = ops.linear(A, W, b, None, 1, False, ops.IMPL_AUTO)
+    via = torch.ops.hicom_b200.linear(A, W, b, None, 1, False, ops.IMPL_AUTO)
+    assert torch.equal(direct, via)
+    X = _rand(1, 8, 6, 6, 1152, seed=4, dtype=torch.bfloat16).cuda()
+    assert torch.equal(ops.grid_pool(X, 4, 3), torch.ops.hicom_b200.grid_pool(X, 4, 3))
+    out = torch.zeros(80, 96, device="cuda")
+    torch.ops.hicom_b200.linear_into(A, W, b, None, 0, out, 5, 70, 0, ops.IMPL_AUTO)
+    assert torch.equal(out[5:75], ops.linear(A, W, b, None, 0, False, ops.IMPL_AUTO))

@@ -99,14 +99,20 @@ def test_reference_failures_are_loud(built_library):
     case = CASES_BY_NAME["coarse_T8"]
     sd, X, E, g, nl = materialise(case)
     m = cuda_module_for(case, sd)
-    for T in (5, 6, 9):
-        x = torch.randn(T, 6, 6, 1152, device="cuda")
-        with pytest.raises(RuntimeError):
-            m(x, x, g.cuda(), "video")
-    with pytest.raises(ValueError):
-        m(X.cuda(), E.cuda(), torch.randn(4, 1152, device="cuda"), "video")  # coarse wants a (d,) vector
-    with pytest.raises(ValueError):
-        m(X.cuda(), E.cuda(), None, "video")
+    with torch.no_grad():
+        for T in (5, 6, 9):
+            x = torch.randn(T, 6, 6, 1152, device="cuda")
+            with pytest.raises(RuntimeError, match="unequal windows"):
+                m(x, x, g.cuda(), "video")
+        with pytest.raises(ValueError):
+            m(X.cuda(), E.cuda(), torch.randn(4, 1152, device="cuda"), "video")  # coarse wants a (d,) vector
+        with pytest.raises(ValueError):
+            m(X.cuda(), E.cuda(), None, "video")
+    # forward-only kernels: autograd-enabled calls on trainable parameters fail loudly, not silently
+    with pytest.raises(RuntimeError, match="forward-only"):
+        m(X.cuda(), E.cuda(), g.cuda(), "video")
+    with torch.inference_mode():
+        assert m(X.cuda(), E.cuda(), g.cuda(), "video").shape[0] == 40
 
 
 def test_full_size_properties_bf16(built_library):
