@@ -42,7 +42,10 @@ struct Params {
   int z_a_k, z_b_k;                //     A / B reduction coordinates start at z*z_a_k / z*z_b_k
   long long z_c_rows;              //     and output rows are shifted by z*z_c_rows
   // EPI_MAX / EPI_PROB / EPI_POOL
-  float* mg; float* lg;            // (B, J) running max / sum of probabilities
+  float* mg; float* lg;            // (B, J) running TRUE max of the scores / sum of probabilities
+  const float* stab;               // (B, J) softmax stabiliser used by EPI_PROB (any value near the max is exact)
+  int n_tile_stride;               // EPI_MAX sampling: this launch visits N tiles 0, stride, 2*stride, ...
+  const int* guard;                // if non-null: the whole kernel is a no-op unless *guard != 0
   __nv_bfloat16* Pt; long long pt_ld;  // (B, J, pt_ld) transposed probabilities
   float* o; int splits;            // (B, splits, J, d) pooled partials
 };
@@ -200,7 +203,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int batch = p.z_slices > 0 ? 0 : blockIdx.z;
   const int m_tile = blockIdx.y;
   // EPI_POOL: blockIdx.x = K split, single N tile.  Otherwise blockIdx.x = N tile, full K.
-  const int n_tile = (EPI == EPI_POOL) ? 0 : blockIdx.x;
+  const int n_tile = (EPI == EPI_POOL) ? 0 : blockIdx.x * (p.n_tile_stride > 0 ? p.n_tile_stride : 1);
+  if (p.guard != nullptr && *p.guard == 0) return;  // guarded fallback launch: nothing to repair
   const int split = (EPI == EPI_POOL) ? blockIdx.x : 0;
   const int k_begin = split * p.k_chunk;
   int k_end = k_begin + p.k_chunk;
@@ -405,8 +409,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (row < p.M) atomic_max_float(p.mg + (size_t)batch * p.M + row, mx);
     } else if (EPI == EPI_PROB) {
       const bool row_ok = row < p.M;
-      const float pre = row_ok ? p.mg[(size_t)batch * p.M + row] * kLog2e : 0.f;
-      float sum = 0.f;
+      const float pre = row_ok ? p.stab[(size_t)batch * p.M + row] * kLog2e : 0.f;
+      float sum = 0.f, mx = -INFINITY;
       __nv_bfloat16* prow = p.Pt + ((size_t)batch * p.M + (row_ok ? row : 0)) * p.pt_ld + (size_t)n_tile * BN;
       for (int c = 0; c < BN / 32; ++c) {
         const int t0 = n_tile * BN + c * 32;
@@ -416,8 +420,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float a = 0.f, b = 0.f;
-          if (any && t0 + i < p.N) a = exp2f(fmaf(v[i], kLog2e, -pre));
-          if (any && t0 + i + 1 < p.N) b = exp2f(fmaf(v[i + 1], kLog2e, -pre));
+          if (any && t0 + i < p.N) { a = exp2f(fmaf(v[i], kLog2e, -pre)); mx = fmaxf(mx, v[i]); }
+          if (any && t0 + i + 1 < p.N) { b = exp2f(fmaf(v[i + 1], kLog2e, -pre)); mx = fmaxf(mx, v[i + 1]); }
           __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
           sum += __low2float(t) + __high2float(t);  // sum what P·V will actually multiply
           pk[i / 2] = *reinterpret_cast<uint32_t*>(&t);
@@ -428,7 +432,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
         }
       }
-      if (row_ok) atomicAdd(p.lg + (size_t)batch * p.M + row, sum);
+      if (row_ok) {
+        atomicAdd(p.lg + (size_t)batch * p.M + row, sum);
+        atomic_max_float(p.mg + (size_t)batch * p.M + row, mx);
+      }
     } else {  // EPI_POOL: rows = channels d (M), columns = score columns j (N = J)
       float* obase = p.o + (((size_t)batch * p.splits + split) * p.N) * p.M + row;
       for (int c = 0; c < (BN + 31) / 32; ++c) {
@@ -450,16 +457,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // small helpers for the global pipeline
 // ---------------------------------------------------------------------------------------------
-__global__ void init_stats_kernel(float* mg, float* lg, int n) {
+__global__ void init_stats_kernel(float* mg, float* lg, int n, int* flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { mg[i] = -INFINITY; lg[i] = 0.f; }
+  if (i == 0) *flag = 0;
 }
-// m[b,s,j] = mg[b,j] for every split; l[b,0,j] = lg[b,j], 0 for the other splits (they share the same max).
-__global__ void spread_stats_kernel(const float* mg, const float* lg, float* m, float* l, int B, int S, int J) {
+// Stabiliser from the sampled max: stab = sampled max + margin.  exp(S - stab) then stays far from both ends of the
+// bf16/fp32 exponent range unless some unsampled score exceeds the sampled max by ~80 nats (checked afterwards).
+constexpr float kStabMargin = 20.f;   // nats
+constexpr float kStabLimit = 60.f;    // true max - stab above this triggers the exact-max fallback
+__global__ void make_stab_kernel(const float* mg, float* stab, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stab[i] = mg[i] + kStabMargin;
+}
+__global__ void check_stab_kernel(const float* mg, const float* stab, int n, int* flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (mg[i] - stab[i] > kStabLimit || !(mg[i] - stab[i] > -1e30f))) atomicExch(flag, 1);
+}
+// fallback only: stabiliser := true max, sums reset
+__global__ void repair_stab_kernel(const float* mg, float* stab, float* lg, int n, const int* flag) {
+  if (*flag == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { stab[i] = mg[i]; lg[i] = 0.f; }
+}
+// m[b,s,j] = stabiliser for every split; l[b,0,j] = lg[b,j], 0 for the other splits (they share the stabiliser).
+__global__ void spread_stats_kernel(const float* stab, const float* lg, float* m, float* l, int B, int S, int J) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * S * J) return;
   const int j = i % J, s = (i / J) % S, b = i / (J * S);
-  m[i] = mg[b * J + j];
+  m[i] = stab[b * J + j];
   l[i] = s == 0 ? lg[b * J + j] : 0.f;
 }
 
@@ -577,7 +603,7 @@ bool tc_global_selected(int dtype, int impl, int d, int J) {
 }
 
 struct GlobalWs {
-  size_t xp, pt, mg, lg, total;
+  size_t xp, pt, mg, lg, stab, flag, total;
   long long pt_ld;
 };
 static GlobalWs global_ws(int B, int T, int H, int W, int d, int J) {
@@ -588,7 +614,9 @@ static GlobalWs global_ws(int B, int T, int H, int W, int d, int J) {
   w.pt = al256((size_t)B * N * d * 2);
   w.mg = w.pt + al256((size_t)B * J * w.pt_ld * 2);
   w.lg = w.mg + al256((size_t)B * J * 4);
-  w.total = w.lg + al256((size_t)B * J * 4);
+  w.stab = w.lg + al256((size_t)B * J * 4);
+  w.flag = w.stab + al256((size_t)B * J * 4);
+  w.total = w.flag + 256;
   return w;
 }
 
@@ -610,8 +638,11 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   float* mg = reinterpret_cast<float*>(ws + w.mg);
   float* lg = reinterpret_cast<float*>(ws + w.lg);
 
+  float* stab = reinterpret_cast<float*>(ws + w.stab);
+  int* flag = reinterpret_cast<int*>(ws + w.flag);
+
   if (launch_posadd(X, Xp, pos_t, pos_h, pos_w, B, T, H, W, d, HICOM_BF16, stream)) return 1;
-  init_stats_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, lg, B * J);
+  init_stats_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, lg, B * J, flag);
   if (check_launch("init_stats_kernel")) return 1;
 
   // scores: S[b] (J x N) = qfold[b] (J x d) · X'[b]ᵀ  — A = qfold (rows j), "W" = X' (rows = tokens)
@@ -620,12 +651,11 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   if (make_map(&tx, Xp, d, N, B, d, (uint64_t)N * d, 256)) return 1;
   Params p{};
   p.M = J; p.N = N; p.K = d; p.k_chunk = d; p.b_box_rows = 256;
-  p.mg = mg; p.lg = lg; p.Pt = Pt; p.pt_ld = w.pt_ld;
-  dim3 gs((N + 255) / 256, (J + BM - 1) / BM, B);
-  if (launch<256, false, false, EPI_MAX>(tq, tx, p, gs, stream)) return 1;
-  if (launch<256, false, false, EPI_PROB>(tq, tx, p, gs, stream)) return 1;
+  p.mg = mg; p.lg = lg; p.stab = stab; p.Pt = Pt; p.pt_ld = w.pt_ld;
+  const int n_tiles = (N + 255) / 256;
+  const int m_tiles = (J + BM - 1) / BM;
 
-  // pooling: O[b,s] (d x J) = X'[b, tokens of s]ᵀ · P[b, tokens of s]  — A = X' read MN-major, B = Ptᵀ rows j
+  // pooling operands: O[b,s] (d x J) = X'[b, tokens of s]ᵀ · P[b, tokens of s]  — A = X' read MN-major, B = Ptᵀ rows j
   CUtensorMap txa, tp;
   if (make_map(&txa, Xp, d, N, B, d, (uint64_t)N * d, 64)) return 1;
   if (make_map(&tp, Pt, w.pt_ld, J, B, w.pt_ld, (uint64_t)J * w.pt_ld, 96)) return 1;
@@ -636,9 +666,35 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   g.k_chunk = chunk; g.b_box_rows = 96;
   g.o = o; g.splits = splits;
   dim3 gp(splits, d / BM, B);
-  if (launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream)) return 1;
 
-  spread_stats_kernel<<<(B * splits * J + 255) / 256, 256, 0, stream>>>(mg, lg, m, l, B, splits, J);
+  // 1. sampled max (a few evenly spaced token tiles) -> stabiliser.  The softmax is invariant to the stabiliser;
+  //    it only has to keep exp() inside the exponent range, so the full max pass is not needed.
+  {
+    Params ps = p;
+    const int n_sample = n_tiles < 4 ? n_tiles : 4;
+    ps.n_tile_stride = n_tiles / n_sample;
+    dim3 gsample(n_sample, m_tiles, B);
+    if (launch<256, false, false, EPI_MAX>(tq, tx, ps, gsample, stream)) return 1;
+    make_stab_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, stab, B * J);
+    if (check_launch("make_stab_kernel")) return 1;
+  }
+  // 2. single full pass: P = exp(S - stab) (bf16, transposed), row sums, and the TRUE max for the safety check
+  dim3 gs(n_tiles, m_tiles, B);
+  if (launch<256, false, false, EPI_PROB>(tq, tx, p, gs, stream)) return 1;
+  check_stab_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, stab, B * J, flag);
+  if (check_launch("check_stab_kernel")) return 1;
+  // 3. pooling
+  if (launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream)) return 1;
+  // 4. guarded exact fallback (no-ops unless some score beat the sampled max by > 80 nats): redo 2-3 with the true max
+  {
+    repair_stab_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, stab, lg, B * J, flag);
+    if (check_launch("repair_stab_kernel")) return 1;
+    Params pf = p; pf.guard = flag;
+    Params gf = g; gf.guard = flag;
+    if (launch<256, false, false, EPI_PROB>(tq, tx, pf, gs, stream)) return 1;
+    if (launch<288, true, false, EPI_POOL>(txa, tp, gf, gp, stream)) return 1;
+  }
+  spread_stats_kernel<<<(B * splits * J + 255) / 256, 256, 0, stream>>>(stab, lg, m, l, B, splits, J);
   return check_launch("spread_stats_kernel");
 }
 

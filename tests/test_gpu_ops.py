@@ -190,3 +190,33 @@ def test_dispatcher_route_matches_direct(built_library):
     out = torch.zeros(80, 96, device="cuda")
     torch.ops.hicom_b200.linear_into(A, W, b, None, 0, out, 5, 70, 0, ops.IMPL_AUTO)
     assert torch.equal(out[5:75], ops.linear(A, W, b, None, 0, False, ops.IMPL_AUTO))
+
+
+def test_global_partial_outlier_triggers_exact_fallback(built_library):
+    """A score far above the sampled stabiliser (an unsampled token ~hundreds of nats above the rest) must take the
+    guarded exact-max path and still match the reference softmax."""
+    from hicom_b200 import ops
+    from hicom_b200.projector import _axis_table
+    dtype = torch.bfloat16
+    B, T, H, W, d, Q, heads = 1, 4, 18, 18, 1152, 32, 9   # 1296 tokens = 6 score tiles, 4 of them sampled
+    X = _rand(B, T, H, W, d, seed=1, dtype=dtype)
+    Xf = X.view(B, -1, d)
+    Xf[0, 1100] = (Xf[0, 1100].float() * 60).to(dtype)      # outlier token in an unsampled tile
+    Qg = _rand(B, Q, d, seed=2, dtype=dtype)
+    Wq, Wk, Wv = (_rand(d, d, seed=s, std=0.1, dtype=dtype) for s in (3, 4, 5))
+    bq, bk, bv = (_rand(d, seed=s, std=0.02, dtype=dtype) for s in (6, 7, 8))
+    tabs = [torch.from_numpy(_axis_table(n, d)).float() for n in (T, H, W)]
+    q = ops.linear(Qg.cuda(), Wq.cuda(), bq.cuda(), None, 0, False, ops.IMPL_AUTO)
+    qf = ops.global_fold_query(q, Wk.cuda(), heads, 128 ** -0.5)
+    m, l, o = ops.global_attend_partial(X.cuda(), tabs[0].cuda(), tabs[1].cuda(), tabs[2].cuda(), qf, 2, ops.IMPL_AUTO)
+    pooled = ops.softmax_merge(m, l, o, True)
+    got = ops.global_value_proj(pooled, Wv.cuda(), bv.cuda(), Q, heads).float().cpu()
+    assert torch.isfinite(got).all()
+    xp = (X[0].float() + O.pos_embed_3d(T, H, W, d)).reshape(-1, d)
+    qq = F.linear(Qg[0].float(), Wq.float(), bq.float()).view(Q, heads, 128).transpose(0, 1)
+    kk = F.linear(xp, Wk.float(), bk.float()).view(-1, heads, 128).transpose(0, 1)
+    vv = F.linear(xp, Wv.float(), bv.float()).view(-1, heads, 128).transpose(0, 1)
+    s = qq @ kk.transpose(1, 2) * 128 ** -0.5
+    assert float((s.max(-1).values - s[..., :1024].max(-1).values).max()) > 100  # really beyond the fast path's range
+    want = (torch.softmax(s, -1) @ vv).transpose(0, 1).reshape(Q, d)
+    assert O.rel_err(got[0], want) <= 2e-2
