@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / TMA GEMM family for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
 //
-// One warp-specialised kernel template, one 128 x BN output tile per CTA:
+// One warp-specialised PERSISTENT kernel template (grid <= #SMs, static tile schedule, 128 x BN output tiles,
+// two accumulator buffers in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1):
 //   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B boxes) into a STAGES-deep smem ring
 //   warp 1      MMA issuer     one elected lane issues tcgen05.mma (M=128, N<=256, K=16) per 32-byte K slice,
 //                              tcgen05.commit releases smem stages and finally publishes the accumulator
@@ -44,6 +45,7 @@ struct Params {
   // EPI_MAX / EPI_PROB / EPI_POOL
   float* mg; float* lg;            // (B, J) running TRUE max of the scores / sum of probabilities
   const float* stab;               // (B, J) softmax stabiliser used by EPI_PROB (any value near the max is exact)
+  int tiles_x, tiles_y, tiles_z;   // tile space walked by the persistent CTAs (filled by launch())
   int n_tile_stride;               // EPI_MAX sampling: this launch visits N tiles 0, stride, 2*stride, ...
   const int* guard;                // if non-null: the whole kernel is a no-op unless *guard != 0
   __nv_bfloat16* Pt; long long pt_ld;  // (B, J, pt_ld) transposed probabilities
@@ -75,6 +77,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -182,9 +187,33 @@ struct Cfg {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t TMEM_COLS = BN <= 256 ? 256 : 512;
+  static constexpr int NBUF = BN <= 256 ? 2 : 1;          // accumulator buffers in TMEM (epilogue/mainloop overlap)
+  static constexpr uint32_t ACC_COLS = BN <= 256 ? 256 : 512;
+  static constexpr uint32_t TMEM_COLS = 512;
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+struct TileInfo { int n_tile, m_tile, batch, zslice, split, k_begin, nkb; };
+
+// Static tile schedule: persistent CTA c handles tiles c, c+grid, c+2*grid, ... of the (x fastest, y, z) tile space.
+// x = N tile (or K split for EPI_POOL), y = M tile, z = tensor batch (or per-head K slice).
+template <int EPI>
+__device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
+  TileInfo t;
+  const int x = tile % p.tiles_x;
+  const int y = (tile / p.tiles_x) % p.tiles_y;
+  const int z = tile / (p.tiles_x * p.tiles_y);
+  t.m_tile = y;
+  t.zslice = p.z_slices > 0 ? z : 0;
+  t.batch = p.z_slices > 0 ? 0 : z;
+  t.n_tile = (EPI == EPI_POOL) ? 0 : x * (p.n_tile_stride > 0 ? p.n_tile_stride : 1);
+  t.split = (EPI == EPI_POOL) ? x : 0;
+  t.k_begin = t.split * p.k_chunk;
+  int k_end = t.k_begin + p.k_chunk;
+  if (k_end > p.K) k_end = p.K;
+  t.nkb = k_end > t.k_begin ? (k_end - t.k_begin + BK - 1) / BK : 0;
+  return t;
+}
 
 // FLAGS (EPI_LINEAR only): bit 0 = GELU, bit 1 = fp32 output
 template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS>
@@ -196,20 +225,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_empty_bar = tmem_full_bar + C::NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + C::NBUF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int zslice = p.z_slices > 0 ? blockIdx.z : 0;
-  const int batch = p.z_slices > 0 ? 0 : blockIdx.z;
-  const int m_tile = blockIdx.y;
-  // EPI_POOL: blockIdx.x = K split, single N tile.  Otherwise blockIdx.x = N tile, full K.
-  const int n_tile = (EPI == EPI_POOL) ? 0 : blockIdx.x * (p.n_tile_stride > 0 ? p.n_tile_stride : 1);
   if (p.guard != nullptr && *p.guard == 0) return;  // guarded fallback launch: nothing to repair
-  const int split = (EPI == EPI_POOL) ? blockIdx.x : 0;
-  const int k_begin = split * p.k_chunk;
-  int k_end = k_begin + p.k_chunk;
-  if (k_end > p.K) k_end = p.K;
-  const int nkb = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_z;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -219,7 +240,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+#pragma unroll
+    for (int b = 0; b < C::NBUF; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -229,30 +254,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: runs ahead across tiles through the STAGES-deep ring =====
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * C::STAGE_BYTES;
-        uint8_t* sb = sa + C::A_BYTES;
-        mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
-        const int k0 = k_begin + kb * BK;
-        if (A_MN) {
-          // A[m, k] stored (k rows, m contiguous): two 64-wide M blocks of (BK rows x 128 B)
-          tma_load_3d(sa, &tmA, &full_bar[s], m_tile * BM, k0, batch);
-          tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], m_tile * BM + 64, k0, batch);
-        } else {
-          tma_load_3d(sa, &tmA, &full_bar[s], k0 + zslice * p.z_a_k, m_tile * BM, batch);
-        }
-        if (B_MN) {
-          // B[k, n] stored (k rows, n contiguous): BN/64 blocks of (BK rows x 128 B)
-          for (int r = 0; r < BN; r += 64)
-            tma_load_3d(sb + (r / 64) * (BK * 128), &tmB, &full_bar[s], n_tile * BN + r, k0 + zslice * p.z_b_k, batch);
-        } else {
-          for (int r = 0; r < BN; r += p.b_box_rows)
-            tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0 + zslice * p.z_b_k, n_tile * BN + r, batch);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo t = decode_tile<EPI>(p, tile);
+        for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          const int k0 = t.k_begin + kb * BK;
+          if (A_MN) {
+            // A[m, k] stored (k rows, m contiguous): two 64-wide M blocks of (BK rows x 128 B)
+            tma_load_3d(sa, &tmA, &full_bar[s], t.m_tile * BM, k0, t.batch);
+            tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], t.m_tile * BM + 64, k0, t.batch);
+          } else {
+            tma_load_3d(sa, &tmA, &full_bar[s], k0 + t.zslice * p.z_a_k, t.m_tile * BM, t.batch);
+          }
+          if (B_MN) {
+            // B[k, n] stored (k rows, n contiguous): BN/64 blocks of (BK rows x 128 B)
+            for (int r = 0; r < BN; r += 64)
+              tma_load_3d(sb + (r / 64) * (BK * 128), &tmB, &full_bar[s], t.n_tile * BN + r,
+                          k0 + t.zslice * p.z_b_k, t.batch);
+          } else {
+            for (int r = 0; r < BN; r += p.b_box_rows)
+              tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0 + t.zslice * p.z_b_k, t.n_tile * BN + r, t.batch);
+          }
         }
       }
     }
@@ -262,41 +292,55 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       static_assert(!(B_MN && BN > 256), "MN-major B is only wired for a single N<=256 instruction");
       constexpr uint32_t idesc_main = make_idesc(BN > 256 ? 256 : BN, A_MN, B_MN);
       constexpr uint32_t idesc_tail = make_idesc(BN > 256 ? BN - 256 : 8, A_MN, B_MN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const TileInfo t = decode_tile<EPI>(p, tile);
+        const uint32_t buf = tcount % C::NBUF;
+        const uint32_t bph = (tcount / C::NBUF) & 1;
+        mbar_wait(&tmem_empty_bar[buf], bph ^ 1);  // the epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint32_t sb = sa + C::A_BYTES;
+        const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
+        for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BK / UK; ++kk) {
-          // K-major: +32 B per 16-element K slice inside the 128 B swizzle row (SBO = 8 rows x 128 B).
-          // MN-major A: 16 k-rows = two 1024 B swizzle atoms per slice; LBO = stride between 64-wide M blocks.
-          const uint64_t adesc = A_MN ? make_smem_desc(sa + kk * 2048, BK * 128, 1024)
-                                      : make_smem_desc(sa + kk * 32, 16, 1024);
-          const uint64_t bdesc = B_MN ? make_smem_desc(sb + kk * 2048, BK * 128, 1024)
-                                      : make_smem_desc(sb + kk * 32, 16, 1024);
-          const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, adesc, bdesc, idesc_main, acc);
-          if (BN > 256) {
-            const uint64_t bdesc2 = make_smem_desc(sb + 256 * 128 + kk * 32, 16, 1024);
-            umma_bf16(tmem_base + 256, adesc, bdesc2, idesc_tail, acc);
+          for (int kk = 0; kk < BK / UK; ++kk) {
+            // K-major: +32 B per 16-element K slice inside the 128 B swizzle row (SBO = 8 rows x 128 B).
+            // MN-major: 16 k-rows = two 1024 B swizzle atoms per slice; LBO = stride between 64-wide MN blocks.
+            const uint64_t adesc = A_MN ? make_smem_desc(sa + kk * 2048, BK * 128, 1024)
+                                        : make_smem_desc(sa + kk * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(sb + kk * 2048, BK * 128, 1024)
+                                        : make_smem_desc(sb + kk * 32, 16, 1024);
+            const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+            umma_bf16(d_tmem, adesc, bdesc, idesc_main, acc);
+            if (BN > 256) {
+              const uint64_t bdesc2 = make_smem_desc(sb + 256 * 128 + kk * 32, 16, 1024);
+              umma_bf16(d_tmem + 256, adesc, bdesc2, idesc_tail, acc);
+            }
           }
+          umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
+        umma_commit(&tmem_full_bar[buf]);  // accumulator of this tile complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
-    const int row = m_tile * BM + q * 32 + lane;  // output row of this thread
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (nkb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-    }
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    const TileInfo t = decode_tile<EPI>(p, tile);
+    const uint32_t buf = tcount % C::NBUF;
+    const uint32_t bph = (tcount / C::NBUF) & 1;
+    const int n_tile = t.n_tile, batch = t.batch, zslice = t.zslice, split = t.split, nkb = t.nkb;
+    (void)n_tile; (void)batch; (void)zslice; (void)split;
+    const int row = t.m_tile * BM + q * 32 + lane;  // output row of this thread
+    const uint32_t taddr = tmem_base + buf * C::ACC_COLS + ((uint32_t)(q * 32) << 16);
+    mbar_wait(&tmem_full_bar[buf], bph);
+    tc_fence_after();
     float v[32];
 
     if (EPI == EPI_LINEAR) {
@@ -447,6 +491,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    // all tcgen05.ld of this tile have completed (tcgen05.wait::ld): hand the accumulator buffer back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }  // tile loop
   }
 
   tc_fence_before();
@@ -538,7 +587,19 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     HICOM_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  Params pp = p;
+  pp.tiles_x = (int)grid.x; pp.tiles_y = (int)grid.y; pp.tiles_z = (int)grid.z;
+  const long long total = (long long)grid.x * grid.y * grid.z;
+  if (total == 0) return 0;
+  const unsigned ctas = (unsigned)(total < num_sms ? total : num_sms);  // persistent: one CTA per SM at most
+  kern<<<ctas, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, pp);
   return check_launch("tc_gemm_kernel");
 }
 
@@ -576,7 +637,6 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   p.C = q.C; p.ldc = q.ldc; p.out_dtype = q.out_dtype; p.act = q.act;
   p.rows_per_group = q.rows_per_group; p.group_stride_rows = q.group_stride_rows;
   dim3 grid((q.N + 255) / 256, (q.M + BM - 1) / BM, q.z_slices > 0 ? q.z_slices : 1);
-  HICOM_REQUIRE(grid.y <= 65535, "tcgen05 linear: too many row tiles");
   const int flags = (q.act == HICOM_ACT_GELU ? 1 : 0) | (q.out_dtype == HICOM_F32 ? 2 : 0);
 #define HICOM_TC_LINEAR_CASE(F)                                                                  \
   case F:                                                                                         \
@@ -629,7 +689,6 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
                      float* m, float* l, float* o, int B, int T, int H, int W, int d, int J, int splits,
                      void* workspace, cudaStream_t stream) {
   using namespace tc;
-  HICOM_REQUIRE(B <= 65535, "global_attend_partial: batch too large for one launch");
   const int N = T * H * W;
   const GlobalWs w = global_ws(B, T, H, W, d, J);
   char* ws = static_cast<char*>(workspace);
