@@ -15,6 +15,7 @@ PyTorch/CPU fallback: tensors must live on a B200.  ``forward_batched`` is the a
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 import re
@@ -34,6 +35,17 @@ __all__ = [
 ]
 
 _IMPL = ops.IMPL_AUTO
+OVERLAP_STREAMS = os.environ.get("HICOM_OVERLAP_STREAMS", "1") == "1"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One cached side stream per device for the local chain (forked from / joined to the caller's stream)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return st
 
 
 # ------------------------------------------------------------------------------------------
@@ -549,13 +561,23 @@ class HIComProjector(nn.Module):
         out = torch.empty((B * total, Dh), dtype=X.dtype, device=X.device)
         if base is not None:
             out.view(B, total, Dh)[:, :n_base] = base
+        # The local chain (HBM-bound window attention + readout) and the global chain (tensor-bound score / pooling
+        # GEMMs) are independent and write disjoint rows of `out`: run them on two streams so they overlap.
+        side = None
+        if lc is not None and gc is not None and OVERLAP_STREAMS:
+            main = torch.cuda.current_stream(X.device)
+            side = _side_stream(X.device)
+            side.wait_stream(main)
         if lc is not None:
-            att = lc.attend(X, frames_embed, guide_embed, modal, self.local_logit_scale, self.local_logit_bias)
-            self._emit_local(att, grid, plan, image_newline, out, n_base, total)
+            with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                att = lc.attend(X, frames_embed, guide_embed, modal, self.local_logit_scale, self.local_logit_bias)
+                self._emit_local(att, grid, plan, image_newline, out, n_base, total)
         if gc is not None:
             Qg = gc.injected_query(guide_embed, B, X.dtype)
             m, l, o = gc.partials(X, gc.fold(Qg, self.global_logit_scale))
             gc.finish(Qg, m, l, o, out, n_base + n_local, total)
+        if side is not None:
+            main.wait_stream(side)
         return out.view(B, total, Dh)
 
     # -- reference signature -----------------------------------------------------------------------
