@@ -187,9 +187,13 @@ int launch_col_softmax(float* S, float* m, float* l, int B, int N, int J, int sp
 // ------------------------------------------------------------------------------------------------
 // Split-softmax merge: one block per (video, column).
 // ------------------------------------------------------------------------------------------------
-template <typename TO>
+// PARTIAL = false: pooled = sum_p o_p e^{m_p-M} / L  (normalised, TO storage)
+// PARTIAL = true : emits ONE un-normalised partial (M, L, sum_p o_p e^{m_p-M}) in fp32 — what a rank sends over
+//                  NVLink after reducing its own token splits (hicom_softmax_reduce).
+template <typename TO, bool PARTIAL>
 __global__ void __launch_bounds__(128) softmax_merge_kernel(const float* __restrict__ m, const float* __restrict__ l,
                                                             const float* __restrict__ o, TO* __restrict__ pooled,
+                                                            float* __restrict__ m_out, float* __restrict__ l_out,
                                                             int P, int J, int d) {
   const int j = blockIdx.x, b = blockIdx.y;
   const float* mp = m + (size_t)b * P * J + j;
@@ -201,7 +205,11 @@ __global__ void __launch_bounds__(128) softmax_merge_kernel(const float* __restr
     const float mv = mp[(size_t)pidx * J];
     if (mv > -INFINITY) L += lp[(size_t)pidx * J] * exp2f((mv - M) * kLog2e);
   }
-  const float invL = 1.f / L;
+  if (PARTIAL && threadIdx.x == 0) {
+    m_out[(size_t)b * J + j] = M;
+    l_out[(size_t)b * J + j] = L;
+  }
+  const float invL = PARTIAL ? 1.f : 1.f / L;
   for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int pidx = 0; pidx < P; ++pidx) {
@@ -310,7 +318,17 @@ extern "C" int hicom_softmax_merge(const float* m, const float* l, const float* 
   if (B == 0) return 0;
   dim3 grid(J, B);
   HICOM_REQUIRE(B <= 65535, "softmax_merge: batch too large");
-  HICOM_DISPATCH_DTYPE(out_dtype, E, softmax_merge_kernel<E><<<grid, 128, 0, as_stream(stream)>>>(
-      m, l, o, static_cast<E*>(pooled), P, J, d));
+  HICOM_DISPATCH_DTYPE(out_dtype, E, (softmax_merge_kernel<E, false><<<grid, 128, 0, as_stream(stream)>>>(
+      m, l, o, static_cast<E*>(pooled), nullptr, nullptr, P, J, d)));
   return check_launch("softmax_merge_kernel");
+}
+
+extern "C" int hicom_softmax_reduce(const float* m, const float* l, const float* o, int B, int P, int J, int d,
+                                    float* m_out, float* l_out, float* o_out, void* stream) {
+  HICOM_REQUIRE(m && l && o && m_out && l_out && o_out, "softmax_reduce: null pointer");
+  HICOM_REQUIRE(B >= 0 && P > 0 && J > 0 && d > 0 && d % 4 == 0 && B <= 65535, "softmax_reduce: bad shape");
+  if (B == 0) return 0;
+  dim3 grid(J, B);
+  softmax_merge_kernel<float, true><<<grid, 128, 0, as_stream(stream)>>>(m, l, o, o_out, m_out, l_out, P, J, d);
+  return check_launch("softmax_reduce_kernel");
 }

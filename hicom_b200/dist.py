@@ -84,7 +84,10 @@ def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, 
     if gc is not None:
         Qg = gc.injected_query(guide_embed, B, X.dtype)
         m, l, o = gc.partials(X, gc.fold(Qg, projector.global_logit_scale), t0=t0)
-        if dist.is_available() and dist.is_initialized():
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            from . import ops
+            if m.shape[1] > 1:  # reduce this rank's token splits first: one J*(d+2) fp32 message per video
+                m, l, o = ops.softmax_reduce(m, l, o)
             m, l, o = gather_partials(m, l, o, group)
         Dh = gc.readout[-1].out_features
         global_tokens = torch.empty((B * Qg.shape[1], Dh), dtype=X.dtype, device=X.device)

@@ -305,6 +305,24 @@ def _impl_softmax_merge(m: Tensor, l: Tensor, o: Tensor, out_bf16: bool) -> Tens
     return out
 
 
+def _impl_softmax_reduce(m: Tensor, l: Tensor, o: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """Reduce the P partials along dim 1 to ONE un-normalised partial (m,l,o) with P=1 — done by every rank before
+    the frame-shard exchange so the message does not grow with the number of token splits."""
+    dev = _need_cuda(m, l, o)
+    m, l, o = m.contiguous(), l.contiguous(), o.contiguous()
+    B, P, J, d = o.shape
+    if m.shape != (B, P, J) or l.shape != (B, P, J) or o.dtype != torch.float32:
+        raise ValueError("softmax_reduce: shape mismatch")
+    mo = torch.empty((B, 1, J), dtype=torch.float32, device=dev)
+    lo = torch.empty((B, 1, J), dtype=torch.float32, device=dev)
+    oo = torch.empty((B, 1, J, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_softmax_reduce(_ptr(m), _ptr(l), _ptr(o), B, P, J, d, _ptr(mo), _ptr(lo), _ptr(oo),
+                                               _stream(dev))
+    _cabi.check(rc, "hicom_softmax_reduce")
+    return mo, lo, oo
+
+
 def _impl_global_value_proj(pooled: Tensor, Wv: Tensor, bv: Optional[Tensor], Q: int, heads: int) -> Tensor:
     """attn[b,i,head h] = Wv[head h rows] · pooled[b,h*Q+i] + bv — v_proj (:182) after pooling + head merge (:223-224)."""
     dev = _need_cuda(pooled, Wv, bv)
@@ -439,4 +457,5 @@ global_fold_query = _wrap("global_fold_query", _impl_global_fold_query, (), lamb
 global_attend_partial = _wrap("global_attend_partial", _impl_global_attend_partial, (),
                               lambda *a: "global_attend_partial")
 softmax_merge = _wrap("softmax_merge", _impl_softmax_merge, (), lambda *a: "softmax_merge")
+softmax_reduce = _wrap("softmax_reduce", _impl_softmax_reduce, (), lambda *a: "softmax_reduce")
 global_value_proj = _wrap("global_value_proj", _impl_global_value_proj, (), lambda *a: "global_value_proj")

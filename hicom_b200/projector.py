@@ -541,6 +541,8 @@ class HIComProjector(nn.Module):
         if X.dim() != 5:
             raise ValueError(f"forward_batched expects (B,T,H,W,d), got {tuple(X.shape)}")
         _require_no_grad(self, X, frames_embed, guide_embed)
+        if not X.is_cuda:
+            raise RuntimeError("hicom_b200 ops run on CUDA tensors only (no CPU fallback)")
         B, T, H, W, d = X.shape
         lc = self.local_compressor
         gc = self.global_compressor if with_global else None

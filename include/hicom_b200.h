@@ -145,6 +145,13 @@ int hicom_global_attend_partial(const void* X, const float* pos_t, const float* 
 int hicom_softmax_merge(const float* m, const float* l, const float* o, int B, int P, int J, int d,
                         void* pooled, int out_dtype, void* stream);
 
+/* hicom_softmax_reduce: same combination but WITHOUT the normalisation — reduces a rank's P token-split partials
+ *   to ONE partial (m_out,l_out (B,J), o_out (B,J,d), fp32) before it is exchanged, so the NVLink message is
+ *   J*(d+2) floats per video regardless of how many splits the kernels used.
+ */
+int hicom_softmax_reduce(const float* m, const float* l, const float* o, int B, int P, int J, int d,
+                         float* m_out, float* l_out, float* o_out, void* stream);
+
 /* hicom_global_value_proj: attn[b,i,h*hd+c] = sum_k Wv[h*hd+c,k] * pooled[b,h*Q+i,k] + bv[h*hd+c]
  *   (v_proj :182 applied after the pooling, and the head merge :223-224).
  */

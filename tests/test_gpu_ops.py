@@ -223,3 +223,16 @@ def test_global_partial_outlier_triggers_exact_fallback(built_library):
     # emulation of this pipeline on the CPU is 4.6e-2 / cos 0.99998 from the fp32 truth on this input
     assert O.cosine(got[0], want) >= 0.9995
     assert O.rel_err(got[0], want) <= 8e-2
+
+
+def test_softmax_reduce_then_merge_equals_merge(built_library):
+    """Reducing a rank's splits to one partial and merging the reduced partials == merging everything at once."""
+    from hicom_b200 import ops
+    B, P, J, d = 2, 6, 288, 128
+    m = _rand(B, P, J, seed=1, std=3.0).cuda()
+    l = _rand(B, P, J, seed=2).abs().cuda() + 0.1
+    o = _rand(B, P, J, d, seed=3).cuda()
+    want = ops.softmax_merge(m, l, o, False)
+    parts = [ops.softmax_reduce(m[:, a:b], l[:, a:b], o[:, a:b]) for a, b in ((0, 2), (2, 3), (3, 6))]
+    got = ops.softmax_merge(*(torch.cat([p[i] for p in parts], 1) for i in range(3)), False)
+    assert O.rel_err(got.cpu(), want.cpu()) <= 1e-5
