@@ -277,11 +277,16 @@ def run_ours(args):
             ms_total = start.elapsed_time(end)
             launches = (graphed.kernels_per_replay * args.steps if graphed is not None
                         else ops.kernel_launch_count() - launches0)
-            # per-op CUDA-event timing (eager launches, same inputs, still inside the clock-sampled region)
+            # per-op CUDA-event timing: eager launches on ONE stream (concurrent streams would fold queueing time
+            # into the events), same inputs, still inside the clock-sampled region
+            import hicom_b200.projector as _proj
             op_steps = max(3, min(args.steps, 10))
+            overlap, _proj.OVERLAP_STREAMS = _proj.OVERLAP_STREAMS, False
+            eager_step()
             with ops.OpTimer() as timer:
                 for _ in range(op_steps):
                     eager_step()
+            _proj.OVERLAP_STREAMS = overlap
             barrier()
         op_times = timer.summary()
         if frame_sharded:
@@ -320,10 +325,13 @@ def run_ours(args):
                "d2h_bytes_per_step": int(out_h.numel() * 2) * world, "ms_per_step": float(e_ms),
                "api": "hicom_b200.pipeline.compress_from_host (pinned host buffers, 2-stream chunked overlap)"}
 
+    graphed = None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        os._exit(0)  # no destructor-time NCCL teardown (a captured graph holding the communicator can hang there)
 
     # ---- roofline of the dominant kernel (CUDA events around each op inside the timed region) ------
     pk = peaks()
@@ -376,7 +384,8 @@ def run_ours(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
