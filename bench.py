@@ -325,6 +325,7 @@ def run_ours(args):
                "d2h_bytes_per_step": int(out_h.numel() * 2) * world, "ms_per_step": float(e_ms),
                "api": "hicom_b200.pipeline.compress_from_host (pinned host buffers, 2-stream chunked overlap)"}
 
+    launch_mode = "cuda-graph replay" if graphed is not None else "eager"
     graphed = None
     if world > 1:
         dist.barrier()
@@ -369,7 +370,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong" if frame_sharded else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "projector_type": PTYPE, "use_guide": USE_GUIDE,
-                   "launch": "cuda-graph replay" if graphed is not None else "eager", "per_gpu_batch": B, "frames_per_video": T, "sharding": "frame" if frame_sharded else "video",
+                   "launch": launch_mode, "per_gpu_batch": B, "frames_per_video": T, "sharding": "frame" if frame_sharded else "video",
                    "l2": f"inputs are {2 * B * w['N'] * D * 2 / 1e9:.2f} GB per GPU per step (> 126 MB L2), "
                          "re-read from HBM every step"},
         "tokens_per_s": value / T * w["tokens_out"],
