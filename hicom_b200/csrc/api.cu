@@ -172,7 +172,7 @@ extern "C" size_t hicom_global_attend_workspace_bytes(int B, int T, int H, int W
                                                       int dtype, int impl) {
   (void)splits;
   const size_t N = (size_t)T * H * W;
-  if (tc_global_selected(dtype, impl, d, J)) return tc_global_workspace_bytes(B, T, H, W, d, J, splits);
+  if (tc_global_selected(dtype, impl, d, J, T, H, W)) return tc_global_workspace_bytes(B, T, H, W, d, J, splits);
   return align256((size_t)B * N * d * elem_size(dtype)) + align256((size_t)B * N * J * sizeof(float));
 }
 
@@ -192,8 +192,8 @@ extern "C" int hicom_global_attend_partial(const void* X, const float* pos_t, co
   cudaStream_t s = as_stream(stream);
   const int N = T * H * W;
   if (impl == HICOM_IMPL_TCGEN05)
-    HICOM_REQUIRE(tc_global_selected(dtype, impl, d, J), "global_attend_partial: tcgen05 path needs bf16, d%%128==0");
-  if (tc_global_selected(dtype, impl, d, J))
+    HICOM_REQUIRE(tc_global_selected(dtype, impl, d, J, T, H, W), "global_attend_partial: tcgen05 path needs bf16, d%%128==0");
+  if (tc_global_selected(dtype, impl, d, J, T, H, W))
     return launch_tc_global(X, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace, s);
 
   const int rows_per_split = (N + splits - 1) / splits;

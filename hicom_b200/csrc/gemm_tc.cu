@@ -50,6 +50,13 @@ struct Params {
   const int* guard;                // if non-null: the whole kernel is a no-op unless *guard != 0
   __nv_bfloat16* Pt; long long pt_ld;  // (B, J, pt_ld) transposed probabilities
   float* o; int splits;            // (B, splits, J, d) pooled partials
+  // position embedding folded in algebraically (no x' = x + PE tensor):
+  int k_ext_blocks;                // EPI_MAX/PROB: extra K blocks taken from the second map pair (spatial PE term)
+  int HW, T;                       // tokens per frame, frames
+  const float* peq_t; long long peq_ld;  // (T, B*J) time term of the scores: pos_t[t]·qfold[b,j]
+  float* margT; int margT_ld;      // (B*J, margT_ld) sum of probabilities per frame (EPI_PROB accumulates)
+  int m_main_tiles;                // EPI_POOL: M tiles >= this read the indicator matrix from the second A map
+  __nv_bfloat16* margS; int ke;    // (B, splits, J, ke) spatial marginals written by those tiles
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -193,7 +200,7 @@ struct Cfg {
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-struct TileInfo { int n_tile, m_tile, batch, zslice, split, k_begin, nkb; };
+struct TileInfo { int n_tile, m_tile, batch, zslice, split, k_begin, nkb, nkb_main; };
 
 // Static tile schedule: persistent CTA c handles tiles c, c+grid, c+2*grid, ... of the (x fastest, y, z) tile space.
 // x = N tile (or K split for EPI_POOL), y = M tile, z = tensor batch (or per-head K slice).
@@ -211,14 +218,16 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
   t.k_begin = t.split * p.k_chunk;
   int k_end = t.k_begin + p.k_chunk;
   if (k_end > p.K) k_end = p.K;
-  t.nkb = k_end > t.k_begin ? (k_end - t.k_begin + BK - 1) / BK : 0;
+  t.nkb_main = k_end > t.k_begin ? (k_end - t.k_begin + BK - 1) / BK : 0;
+  t.nkb = t.nkb_main + ((EPI == EPI_MAX || EPI == EPI_PROB) ? p.k_ext_blocks : 0);
   return t;
 }
 
 // FLAGS (EPI_LINEAR only): bit 0 = GELU, bit 1 = fp32 output
 template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -267,14 +276,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + C::A_BYTES;
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           const int k0 = t.k_begin + kb * BK;
+          const bool ext = (EPI == EPI_MAX || EPI == EPI_PROB) && kb >= t.nkb_main;
           if (A_MN) {
             // A[m, k] stored (k rows, m contiguous): two 64-wide M blocks of (BK rows x 128 B)
-            tma_load_3d(sa, &tmA, &full_bar[s], t.m_tile * BM, k0, t.batch);
-            tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], t.m_tile * BM + 64, k0, t.batch);
+            if (EPI == EPI_POOL && t.m_tile >= p.m_main_tiles) {  // indicator matrix (tokens x ke), shared by all videos
+              const int me = (t.m_tile - p.m_main_tiles) * BM;
+              tma_load_3d(sa, &tmA2, &full_bar[s], me, k0, 0);
+              tma_load_3d(sa + BK * 128, &tmA2, &full_bar[s], me + 64, k0, 0);
+            } else {
+              tma_load_3d(sa, &tmA, &full_bar[s], t.m_tile * BM, k0, t.batch);
+              tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], t.m_tile * BM + 64, k0, t.batch);
+            }
+          } else if (ext) {
+            tma_load_3d(sa, &tmA2, &full_bar[s], (kb - t.nkb_main) * BK, t.m_tile * BM, t.batch);
           } else {
             tma_load_3d(sa, &tmA, &full_bar[s], k0 + t.zslice * p.z_a_k, t.m_tile * BM, t.batch);
           }
-          if (B_MN) {
+          if (ext) {
+            tma_load_3d(sb, &tmB2, &full_bar[s], (kb - t.nkb_main) * BK, t.n_tile * BN, 0);  // (tokens x ke) indicator
+          } else if (B_MN) {
             // B[k, n] stored (k rows, n contiguous): BN/64 blocks of (BK rows x 128 B)
             for (int r = 0; r < BN; r += 64)
               tma_load_3d(sb + (r / 64) * (BK * 128), &tmB, &full_bar[s], t.n_tile * BN + r,
@@ -346,6 +366,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (EPI == EPI_LINEAR) {
       constexpr bool kGelu = (FLAGS & 1) != 0;
       constexpr bool kOutF32 = (FLAGS & 2) != 0;
+      constexpr bool kAccum = (FLAGS & 4) != 0;  // C += result (fp32 C only)
       const bool row_ok = row < p.M;
       long long orow = row_ok ? (long long)(row / p.rows_per_group) * p.group_stride_rows +
                                     (row % p.rows_per_group) : 0;
@@ -429,8 +450,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* dst = static_cast<float*>(p.C) + orow * p.ldc + n0;
             if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g)
-                reinterpret_cast<float4*>(dst)[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              for (int g = 0; g < 8; ++g) {
+                float4 r = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                if (kAccum) {
+                  const float4 old = reinterpret_cast<float4*>(dst)[g];
+                  r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+                }
+                reinterpret_cast<float4*>(dst)[g] = r;
+              }
+            } else if (kAccum) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvalid) dst[i] += v[i];
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -441,34 +472,70 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     } else if (EPI == EPI_MAX) {
       // rows = score columns j (M = J), columns = tokens of this tile
+      const bool row_ok = row < p.M;
+      const float* peq = p.peq_t + (size_t)batch * p.M + (row_ok ? row : 0);
       float mx = -INFINITY;
       for (int c = 0; c < BN / 32; ++c) {
         const int t0 = n_tile * BN + c * 32;
         if (t0 >= p.N) break;
         tmem_ld32(taddr + c * 32, v);
+        // time term of the position embedding: a 32-token chunk touches at most two frames (HW >= 32)
+        const int f0 = t0 / p.HW;
+        const int nb = (f0 + 1) * p.HW - t0;
+        const float pt0 = peq[(size_t)f0 * p.peq_ld];
+        const float pt1 = (f0 + 1 < p.T) ? peq[(size_t)(f0 + 1) * p.peq_ld] : 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (t0 + i < p.N) mx = fmaxf(mx, v[i]);
+          if (t0 + i < p.N) mx = fmaxf(mx, v[i] + (i < nb ? pt0 : pt1));
       }
-      if (row < p.M) atomic_max_float(p.mg + (size_t)batch * p.M + row, mx);
+      if (row_ok) atomic_max_float(p.mg + (size_t)batch * p.M + row, mx);
     } else if (EPI == EPI_PROB) {
       const bool row_ok = row < p.M;
-      const float pre = row_ok ? p.stab[(size_t)batch * p.M + row] * kLog2e : 0.f;
-      float sum = 0.f, mx = -INFINITY;
-      __nv_bfloat16* prow = p.Pt + ((size_t)batch * p.M + (row_ok ? row : 0)) * p.pt_ld + (size_t)n_tile * BN;
+      const size_t col = (size_t)batch * p.M + (row_ok ? row : 0);
+      const float pre = row_ok ? p.stab[col] * kLog2e : 0.f;
+      const float* peq = p.peq_t + col;
+      float* mrow = p.margT + col * p.margT_ld;
+      float sum = 0.f, mx = -INFINITY, fsum = 0.f;
+      int fcur = -1;
+      __nv_bfloat16* prow = p.Pt + col * p.pt_ld + (size_t)n_tile * BN;
       for (int c = 0; c < BN / 32; ++c) {
         const int t0 = n_tile * BN + c * 32;
         const bool any = t0 < p.N;  // warp-uniform
-        if (any) tmem_ld32(taddr + c * 32, v);
         uint32_t pk[16];
+        float s0 = 0.f, s1 = 0.f;
+        int f0 = 0, nb = 32;
+        if (any) {
+          tmem_ld32(taddr + c * 32, v);
+          f0 = t0 / p.HW;
+          nb = (f0 + 1) * p.HW - t0;
+          const float pt0 = peq[(size_t)f0 * p.peq_ld];
+          const float pt1 = (f0 + 1 < p.T) ? peq[(size_t)(f0 + 1) * p.peq_ld] : 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += (i < nb ? pt0 : pt1);
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float a = 0.f, b = 0.f;
           if (any && t0 + i < p.N) { a = exp2f(fmaf(v[i], kLog2e, -pre)); mx = fmaxf(mx, v[i]); }
           if (any && t0 + i + 1 < p.N) { b = exp2f(fmaf(v[i + 1], kLog2e, -pre)); mx = fmaxf(mx, v[i + 1]); }
-          __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-          sum += __low2float(t) + __high2float(t);  // sum what P·V will actually multiply
-          pk[i / 2] = *reinterpret_cast<uint32_t*>(&t);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(a, b);
+          const float ra = __low2float(t2), rb = __high2float(t2);  // what the pooling GEMM will actually multiply
+          if (i < nb) s0 += ra; else s1 += ra;
+          if (i + 1 < nb) s0 += rb; else s1 += rb;
+          pk[i / 2] = *reinterpret_cast<uint32_t*>(&t2);
+        }
+        sum += s0 + s1;
+        if (row_ok && any) {
+          // per-frame probability mass (time marginals): flush when the frame changes
+          if (f0 != fcur) {
+            if (fcur >= 0 && fcur < p.T) atomicAdd(mrow + fcur, fsum);
+            fcur = f0; fsum = 0.f;
+          }
+          fsum += s0;
+          if (nb < 32) {
+            if (fcur < p.T) atomicAdd(mrow + fcur, fsum);
+            fcur = f0 + 1; fsum = s1;
+          }
         }
         if (row_ok) {
           uint4* dst = reinterpret_cast<uint4*>(prow + c * 32);
@@ -477,17 +544,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       if (row_ok) {
-        atomicAdd(p.lg + (size_t)batch * p.M + row, sum);
-        atomic_max_float(p.mg + (size_t)batch * p.M + row, mx);
+        if (fcur >= 0 && fcur < p.T) atomicAdd(mrow + fcur, fsum);
+        atomicAdd(p.lg + col, sum);
+        atomic_max_float(p.mg + col, mx);
       }
-    } else {  // EPI_POOL: rows = channels d (M), columns = score columns j (N = J)
+    } else {  // EPI_POOL: rows = channels d (M) or indicator columns (extra tiles), columns = score columns j (N = J)
+      const bool extra = t.m_tile >= p.m_main_tiles;
+      const int erow = (t.m_tile - p.m_main_tiles) * BM + q * 32 + lane;  // indicator column of this thread
       float* obase = p.o + (((size_t)batch * p.splits + split) * p.N) * p.M + row;
+      __nv_bfloat16* mbase = p.margS + (((size_t)batch * p.splits + split) * p.N) * p.ke + erow;
       for (int c = 0; c < (BN + 31) / 32; ++c) {
         if (nkb > 0) tmem_ld32(taddr + c * 32, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int j = c * 32 + i;
-          if (j < p.N && row < p.M) obase[(size_t)j * p.M] = nkb > 0 ? v[i] : 0.f;
+          const float val = nkb > 0 ? v[i] : 0.f;
+          if (j < p.N) {
+            if (!extra) { if (row < p.M) obase[(size_t)j * p.M] = val; }
+            else if (erow < p.ke) mbase[(size_t)j * p.ke] = __float2bfloat16_rn(val);
+          }
         }
       }
     }
@@ -579,7 +654,8 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS = 0>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t stream,
+                  const CUtensorMap* ta2 = nullptr, const CUtensorMap* tb2 = nullptr) {
   static bool configured = false;
   auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI, FLAGS>;
   if (!configured) {
@@ -599,7 +675,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   const long long total = (long long)grid.x * grid.y * grid.z;
   if (total == 0) return 0;
   const unsigned ctas = (unsigned)(total < num_sms ? total : num_sms);  // persistent: one CTA per SM at most
-  kern<<<ctas, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, pp);
+  kern<<<ctas, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, pp);
   return check_launch("tc_gemm_kernel");
 }
 
@@ -631,12 +707,18 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   Params p{};
   p.alpha = q.alpha; p.diag_heads = q.diag_heads; p.diag_rows = q.diag_rows; p.diag_cols = q.diag_cols;
   p.z_slices = q.z_slices; p.z_a_k = q.z_a_k; p.z_b_k = q.z_b_k; p.z_c_rows = q.z_c_rows;
+  p.guard = q.guard;
   p.M = q.M; p.N = q.N; p.K = q.K; p.k_chunk = q.K; p.b_box_rows = 256;
   p.bias = static_cast<const __nv_bfloat16*>(q.bias);
   p.R = static_cast<const __nv_bfloat16*>(q.R); p.ldr = q.ldr;
   p.C = q.C; p.ldc = q.ldc; p.out_dtype = q.out_dtype; p.act = q.act;
   p.rows_per_group = q.rows_per_group; p.group_stride_rows = q.group_stride_rows;
   dim3 grid((q.N + 255) / 256, (q.M + BM - 1) / BM, q.z_slices > 0 ? q.z_slices : 1);
+  if (q.accumulate) {
+    HICOM_REQUIRE(q.w_is_kn && q.out_dtype == HICOM_F32 && q.act == HICOM_ACT_NONE,
+                  "tcgen05 linear: accumulate is only built for fp32 C, (K,N) weights, no activation");
+    return launch<256, false, true, EPI_LINEAR, 6>(ta, tb, p, grid, stream);
+  }
   const int flags = (q.act == HICOM_ACT_GELU ? 1 : 0) | (q.out_dtype == HICOM_F32 ? 2 : 0);
 #define HICOM_TC_LINEAR_CASE(F)                                                                  \
   case F:                                                                                         \
@@ -657,74 +739,166 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-bool tc_global_selected(int dtype, int impl, int d, int J) {
+constexpr int kKe = 64;  // spatial indicator columns (H + W <= 64): one extra K block / half an extra M tile
+
+bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W) {
+  (void)T;
   if (impl == HICOM_IMPL_SIMT) return false;
-  return dtype == HICOM_BF16 && d % 128 == 0 && J == 288;
+  // the algebraic position-embedding path needs: chunks of 32 tokens spanning <= 2 frames, H + W indicator columns
+  return dtype == HICOM_BF16 && d % 128 == 0 && J == 288 && H * W >= 32 && H + W <= kKe;
 }
 
 struct GlobalWs {
-  size_t xp, pt, mg, lg, stab, flag, total;
+  size_t pt, mg, lg, stab, flag, pe_t, pe_s, ind, peq_s, peq_t, margT, margTb, margS, total;
   long long pt_ld;
+  int Tk;
 };
-static GlobalWs global_ws(int B, int T, int H, int W, int d, int J) {
+static GlobalWs global_ws(int B, int T, int H, int W, int d, int J, int splits) {
   const size_t N = (size_t)T * H * W;
   GlobalWs w;
   w.pt_ld = (long long)((N + 255) / 256) * 256;
-  w.xp = 0;
-  w.pt = al256((size_t)B * N * d * 2);
-  w.mg = w.pt + al256((size_t)B * J * w.pt_ld * 2);
-  w.lg = w.mg + al256((size_t)B * J * 4);
-  w.stab = w.lg + al256((size_t)B * J * 4);
-  w.flag = w.stab + al256((size_t)B * J * 4);
-  w.total = w.flag + 256;
+  w.Tk = (T + 7) / 8 * 8;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  w.pt = take((size_t)B * J * w.pt_ld * 2);
+  w.mg = take((size_t)B * J * 4);
+  w.lg = take((size_t)B * J * 4);
+  w.stab = take((size_t)B * J * 4);
+  w.flag = take(256);
+  w.pe_t = take((size_t)w.Tk * d * 2);            // pos_t rounded to bf16, zero rows up to Tk
+  w.pe_s = take((size_t)kKe * d * 2);             // [pos_h ; pos_w ; 0] bf16
+  w.ind = take(N * kKe * 2);                      // one-hot (token -> h, H + w) bf16
+  w.peq_s = take((size_t)B * J * kKe * 2);        // qfold · pe_sᵀ  (bf16, K-major rows j)
+  w.peq_t = take((size_t)T * B * J * 4);          // pe_t · qfoldᵀ  (fp32, (T, B*J))
+  w.margT = take((size_t)B * J * w.Tk * 4);       // probability mass per frame (fp32 atomics)
+  w.margTb = take((size_t)B * J * w.Tk * 2);      // ... rounded to bf16 for the tensor core
+  w.margS = take((size_t)B * splits * J * kKe * 2);
+  w.total = off;
   return w;
 }
 
 size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits) {
-  (void)splits;
-  return global_ws(B, T, H, W, d, J).total;
+  return global_ws(B, T, H, W, d, J, splits).total;
 }
+
+namespace tc {
+// bf16 copies of the per-axis tables: pe_t (Tk x d, rows >= T zero) and pe_s = [pos_h ; pos_w ; 0] (64 x d)
+__global__ void build_pe_kernel(const float* pt, const float* ph, const float* pw, __nv_bfloat16* pe_t,
+                                __nv_bfloat16* pe_s, int T, int Tk, int H, int W, int d) {
+  const int r = blockIdx.x;  // 0..Tk-1 -> pe_t rows, Tk..Tk+63 -> pe_s rows
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    if (r < Tk) {
+      pe_t[(size_t)r * d + c] = __float2bfloat16_rn(r < T ? pt[(size_t)r * d + c] : 0.f);
+    } else {
+      const int s = r - Tk;
+      const float v = s < H ? ph[(size_t)s * d + c] : (s < H + W ? pw[(size_t)(s - H) * d + c] : 0.f);
+      pe_s[(size_t)s * d + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+// ind[n][c] = 1 for c == h(n) and c == H + w(n)
+__global__ void build_ind_kernel(__nv_bfloat16* ind, long long N, int H, int W) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * kKe) return;
+  const long long n = i / kKe;
+  const int c = (int)(i % kKe);
+  const int w = (int)(n % W), h = (int)((n / W) % H);
+  ind[i] = __float2bfloat16_rn((c == h || c == H + w) ? 1.f : 0.f);
+}
+__global__ void zero_f32_kernel(float* p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+__global__ void to_bf16_kernel(const float* src, __nv_bfloat16* dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+// fallback only: stabiliser := true max, sums and time marginals reset
+__global__ void repair_margT_kernel(float* margT, long long n, const int* flag) {
+  if (*flag == 0) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) margT[i] = 0.f;
+}
+}  // namespace tc
 
 int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, const float* pos_w, const void* qfold,
                      float* m, float* l, float* o, int B, int T, int H, int W, int d, int J, int splits,
                      void* workspace, cudaStream_t stream) {
   using namespace tc;
   const int N = T * H * W;
-  const GlobalWs w = global_ws(B, T, H, W, d, J);
+  const GlobalWs w = global_ws(B, T, H, W, d, J, splits);
   char* ws = static_cast<char*>(workspace);
-  __nv_bfloat16* Xp = reinterpret_cast<__nv_bfloat16*>(ws + w.xp);
   __nv_bfloat16* Pt = reinterpret_cast<__nv_bfloat16*>(ws + w.pt);
   float* mg = reinterpret_cast<float*>(ws + w.mg);
   float* lg = reinterpret_cast<float*>(ws + w.lg);
-
   float* stab = reinterpret_cast<float*>(ws + w.stab);
   int* flag = reinterpret_cast<int*>(ws + w.flag);
+  __nv_bfloat16* pe_t = reinterpret_cast<__nv_bfloat16*>(ws + w.pe_t);
+  __nv_bfloat16* pe_s = reinterpret_cast<__nv_bfloat16*>(ws + w.pe_s);
+  __nv_bfloat16* ind = reinterpret_cast<__nv_bfloat16*>(ws + w.ind);
+  __nv_bfloat16* peq_s = reinterpret_cast<__nv_bfloat16*>(ws + w.peq_s);
+  float* peq_t = reinterpret_cast<float*>(ws + w.peq_t);
+  float* margT = reinterpret_cast<float*>(ws + w.margT);
+  __nv_bfloat16* margTb = reinterpret_cast<__nv_bfloat16*>(ws + w.margTb);
+  __nv_bfloat16* margS = reinterpret_cast<__nv_bfloat16*>(ws + w.margS);
+  const long long BJ = (long long)B * J;
 
-  if (launch_posadd(X, Xp, pos_t, pos_h, pos_w, B, T, H, W, d, HICOM_BF16, stream)) return 1;
-  init_stats_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, lg, B * J, flag);
+  // 0. tables: PE is separable, PE[t,h,w] = pos_t[t] + pos_h[h] + pos_w[w], so
+  //      S = x·qfold + pos_t[t]·qfold + (pos_h[h] + pos_w[w])·qfold        (time term in the epilogue, spatial term as
+  //      O = sum_n p_n x_n + sum_t (sum_{n in t} p_n) pos_t[t] + ...         one extra K block against a one-hot matrix)
+  build_pe_kernel<<<w.Tk + kKe, 256, 0, stream>>>(pos_t, pos_h, pos_w, pe_t, pe_s, T, w.Tk, H, W, d);
+  if (check_launch("build_pe_kernel")) return 1;
+  build_ind_kernel<<<(unsigned)(((long long)N * kKe + 255) / 256), 256, 0, stream>>>(ind, N, H, W);
+  if (check_launch("build_ind_kernel")) return 1;
+  init_stats_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, lg, (int)BJ, flag);
   if (check_launch("init_stats_kernel")) return 1;
+  zero_f32_kernel<<<(unsigned)((BJ * w.Tk + 255) / 256), 256, 0, stream>>>(margT, BJ * w.Tk);
+  if (check_launch("zero_f32_kernel")) return 1;
+  {  // peq_s (B*J, 64) bf16 = qfold · pe_sᵀ ;  peq_t (T, B*J) fp32 = pe_t · qfoldᵀ
+    TcLinearParams a{};
+    a.A = qfold; a.W = pe_s; a.C = peq_s; a.lda = d; a.ldw = d; a.ldc = kKe; a.M = (int)BJ; a.N = kKe; a.K = d;
+    a.act = HICOM_ACT_NONE; a.out_dtype = HICOM_BF16; a.rows_per_group = 1 << 30;
+    if (launch_tc_linear(a, stream)) return 1;
+    TcLinearParams b{};
+    b.A = pe_t; b.W = qfold; b.C = peq_t; b.lda = d; b.ldw = d; b.ldc = BJ; b.M = T; b.N = (int)BJ; b.K = d;
+    b.act = HICOM_ACT_NONE; b.out_dtype = HICOM_F32; b.rows_per_group = 1 << 30;
+    if (launch_tc_linear(b, stream)) return 1;
+  }
 
-  // scores: S[b] (J x N) = qfold[b] (J x d) · X'[b]ᵀ  — A = qfold (rows j), "W" = X' (rows = tokens)
-  CUtensorMap tq, tx;
+  // scores: S[b] (J x N) = [qfold[b] | peq_s[b]] · [X[b] | ind]ᵀ  — A rows j, B rows = tokens
+  CUtensorMap tq, tx, tq2, tind;
   if (make_map(&tq, qfold, d, J, B, d, (uint64_t)J * d, BM)) return 1;
-  if (make_map(&tx, Xp, d, N, B, d, (uint64_t)N * d, 256)) return 1;
+  if (make_map(&tx, X, d, N, B, d, (uint64_t)N * d, 256)) return 1;
+  if (make_map(&tq2, peq_s, kKe, J, B, kKe, (uint64_t)J * kKe, BM)) return 1;
+  if (make_map(&tind, ind, kKe, N, 1, kKe, 0, 256)) return 1;
   Params p{};
   p.M = J; p.N = N; p.K = d; p.k_chunk = d; p.b_box_rows = 256;
   p.mg = mg; p.lg = lg; p.stab = stab; p.Pt = Pt; p.pt_ld = w.pt_ld;
+  p.k_ext_blocks = kKe / BK; p.HW = H * W; p.T = T; p.peq_t = peq_t; p.peq_ld = BJ;
+  p.margT = margT; p.margT_ld = w.Tk;
   const int n_tiles = (N + 255) / 256;
   const int m_tiles = (J + BM - 1) / BM;
 
-  // pooling operands: O[b,s] (d x J) = X'[b, tokens of s]ᵀ · P[b, tokens of s]  — A = X' read MN-major, B = Ptᵀ rows j
-  CUtensorMap txa, tp;
-  if (make_map(&txa, Xp, d, N, B, d, (uint64_t)N * d, 64)) return 1;
+  // pooling: O[b,s] (d x J) = X[b, tokens of s]ᵀ · P ; one more M tile multiplies the indicator matrix instead of X
+  // and yields the spatial probability marginals (ke x J)
+  CUtensorMap txa, tp, tinda;
+  if (make_map(&txa, X, d, N, B, d, (uint64_t)N * d, 64)) return 1;
   if (make_map(&tp, Pt, w.pt_ld, J, B, w.pt_ld, (uint64_t)J * w.pt_ld, 96)) return 1;
+  if (make_map(&tinda, ind, kKe, N, 1, kKe, 0, 64)) return 1;
   Params g{};
   g.M = d; g.N = J; g.K = N;
   int chunk = (N + splits - 1) / splits;
   chunk = (chunk + BK - 1) / BK * BK;
   g.k_chunk = chunk; g.b_box_rows = 96;
   g.o = o; g.splits = splits;
-  dim3 gp(splits, d / BM, B);
+  g.m_main_tiles = d / BM; g.margS = margS; g.ke = kKe;
+  dim3 gp(splits, d / BM + 1, B);
+
+  // o[b,s] += margS[b,s] (J x 64) · pe_s (64 x d)
+  TcLinearParams accS{};
+  accS.A = margS; accS.W = pe_s; accS.C = o; accS.lda = kKe; accS.ldw = d; accS.ldc = d;
+  accS.M = (int)(BJ * splits); accS.N = d; accS.K = kKe; accS.act = HICOM_ACT_NONE; accS.out_dtype = HICOM_F32;
+  accS.rows_per_group = 1 << 30; accS.w_is_kn = 1; accS.accumulate = 1;
 
   // 1. sampled max (a few evenly spaced token tiles) -> stabiliser.  The softmax is invariant to the stabiliser;
   //    it only has to keep exp() inside the exponent range, so the full max pass is not needed.
@@ -733,27 +907,43 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
     const int n_sample = n_tiles < 4 ? n_tiles : 4;
     ps.n_tile_stride = n_tiles / n_sample;
     dim3 gsample(n_sample, m_tiles, B);
-    if (launch<256, false, false, EPI_MAX>(tq, tx, ps, gsample, stream)) return 1;
-    make_stab_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, stab, B * J);
+    if (launch<256, false, false, EPI_MAX>(tq, tx, ps, gsample, stream, &tq2, &tind)) return 1;
+    make_stab_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, stab, (int)BJ);
     if (check_launch("make_stab_kernel")) return 1;
   }
-  // 2. single full pass: P = exp(S - stab) (bf16, transposed), row sums, and the TRUE max for the safety check
+  // 2. single full pass: P = exp(S - stab) (bf16, transposed), row sums, time marginals, TRUE max for the check
   dim3 gs(n_tiles, m_tiles, B);
-  if (launch<256, false, false, EPI_PROB>(tq, tx, p, gs, stream)) return 1;
-  check_stab_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, stab, B * J, flag);
+  if (launch<256, false, false, EPI_PROB>(tq, tx, p, gs, stream, &tq2, &tind)) return 1;
+  check_stab_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, stab, (int)BJ, flag);
   if (check_launch("check_stab_kernel")) return 1;
-  // 3. pooling
-  if (launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream)) return 1;
+  // 3. pooling + spatial position term
+  if (launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream, &tinda, nullptr)) return 1;
+  if (launch_tc_linear(accS, stream)) return 1;
   // 4. guarded exact fallback (no-ops unless some score beat the sampled max by > 80 nats): redo 2-3 with the true max
   {
-    repair_stab_kernel<<<(B * J + 255) / 256, 256, 0, stream>>>(mg, stab, lg, B * J, flag);
+    repair_stab_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, stab, lg, (int)BJ, flag);
     if (check_launch("repair_stab_kernel")) return 1;
+    repair_margT_kernel<<<(unsigned)((BJ * w.Tk + 255) / 256), 256, 0, stream>>>(margT, BJ * w.Tk, flag);
+    if (check_launch("repair_margT_kernel")) return 1;
     Params pf = p; pf.guard = flag;
     Params gf = g; gf.guard = flag;
-    if (launch<256, false, false, EPI_PROB>(tq, tx, pf, gs, stream)) return 1;
-    if (launch<288, true, false, EPI_POOL>(txa, tp, gf, gp, stream)) return 1;
+    if (launch<256, false, false, EPI_PROB>(tq, tx, pf, gs, stream, &tq2, &tind)) return 1;
+    if (launch<288, true, false, EPI_POOL>(txa, tp, gf, gp, stream, &tinda, nullptr)) return 1;
+    TcLinearParams accSf = accS; accSf.guard = flag;
+    if (launch_tc_linear(accSf, stream)) return 1;
   }
-  spread_stats_kernel<<<(B * splits * J + 255) / 256, 256, 0, stream>>>(stab, lg, m, l, B, splits, J);
+  // 5. time position term, once, into split 0 (all splits share the stabiliser, so the merge just adds them):
+  //    o[b,0] += margT[b] (J x Tk) · pe_t (Tk x d)
+  to_bf16_kernel<<<(unsigned)((BJ * w.Tk + 255) / 256), 256, 0, stream>>>(margT, margTb, BJ * w.Tk);
+  if (check_launch("to_bf16_kernel")) return 1;
+  {
+    TcLinearParams accT{};
+    accT.A = margTb; accT.W = pe_t; accT.C = o; accT.lda = w.Tk; accT.ldw = d; accT.ldc = d;
+    accT.M = (int)BJ; accT.N = d; accT.K = w.Tk; accT.act = HICOM_ACT_NONE; accT.out_dtype = HICOM_F32;
+    accT.rows_per_group = J; accT.group_stride_rows = (long long)splits * J; accT.w_is_kn = 1; accT.accumulate = 1;
+    if (launch_tc_linear(accT, stream)) return 1;
+  }
+  spread_stats_kernel<<<(unsigned)((BJ * splits + 255) / 256), 256, 0, stream>>>(stab, lg, m, l, B, splits, J);
   return check_launch("spread_stats_kernel");
 }
 

@@ -13,13 +13,15 @@ struct TcLinearParams {
   int w_is_kn = 0;          // W stored (K, N) row-major instead of torch's (N, K)
   int diag_heads = 0, diag_rows = 0, diag_cols = 0;  // block-diagonal store (see gemm_tc.cu)
   int z_slices = 0, z_a_k = 0, z_b_k = 0; long long z_c_rows = 0;  // per-head K slices on blockIdx.z
+  int accumulate = 0;       // C += result (fp32 C, w_is_kn, no activation)
+  const int* guard = nullptr;  // device flag: the launch is a no-op unless *guard != 0
 };
 
 bool tc_linear_supported(int in_dtype, int out_dtype, int M, int N, int K, long long lda, long long ldw,
                          long long ldc, const void* A, const void* W, const void* C);
 int launch_tc_linear(const TcLinearParams& p, cudaStream_t stream);
 
-bool tc_global_selected(int dtype, int impl, int d, int J);
+bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W);
 size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits);
 int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, const float* pos_w,
                      const void* qfold, float* m, float* l, float* o, int B, int T, int H, int W, int d, int J,
