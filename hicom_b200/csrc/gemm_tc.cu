@@ -26,7 +26,7 @@ constexpr int BM = 128;  // UMMA M (rows of the accumulator = TMEM lanes)
 constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UK = 16;   // K per tcgen05.mma for 16-bit inputs
 constexpr int STAGES = 4;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 enum { EPI_LINEAR = 0, EPI_MAX = 1, EPI_PROB = 2, EPI_POOL = 3 };
 
@@ -84,6 +84,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// producer-side wait: the ring is STAGES deep, so back off instead of stealing issue slots from the epilogue warps
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -252,7 +261,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int b = 0; b < C::NBUF; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], 8);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -271,7 +280,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
@@ -348,8 +357,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+    // ===== epilogue warps: TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 32-column chunks =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
     const TileInfo t = decode_tile<EPI>(p, tile);
@@ -378,7 +388,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       orow += (long long)zslice * p.z_c_rows;
       const bool has_bias = p.bias != nullptr, has_res = p.R != nullptr;
       const int n_chunks = (p.N - n_tile * BN + 31) / 32 < BN / 32 ? (p.N - n_tile * BN + 31) / 32 : BN / 32;
-      for (int c = 0; c < n_chunks; ++c) {  // warp-uniform trip count: tcgen05.ld needs the whole warp
+      for (int c = half; c < n_chunks; c += 2) {  // warp-uniform trip count: tcgen05.ld needs the whole warp
         const int n0 = n_tile * BN + c * 32;
         tmem_ld32(taddr + c * 32, v);
         const bool keep = row_ok && (p.diag_heads == 0 || n0 / p.diag_cols == my_head);
@@ -475,7 +485,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const float* peq = p.peq_t + (size_t)batch * p.M + (row_ok ? row : 0);
       float mx = -INFINITY;
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int t0 = n_tile * BN + c * 32;
         if (t0 >= p.N) break;
         tmem_ld32(taddr + c * 32, v);
@@ -498,7 +508,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float sum = 0.f, mx = -INFINITY, fsum = 0.f;
       int fcur = -1;
       __nv_bfloat16* prow = p.Pt + col * p.pt_ld + (size_t)n_tile * BN;
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int t0 = n_tile * BN + c * 32;
         const bool any = t0 < p.N;  // warp-uniform
         uint32_t pk[16];
@@ -508,21 +518,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(taddr + c * 32, v);
           f0 = t0 / p.HW;
           nb = (f0 + 1) * p.HW - t0;
+        }
+        if (any && nb >= 32 && t0 + 32 <= p.N) {
+          // fast path (warp-uniform): all 32 tokens valid and inside one frame
+          const float pt0 = peq[(size_t)f0 * p.peq_ld];
+          const float pb = fmaf(pt0, kLog2e, -pre);  // (x + pt0) * log2e - stab * log2e
+          float cm = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            cm = fmaxf(cm, fmaxf(v[i], v[i + 1]));
+            const float a = ex2_approx(fmaf(v[i], kLog2e, pb));
+            const float b = ex2_approx(fmaf(v[i + 1], kLog2e, pb));
+            s0 += a + b;
+            pk[i / 2] = pack_bf16(a, b);
+          }
+          mx = fmaxf(mx, cm + pt0);  // true max of the scores, for the stabiliser check
+        } else if (any) {
           const float pt0 = peq[(size_t)f0 * p.peq_ld];
           const float pt1 = (f0 + 1 < p.T) ? peq[(size_t)(f0 + 1) * p.peq_ld] : 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += (i < nb ? pt0 : pt1);
-        }
+          for (int i = 0; i < 32; i += 2) {
+            float a = 0.f, b = 0.f;
+            if (t0 + i < p.N) {
+              const float x = v[i] + (i < nb ? pt0 : pt1);
+              a = ex2_approx(fmaf(x, kLog2e, -pre));
+              mx = fmaxf(mx, x);
+            }
+            if (t0 + i + 1 < p.N) {
+              const float x = v[i + 1] + (i + 1 < nb ? pt0 : pt1);
+              b = ex2_approx(fmaf(x, kLog2e, -pre));
+              mx = fmaxf(mx, x);
+            }
+            if (i < nb) s0 += a; else s1 += a;
+            if (i + 1 < nb) s0 += b; else s1 += b;
+            pk[i / 2] = pack_bf16(a, b);
+          }
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a = 0.f, b = 0.f;
-          if (any && t0 + i < p.N) { a = exp2f(fmaf(v[i], kLog2e, -pre)); mx = fmaxf(mx, v[i]); }
-          if (any && t0 + i + 1 < p.N) { b = exp2f(fmaf(v[i + 1], kLog2e, -pre)); mx = fmaxf(mx, v[i + 1]); }
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(a, b);
-          const float ra = __low2float(t2), rb = __high2float(t2);  // what the pooling GEMM will actually multiply
-          if (i < nb) s0 += ra; else s1 += ra;
-          if (i + 1 < nb) s0 += rb; else s1 += rb;
-          pk[i / 2] = *reinterpret_cast<uint32_t*>(&t2);
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
         }
         sum += s0 + s1;
         if (row_ok && any) {
@@ -553,7 +586,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int erow = (t.m_tile - p.m_main_tiles) * BM + q * 32 + lane;  // indicator column of this thread
       float* obase = p.o + (((size_t)batch * p.splits + split) * p.N) * p.M + row;
       __nv_bfloat16* mbase = p.margS + (((size_t)batch * p.splits + split) * p.N) * p.ke + erow;
-      for (int c = 0; c < (BN + 31) / 32; ++c) {
+      for (int c = half; c < (BN + 31) / 32; c += 2) {
         if (nkb > 0) tmem_ld32(taddr + c * 32, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
