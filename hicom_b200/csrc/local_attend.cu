@@ -12,6 +12,8 @@
 // (d = 128*CPL), so every row read is a fully coalesced 256 B (bf16) / 512 B (fp32) request per
 // chunk, and all per-channel state (query, accumulator, FiLM vectors) lives in registers.
 // Softmax is the online form so arbitrary window sizes (e.g. local412: 576 members) work.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hicom {
@@ -210,6 +212,244 @@ __global__ void __launch_bounds__(256) local_attend_kernel(const LocalParams p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2: TMA-staged variant.  Each warp owns a ring of RM (key row, value row) slots in shared memory; one lane issues
+// `cp.async.bulk` (1-D TMA, SASS UBLKCP) copies of whole rows that complete on a per-slot mbarrier, so RM members
+// (RM * 2 rows * d elements) are in flight per warp without holding them in registers — twice the bytes in flight and
+// twice the resident warps of the register-staged kernel.  Same math, same accumulation order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t la_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void la_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(la_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void la_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(la_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void la_bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(la_smem_u32(dst)), "l"(src), "r"(bytes), "r"(la_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void la_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(la_smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+
+template <typename T, int CPL, int RM>
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1) local_attend_v2_kernel(const LocalParams p) {
+  extern __shared__ __align__(128) uint8_t la_smem[];
+  constexpr int ROWB = CPL * 128 * (int)sizeof(T);
+  constexpr int SLOTB = 2 * ROWB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  uint8_t* ring = la_smem + (size_t)warp * RM * SLOTB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(la_smem + (size_t)warps_per_block * RM * SLOTB) + warp * RM;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < RM; ++i) la_mbar_init(&bars[i]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const long long nwin_video = (long long)p.wt.count * p.wh.count * p.ww.count;
+  const long long total = nwin_video * p.B;
+  const int d = p.d;
+  const T* __restrict__ Kp = static_cast<const T*>(p.K);
+  const T* __restrict__ Vp = static_cast<const T*>(p.V);
+  const T* __restrict__ Pp = static_cast<const T*>(p.P);
+  T* __restrict__ outp = static_cast<T*>(p.out);
+  const uint32_t tx_bytes = p.same_kv ? ROWB : SLOTB;
+  uint32_t produced = 0, consumed = 0;  // members issued / consumed by this warp since kernel start (slot + phase)
+
+  for (long long wi = (long long)blockIdx.x * warps_per_block + warp; wi < total;
+       wi += (long long)gridDim.x * warps_per_block) {
+    const int b = (int)(wi / nwin_video);
+    const int r = (int)(wi % nwin_video);
+    const int t1 = r / (p.wh.count * p.ww.count);
+    const int h1 = (r / p.ww.count) % p.wh.count;
+    const int w1 = r % p.ww.count;
+    const size_t video_off = (size_t)b * p.T * p.H * p.W * d;
+    const int t0 = axis_win_start(p.wt, t1), h0 = axis_win_start(p.wh, h1), w0 = axis_win_start(p.ww, w1);
+    const int Lt = p.wt.len, Lh = p.wh.len, Lw = p.ww.len;
+    const int members = Lt * Lh * Lw;
+
+    auto issue = [&](int mj) {  // lane 0 only
+      const int t2 = mj / (Lh * Lw), h2 = (mj / Lw) % Lh, w2 = mj % Lw;
+      const size_t off = video_off + ((size_t)((t0 + t2) * p.H + h0 + h2) * p.W + w0 + w2) * d;
+      const uint32_t slot = produced % RM;
+      uint8_t* dst = ring + (size_t)slot * SLOTB;
+      la_expect_tx(&bars[slot], tx_bytes);
+      la_bulk_copy(dst, Kp + off, ROWB, &bars[slot]);
+      if (!p.same_kv) la_bulk_copy(dst + ROWB, Vp + off, ROWB, &bars[slot]);
+      ++produced;
+    };
+    // start the window's first RM members before computing the query (their latency hides the query's)
+    if (lane == 0) {
+      for (int k = 0; k < RM && k < members; ++k) issue(k);
+    }
+
+    float q[CPL][4];
+    // ---- query (identical to v1) -------------------------------------------------------------
+    if (p.qmode == HICOM_Q_POOLED || p.qmode == HICOM_Q_FILM_LN) {
+      const Tap tt = linear_tap(t1, p.T, p.wt.count);
+      const Tap th = linear_tap(h1, p.H, p.wh.count);
+      const Tap tw = linear_tap(w1, p.W, p.ww.count);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[c][e] = 0.f;
+      const int ti[2] = {tt.i0, tt.i1}; const float tw_[2] = {tt.w0, tt.w1};
+      const int hi[2] = {th.i0, th.i1}; const float hw_[2] = {th.w0, th.w1};
+      const int wi_[2] = {tw.i0, tw.i1}; const float ww_[2] = {tw.w0, tw.w1};
+      for (int a = 0; a < 2; ++a) {
+        if (tw_[a] == 0.f) continue;
+        for (int bb = 0; bb < 2; ++bb) {
+          if (hw_[bb] == 0.f) continue;
+          for (int cc = 0; cc < 2; ++cc) {
+            if (ww_[cc] == 0.f) continue;
+            const float wgt = tw_[a] * (hw_[bb] * ww_[cc]);
+            const T* row = Pp + video_off + ((size_t)(ti[a] * p.H + hi[bb]) * p.W + wi_[cc]) * d;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+              float x[4];
+              Vec4<T>::load(row + (lane + 32 * c) * 4, x);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) q[c][e] = fmaf(wgt, x[e], q[c][e]);
+            }
+          }
+        }
+      }
+      if (p.qmode == HICOM_Q_FILM_LN) {
+        const float* sc = p.film + (size_t)b * 2 * d;
+        const float* sh = sc + d;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          float s4[4], h4[4];
+          Vec4<float>::load(sc + (lane + 32 * c) * 4, s4);
+          Vec4<float>::load(sh + (lane + 32 * c) * 4, h4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            q[c][e] = fmaf(q[c][e], 1.f + s4[e], h4[e]);
+            sum += q[c][e];
+          }
+        }
+        const float mean = warp_sum(sum) / (float)d;
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float dv = q[c][e] - mean;
+            var = fmaf(dv, dv, var);
+          }
+        const float rstd = rsqrtf(warp_sum(var) / (float)d + kLnEps);
+        const T* gw = static_cast<const T*>(p.ln_w);
+        const T* gb = static_cast<const T*>(p.ln_b);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          float g4[4], b4[4];
+          Vec4<T>::load(gw + (lane + 32 * c) * 4, g4);
+          Vec4<T>::load(gb + (lane + 32 * c) * 4, b4);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) q[c][e] = fmaf((q[c][e] - mean) * rstd, g4[e], b4[e]);
+        }
+      }
+    } else {
+      const T* qrow = static_cast<const T*>(p.q_aux) +
+                      (p.qmode == HICOM_Q_VECTOR ? (size_t)b * d : (size_t)wi * d);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) Vec4<T>::load(qrow + (lane + 32 * c) * 4, q[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) q[c][e] *= p.scale_log2;
+
+    // ---- members from the smem ring: online softmax ----------------------------------------------
+    float acc[CPL][4];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[c][e] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int mi = 0; mi < members; ++mi) {
+      const uint32_t slot = consumed % RM;
+      la_wait(&bars[slot], (consumed / RM) & 1);
+      const T* krow = reinterpret_cast<const T*>(ring + (size_t)slot * SLOTB);
+      const T* vrow = p.same_kv ? krow : krow + CPL * 128;
+      float dot = 0.f, kk = 0.f;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        float x[4];
+        Vec4<T>::load(krow + (lane + 32 * c) * 4, x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          dot = fmaf(q[c][e], x[e], dot);
+          if (p.k_l2norm) kk = fmaf(x[e], x[e], kk);
+        }
+      }
+      float s = warp_sum(dot);
+      if (p.k_l2norm) s *= rsqrtf(warp_sum(kk));
+      const float m_new = fmaxf(m_run, s);
+      const float corr = exp2f(m_run - m_new);
+      const float pw = exp2f(s - m_new);
+      l_run = fmaf(l_run, corr, pw);
+      m_run = m_new;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        float x[4];
+        Vec4<T>::load(vrow + (lane + 32 * c) * 4, x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[c][e] = fmaf(acc[c][e], corr, pw * x[e]);
+      }
+      ++consumed;
+      __syncwarp();  // every lane is done with this slot before it is refilled
+      if (lane == 0 && mi + RM < members) issue(mi + RM);
+    }
+    const float inv = 1.f / l_run;
+    T* orow = outp + (size_t)wi * d;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[c][e] *= inv;
+      Vec4<T>::store(orow + (lane + 32 * c) * 4, acc[c]);
+    }
+  }
+}
+
+template <typename T, int CPL>
+static int launch_local_v2(const LocalParams& p, cudaStream_t stream) {
+  constexpr int RM = sizeof(T) == 2 ? 3 : 2;  // members in flight per warp
+  constexpr int WPB = 8;
+  constexpr size_t smem = (size_t)WPB * RM * 2 * CPL * 128 * sizeof(T) + WPB * RM * 8;
+  static bool configured = false;
+  auto kern = local_attend_v2_kernel<T, CPL, RM>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HICOM_REQUIRE(e == cudaSuccess, "local_attend: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  const long long total = (long long)p.wt.count * p.wh.count * p.ww.count * p.B;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  long long blocks = (total + WPB - 1) / WPB;
+  const long long resident = (long long)num_sms * (sizeof(T) == 2 ? 2 : 1);
+  if (blocks > resident) blocks = resident;  // persistent warps: the ring stays primed across windows
+  kern<<<(unsigned)blocks, WPB * 32, smem, stream>>>(p);
+  return check_launch("local_attend_v2_kernel");
+}
+
 template <typename T>
 static int launch_local(const LocalParams& p, cudaStream_t stream) {
   const long long total = (long long)p.wt.count * p.wh.count * p.ww.count * p.B;
@@ -218,6 +458,17 @@ static int launch_local(const LocalParams& p, cudaStream_t stream) {
   long long blocks = (total + warps_per_block - 1) / warps_per_block;
   if (blocks > (1 << 20)) blocks = 1 << 20;
   const int cpl = p.d / 128;
+  static int use_v1 = -1;
+  if (use_v1 < 0) { const char* e = getenv("HICOM_LOCAL_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
+  const bool aligned = (((uintptr_t)p.K | (uintptr_t)p.V) & 15) == 0;
+  if (!p.pool_only && !use_v1 && aligned) {
+    switch (cpl) {
+      case 9: return launch_local_v2<T, 9>(p, stream);
+      case 6: return launch_local_v2<T, 6>(p, stream);
+      case 8: return launch_local_v2<T, 8>(p, stream);
+      default: break;
+    }
+  }
   switch (cpl) {
     case 9: local_attend_kernel<T, 9><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(p); break;
     case 6: local_attend_kernel<T, 6><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(p); break;
