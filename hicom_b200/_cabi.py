@@ -16,6 +16,8 @@ PROTOTYPES = {
     "hicom_abi_version": (c_int, []),
     "hicom_last_error": (c_char_p, []),
     "hicom_kernel_launch_count": (ctypes.c_uint64, []),
+    "hicom_kernel_timing_enable": (c_int, [c_int]),
+    "hicom_kernel_timing_collect": (c_size_t, [ctypes.c_char_p, c_size_t]),
     "hicom_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
     "hicom_grid_pool": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "hicom_local_attend": (c_int, [c_void_p] * 8 + [c_int] * 8 + [c_float, c_int, c_int, c_void_p]),

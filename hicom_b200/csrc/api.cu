@@ -1,6 +1,11 @@
 // C-ABI entry points that are compositions of kernels: library info, hicom_linear, and the global
 // compressor ops.  See include/hicom_b200.h for the contract of each.
 #include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -32,6 +37,23 @@ int launch_posadd(const void* X, void* Y, const float* pt, const float* ph, cons
 int launch_col_softmax(float* S, float* m, float* l, int B, int N, int J, int splits, int rows_per_split,
                        cudaStream_t stream);
 
+// ---- optional per-kernel timing -------------------------------------------------------------------
+struct TimedLaunch { char label[96]; cudaEvent_t a, b; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+bool kernel_timing_enabled() { return g_timing; }
+void kernel_timing_begin(const char* label, cudaStream_t stream) {
+  TimedLaunch t;
+  snprintf(t.label, sizeof(t.label), "%s", label);
+  cudaEventCreate(&t.a);
+  cudaEventCreate(&t.b);
+  cudaEventRecord(t.a, stream);
+  g_timed.push_back(t);
+}
+void kernel_timing_end(cudaStream_t stream) {
+  if (!g_timed.empty()) cudaEventRecord(g_timed.back().b, stream);
+}
+
 static GemmParams plain_gemm() {
   GemmParams g{};
   g.nb1 = g.nb2 = 1;
@@ -51,6 +73,41 @@ using namespace hicom;
 extern "C" int hicom_abi_version(void) { return HICOM_ABI_VERSION; }
 extern "C" const char* hicom_last_error(void) { return g_err; }
 extern "C" uint64_t hicom_kernel_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+extern "C" int hicom_kernel_timing_enable(int on) {
+  g_timing = on != 0;
+  if (!g_timing) {
+    for (auto& t : g_timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    g_timed.clear();
+  }
+  return 0;
+}
+
+// Writes "label\tcount\ttotal_ms\n" lines into buf (synchronises the device); returns bytes needed.
+extern "C" size_t hicom_kernel_timing_collect(char* buf, size_t cap) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& t : g_timed) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+      auto& e = agg[t.label];
+      e.first += 1;
+      e.second += ms;
+    }
+  }
+  std::string out;
+  for (auto& kv : agg) {
+    char line[192];
+    snprintf(line, sizeof(line), "%s\t%d\t%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return out.size() + 1;
+}
 
 extern "C" int hicom_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

@@ -13,6 +13,19 @@ namespace hicom {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaGetLastError -> 0 / 1 (message recorded)
 
+// Optional per-kernel timing (bench.py's roofline): when enabled, launches wrapped in a KernelTimer are bracketed by
+// CUDA events on the launching stream; hicom_kernel_timing_collect() synchronises and sums them per label.
+bool kernel_timing_enabled();
+void kernel_timing_begin(const char* label, cudaStream_t stream);
+void kernel_timing_end(cudaStream_t stream);
+struct KernelTimer {
+  cudaStream_t s; bool on;
+  KernelTimer(const char* label, cudaStream_t stream) : s(stream), on(kernel_timing_enabled()) {
+    if (on) kernel_timing_begin(label, s);
+  }
+  ~KernelTimer() { if (on) kernel_timing_end(s); }
+};
+
 #define HICOM_REQUIRE(cond, ...)        \
   do {                                  \
     if (!(cond)) {                      \

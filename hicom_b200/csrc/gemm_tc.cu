@@ -708,6 +708,13 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   const long long total = (long long)grid.x * grid.y * grid.z;
   if (total == 0) return 0;
   const unsigned ctas = (unsigned)(total < num_sms ? total : num_sms);  // persistent: one CTA per SM at most
+  char label[96];
+  if (kernel_timing_enabled()) {
+    static const char* names[] = {"tc_linear", "tc_scores_max", "tc_scores_prob", "tc_pool"};
+    snprintf(label, sizeof(label), "%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI], (FLAGS & 1) ? "+gelu" : "", p.M, p.N,
+             p.K, total, p.guard ? " guarded" : "");
+  }
+  KernelTimer timer(label, stream);
   kern<<<ctas, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, pp);
   return check_launch("tc_gemm_kernel");
 }

@@ -446,6 +446,7 @@ static int launch_local_v2(const LocalParams& p, cudaStream_t stream) {
   long long blocks = (total + WPB - 1) / WPB;
   const long long resident = (long long)num_sms * (sizeof(T) == 2 ? 2 : 1);
   if (blocks > resident) blocks = resident;  // persistent warps: the ring stays primed across windows
+  KernelTimer timer("local_attend_v2", stream);
   kern<<<(unsigned)blocks, WPB * 32, smem, stream>>>(p);
   return check_launch("local_attend_v2_kernel");
 }

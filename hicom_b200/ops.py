@@ -343,6 +343,29 @@ def kernel_launch_count() -> int:
     return int(_cabi.load().hicom_kernel_launch_count())
 
 
+class KernelTimer:
+    """Per-kernel CUDA-event timing inside libhicom_b200 (tcgen05 GEMMs and the local kernel).
+    ``with KernelTimer() as kt: ...; kt.summary()`` -> {label: (launches, total_ms)}."""
+
+    def __enter__(self):
+        _cabi.load().hicom_kernel_timing_enable(1)
+        return self
+
+    def __exit__(self, *exc):
+        lib = _cabi.load()
+        n = lib.hicom_kernel_timing_collect(None, 0)
+        buf = ctypes.create_string_buffer(int(n) + 16)
+        lib.hicom_kernel_timing_collect(buf, len(buf))
+        self._table = {}
+        for line in buf.value.decode().splitlines():
+            label, count, ms = line.split("\t")
+            self._table[label] = (int(count), float(ms))
+        lib.hicom_kernel_timing_enable(0)
+
+    def summary(self):
+        return dict(self._table)
+
+
 class OpTimer:
     """Times every hicom_b200 op with CUDA events on the launching stream (no synchronisation while
     recording).  ``with OpTimer() as t: ...; t.summary()`` -> {op: (calls, total_ms)}."""

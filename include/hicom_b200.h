@@ -39,6 +39,10 @@ int hicom_abi_version(void);
 const char* hicom_last_error(void);
 /* Number of CUDA kernels this library has enqueued since load (monotonic; for launch accounting). */
 uint64_t hicom_kernel_launch_count(void);
+/* Per-kernel timing for measurement (off by default): when enabled, the dominant kernels are bracketed by CUDA
+ * events on their launching stream; collect() synchronises the device and writes "label\tcount\ttotal_ms" lines. */
+int hicom_kernel_timing_enable(int on);
+size_t hicom_kernel_timing_collect(char* buf, size_t cap);
 /* Fills SM count / compute capability of the current device; fails if it is not sm_100. */
 int hicom_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
