@@ -55,8 +55,7 @@ struct Params {
   int HW, T;                       // tokens per frame, frames
   const float* peq_t; long long peq_ld;  // (T, B*J) time term of the scores: pos_t[t]·qfold[b,j]
   float* margT; int margT_ld;      // (B*J, margT_ld) sum of probabilities per frame (EPI_PROB accumulates)
-  int m_main_tiles;                // EPI_POOL: M tiles >= this read the indicator matrix from the second A map
-  __nv_bfloat16* margS; int ke;    // (B, splits, J, ke) spatial marginals written by those tiles
+
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -228,7 +227,7 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
   int k_end = t.k_begin + p.k_chunk;
   if (k_end > p.K) k_end = p.K;
   t.nkb_main = k_end > t.k_begin ? (k_end - t.k_begin + BK - 1) / BK : 0;
-  t.nkb = t.nkb_main + ((EPI == EPI_MAX || EPI == EPI_PROB) ? p.k_ext_blocks : 0);
+  t.nkb = t.nkb_main + ((EPI == EPI_MAX || EPI == EPI_PROB || (EPI == EPI_POOL && t.split == 0)) ? p.k_ext_blocks : 0);
   return t;
 }
 
@@ -285,13 +284,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + C::A_BYTES;
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           const int k0 = t.k_begin + kb * BK;
-          const bool ext = (EPI == EPI_MAX || EPI == EPI_PROB) && kb >= t.nkb_main;
+          const bool ext = (EPI == EPI_MAX || EPI == EPI_PROB || EPI == EPI_POOL) && kb >= t.nkb_main;
           if (A_MN) {
             // A[m, k] stored (k rows, m contiguous): two 64-wide M blocks of (BK rows x 128 B)
-            if (EPI == EPI_POOL && t.m_tile >= p.m_main_tiles) {  // indicator matrix (tokens x ke), shared by all videos
-              const int me = (t.m_tile - p.m_main_tiles) * BM;
-              tma_load_3d(sa, &tmA2, &full_bar[s], me, k0, 0);
-              tma_load_3d(sa + BK * 128, &tmA2, &full_bar[s], me + 64, k0, 0);
+            if (ext) {  // position tables (ke2 rows x d), shared by all videos: rows = [pos_h ; pos_w ; 0 | pos_t ; 0]
+              const int kx = (kb - t.nkb_main) * BK;
+              tma_load_3d(sa, &tmA2, &full_bar[s], t.m_tile * BM, kx, 0);
+              tma_load_3d(sa + BK * 128, &tmA2, &full_bar[s], t.m_tile * BM + 64, kx, 0);
             } else {
               tma_load_3d(sa, &tmA, &full_bar[s], t.m_tile * BM, k0, t.batch);
               tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], t.m_tile * BM + 64, k0, t.batch);
@@ -301,7 +300,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_3d(sa, &tmA, &full_bar[s], k0 + t.zslice * p.z_a_k, t.m_tile * BM, t.batch);
           }
-          if (ext) {
+          if (ext && EPI == EPI_POOL) {  // probability marginals (J x ke2) of this video, K-major
+            for (int r = 0; r < BN; r += p.b_box_rows)
+              tma_load_3d(sb + r * 128, &tmB2, &full_bar[s], (kb - t.nkb_main) * BK, r, t.batch);
+          } else if (ext) {
             tma_load_3d(sb, &tmB2, &full_bar[s], (kb - t.nkb_main) * BK, t.n_tile * BN, 0);  // (tokens x ke) indicator
           } else if (B_MN) {
             // B[k, n] stored (k rows, n contiguous): BN/64 blocks of (BK rows x 128 B)
@@ -581,21 +583,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         atomicAdd(p.lg + col, sum);
         atomic_max_float(p.mg + col, mx);
       }
-    } else {  // EPI_POOL: rows = channels d (M) or indicator columns (extra tiles), columns = score columns j (N = J)
-      const bool extra = t.m_tile >= p.m_main_tiles;
-      const int erow = (t.m_tile - p.m_main_tiles) * BM + q * 32 + lane;  // indicator column of this thread
+    } else {  // EPI_POOL: rows = channels d (M), columns = score columns j (N = J)
       float* obase = p.o + (((size_t)batch * p.splits + split) * p.N) * p.M + row;
-      __nv_bfloat16* mbase = p.margS + (((size_t)batch * p.splits + split) * p.N) * p.ke + erow;
       for (int c = half; c < (BN + 31) / 32; c += 2) {
         if (nkb > 0) tmem_ld32(taddr + c * 32, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int j = c * 32 + i;
-          const float val = nkb > 0 ? v[i] : 0.f;
-          if (j < p.N) {
-            if (!extra) { if (row < p.M) obase[(size_t)j * p.M] = val; }
-            else if (erow < p.ke) mbase[(size_t)j * p.ke] = __float2bfloat16_rn(val);
-          }
+          if (j < p.N && row < p.M) obase[(size_t)j * p.M] = nkb > 0 ? v[i] : 0.f;
         }
       }
     }
@@ -789,15 +784,17 @@ bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W) 
 }
 
 struct GlobalWs {
-  size_t pt, mg, lg, stab, flag, pe_t, pe_s, ind, peq_s, peq_t, margT, margTb, margS, total;
+  size_t pt, mg, lg, stab, flag, pe_t, pe2, ind, peq_s, peq_t, margT, marg, total;
   long long pt_ld;
-  int Tk;
+  int Tk, ke2;
 };
 static GlobalWs global_ws(int B, int T, int H, int W, int d, int J, int splits) {
+  (void)splits;
   const size_t N = (size_t)T * H * W;
   GlobalWs w;
   w.pt_ld = (long long)((N + 255) / 256) * 256;
   w.Tk = (T + 7) / 8 * 8;
+  w.ke2 = kKe + (T + 63) / 64 * 64;  // [spatial 64 | time, padded to whole K blocks]
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   w.pt = take((size_t)B * J * w.pt_ld * 2);
@@ -805,14 +802,13 @@ static GlobalWs global_ws(int B, int T, int H, int W, int d, int J, int splits) 
   w.lg = take((size_t)B * J * 4);
   w.stab = take((size_t)B * J * 4);
   w.flag = take(256);
-  w.pe_t = take((size_t)w.Tk * d * 2);            // pos_t rounded to bf16, zero rows up to Tk
-  w.pe_s = take((size_t)kKe * d * 2);             // [pos_h ; pos_w ; 0] bf16
+  w.pe_t = take((size_t)w.Tk * d * 2);            // pos_t rounded to bf16, zero rows up to Tk (score time term)
+  w.pe2 = take((size_t)w.ke2 * d * 2);            // [pos_h ; pos_w ; 0 | pos_t ; 0] bf16: spatial + time tables
   w.ind = take(N * kKe * 2);                      // one-hot (token -> h, H + w) bf16
   w.peq_s = take((size_t)B * J * kKe * 2);        // qfold · pe_sᵀ  (bf16, K-major rows j)
   w.peq_t = take((size_t)T * B * J * 4);          // pe_t · qfoldᵀ  (fp32, (T, B*J))
   w.margT = take((size_t)B * J * w.Tk * 4);       // probability mass per frame (fp32 atomics)
-  w.margTb = take((size_t)B * J * w.Tk * 2);      // ... rounded to bf16 for the tensor core
-  w.margS = take((size_t)B * splits * J * kKe * 2);
+  w.marg = take((size_t)B * J * w.ke2 * 2);       // [spatial marginals | time marginals] bf16, K-major rows j
   w.total = off;
   return w;
 }
@@ -824,15 +820,18 @@ size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int s
 namespace tc {
 // bf16 copies of the per-axis tables: pe_t (Tk x d, rows >= T zero) and pe_s = [pos_h ; pos_w ; 0] (64 x d)
 __global__ void build_pe_kernel(const float* pt, const float* ph, const float* pw, __nv_bfloat16* pe_t,
-                                __nv_bfloat16* pe_s, int T, int Tk, int H, int W, int d) {
-  const int r = blockIdx.x;  // 0..Tk-1 -> pe_t rows, Tk..Tk+63 -> pe_s rows
+                                __nv_bfloat16* pe2, int T, int Tk, int ke2, int H, int W, int d) {
+  const int r = blockIdx.x;  // 0..Tk-1 -> pe_t rows; Tk..Tk+ke2-1 -> pe2 rows ([pos_h ; pos_w ; 0 | pos_t ; 0])
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     if (r < Tk) {
       pe_t[(size_t)r * d + c] = __float2bfloat16_rn(r < T ? pt[(size_t)r * d + c] : 0.f);
     } else {
       const int s = r - Tk;
-      const float v = s < H ? ph[(size_t)s * d + c] : (s < H + W ? pw[(size_t)(s - H) * d + c] : 0.f);
-      pe_s[(size_t)s * d + c] = __float2bfloat16_rn(v);
+      float v = 0.f;
+      if (s < H) v = ph[(size_t)s * d + c];
+      else if (s < H + W) v = pw[(size_t)(s - H) * d + c];
+      else if (s >= kKe && s - kKe < T) v = pt[(size_t)(s - kKe) * d + c];
+      pe2[(size_t)s * d + c] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -849,9 +848,16 @@ __global__ void zero_f32_kernel(float* p, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0.f;
 }
-__global__ void to_bf16_kernel(const float* src, __nv_bfloat16* dst, long long n) {
+// time marginals (rows x Tk fp32) -> columns [col0, col0 + tcols) of the bf16 marginal matrix (rows x ld); columns past
+// Tk are zero.  `flag` non-null: only when *flag != 0 (fallback re-run).
+__global__ void pack_margT_kernel(const float* src, int Tk, __nv_bfloat16* dst, int ld, int col0, int tcols,
+                                  long long rows, const int* flag) {
+  if (flag != nullptr && *flag == 0) return;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+  if (i >= rows * tcols) return;
+  const long long r = i / tcols;
+  const int c = (int)(i % tcols);
+  dst[r * ld + col0 + c] = __float2bfloat16_rn(c < Tk ? src[r * Tk + c] : 0.f);
 }
 // fallback only: stabiliser := true max, sums and time marginals reset
 __global__ void repair_margT_kernel(float* margT, long long n, const int* flag) {
@@ -874,19 +880,21 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   float* stab = reinterpret_cast<float*>(ws + w.stab);
   int* flag = reinterpret_cast<int*>(ws + w.flag);
   __nv_bfloat16* pe_t = reinterpret_cast<__nv_bfloat16*>(ws + w.pe_t);
-  __nv_bfloat16* pe_s = reinterpret_cast<__nv_bfloat16*>(ws + w.pe_s);
+  __nv_bfloat16* pe2 = reinterpret_cast<__nv_bfloat16*>(ws + w.pe2);
   __nv_bfloat16* ind = reinterpret_cast<__nv_bfloat16*>(ws + w.ind);
   __nv_bfloat16* peq_s = reinterpret_cast<__nv_bfloat16*>(ws + w.peq_s);
   float* peq_t = reinterpret_cast<float*>(ws + w.peq_t);
   float* margT = reinterpret_cast<float*>(ws + w.margT);
-  __nv_bfloat16* margTb = reinterpret_cast<__nv_bfloat16*>(ws + w.margTb);
-  __nv_bfloat16* margS = reinterpret_cast<__nv_bfloat16*>(ws + w.margS);
+  __nv_bfloat16* marg = reinterpret_cast<__nv_bfloat16*>(ws + w.marg);
   const long long BJ = (long long)B * J;
+  const int tcols = w.ke2 - kKe;
 
-  // 0. tables: PE is separable, PE[t,h,w] = pos_t[t] + pos_h[h] + pos_w[w], so
-  //      S = x·qfold + pos_t[t]·qfold + (pos_h[h] + pos_w[w])·qfold        (time term in the epilogue, spatial term as
-  //      O = sum_n p_n x_n + sum_t (sum_{n in t} p_n) pos_t[t] + ...         one extra K block against a one-hot matrix)
-  build_pe_kernel<<<w.Tk + kKe, 256, 0, stream>>>(pos_t, pos_h, pos_w, pe_t, pe_s, T, w.Tk, H, W, d);
+  // 0. tables.  PE is separable, PE[t,h,w] = pos_t[t] + pos_h[h] + pos_w[w], so no x' = x + PE tensor is needed:
+  //      S = x·qfold + pos_t[t]·qfold + (pos_h[h] + pos_w[w])·qfold      time term: added in the score epilogue;
+  //                                                                     spatial term: one extra K block against `ind`
+  //      O = sum_n p_n x_n + sum_c marg[c] · pe2[c]                      marg = probability mass per (h | w | t):
+  //                                                                     extra K blocks of the pooling GEMM
+  build_pe_kernel<<<w.Tk + w.ke2, 256, 0, stream>>>(pos_t, pos_h, pos_w, pe_t, pe2, T, w.Tk, w.ke2, H, W, d);
   if (check_launch("build_pe_kernel")) return 1;
   build_ind_kernel<<<(unsigned)(((long long)N * kKe + 255) / 256), 256, 0, stream>>>(ind, N, H, W);
   if (check_launch("build_ind_kernel")) return 1;
@@ -894,9 +902,9 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   if (check_launch("init_stats_kernel")) return 1;
   zero_f32_kernel<<<(unsigned)((BJ * w.Tk + 255) / 256), 256, 0, stream>>>(margT, BJ * w.Tk);
   if (check_launch("zero_f32_kernel")) return 1;
-  {  // peq_s (B*J, 64) bf16 = qfold · pe_sᵀ ;  peq_t (T, B*J) fp32 = pe_t · qfoldᵀ
+  {  // peq_s (B*J, 64) bf16 = qfold · pe_sᵀ (pe_s = first 64 rows of pe2);  peq_t (T, B*J) fp32 = pe_t · qfoldᵀ
     TcLinearParams a{};
-    a.A = qfold; a.W = pe_s; a.C = peq_s; a.lda = d; a.ldw = d; a.ldc = kKe; a.M = (int)BJ; a.N = kKe; a.K = d;
+    a.A = qfold; a.W = pe2; a.C = peq_s; a.lda = d; a.ldw = d; a.ldc = kKe; a.M = (int)BJ; a.N = kKe; a.K = d;
     a.act = HICOM_ACT_NONE; a.out_dtype = HICOM_BF16; a.rows_per_group = 1 << 30;
     if (launch_tc_linear(a, stream)) return 1;
     TcLinearParams b{};
@@ -919,26 +927,26 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   const int n_tiles = (N + 255) / 256;
   const int m_tiles = (J + BM - 1) / BM;
 
-  // pooling: O[b,s] (d x J) = X[b, tokens of s]ᵀ · P ; one more M tile multiplies the indicator matrix instead of X
-  // and yields the spatial probability marginals (ke x J)
-  CUtensorMap txa, tp, tinda;
+  // spatial marginals: marg[:, 0:64] (B*J x 64) = Pt (B*J x tokens) · ind (tokens x 64)
+  TcLinearParams ms{};
+  ms.A = Pt; ms.W = ind; ms.C = marg; ms.lda = w.pt_ld; ms.ldw = kKe; ms.ldc = w.ke2;
+  ms.M = (int)BJ; ms.N = kKe; ms.K = N; ms.act = HICOM_ACT_NONE; ms.out_dtype = HICOM_BF16;
+  ms.rows_per_group = 1 << 30; ms.w_is_kn = 1;
+
+  // pooling: O[b,s] (d x J) = [X[b, tokens of s] ; pe2]ᵀ · [P ; marg]  — the table/marginal K blocks ride on split 0
+  CUtensorMap txa, tp, tpe, tmg;
   if (make_map(&txa, X, d, N, B, d, (uint64_t)N * d, 64)) return 1;
   if (make_map(&tp, Pt, w.pt_ld, J, B, w.pt_ld, (uint64_t)J * w.pt_ld, 96)) return 1;
-  if (make_map(&tinda, ind, kKe, N, 1, kKe, 0, 64)) return 1;
+  if (make_map(&tpe, pe2, d, w.ke2, 1, d, 0, 64)) return 1;
+  if (make_map(&tmg, marg, w.ke2, J, B, w.ke2, (uint64_t)J * w.ke2, 96)) return 1;
   Params g{};
   g.M = d; g.N = J; g.K = N;
   int chunk = (N + splits - 1) / splits;
   chunk = (chunk + BK - 1) / BK * BK;
   g.k_chunk = chunk; g.b_box_rows = 96;
-  g.o = o; g.splits = splits;
-  g.m_main_tiles = d / BM; g.margS = margS; g.ke = kKe;
-  dim3 gp(splits, d / BM + 1, B);
-
-  // o[b,s] += margS[b,s] (J x 64) · pe_s (64 x d)
-  TcLinearParams accS{};
-  accS.A = margS; accS.W = pe_s; accS.C = o; accS.lda = kKe; accS.ldw = d; accS.ldc = d;
-  accS.M = (int)(BJ * splits); accS.N = d; accS.K = kKe; accS.act = HICOM_ACT_NONE; accS.out_dtype = HICOM_F32;
-  accS.rows_per_group = 1 << 30; accS.w_is_kn = 1; accS.accumulate = 1;
+  g.o = o; g.splits = splits; g.k_ext_blocks = w.ke2 / BK;
+  dim3 gp(splits, d / BM, B);
+  const unsigned pack_blocks = (unsigned)((BJ * tcols + 255) / 256);
 
   // 1. sampled max (a few evenly spaced token tiles) -> stabiliser.  The softmax is invariant to the stabiliser;
   //    it only has to keep exp() inside the exponent range, so the full max pass is not needed.
@@ -956,9 +964,11 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   if (launch<256, false, false, EPI_PROB>(tq, tx, p, gs, stream, &tq2, &tind)) return 1;
   check_stab_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, stab, (int)BJ, flag);
   if (check_launch("check_stab_kernel")) return 1;
-  // 3. pooling + spatial position term
-  if (launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream, &tinda, nullptr)) return 1;
-  if (launch_tc_linear(accS, stream)) return 1;
+  // 3. marginals, then pooling with the position terms folded in as K blocks
+  if (launch_tc_linear(ms, stream)) return 1;
+  pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kKe, tcols, BJ, nullptr);
+  if (check_launch("pack_margT_kernel")) return 1;
+  if (launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream, &tpe, &tmg)) return 1;
   // 4. guarded exact fallback (no-ops unless some score beat the sampled max by > 80 nats): redo 2-3 with the true max
   {
     repair_stab_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, stab, lg, (int)BJ, flag);
@@ -967,21 +977,12 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
     if (check_launch("repair_margT_kernel")) return 1;
     Params pf = p; pf.guard = flag;
     Params gf = g; gf.guard = flag;
+    TcLinearParams msf = ms; msf.guard = flag;
     if (launch<256, false, false, EPI_PROB>(tq, tx, pf, gs, stream, &tq2, &tind)) return 1;
-    if (launch<288, true, false, EPI_POOL>(txa, tp, gf, gp, stream, &tinda, nullptr)) return 1;
-    TcLinearParams accSf = accS; accSf.guard = flag;
-    if (launch_tc_linear(accSf, stream)) return 1;
-  }
-  // 5. time position term, once, into split 0 (all splits share the stabiliser, so the merge just adds them):
-  //    o[b,0] += margT[b] (J x Tk) · pe_t (Tk x d)
-  to_bf16_kernel<<<(unsigned)((BJ * w.Tk + 255) / 256), 256, 0, stream>>>(margT, margTb, BJ * w.Tk);
-  if (check_launch("to_bf16_kernel")) return 1;
-  {
-    TcLinearParams accT{};
-    accT.A = margTb; accT.W = pe_t; accT.C = o; accT.lda = w.Tk; accT.ldw = d; accT.ldc = d;
-    accT.M = (int)BJ; accT.N = d; accT.K = w.Tk; accT.act = HICOM_ACT_NONE; accT.out_dtype = HICOM_F32;
-    accT.rows_per_group = J; accT.group_stride_rows = (long long)splits * J; accT.w_is_kn = 1; accT.accumulate = 1;
-    if (launch_tc_linear(accT, stream)) return 1;
+    if (launch_tc_linear(msf, stream)) return 1;
+    pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kKe, tcols, BJ, flag);
+    if (check_launch("pack_margT_kernel")) return 1;
+    if (launch<288, true, false, EPI_POOL>(txa, tp, gf, gp, stream, &tpe, &tmg)) return 1;
   }
   spread_stats_kernel<<<(unsigned)((BJ * splits + 255) / 256), 256, 0, stream>>>(stab, lg, m, l, B, splits, J);
   return check_launch("spread_stats_kernel");
