@@ -368,6 +368,9 @@ def run_ours(args):
         roof.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak)
     roof["peak_source"] = pk["source"] + (" (sustained bf16)" if kind != "hbm" else " (copy)")
     roof["traffic"] = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if args.workload == "c2" and os.path.exists(tpath):  # DRAM bytes per launch from the committed ncu --set full capture
+        roof["traffic"] = json.load(open(tpath)).get(dname.split()[0])
     exec_flops = videos_per_step * (w["flops_scores"] + w["flops_pool"] + w["flops_local_readout"])
     ops_table = {k: {"calls": c, "ms_per_step": ms / op_steps} for k, (c, ms) in
                  sorted(op_times.items(), key=lambda kv: -kv[1][1])}
