@@ -188,7 +188,8 @@ def test_graph_replay_and_host_pipeline_match_eager(built_library):
         got_host = compress_from_host(m, Xh, Eh, Gh, "video", chunk=2)
     torch.cuda.synchronize()
     assert g.kernels_per_replay > 10
-    assert torch.equal(got_graph, want)
-    assert torch.equal(got_graph2, want.flip(0))
+    # fp32 atomics (row sums, per-frame mass) make runs differ in the last bf16 bit, so compare with a tolerance
+    assert O.rel_err(got_graph.float().cpu(), want.float().cpu()) <= 8e-3
+    assert O.rel_err(got_graph2.float().cpu(), want.flip(0).float().cpu()) <= 8e-3
     assert not got_host.is_cuda and got_host.shape == want.shape
     assert O.rel_err(got_host.float(), want.float().cpu()) <= 8e-3  # chunks of 2 take other split counts than B=5
