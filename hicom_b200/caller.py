@@ -1,0 +1,52 @@
+"""Batched replacement for the per-sample loop of ``HIComMetaForCausalLM.encode_images_or_videos``
+(hicom/model/hicom_arch.py:167-178), SURVEY §8 row f1.
+
+The reference calls ``mm_projector`` once per sample in a Python loop.  ``compress_samples`` takes the same per-sample
+inputs, groups the plain video tensors that share a shape / dtype / guide shape, runs each group through ONE
+``forward_batched`` call, and sends everything else (any-res image dicts, odd shapes) through the reference-signature
+``forward`` — returning the per-sample token tensors in the original order, exactly what the loop produced.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import List, Optional, Sequence
+
+import torch
+
+
+def _key(feat, embed, guide, modal):
+    return (modal, tuple(feat.shape), feat.dtype, feat.device, embed is None,
+            None if guide is None else tuple(guide.shape))
+
+
+@torch.no_grad()
+def compress_samples(projector, frames_features: Sequence, frames_embeds: Optional[Sequence],
+                     guide_embeds: Optional[Sequence], modalities: Sequence[str], image_newline=None,
+                     min_group: int = 2) -> List[torch.Tensor]:
+    """``frames_features[i]`` is a (T,H,W,d) tensor or an any-res dict, ``frames_embeds[i]`` / ``guide_embeds[i]`` the
+    matching embeds (the sequences themselves may be None, hicom_arch.py:169-170).  Returns ``[tokens_i]``."""
+    n = len(frames_features)
+    out: List[Optional[torch.Tensor]] = [None] * n
+    groups = defaultdict(list)
+    for i in range(n):
+        f = frames_features[i]
+        e = None if frames_embeds is None else frames_embeds[i]
+        g = None if guide_embeds is None else guide_embeds[i]
+        if isinstance(f, dict) or f.dim() != 4:
+            out[i] = projector(f, e, g, modalities[i], image_newline)
+        else:
+            groups[_key(f, e, g, modalities[i])].append(i)
+    for key, idx in groups.items():
+        modal = key[0]
+        if len(idx) < min_group:
+            for i in idx:
+                out[i] = projector(frames_features[i], None if frames_embeds is None else frames_embeds[i],
+                                   None if guide_embeds is None else guide_embeds[i], modal, image_newline)
+            continue
+        X = torch.stack([frames_features[i] for i in idx])
+        E = None if frames_embeds is None or frames_embeds[idx[0]] is None else torch.stack([frames_embeds[i] for i in idx])
+        G = None if guide_embeds is None or guide_embeds[idx[0]] is None else torch.stack([guide_embeds[i] for i in idx])
+        tokens = projector.forward_batched(X, E, G, modal, image_newline)
+        for j, i in enumerate(idx):
+            out[i] = tokens[j]
+    return out

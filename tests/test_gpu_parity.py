@@ -193,3 +193,30 @@ def test_graph_replay_and_host_pipeline_match_eager(built_library):
     assert O.rel_err(got_graph2.float().cpu(), want.flip(0).float().cpu()) <= 8e-3
     assert not got_host.is_cuda and got_host.shape == want.shape
     assert O.rel_err(got_host.float(), want.float().cpu()) <= 8e-3  # chunks of 2 take other split counts than B=5
+
+
+def test_batched_caller_matches_per_sample_loop(built_library):
+    """hicom_b200.caller.compress_samples == the reference's per-sample loop (hicom_arch.py:167-178)
+    on a mixed batch: same-shape videos (grouped), an odd-length video and an any-res image dict (per item)."""
+    from hicom_b200.caller import compress_samples
+    case = CASES_BY_NAME["image_T1_newline"]  # spatial_unpad + newline layouts
+    sd, _, _, _, nl = materialise(case)
+    m = cuda_module_for(case, sd)
+    mk = lambda T, s: tuple(t.cuda() for t in O.synth_inputs(T, 6, 6, "vec", seed=s))
+    v = [mk(8, 1), mk(8, 2), mk(4, 3), mk(8, 4)]
+    gen = torch.Generator().manual_seed(9)
+    img = {"base": (0.5 * torch.randn(6, 6, 1152, generator=gen)).cuda(),
+           "patch": (0.5 * torch.randn(12, 6, 1152, generator=gen)).cuda()}
+    img_e = {"base": (0.5 * torch.randn(6, 6, 1152, generator=gen)).cuda(),
+             "patch": (0.5 * torch.randn(12, 6, 1152, generator=gen)).cuda()}
+    feats = [v[0][0], img, v[1][0], v[2][0], v[3][0]]
+    embeds = [v[0][1], img_e, v[1][1], v[2][1], v[3][1]]
+    guides = [v[0][2], v[1][2], v[1][2], v[2][2], v[3][2]]
+    modal = ["video", "image", "video", "video", "video"]
+    nl = nl.cuda()
+    got = compress_samples(m, feats, embeds, guides, modal, nl)
+    with torch.no_grad():
+        want = [m(f, e, g, md, nl) for f, e, g, md in zip(feats, embeds, guides, modal)]
+    assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in want]
+    for a, b in zip(got, want):
+        assert O.rel_err(a.cpu(), b.cpu()) <= 1e-5
