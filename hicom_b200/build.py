@@ -62,6 +62,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hd = _header_digest()
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, hd, force), SOURCES))
+    for f in os.listdir(OBJ_DIR):  # drop objects of older source versions
+        if f.endswith(".o") and os.path.join(OBJ_DIR, f) not in objs:
+            os.remove(os.path.join(OBJ_DIR, f))
     stamp = os.path.join(LIB_DIR, ".stamp")
     want = "\n".join(objs)
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == want:

@@ -41,7 +41,8 @@ struct Params {
   int diag_heads, diag_rows, diag_cols;  // >0: row r=(g,h,i) keeps only columns of head h, written to row g*diag_rows+i
   int z_slices;                    // >0: blockIdx.z is not a tensor batch but a K-slice (one head) of the SAME A/B:
   int z_a_k, z_b_k;                //     A / B reduction coordinates start at z*z_a_k / z*z_b_k
-  long long z_c_rows;              //     and output rows are shifted by z*z_c_rows
+  long long z_c_rows;              //     and output rows are shifted by z*z_c_rows,
+  int z_c_cols;                    //     output columns by z*z_c_cols
   // EPI_MAX / EPI_PROB / EPI_POOL
   float* mg; float* lg;            // (B, J) running TRUE max of the scores / sum of probabilities
   const float* stab;               // (B, J) softmax stabiliser used by EPI_PROB (any value near the max is exact)
@@ -442,7 +443,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if (!kOutF32) {
-            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n0;
+            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n0 + zslice * p.z_c_cols;
             if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -459,7 +460,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (i < nvalid) dst[i] = __float2bfloat16_rn(v[i]);
             }
           } else {
-            float* dst = static_cast<float*>(p.C) + orow * p.ldc + n0;
+            float* dst = static_cast<float*>(p.C) + orow * p.ldc + n0 + zslice * p.z_c_cols;
             if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
@@ -482,6 +483,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+    } else if (EPI == EPI_MAX && t.m_tile * BM + q * 32 >= p.M) {
+      // every row of this warp is padding (J = 288 fills 2.25 M tiles): nothing to read, just release the buffer
+    } else if (EPI == EPI_PROB && t.m_tile * BM + q * 32 >= p.M) {
+      // same for the probability pass
     } else if (EPI == EPI_MAX) {
       // rows = score columns j (M = J), columns = tokens of this tile
       const bool row_ok = row < p.M;
@@ -732,7 +737,8 @@ bool tc_linear_supported(int in_dtype, int out_dtype, int M, int N, int K, long 
 int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   using namespace tc;
   CUtensorMap ta, tb;
-  const uint64_t kext = (uint64_t)q.K * (q.z_slices > 0 ? q.z_slices : 1);  // full reduction extent in memory
+  // full reduction extent in memory (slices may overhang it: out-of-range elements read as zero)
+  const uint64_t kext = q.k_total > 0 ? (uint64_t)q.k_total : (uint64_t)q.K * (q.z_slices > 0 ? q.z_slices : 1);
   if (make_map(&ta, q.A, kext, q.M, 1, q.lda, 0, BM)) return 1;
   if (q.w_is_kn) {  // W given as (K, N) row-major: MN-major B operand, boxes of 64 n x 64 k
     if (make_map(&tb, q.W, q.N, kext, 1, q.ldw, 0, 64)) return 1;
@@ -741,7 +747,7 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   }
   Params p{};
   p.alpha = q.alpha; p.diag_heads = q.diag_heads; p.diag_rows = q.diag_rows; p.diag_cols = q.diag_cols;
-  p.z_slices = q.z_slices; p.z_a_k = q.z_a_k; p.z_b_k = q.z_b_k; p.z_c_rows = q.z_c_rows;
+  p.z_slices = q.z_slices; p.z_a_k = q.z_a_k; p.z_b_k = q.z_b_k; p.z_c_rows = q.z_c_rows; p.z_c_cols = q.z_c_cols;
   p.guard = q.guard;
   p.M = q.M; p.N = q.N; p.K = q.K; p.k_chunk = q.K; p.b_box_rows = 256;
   p.bias = static_cast<const __nv_bfloat16*>(q.bias);
@@ -774,7 +780,8 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-constexpr int kKe = 64;  // spatial indicator columns (H + W <= 64): one extra K block / half an extra M tile
+constexpr int kKe = 64;  // spatial indicator columns (H + W <= 64): one extra K block
+constexpr int kSpatialSlices = 2;  // the marginal GEMM splits its token range in two (tile z axis) to fill the SMs
 
 bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W) {
   (void)T;
@@ -794,7 +801,7 @@ static GlobalWs global_ws(int B, int T, int H, int W, int d, int J, int splits) 
   GlobalWs w;
   w.pt_ld = (long long)((N + 255) / 256) * 256;
   w.Tk = (T + 7) / 8 * 8;
-  w.ke2 = kKe + (T + 63) / 64 * 64;  // [spatial 64 | time, padded to whole K blocks]
+  w.ke2 = kSpatialSlices * kKe + (T + 63) / 64 * 64;  // [spatial 64 x slices | time, padded to whole K blocks]
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   w.pt = take((size_t)B * J * w.pt_ld * 2);
@@ -827,10 +834,14 @@ __global__ void build_pe_kernel(const float* pt, const float* ph, const float* p
       pe_t[(size_t)r * d + c] = __float2bfloat16_rn(r < T ? pt[(size_t)r * d + c] : 0.f);
     } else {
       const int s = r - Tk;
+      const int ss = s % kKe;  // the spatial table is repeated once per marginal slice
       float v = 0.f;
-      if (s < H) v = ph[(size_t)s * d + c];
-      else if (s < H + W) v = pw[(size_t)(s - H) * d + c];
-      else if (s >= kKe && s - kKe < T) v = pt[(size_t)(s - kKe) * d + c];
+      if (s < kSpatialSlices * kKe) {
+        if (ss < H) v = ph[(size_t)ss * d + c];
+        else if (ss < H + W) v = pw[(size_t)(ss - H) * d + c];
+      } else if (s - kSpatialSlices * kKe < T) {
+        v = pt[(size_t)(s - kSpatialSlices * kKe) * d + c];
+      }
       pe2[(size_t)s * d + c] = __float2bfloat16_rn(v);
     }
   }
@@ -887,7 +898,7 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   float* margT = reinterpret_cast<float*>(ws + w.margT);
   __nv_bfloat16* marg = reinterpret_cast<__nv_bfloat16*>(ws + w.marg);
   const long long BJ = (long long)B * J;
-  const int tcols = w.ke2 - kKe;
+  const int tcols = w.ke2 - kSpatialSlices * kKe;
 
   // 0. tables.  PE is separable, PE[t,h,w] = pos_t[t] + pos_h[h] + pos_w[w], so no x' = x + PE tensor is needed:
   //      S = x·qfold + pos_t[t]·qfold + (pos_h[h] + pos_w[w])·qfold      time term: added in the score epilogue;
@@ -930,8 +941,10 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   // spatial marginals: marg[:, 0:64] (B*J x 64) = Pt (B*J x tokens) · ind (tokens x 64)
   TcLinearParams ms{};
   ms.A = Pt; ms.W = ind; ms.C = marg; ms.lda = w.pt_ld; ms.ldw = kKe; ms.ldc = w.ke2;
-  ms.M = (int)BJ; ms.N = kKe; ms.K = N; ms.act = HICOM_ACT_NONE; ms.out_dtype = HICOM_BF16;
+  const int kslice = ((N + kSpatialSlices - 1) / kSpatialSlices + BK - 1) / BK * BK;  // tokens per slice
+  ms.M = (int)BJ; ms.N = kKe; ms.K = kslice; ms.act = HICOM_ACT_NONE; ms.out_dtype = HICOM_BF16;
   ms.rows_per_group = 1 << 30; ms.w_is_kn = 1;
+  ms.z_slices = kSpatialSlices; ms.z_a_k = kslice; ms.z_b_k = kslice; ms.z_c_cols = kKe; ms.k_total = N;
 
   // pooling: O[b,s] (d x J) = [X[b, tokens of s] ; pe2]ᵀ · [P ; marg]  — the table/marginal K blocks ride on split 0
   CUtensorMap txa, tp, tpe, tmg;
@@ -966,7 +979,7 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   if (check_launch("check_stab_kernel")) return 1;
   // 3. marginals, then pooling with the position terms folded in as K blocks
   if (launch_tc_linear(ms, stream)) return 1;
-  pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kKe, tcols, BJ, nullptr);
+  pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kSpatialSlices * kKe, tcols, BJ, nullptr);
   if (check_launch("pack_margT_kernel")) return 1;
   if (launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream, &tpe, &tmg)) return 1;
   // 4. guarded exact fallback (no-ops unless some score beat the sampled max by > 80 nats): redo 2-3 with the true max
@@ -980,7 +993,7 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
     TcLinearParams msf = ms; msf.guard = flag;
     if (launch<256, false, false, EPI_PROB>(tq, tx, pf, gs, stream, &tq2, &tind)) return 1;
     if (launch_tc_linear(msf, stream)) return 1;
-    pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kKe, tcols, BJ, flag);
+    pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kSpatialSlices * kKe, tcols, BJ, flag);
     if (check_launch("pack_margT_kernel")) return 1;
     if (launch<288, true, false, EPI_POOL>(txa, tp, gf, gp, stream, &tpe, &tmg)) return 1;
   }

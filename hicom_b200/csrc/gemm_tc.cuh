@@ -12,7 +12,8 @@ struct TcLinearParams {
   float alpha = 1.f;        // C = act(alpha * A·op(W) + bias) + R
   int w_is_kn = 0;          // W stored (K, N) row-major instead of torch's (N, K)
   int diag_heads = 0, diag_rows = 0, diag_cols = 0;  // block-diagonal store (see gemm_tc.cu)
-  int z_slices = 0, z_a_k = 0, z_b_k = 0; long long z_c_rows = 0;  // per-head K slices on blockIdx.z
+  int z_slices = 0, z_a_k = 0, z_b_k = 0; long long z_c_rows = 0;  // K slices on the tile z axis (one head / one range)
+  int z_c_cols = 0; long long k_total = 0;                           // per-slice output column shift; true K extent
   int accumulate = 0;       // C += result (fp32 C, w_is_kn, no activation)
   const int* guard = nullptr;  // device flag: the launch is a no-op unless *guard != 0
 };
