@@ -474,6 +474,20 @@ class HIComProjector(nn.Module):
         assert local_compressor is not None or global_compressor is not None, \
             "At least one compressor should be provided."
 
+    def _fp32_shadow(self):
+        """fp32 copy of this projector for fp16 callers, rebuilt when a parameter changes.  Kept out of
+        ``_modules`` so it never shows up in ``state_dict()``."""
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in self.parameters())
+        cached = self.__dict__.get("_shadow")
+        if cached is None or cached[0] != key:
+            import copy
+            self.__dict__.pop("_shadow", None)
+            clone = copy.deepcopy(self)
+            clone.float()
+            clone.eval()
+            self.__dict__["_shadow"] = (key, clone)
+        return self.__dict__["_shadow"][1]
+
     # -- layout (mm_utils.py:92-140) -------------------------------------------------------------
     def _layout(self):
         merge = getattr(self.config, "mm_patch_merge_type", "flat")
@@ -543,6 +557,15 @@ class HIComProjector(nn.Module):
         _require_no_grad(self, X, frames_embed, guide_embed)
         if not X.is_cuda:
             raise RuntimeError("hicom_b200 ops run on CUDA tensors only (no CPU fallback)")
+        if X.dtype == torch.float16:
+            # The reference's inference path runs in fp16 (model/__init__.py:44, hicom/__init__.py:68, projector.py:53).
+            # fp16 has no kernel family of its own yet: evaluate on an fp32 shadow of the weights (fp32 is an exact
+            # superset of fp16, fp32 CUDA kernels) and round the tokens back once.
+            f32 = lambda t: None if t is None else t.float()
+            shadow = self._fp32_shadow()
+            out = shadow.forward_batched(X.float(), f32(frames_embed), f32(guide_embed), modal, f32(image_newline),
+                                         is_anyres=is_anyres, base=f32(base), with_global=with_global)
+            return None if out is None else out.to(torch.float16)
         B, T, H, W, d = X.shape
         lc = self.local_compressor
         gc = self.global_compressor if with_global else None

@@ -220,3 +220,21 @@ def test_batched_caller_matches_per_sample_loop(built_library):
     assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in want]
     for a, b in zip(got, want):
         assert O.rel_err(a.cpu(), b.cpu()) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["coarse_T8", "direct_T8", "fine_T8", "image_T1_newline"])
+def test_fp16_inference_dtype(name, built_library):
+    """The reference's inference path is fp16 (model/__init__.py:44; mm_infer casts inputs to fp16): fp16 weights and
+    inputs must work and match the fp32 oracle on the fp16-rounded values to fp16 rounding of the output."""
+    import dataclasses
+    case = dataclasses.replace(CASES_BY_NAME[name], dtype="float16")
+    sd, X, E, g, nl = materialise(case)
+    m = cuda_module_for(case, sd)
+    assert next(m.parameters()).dtype == torch.float16
+    with torch.inference_mode():
+        out = m(to_dev(X), to_dev(E), to_dev(g), case.modal, to_dev(nl))
+    assert out.dtype == torch.float16
+    assert set(m.state_dict().keys()) == set(sd.keys())  # the fp32 shadow never leaks into the state_dict
+    truth = truth_fp32(case)
+    assert out.shape == truth.shape
+    assert O.rel_err(out.float().cpu(), truth) <= 2e-3
