@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhicom_b200.so")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
-SOURCES = ["api.cu", "local_attend.cu", "gemm_simt.cu", "rowwise.cu", "gemm_tc.cu"]
+SOURCES = ["api.cu", "local_attend.cu", "gemm_simt.cu", "rowwise.cu", "gemm_tc.cu", "skinny.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

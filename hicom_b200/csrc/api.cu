@@ -54,6 +54,16 @@ void kernel_timing_end(cudaStream_t stream) {
   if (!g_timed.empty()) cudaEventRecord(g_timed.back().b, stream);
 }
 
+struct SkinnyParams {
+  const void* A; const void* W; const void* bias; const void* R; void* C;
+  long long lda, ldw, ldr, ldc;
+  int M, N, K, act;
+  float alpha;
+  int rows_per_group; long long group_stride_rows;
+};
+bool skinny_supported(int in_dtype, int M, int N, int K, long long lda, long long ldw, const void* A, const void* W);
+int launch_skinny(const SkinnyParams& p, int in_dtype, int out_dtype, cudaStream_t stream);
+
 static GemmParams plain_gemm() {
   GemmParams g{};
   g.nb1 = g.nb2 = 1;
@@ -133,6 +143,15 @@ extern "C" int hicom_linear(const void* A, int64_t lda, const void* W, int64_t l
   HICOM_REQUIRE(rows_per_group > 0, "linear: rows_per_group must be positive");
   HICOM_REQUIRE(act == HICOM_ACT_NONE || act == HICOM_ACT_GELU, "linear: bad activation %d", act);
   if (M == 0) return 0;
+  // skinny problems (M <= 32): warp-per-column kernel, all SMs stream the weights (see skinny.cu)
+  if (impl == HICOM_IMPL_AUTO && !(in_dtype == HICOM_F32 && out_dtype == HICOM_BF16) &&
+      skinny_supported(in_dtype, M, N, K, lda, ldw, A, W)) {
+    SkinnyParams k{};
+    k.A = A; k.W = W; k.bias = bias; k.R = R; k.C = C; k.lda = lda; k.ldw = ldw; k.ldr = ldr; k.ldc = ldc;
+    k.M = M; k.N = N; k.K = K; k.act = act; k.alpha = 1.f;
+    k.rows_per_group = rows_per_group; k.group_stride_rows = group_stride_rows;
+    return launch_skinny(k, in_dtype, out_dtype, as_stream(stream));
+  }
   const bool tc_ok = tc_linear_supported(in_dtype, out_dtype, M, N, K, lda, ldw, ldc, A, W, C);
   if (impl == HICOM_IMPL_TCGEN05) HICOM_REQUIRE(tc_ok, "linear: tcgen05 path does not support this problem");
   if (impl == HICOM_IMPL_TCGEN05 || (impl == HICOM_IMPL_AUTO && tc_ok)) {

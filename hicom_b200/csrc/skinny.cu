@@ -1,0 +1,135 @@
+// Skinny linear layer: C = act(alpha * A·Wᵀ + bias) + R for M <= 32 rows (one instruction vector per video: FiLM MLPs,
+// query/out projections, global readout at batch 1).  A 128-row tensor-core tile would be > 75 % padding and only
+// N/256 CTAs would stream the weights; here every warp owns output columns, streams W[n,:] once with 16-byte loads and
+// keeps the M x K activations in shared memory, so all SMs pull weights at HBM speed.  fp32 accumulation.
+#include "common.cuh"
+
+namespace hicom {
+
+struct SkinnyParams {
+  const void* A; const void* W; const void* bias; const void* R; void* C;
+  long long lda, ldw, ldr, ldc;
+  int M, N, K, act;
+  float alpha;
+  int rows_per_group; long long group_stride_rows;
+};
+
+template <typename T> struct Elems16;  // elements per 16-byte load
+template <> struct Elems16<float> { static constexpr int n = 4; };
+template <> struct Elems16<__nv_bfloat16> { static constexpr int n = 8; };
+
+template <typename T>
+__device__ __forceinline__ void load16(const T* p, float (&v)[Elems16<T>::n]);
+template <>
+__device__ __forceinline__ void load16<float>(const float* p, float (&v)[4]) {
+  const float4 r = *reinterpret_cast<const float4*>(p);
+  v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+template <>
+__device__ __forceinline__ void load16<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = __uint_as_float(w[e] << 16);
+    v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+
+template <typename TI, typename TO, int MMAX>
+__global__ void __launch_bounds__(256) skinny_linear_kernel(const SkinnyParams p) {
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  TI* As = reinterpret_cast<TI*>(sk_smem);  // (M, Kp) row-major, Kp = K rounded up to 16-byte chunks
+  constexpr int E = Elems16<TI>::n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int K = p.K, M = p.M;
+  const TI* A = static_cast<const TI*>(p.A);
+  for (int idx = threadIdx.x * E; idx < M * K; idx += blockDim.x * E) {
+    const int m = idx / K, k = idx % K;  // K % E == 0, so a chunk never crosses a row
+    *reinterpret_cast<uint4*>(As + (size_t)m * K + k) = *reinterpret_cast<const uint4*>(A + (size_t)m * p.lda + k);
+  }
+  __syncthreads();
+
+  const TI* W = static_cast<const TI*>(p.W);
+  for (int n = blockIdx.x * nwarps + warp; n < p.N; n += gridDim.x * nwarps) {
+    float acc[MMAX];
+#pragma unroll
+    for (int m = 0; m < MMAX; ++m) acc[m] = 0.f;
+    const TI* wrow = W + (size_t)n * p.ldw;
+    for (int k = lane * E; k < K; k += 32 * E) {
+      float w[E];
+      load16<TI>(wrow + k, w);
+#pragma unroll
+      for (int m = 0; m < MMAX; ++m) {
+        if (m < M) {
+          float a[E];
+          load16<TI>(As + (size_t)m * K + k, a);
+#pragma unroll
+          for (int e = 0; e < E; ++e) acc[m] = fmaf(a[e], w[e], acc[m]);
+        }
+      }
+    }
+    // reduce every accumulator over the warp; lane m ends up owning row m
+    float mine = 0.f;
+#pragma unroll
+    for (int m = 0; m < MMAX; ++m) {
+      const float s = warp_sum(acc[m]);
+      if (lane == m) mine = s;
+    }
+    if (lane < M) {
+      float v = mine * p.alpha;
+      if (p.bias) v += to_f32<TI>(static_cast<const TI*>(p.bias)[n]);
+      if (p.act == HICOM_ACT_GELU) v = gelu_erf(v);
+      if (p.R) v += to_f32<TI>(static_cast<const TI*>(p.R)[(size_t)lane * p.ldr + n]);
+      const long long orow = (long long)(lane / p.rows_per_group) * p.group_stride_rows + (lane % p.rows_per_group);
+      static_cast<TO*>(p.C)[orow * p.ldc + n] = from_f32<TO>(v);
+    }
+  }
+}
+
+bool skinny_supported(int in_dtype, int M, int N, int K, long long lda, long long ldw, const void* A, const void* W) {
+  (void)N;
+  const size_t es = in_dtype == HICOM_BF16 ? 2 : 4;
+  const int e16 = 16 / (int)es;
+  if (M < 1 || M > 32) return false;
+  if (K % e16 || lda % e16 || ldw % e16) return false;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) return false;
+  return (size_t)M * K * es <= 160 * 1024;
+}
+
+template <typename TI, typename TO>
+static int launch_skinny_t(const SkinnyParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t)p.M * p.K * sizeof(TI);
+  auto launch = [&](auto kern) -> int {
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      HICOM_REQUIRE(e == cudaSuccess, "skinny_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      configured = 160 * 1024;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (num_sms <= 0) num_sms = 148;
+    }
+    int blocks = (p.N + 7) / 8;
+    if (blocks > num_sms) blocks = num_sms;
+    KernelTimer timer("skinny_linear", stream);
+    kern<<<blocks, 256, smem, stream>>>(p);
+    return check_launch("skinny_linear_kernel");
+  };
+  if (p.M <= 8) return launch(skinny_linear_kernel<TI, TO, 8>);
+  return launch(skinny_linear_kernel<TI, TO, 32>);
+}
+
+int launch_skinny(const SkinnyParams& p, int in_dtype, int out_dtype, cudaStream_t stream) {
+  if (in_dtype == HICOM_BF16 && out_dtype == HICOM_BF16) return launch_skinny_t<__nv_bfloat16, __nv_bfloat16>(p, stream);
+  if (in_dtype == HICOM_BF16 && out_dtype == HICOM_F32) return launch_skinny_t<__nv_bfloat16, float>(p, stream);
+  if (in_dtype == HICOM_F32 && out_dtype == HICOM_F32) return launch_skinny_t<float, float>(p, stream);
+  set_error("skinny_linear: unsupported dtype combination %d/%d", in_dtype, out_dtype);
+  return 1;
+}
+
+}  // namespace hicom
