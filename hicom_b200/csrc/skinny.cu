@@ -97,31 +97,34 @@ bool skinny_supported(int in_dtype, int M, int N, int K, long long lda, long lon
   return (size_t)M * K * es <= 160 * 1024;
 }
 
+template <typename TI, typename TO, int MMAX>
+static int launch_skinny_m(const SkinnyParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t)p.M * p.K * sizeof(TI);
+  auto kern = skinny_linear_kernel<TI, TO, MMAX>;
+  static bool configured = false;  // one flag per kernel instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    HICOM_REQUIRE(e == cudaSuccess, "skinny_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  int blocks = (p.N + 7) / 8;
+  if (blocks > num_sms) blocks = num_sms;
+  KernelTimer timer("skinny_linear", stream);
+  kern<<<blocks, 256, smem, stream>>>(p);
+  return check_launch("skinny_linear_kernel");
+}
+
 template <typename TI, typename TO>
 static int launch_skinny_t(const SkinnyParams& p, cudaStream_t stream) {
-  const size_t smem = (size_t)p.M * p.K * sizeof(TI);
-  auto launch = [&](auto kern) -> int {
-    static size_t configured = 0;
-    if (smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-      HICOM_REQUIRE(e == cudaSuccess, "skinny_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      configured = 160 * 1024;
-    }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-      if (num_sms <= 0) num_sms = 148;
-    }
-    int blocks = (p.N + 7) / 8;
-    if (blocks > num_sms) blocks = num_sms;
-    KernelTimer timer("skinny_linear", stream);
-    kern<<<blocks, 256, smem, stream>>>(p);
-    return check_launch("skinny_linear_kernel");
-  };
-  if (p.M <= 8) return launch(skinny_linear_kernel<TI, TO, 8>);
-  return launch(skinny_linear_kernel<TI, TO, 32>);
+  if (p.M <= 8) return launch_skinny_m<TI, TO, 8>(p, stream);
+  return launch_skinny_m<TI, TO, 32>(p, stream);
 }
 
 int launch_skinny(const SkinnyParams& p, int in_dtype, int out_dtype, cudaStream_t stream) {
