@@ -25,7 +25,6 @@ namespace tc {
 constexpr int BM = 128;  // UMMA M (rows of the accumulator = TMEM lanes)
 constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UK = 16;   // K per tcgen05.mma for 16-bit inputs
-constexpr int STAGES = 4;
 constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 enum { EPI_LINEAR = 0, EPI_MAX = 1, EPI_PROB = 2, EPI_POOL = 3 };
@@ -200,6 +199,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // ---------------------------------------------------------------------------------------------
 template <int BN>
 struct Cfg {
+  // 128x64 tiles are for small problems (few tiles): more CTAs, deeper ring, so more weight bytes are in flight
+  static constexpr int STAGES = BN == 64 ? 8 : 4;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -240,9 +241,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + C::NBUF;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + C::NBUF);
 
@@ -254,7 +255,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -272,14 +273,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer: runs ahead across tiles through the STAGES-deep ring =====
+    // ===== TMA producer: runs ahead across tiles through the C::STAGES-deep ring =====
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile<EPI>(p, tile);
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+          const int s = it % C::STAGES;
+          const uint32_t ph = (it / C::STAGES) & 1;
           mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
@@ -333,8 +334,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+          const int s = it % C::STAGES;
+          const uint32_t ph = (it / C::STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
@@ -761,6 +762,19 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
     return launch<256, false, true, EPI_LINEAR, 6>(ta, tb, p, grid, stream);
   }
   const int flags = (q.act == HICOM_ACT_GELU ? 1 : 0) | (q.out_dtype == HICOM_F32 ? 2 : 0);
+  // small problems: 128x64 tiles spread over 4x more CTAs with an 8-deep ring (latency-bound otherwise)
+  if (!q.w_is_kn && q.z_slices == 0 && (long long)grid.x * grid.y < 74 && q.N >= 64) {
+    CUtensorMap tb64;
+    if (make_map(&tb64, q.W, kext, q.N, 1, q.ldw, 0, 64)) return 1;
+    p.b_box_rows = 64;
+    dim3 g64((q.N + 63) / 64, grid.y, 1);
+    switch (flags) {
+      case 0: return launch<64, false, false, EPI_LINEAR, 0>(ta, tb64, p, g64, stream);
+      case 1: return launch<64, false, false, EPI_LINEAR, 1>(ta, tb64, p, g64, stream);
+      case 2: return launch<64, false, false, EPI_LINEAR, 2>(ta, tb64, p, g64, stream);
+      case 3: return launch<64, false, false, EPI_LINEAR, 3>(ta, tb64, p, g64, stream);
+    }
+  }
 #define HICOM_TC_LINEAR_CASE(F)                                                                  \
   case F:                                                                                         \
     return q.w_is_kn ? launch<256, false, true, EPI_LINEAR, F>(ta, tb, p, grid, stream)          \

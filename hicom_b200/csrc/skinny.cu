@@ -1,7 +1,9 @@
-// Skinny linear layer: C = act(alpha * A·Wᵀ + bias) + R for M <= 32 rows (one instruction vector per video: FiLM MLPs,
-// query/out projections, global readout at batch 1).  A 128-row tensor-core tile would be > 75 % padding and only
+// Skinny linear layer: C = act(alpha * A·Wᵀ + bias) + R for M <= 8 rows (one instruction vector per video: the FiLM
+// MLPs at small batch).  A 128-row tensor-core tile would be > 75 % padding and only
 // N/256 CTAs would stream the weights; here every warp owns output columns, streams W[n,:] once with 16-byte loads and
 // keeps the M x K activations in shared memory, so all SMs pull weights at HBM speed.  fp32 accumulation.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hicom {
@@ -51,47 +53,66 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const SkinnyParams p
   __syncthreads();
 
   const TI* W = static_cast<const TI*>(p.W);
-  for (int n = blockIdx.x * nwarps + warp; n < p.N; n += gridDim.x * nwarps) {
-    float acc[MMAX];
+  // each warp owns two output columns at a time (twice the weight loads in flight)
+  for (int n0 = (blockIdx.x * nwarps + warp) * 2; n0 < p.N; n0 += gridDim.x * nwarps * 2) {
+    const bool two = n0 + 1 < p.N;
+    float acc[2][MMAX];
 #pragma unroll
-    for (int m = 0; m < MMAX; ++m) acc[m] = 0.f;
-    const TI* wrow = W + (size_t)n * p.ldw;
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int m = 0; m < MMAX; ++m) acc[c][m] = 0.f;
+    const TI* w0 = W + (size_t)n0 * p.ldw;
+    const TI* w1 = W + (size_t)(two ? n0 + 1 : n0) * p.ldw;
+#pragma unroll 3
     for (int k = lane * E; k < K; k += 32 * E) {
-      float w[E];
-      load16<TI>(wrow + k, w);
+      float wa[E], wb[E];
+      load16<TI>(w0 + k, wa);
+      load16<TI>(w1 + k, wb);
 #pragma unroll
       for (int m = 0; m < MMAX; ++m) {
         if (m < M) {
           float a[E];
           load16<TI>(As + (size_t)m * K + k, a);
 #pragma unroll
-          for (int e = 0; e < E; ++e) acc[m] = fmaf(a[e], w[e], acc[m]);
+          for (int e = 0; e < E; ++e) {
+            acc[0][m] = fmaf(a[e], wa[e], acc[0][m]);
+            acc[1][m] = fmaf(a[e], wb[e], acc[1][m]);
+          }
         }
       }
     }
-    // reduce every accumulator over the warp; lane m ends up owning row m
-    float mine = 0.f;
 #pragma unroll
-    for (int m = 0; m < MMAX; ++m) {
-      const float s = warp_sum(acc[m]);
-      if (lane == m) mine = s;
-    }
-    if (lane < M) {
-      float v = mine * p.alpha;
-      if (p.bias) v += to_f32<TI>(static_cast<const TI*>(p.bias)[n]);
-      if (p.act == HICOM_ACT_GELU) v = gelu_erf(v);
-      if (p.R) v += to_f32<TI>(static_cast<const TI*>(p.R)[(size_t)lane * p.ldr + n]);
-      const long long orow = (long long)(lane / p.rows_per_group) * p.group_stride_rows + (lane % p.rows_per_group);
-      static_cast<TO*>(p.C)[orow * p.ldc + n] = from_f32<TO>(v);
+    for (int c = 0; c < 2; ++c) {
+      if (c == 1 && !two) break;
+      const int n = n0 + c;
+      // reduce every accumulator over the warp; lane m ends up owning row m
+      float mine = 0.f;
+#pragma unroll
+      for (int m = 0; m < MMAX; ++m) {
+        const float sum = warp_sum(acc[c][m]);
+        if (lane == m) mine = sum;
+      }
+      if (lane < M) {
+        float v = mine * p.alpha;
+        if (p.bias) v += to_f32<TI>(static_cast<const TI*>(p.bias)[n]);
+        if (p.act == HICOM_ACT_GELU) v = gelu_erf(v);
+        if (p.R) v += to_f32<TI>(static_cast<const TI*>(p.R)[(size_t)lane * p.ldr + n]);
+        const long long orow = (long long)(lane / p.rows_per_group) * p.group_stride_rows + (lane % p.rows_per_group);
+        static_cast<TO*>(p.C)[orow * p.ldc + n] = from_f32<TO>(v);
+      }
     }
   }
 }
 
+static int kSkinnyMaxRows = 8;  // beyond this the 128-row tensor tile is faster (measured); HICOM_SKINNY_MAX overrides
+
 bool skinny_supported(int in_dtype, int M, int N, int K, long long lda, long long ldw, const void* A, const void* W) {
   (void)N;
+  static bool init = false;
+  if (!init) { const char* e = getenv("HICOM_SKINNY_MAX"); if (e) kSkinnyMaxRows = atoi(e); init = true; }
   const size_t es = in_dtype == HICOM_BF16 ? 2 : 4;
   const int e16 = 16 / (int)es;
-  if (M < 1 || M > 32) return false;
+  if (M < 1 || M > kSkinnyMaxRows) return false;
   if (K % e16 || lda % e16 || ldw % e16) return false;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) return false;
   return (size_t)M * K * es <= 160 * 1024;
@@ -114,7 +135,7 @@ static int launch_skinny_m(const SkinnyParams& p, cudaStream_t stream) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  int blocks = (p.N + 7) / 8;
+  int blocks = (p.N + 15) / 16;  // 8 warps x 2 columns per block
   if (blocks > num_sms) blocks = num_sms;
   KernelTimer timer("skinny_linear", stream);
   kern<<<blocks, 256, smem, stream>>>(p);
@@ -123,6 +144,7 @@ static int launch_skinny_m(const SkinnyParams& p, cudaStream_t stream) {
 
 template <typename TI, typename TO>
 static int launch_skinny_t(const SkinnyParams& p, cudaStream_t stream) {
+  if (p.M <= 2) return launch_skinny_m<TI, TO, 2>(p, stream);
   if (p.M <= 8) return launch_skinny_m<TI, TO, 8>(p, stream);
   return launch_skinny_m<TI, TO, 32>(p, stream);
 }

@@ -29,7 +29,7 @@ def test_grid_pool(shape, dtype, built_library):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("M,N,K", [(1, 2304, 1152), (7, 1152, 1152), (32, 2304, 2304), (32, 3584, 1152), (33, 64, 1152),
+@pytest.mark.parametrize("M,N,K", [(1, 2304, 1152), (2, 2305, 1152), (7, 1152, 1152), (8, 2304, 2304), (32, 3584, 1152), (33, 64, 1152),
                                    (324, 896, 1152), (700, 1152, 1152), (64, 3584, 3584)])
 @pytest.mark.parametrize("act", [0, 1])
 def test_linear(M, N, K, act, dtype, built_library):
