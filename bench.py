@@ -177,6 +177,37 @@ def cpu_reference(hidden, T, videos, steps, warmup):
     return videos * T / sec, sec * 1e3, cores
 
 
+def gpu_eager_reference(hidden, T, videos, device, steps=5, warmup=2):
+    """frames/s of the reference algorithm as plain torch ops in eager PyTorch/cuBLAS ON THE SAME B200 (bf16, per-video
+    loop like hicom_arch.py:167-178) — BASELINE.md §5 'Baseline B', the existing-Blackwell bar.  Oracle code, reported
+    only."""
+    from oracle import hicom_oracle as O
+    sd = {k: v.to(device=device, dtype=torch.bfloat16) for k, v in O.synth_state_dict(PTYPE, USE_GUIDE, hidden, seed=0).items()}
+    orc = O.OracleProjector(PTYPE, USE_GUIDE, "flat", "one_token", sd)
+    inputs = [tuple(t.to(device=device, dtype=torch.bfloat16) for t in O.synth_inputs(T, H, W, "vec", seed=1234 + i))
+              for i in range(videos)]
+    pe = O.pos_embed_3d(T, H, W, D).to(device)
+    O_pos = O.pos_embed_3d
+    O.pos_embed_3d = lambda t, h, w, d: pe[:t, :h, :w]  # the reference keeps this table as a resident buffer
+    try:
+        with torch.no_grad():
+            for _ in range(warmup):
+                for X, E, g in inputs:
+                    orc.forward(X, E, g, "video")
+            torch.cuda.synchronize(device)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                for X, E, g in inputs:
+                    orc.forward(X, E, g, "video")
+            b.record()
+            torch.cuda.synchronize(device)
+    finally:
+        O.pos_embed_3d = O_pos
+    ms = a.elapsed_time(b) / steps
+    return videos * T / (ms * 1e-3), ms
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -386,6 +417,16 @@ def run_ours(args):
                "sample": f"2 videos of {Tc} frames per step x 3 steps, fp32, torch CPU oracle port of "
                          "projector.py:676-708 (the reference has no native code to compile)"}
 
+    gpu_eager = None
+    if world == 1 and not args.no_cpu_baseline and not frame_sharded:
+        try:
+            fps_e, ms_e = gpu_eager_reference(hidden, T, 4, device)
+            gpu_eager = {"value": fps_e, "unit": "frames/s", "ms_per_step": ms_e, "kind": "port",
+                         "sample": "4 videos per step x 5 steps, bf16, the reference algorithm as plain torch ops in eager "
+                                   "PyTorch/cuBLAS on this B200 (per-video loop), inputs resident"}
+        except Exception as exc:  # reported, never fatal
+            gpu_eager = {"unavailable": repr(exc)[:200]}
+
     line = {
         "metric": "frames/s through the HICom compressor", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -403,6 +444,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": roof,
         "cpu_baseline": cpu,
+        "gpu_eager_baseline": gpu_eager,
         "ops": ops_table,
         "kernels": kernels_table,
     }
