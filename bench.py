@@ -70,7 +70,8 @@ def work_per_video(hidden, T):
         # what this implementation executes on the tensor pipe (reassociated global path)
         "flops_scores": 2 * N * J * D, "flops_pool": 2 * N * J * D,
         "flops_local_readout": 2 * Nw * (D * hidden + hidden * hidden),
-        "bytes_local": (2 * N * D + Nw * D) * 2,  # read X and E once, write attended windows (bf16)
+        # read X (and E when an instruction is given) once, write attended windows (bf16)
+        "bytes_local": ((1 if USE_GUIDE is None else 2) * N * D + Nw * D) * 2,
         "bytes_in": 2 * N * D * 2, "bytes_out": (Nw + Q) * hidden * 2,
     }
 
@@ -164,7 +165,7 @@ def cpu_reference(hidden, T, videos, steps, warmup):
     torch.set_num_threads(cores)
     sd = O.synth_state_dict(PTYPE, USE_GUIDE, hidden, seed=0)
     orc = O.OracleProjector(PTYPE, USE_GUIDE, "flat", "one_token", sd)
-    inputs = [O.synth_inputs(T, H, W, "vec", seed=1234 + i) for i in range(videos)]
+    inputs = [O.synth_inputs(T, H, W, O.guide_kind_for(USE_GUIDE), seed=1234 + i) for i in range(videos)]
     times = []
     with torch.no_grad():
         for it in range(warmup + steps):
@@ -184,8 +185,8 @@ def gpu_eager_reference(hidden, T, videos, device, steps=5, warmup=2):
     from oracle import hicom_oracle as O
     sd = {k: v.to(device=device, dtype=torch.bfloat16) for k, v in O.synth_state_dict(PTYPE, USE_GUIDE, hidden, seed=0).items()}
     orc = O.OracleProjector(PTYPE, USE_GUIDE, "flat", "one_token", sd)
-    inputs = [tuple(t.to(device=device, dtype=torch.bfloat16) for t in O.synth_inputs(T, H, W, "vec", seed=1234 + i))
-              for i in range(videos)]
+    inputs = [tuple(None if t is None else t.to(device=device, dtype=torch.bfloat16)
+                    for t in O.synth_inputs(T, H, W, O.guide_kind_for(USE_GUIDE), seed=1234 + i)) for i in range(videos)]
     pe = O.pos_embed_3d(T, H, W, D).to(device)
     O_pos = O.pos_embed_3d
     O.pos_embed_3d = lambda t, h, w, d: pe[:t, :h, :w]  # the reference keeps this table as a resident buffer
@@ -281,6 +282,8 @@ def run_ours(args):
     X, E, G = synth_batch(B, T_local, device, 1234 + rank)
     if frame_sharded:  # every rank must see the same instruction vector
         G = synth_batch(1, 4, device, 99)[2]
+    if USE_GUIDE is None:  # stage-1 mode: no instruction, keys = features (frames_embed is None, encoder.py:288-290)
+        E = G = None
 
     def eager_step():
         if frame_sharded:
@@ -350,7 +353,7 @@ def run_ours(args):
     # ---- end-to-end through the public host API (rank-local; copies inside the timed region) -------
     e2e = None
     if not frame_sharded:
-        Xh, Eh, Gh = (t.cpu().pin_memory() for t in (X, E, G))
+        Xh, Eh, Gh = (None if t is None else t.cpu().pin_memory() for t in (X, E, G))
         n_tok = out.shape[1]
         out_h = torch.empty((B, n_tok, hidden), dtype=torch.bfloat16).pin_memory()
         for _ in range(2):
@@ -368,7 +371,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
         e2e = {"value": B * T * world / (float(e_ms) * 1e-3), "unit": "frames/s",
-               "h2d_bytes_per_step": int(Xh.numel() * 2 + Eh.numel() * 2 + Gh.numel() * 2) * world,
+               "h2d_bytes_per_step": int(sum(t.numel() * 2 for t in (Xh, Eh, Gh) if t is not None)) * world,
                "d2h_bytes_per_step": int(out_h.numel() * 2) * world, "ms_per_step": float(e_ms),
                "api": "hicom_b200.pipeline.compress_from_host (pinned host buffers, 2-stream chunked overlap)"}
 
@@ -461,9 +464,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--use-guide", default=USE_GUIDE, choices=["coarse", "direct", "none"],
+                    help="guide mode (headline: coarse; direct = what the released checkpoint runs; none = stage 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
+    global USE_GUIDE
+    USE_GUIDE = None if args.use_guide == "none" else args.use_guide
     if args.impl == "reference":
         run_reference(args)
     else:

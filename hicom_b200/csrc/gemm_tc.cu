@@ -801,7 +801,7 @@ bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W) 
   (void)T;
   if (impl == HICOM_IMPL_SIMT) return false;
   // the algebraic position-embedding path needs: chunks of 32 tokens spanning <= 2 frames, H + W indicator columns
-  return dtype == HICOM_BF16 && d % 128 == 0 && J == 288 && H * W >= 32 && H + W <= kKe;
+  return dtype == HICOM_BF16 && d % 128 == 0 && J >= 1 && J <= 288 && H * W >= 32 && H + W <= kKe;
 }
 
 struct GlobalWs {
@@ -963,14 +963,18 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   // pooling: O[b,s] (d x J) = [X[b, tokens of s] ; pe2]ᵀ · [P ; marg]  — the table/marginal K blocks ride on split 0
   CUtensorMap txa, tp, tpe, tmg;
   if (make_map(&txa, X, d, N, B, d, (uint64_t)N * d, 64)) return 1;
-  if (make_map(&tp, Pt, w.pt_ld, J, B, w.pt_ld, (uint64_t)J * w.pt_ld, 96)) return 1;
+  // J <= 64 (e.g. `direct` mode: one distinct query per video -> 9 columns) uses the narrow 128x64 pooling tile, which is
+  // bound by streaming X instead of by MMAs on padding columns
+  const bool narrow = J <= 64;
+  const uint32_t pool_box = narrow ? 64 : 96;
+  if (make_map(&tp, Pt, w.pt_ld, J, B, w.pt_ld, (uint64_t)J * w.pt_ld, pool_box)) return 1;
   if (make_map(&tpe, pe2, d, w.ke2, 1, d, 0, 64)) return 1;
-  if (make_map(&tmg, marg, w.ke2, J, B, w.ke2, (uint64_t)J * w.ke2, 96)) return 1;
+  if (make_map(&tmg, marg, w.ke2, J, B, w.ke2, (uint64_t)J * w.ke2, pool_box)) return 1;
   Params g{};
   g.M = d; g.N = J; g.K = N;
   int chunk = (N + splits - 1) / splits;
   chunk = (chunk + BK - 1) / BK * BK;
-  g.k_chunk = chunk; g.b_box_rows = 96;
+  g.k_chunk = chunk; g.b_box_rows = (int)pool_box;
   g.o = o; g.splits = splits; g.k_ext_blocks = w.ke2 / BK;
   dim3 gp(splits, d / BM, B);
   const unsigned pack_blocks = (unsigned)((BJ * tcols + 255) / 256);
@@ -995,7 +999,8 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
   if (launch_tc_linear(ms, stream)) return 1;
   pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kSpatialSlices * kKe, tcols, BJ, nullptr);
   if (check_launch("pack_margT_kernel")) return 1;
-  if (launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream, &tpe, &tmg)) return 1;
+  if (narrow ? launch<64, true, false, EPI_POOL>(txa, tp, g, gp, stream, &tpe, &tmg)
+             : launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream, &tpe, &tmg)) return 1;
   // 4. guarded exact fallback (no-ops unless some score beat the sampled max by > 80 nats): redo 2-3 with the true max
   {
     repair_stab_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, stab, lg, (int)BJ, flag);
@@ -1009,7 +1014,8 @@ int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, cons
     if (launch_tc_linear(msf, stream)) return 1;
     pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kSpatialSlices * kKe, tcols, BJ, flag);
     if (check_launch("pack_margT_kernel")) return 1;
-    if (launch<288, true, false, EPI_POOL>(txa, tp, gf, gp, stream, &tpe, &tmg)) return 1;
+    if (narrow ? launch<64, true, false, EPI_POOL>(txa, tp, gf, gp, stream, &tpe, &tmg)
+               : launch<288, true, false, EPI_POOL>(txa, tp, gf, gp, stream, &tpe, &tmg)) return 1;
   }
   spread_stats_kernel<<<(unsigned)((BJ * splits + 255) / 256), 256, 0, stream>>>(stab, lg, m, l, B, splits, J);
   return check_launch("spread_stats_kernel");

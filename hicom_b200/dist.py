@@ -90,7 +90,8 @@ def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, 
                 m, l, o = ops.softmax_reduce(m, l, o)
             m, l, o = gather_partials(m, l, o, group)
         Dh = gc.readout[-1].out_features
-        global_tokens = torch.empty((B * Qg.shape[1], Dh), dtype=X.dtype, device=X.device)
-        gc.finish(Qg, m, l, o, global_tokens, 0, Qg.shape[1])
-        global_tokens = global_tokens.view(B, Qg.shape[1], Dh)
+        nq = gc.query.shape[0]  # Qg may hold one row per video (direct mode); finish() replicates it
+        global_tokens = torch.empty((B * nq, Dh), dtype=X.dtype, device=X.device)
+        gc.finish(Qg, m, l, o, global_tokens, 0, nq)
+        global_tokens = global_tokens.view(B, nq, Dh)
     return local_tokens, global_tokens

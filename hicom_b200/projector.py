@@ -394,8 +394,13 @@ class GlobalCompressor(nn.Module):
         return pt[t0:t0 + T].contiguous(), ph[:H].contiguous(), pw[:W].contiguous()
 
     def injected_query(self, guide, B, dtype):
-        """(B,Q,d) queries after the guide injector (projector.py:642)."""
+        """(B,Q,d) queries after the guide injector (projector.py:642).  In `direct` mode the injector returns the
+        guide for every query (projector.py:367-368), so all Q rows are identical: only ONE row per video is returned
+        and `finish` replicates the resulting token Q times — exact, and 32x less score/pooling work."""
         Q, d = self.query.shape
+        if self.use_guide == "direct":
+            self.guide_injector.check_guide(guide, 0)
+            return self.guide_injector.prepared_guide(guide).unsqueeze(1).contiguous()  # (B,1,d)
         rows = self.query.to(dtype).unsqueeze(0).expand(B, Q, d).contiguous()
         if self.use_guide in (None, "off"):
             return rows
@@ -414,10 +419,15 @@ class GlobalCompressor(nn.Module):
     def finish(self, Qg, m, l, o, out, row_offset, group_stride):
         """merge -> v_proj -> out_proj + residual -> readout, written into rows of ``out`` (projector.py:215-226,646)."""
         attn = self.attn_layer
+        nq, nrows = self.query.shape[0], Qg.shape[1]
         pooled = ops.softmax_merge(m, l, o, Qg.dtype == torch.bfloat16)
-        a = ops.global_value_proj(pooled, attn.v_proj.weight, attn.v_proj.bias, Qg.shape[1], attn.num_heads)
+        a = ops.global_value_proj(pooled, attn.v_proj.weight, attn.v_proj.bias, nrows, attn.num_heads)
         x = ops.linear(a, attn.out_proj.weight, attn.out_proj.bias, Qg, ops.ACT_NONE, False, _IMPL)
-        _mlp_into(self.readout, x, out, row_offset, Qg.shape[1], group_stride)
+        _mlp_into(self.readout, x, out, row_offset, nrows, group_stride)
+        if nrows != nq:  # direct mode: one distinct query per video -> replicate its token (projector.py:367-368)
+            B = Qg.shape[0]
+            view = out.view(B, group_stride, -1) if group_stride else out.unsqueeze(0)
+            view[:, row_offset + 1:row_offset + nq] = view[:, row_offset:row_offset + 1]
 
     def fold(self, Qg, logit_scale=None):
         attn = self.attn_layer
@@ -434,7 +444,7 @@ class GlobalCompressor(nn.Module):
         g = None if guide_embed is None else guide_embed.unsqueeze(0)
         Qg = self.injected_query(g, 1, X.dtype)
         m, l, o = self.partials(X, self.fold(Qg, logit_scale))
-        out = torch.empty((Qg.shape[1], self.readout[-1].out_features), dtype=X.dtype, device=X.device)
+        out = torch.empty((self.query.shape[0], self.readout[-1].out_features), dtype=X.dtype, device=X.device)
         self.finish(Qg, m, l, o, out, 0, 0)
         return out
 
