@@ -458,6 +458,7 @@ def run_ours(args):
 
 
 def main():
+    global USE_GUIDE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -469,7 +470,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
-    global USE_GUIDE
     USE_GUIDE = None if args.use_guide == "none" else args.use_guide
     if args.impl == "reference":
         run_reference(args)
