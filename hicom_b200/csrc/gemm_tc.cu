@@ -27,7 +27,7 @@ constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UK = 16;   // K per tcgen05.mma for 16-bit inputs
 constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
-enum { EPI_LINEAR = 0, EPI_MAX = 1, EPI_PROB = 2, EPI_POOL = 3 };
+enum { EPI_LINEAR = 0, EPI_MAX = 1, EPI_PROB = 2, EPI_POOL = 3, EPI_PROB2 = 4 };
 
 struct Params {
   int M, N, K;       // valid rows of A / rows of B / reduction length (per batch)
@@ -53,6 +53,8 @@ struct Params {
   // position embedding folded in algebraically (no x' = x + PE tensor):
   int k_ext_blocks;                // EPI_MAX/PROB: extra K blocks taken from the second map pair (spatial PE term)
   int HW, T;                       // tokens per frame, frames
+  long long c_batch_rows;          // EPI_LINEAR: output rows are shifted by batch*c_batch_rows (batched GEMMs)
+  __nv_bfloat16* P2; long long p2_ld;  // EPI_PROB2: probabilities (B, tokens, p2_ld), token-major
   const float* peq_t; long long peq_ld;  // (T, B*J) time term of the scores: pos_t[t]·qfold[b,j]
   float* margT; int margT_ld;      // (B*J, margT_ld) sum of probabilities per frame (EPI_PROB accumulates)
 
@@ -202,7 +204,7 @@ struct Cfg {
   // 128x64 tiles are for small problems (few tiles): more CTAs, deeper ring, so more weight bytes are in flight
   static constexpr int STAGES = BN == 64 ? 8 : 4;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
-  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t B_BYTES = ((BN + 63) / 64) * 64 * BK * 2;  // whole 64-wide blocks (MN-major B needs them)
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NBUF = BN <= 256 ? 2 : 1;          // accumulator buffers in TMEM (epilogue/mainloop overlap)
   static constexpr uint32_t ACC_COLS = BN <= 256 ? 256 : 512;
@@ -221,15 +223,16 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
   const int y = (tile / p.tiles_x) % p.tiles_y;
   const int z = tile / (p.tiles_x * p.tiles_y);
   t.m_tile = y;
-  t.zslice = p.z_slices > 0 ? z : 0;
-  t.batch = p.z_slices > 0 ? 0 : z;
+  t.zslice = p.z_slices > 0 ? z % p.z_slices : 0;
+  t.batch = p.z_slices > 0 ? z / p.z_slices : z;
   t.n_tile = (EPI == EPI_POOL) ? 0 : x * (p.n_tile_stride > 0 ? p.n_tile_stride : 1);
   t.split = (EPI == EPI_POOL) ? x : 0;
   t.k_begin = t.split * p.k_chunk;
   int k_end = t.k_begin + p.k_chunk;
   if (k_end > p.K) k_end = p.K;
   t.nkb_main = k_end > t.k_begin ? (k_end - t.k_begin + BK - 1) / BK : 0;
-  t.nkb = t.nkb_main + ((EPI == EPI_MAX || EPI == EPI_PROB || (EPI == EPI_POOL && t.split == 0)) ? p.k_ext_blocks : 0);
+  t.nkb = t.nkb_main + ((EPI == EPI_MAX || EPI == EPI_PROB || EPI == EPI_PROB2 || (EPI == EPI_POOL && t.split == 0))
+                            ? p.k_ext_blocks : 0);
   return t;
 }
 
@@ -237,7 +240,8 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
 template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const Params p) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB3, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -284,31 +288,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           const int k0 = t.k_begin + kb * BK;
-          const bool ext = (EPI == EPI_MAX || EPI == EPI_PROB || EPI == EPI_POOL) && kb >= t.nkb_main;
+          const bool ext = (EPI != EPI_LINEAR) && kb >= t.nkb_main;
+          const int ke = ext ? kb - t.nkb_main : 0;  // which extension block
+          // MN-major B arrives as whole 64-wide blocks; K-major B as BN rows
+          const bool b_mn_now = B_MN && !(EPI == EPI_POOL && ext);
+          mbar_expect_tx(&full_bar[s], C::A_BYTES + (b_mn_now ? C::B_BYTES : (uint32_t)BN * BK * 2));
           if (A_MN) {
             // A[m, k] stored (k rows, m contiguous): two 64-wide M blocks of (BK rows x 128 B)
             if (ext) {  // position tables (ke2 rows x d), shared by all videos: rows = [pos_h ; pos_w ; 0 | pos_t ; 0]
-              const int kx = (kb - t.nkb_main) * BK;
-              tma_load_3d(sa, &tmA2, &full_bar[s], t.m_tile * BM, kx, 0);
-              tma_load_3d(sa + BK * 128, &tmA2, &full_bar[s], t.m_tile * BM + 64, kx, 0);
+              tma_load_3d(sa, &tmA2, &full_bar[s], t.m_tile * BM, ke * BK, 0);
+              tma_load_3d(sa + BK * 128, &tmA2, &full_bar[s], t.m_tile * BM + 64, ke * BK, 0);
             } else {
               tma_load_3d(sa, &tmA, &full_bar[s], t.m_tile * BM, k0, t.batch);
               tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], t.m_tile * BM + 64, k0, t.batch);
             }
+          } else if (ext && EPI == EPI_PROB2) {
+            // token-side extension columns (shared by all videos): block 0 = [h | w one-hot, ones], block 1 = frame
+            // index relative to the first token of this 128-token tile
+            tma_load_3d(sa, ke == 0 ? &tmA2 : &tmA3, &full_bar[s], 0, t.m_tile * BM, 0);
           } else if (ext) {
-            tma_load_3d(sa, &tmA2, &full_bar[s], (kb - t.nkb_main) * BK, t.m_tile * BM, t.batch);
+            tma_load_3d(sa, &tmA2, &full_bar[s], ke * BK, t.m_tile * BM, t.batch);
           } else {
             tma_load_3d(sa, &tmA, &full_bar[s], k0 + t.zslice * p.z_a_k, t.m_tile * BM, t.batch);
           }
-          if (ext && EPI == EPI_POOL) {  // probability marginals (J x ke2) of this video, K-major
+          if (ext && EPI == EPI_PROB2) {
+            // query-side extension rows: block 0 = [pos_h·q | pos_w·q | -stab]; block 1 = pos_t[f0 + k]·q, i.e. the
+            // time table read at the tile's first frame (a TMA coordinate), matching the relative one-hot above
+            const int f0 = (t.m_tile * BM) / p.HW;
             for (int r = 0; r < BN; r += p.b_box_rows)
-              tma_load_3d(sb + r * 128, &tmB2, &full_bar[s], (kb - t.nkb_main) * BK, r, t.batch);
+              tma_load_3d(sb + r * 128, ke == 0 ? &tmB2 : &tmB3, &full_bar[s], ke == 0 ? 0 : f0, t.n_tile * BN + r, t.batch);
+          } else if (ext && EPI == EPI_POOL) {  // probability marginals (J x ke2) of this video, K-major
+            for (int r = 0; r < BN; r += p.b_box_rows)
+              tma_load_3d(sb + r * 128, &tmB2, &full_bar[s], ke * BK, r, t.batch);
           } else if (ext) {
-            tma_load_3d(sb, &tmB2, &full_bar[s], (kb - t.nkb_main) * BK, t.n_tile * BN, 0);  // (tokens x ke) indicator
+            tma_load_3d(sb, &tmB2, &full_bar[s], ke * BK, t.n_tile * BN, 0);  // (tokens x ke) indicator
           } else if (B_MN) {
-            // B[k, n] stored (k rows, n contiguous): BN/64 blocks of (BK rows x 128 B)
+            // B[k, n] stored (k rows, n contiguous): whole 64-wide blocks of (BK rows x 128 B)
             for (int r = 0; r < BN; r += 64)
               tma_load_3d(sb + (r / 64) * (BK * 128), &tmB, &full_bar[s], t.n_tile * BN + r,
                           k0 + t.zslice * p.z_b_k, t.batch);
@@ -322,9 +338,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      static_assert(!(B_MN && BN > 256), "MN-major B is only wired for a single N<=256 instruction");
-      constexpr uint32_t idesc_main = make_idesc(BN > 256 ? 256 : BN, A_MN, B_MN);
-      constexpr uint32_t idesc_tail = make_idesc(BN > 256 ? BN - 256 : 8, A_MN, B_MN);
+      constexpr int N_MAIN = BN > 256 ? 256 : BN, N_TAIL = BN > 256 ? BN - 256 : 8;
+      constexpr uint32_t idesc_main_mn = make_idesc(N_MAIN, A_MN, true), idesc_main_k = make_idesc(N_MAIN, A_MN, false);
+      constexpr uint32_t idesc_tail_mn = make_idesc(N_TAIL, A_MN, true), idesc_tail_k = make_idesc(N_TAIL, A_MN, false);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const TileInfo t = decode_tile<EPI>(p, tile);
@@ -340,18 +356,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
+          // the pooling GEMM's extension blocks carry a K-major B (marginals) next to an MN-major main B (probabilities)
+          const bool b_mn_now = B_MN && !(EPI == EPI_POOL && kb >= t.nkb_main);
+          const uint32_t idesc_main = b_mn_now ? idesc_main_mn : idesc_main_k;
+          const uint32_t idesc_tail = b_mn_now ? idesc_tail_mn : idesc_tail_k;
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk) {
             // K-major: +32 B per 16-element K slice inside the 128 B swizzle row (SBO = 8 rows x 128 B).
             // MN-major: 16 k-rows = two 1024 B swizzle atoms per slice; LBO = stride between 64-wide MN blocks.
             const uint64_t adesc = A_MN ? make_smem_desc(sa + kk * 2048, BK * 128, 1024)
                                         : make_smem_desc(sa + kk * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(sb + kk * 2048, BK * 128, 1024)
-                                        : make_smem_desc(sb + kk * 32, 16, 1024);
+            const uint64_t bdesc = b_mn_now ? make_smem_desc(sb + kk * 2048, BK * 128, 1024)
+                                            : make_smem_desc(sb + kk * 32, 16, 1024);
             const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
             umma_bf16(d_tmem, adesc, bdesc, idesc_main, acc);
             if (BN > 256) {
-              const uint64_t bdesc2 = make_smem_desc(sb + 256 * 128 + kk * 32, 16, 1024);
+              // columns 256.. : K-major -> 256 rows further; MN-major -> the fifth 64-wide block
+              const uint64_t bdesc2 = b_mn_now ? make_smem_desc(sb + 4 * (BK * 128) + kk * 2048, BK * 128, 1024)
+                                               : make_smem_desc(sb + 256 * 128 + kk * 32, 16, 1024);
               umma_bf16(d_tmem + 256, adesc, bdesc2, idesc_tail, acc);
             }
           }
@@ -389,7 +411,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         my_head = (row / p.diag_rows) % p.diag_heads;
         orow = (long long)(row / (p.diag_rows * p.diag_heads)) * p.diag_rows + row % p.diag_rows;
       }
-      orow += (long long)zslice * p.z_c_rows;
+      orow += (long long)zslice * p.z_c_rows + (long long)batch * p.c_batch_rows;
       const bool has_bias = p.bias != nullptr, has_res = p.R != nullptr;
       const int n_chunks = (p.N - n_tile * BN + 31) / 32 < BN / 32 ? (p.N - n_tile * BN + 31) / 32 : BN / 32;
       for (int c = half; c < n_chunks; c += 2) {  // warp-uniform trip count: tcgen05.ld needs the whole warp
@@ -482,6 +504,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (i < nvalid) dst[i] = v[i];
             }
           }
+        }
+      }
+    } else if (EPI == EPI_PROB2) {
+      // rows = tokens (M), columns = score columns j (N).  The accumulator already holds S - stab in natural units
+      // (position terms and the stabiliser ride on extension K blocks), so the epilogue is exp2 + pack + 16-byte stores.
+      const bool row_ok = row < p.M;
+      __nv_bfloat16* prow = p.P2 + ((size_t)batch * p.M + (row_ok ? row : 0)) * p.p2_ld + (size_t)n_tile * BN;
+      const int ncols = (int)p.p2_ld - n_tile * BN;  // columns of this tile that exist in memory (multiple of 32)
+      for (int c = half; c < (BN + 31) / 32; c += 2) {
+        if (c * 32 >= ncols) break;  // warp-uniform
+        tmem_ld32(taddr + c * 32, v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) pk[i / 2] = pack_bf16(ex2_approx(v[i] * kLog2e), ex2_approx(v[i + 1] * kLog2e));
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(prow + c * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
         }
       }
     } else if (EPI == EPI_MAX && t.m_tile * BM + q * 32 >= p.M) {
@@ -689,7 +729,8 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS = 0>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t stream,
-                  const CUtensorMap* ta2 = nullptr, const CUtensorMap* tb2 = nullptr) {
+                  const CUtensorMap* ta2 = nullptr, const CUtensorMap* tb2 = nullptr,
+                  const CUtensorMap* ta3 = nullptr, const CUtensorMap* tb3 = nullptr) {
   static bool configured = false;
   auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI, FLAGS>;
   if (!configured) {
@@ -711,12 +752,13 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   const unsigned ctas = (unsigned)(total < num_sms ? total : num_sms);  // persistent: one CTA per SM at most
   char label[96];
   if (kernel_timing_enabled()) {
-    static const char* names[] = {"tc_linear", "tc_scores_max", "tc_scores_prob", "tc_pool"};
+    static const char* names[] = {"tc_linear", "tc_scores_max", "tc_scores_prob", "tc_pool", "tc_scores_prob2"};
     snprintf(label, sizeof(label), "%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI], (FLAGS & 1) ? "+gelu" : "", p.M, p.N,
              p.K, total, p.guard ? " guarded" : "");
   }
   KernelTimer timer(label, stream);
-  kern<<<ctas, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, pp);
+  kern<<<ctas, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, ta3 ? *ta3 : ta,
+                                                           tb3 ? *tb3 : tb, pp);
   return check_launch("tc_gemm_kernel");
 }
 
