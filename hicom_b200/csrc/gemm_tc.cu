@@ -13,6 +13,7 @@
 //   EPI_PROB    P = exp(S - max) (bf16) and its row sums  global scores, pass 2
 //   EPI_POOL    O = X'ᵀ·P (A operand MN-major)            global P·V in reassociated form (projector.py:215)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm_tc.cuh"
 
@@ -54,6 +55,7 @@ struct Params {
   int k_ext_blocks;                // EPI_MAX/PROB: extra K blocks taken from the second map pair (spatial PE term)
   int HW, T;                       // tokens per frame, frames
   long long c_batch_rows;          // EPI_LINEAR: output rows are shifted by batch*c_batch_rows (batched GEMMs)
+  int b_shared;                    // B operand has no batch axis (coordinate 0 for every batch entry)
   __nv_bfloat16* P2; long long p2_ld;  // EPI_PROB2: probabilities (B, tokens, p2_ld), token-major
   const float* peq_t; long long peq_ld;  // (T, B*J) time term of the scores: pos_t[t]·qfold[b,j]
   float* margT; int margT_ld;      // (B*J, margT_ld) sum of probabilities per frame (EPI_PROB accumulates)
@@ -300,13 +302,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_3d(sa, &tmA2, &full_bar[s], t.m_tile * BM, ke * BK, 0);
               tma_load_3d(sa + BK * 128, &tmA2, &full_bar[s], t.m_tile * BM + 64, ke * BK, 0);
             } else {
-              tma_load_3d(sa, &tmA, &full_bar[s], t.m_tile * BM, k0, t.batch);
-              tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], t.m_tile * BM + 64, k0, t.batch);
+              tma_load_3d(sa, &tmA, &full_bar[s], t.m_tile * BM, k0 + t.zslice * p.z_a_k, t.batch);
+              tma_load_3d(sa + BK * 128, &tmA, &full_bar[s], t.m_tile * BM + 64, k0 + t.zslice * p.z_a_k, t.batch);
             }
           } else if (ext && EPI == EPI_PROB2) {
             // token-side extension columns (shared by all videos): block 0 = [h | w one-hot, ones], block 1 = frame
             // index relative to the first token of this 128-token tile
-            tma_load_3d(sa, ke == 0 ? &tmA2 : &tmA3, &full_bar[s], 0, t.m_tile * BM, 0);
+            // (separate calls: the descriptor operand must be the kernel parameter itself, not a selected pointer)
+            if (ke == 0) tma_load_3d(sa, &tmA2, &full_bar[s], 0, t.m_tile * BM, 0);
+            else tma_load_3d(sa, &tmA3, &full_bar[s], 0, t.m_tile * BM, 0);
           } else if (ext) {
             tma_load_3d(sa, &tmA2, &full_bar[s], ke * BK, t.m_tile * BM, t.batch);
           } else {
@@ -315,9 +319,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ext && EPI == EPI_PROB2) {
             // query-side extension rows: block 0 = [pos_h·q | pos_w·q | -stab]; block 1 = pos_t[f0 + k]·q, i.e. the
             // time table read at the tile's first frame (a TMA coordinate), matching the relative one-hot above
-            const int f0 = (t.m_tile * BM) / p.HW;
-            for (int r = 0; r < BN; r += p.b_box_rows)
-              tma_load_3d(sb + r * 128, ke == 0 ? &tmB2 : &tmB3, &full_bar[s], ke == 0 ? 0 : f0, t.n_tile * BN + r, t.batch);
+            const int f0 = ((t.m_tile * BM) / p.HW) & ~7;  // TMA box starts must be 16-byte aligned: 8 bf16
+            for (int r = 0; r < BN; r += p.b_box_rows) {
+              if (ke == 0) tma_load_3d(sb + r * 128, &tmB2, &full_bar[s], 0, t.n_tile * BN + r, t.batch);
+              else tma_load_3d(sb + r * 128, &tmB3, &full_bar[s], f0, t.n_tile * BN + r, t.batch);
+            }
           } else if (ext && EPI == EPI_POOL) {  // probability marginals (J x ke2) of this video, K-major
             for (int r = 0; r < BN; r += p.b_box_rows)
               tma_load_3d(sb + r * 128, &tmB2, &full_bar[s], ke * BK, r, t.batch);
@@ -327,7 +333,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // B[k, n] stored (k rows, n contiguous): whole 64-wide blocks of (BK rows x 128 B)
             for (int r = 0; r < BN; r += 64)
               tma_load_3d(sb + (r / 64) * (BK * 128), &tmB, &full_bar[s], t.n_tile * BN + r,
-                          k0 + t.zslice * p.z_b_k, t.batch);
+                          k0 + t.zslice * p.z_b_k, p.b_shared ? 0 : t.batch);
           } else {
             for (int r = 0; r < BN; r += p.b_box_rows)
               tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0 + t.zslice * p.z_b_k, t.n_tile * BN + r, t.batch);
@@ -339,8 +345,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr int N_MAIN = BN > 256 ? 256 : BN, N_TAIL = BN > 256 ? BN - 256 : 8;
+      // an MN-major operand is made of whole 64-wide swizzle blocks: its tail instruction covers the full fifth block
+      // (columns 288..319 are padding whose results the epilogue never reads)
+      constexpr int N_TAIL_MN = (N_TAIL + 63) / 64 * 64;
       constexpr uint32_t idesc_main_mn = make_idesc(N_MAIN, A_MN, true), idesc_main_k = make_idesc(N_MAIN, A_MN, false);
-      constexpr uint32_t idesc_tail_mn = make_idesc(N_TAIL, A_MN, true), idesc_tail_k = make_idesc(N_TAIL, A_MN, false);
+      constexpr uint32_t idesc_tail_mn = make_idesc(N_TAIL_MN, A_MN, true), idesc_tail_k = make_idesc(N_TAIL, A_MN, false);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const TileInfo t = decode_tile<EPI>(p, tile);
@@ -751,15 +760,15 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   if (total == 0) return 0;
   const unsigned ctas = (unsigned)(total < num_sms ? total : num_sms);  // persistent: one CTA per SM at most
   char label[96];
-  if (kernel_timing_enabled()) {
-    static const char* names[] = {"tc_linear", "tc_scores_max", "tc_scores_prob", "tc_pool", "tc_scores_prob2"};
-    snprintf(label, sizeof(label), "%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI], (FLAGS & 1) ? "+gelu" : "", p.M, p.N,
-             p.K, total, p.guard ? " guarded" : "");
-  }
+  static const char* names[] = {"tc_linear", "tc_scores_max", "tc_scores_prob", "tc_pool", "tc_scores_prob2"};
+  snprintf(label, sizeof(label), "%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI], (FLAGS & 1) ? "+gelu" : "", p.M, p.N,
+           p.K, total, p.guard ? " guarded" : "");
   KernelTimer timer(label, stream);
   kern<<<ctas, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, ta3 ? *ta3 : ta,
                                                            tb3 ? *tb3 : tb, pp);
-  return check_launch("tc_gemm_kernel");
+  char what[160];
+  snprintf(what, sizeof(what), "tc_gemm_kernel<%d,%d,%d> %s", BN, (int)A_MN, (int)B_MN, label);
+  return check_launch(what);
 }
 
 }  // namespace tc
@@ -782,6 +791,23 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   CUtensorMap ta, tb;
   // full reduction extent in memory (slices may overhang it: out-of-range elements read as zero)
   const uint64_t kext = q.k_total > 0 ? (uint64_t)q.k_total : (uint64_t)q.K * (q.z_slices > 0 ? q.z_slices : 1);
+  if (q.a_is_km) {
+    // batched GEMM with A stored (K, M) row-major per batch entry and W stored (K, N), shared by the batch:
+    // C[b, slice] (M x N, fp32) = A[b][K range of slice]ᵀ · W[K range]      (probability marginals)
+    HICOM_REQUIRE(q.w_is_kn && q.out_dtype == HICOM_F32 && q.act == HICOM_ACT_NONE && !q.accumulate,
+                  "tcgen05 linear: (K,M) activations are only built for fp32 C, (K,N) weights, no activation");
+    const int nb = q.batch > 0 ? q.batch : 1;
+    if (make_map(&ta, q.A, q.M, kext, nb, q.lda, q.a_batch_stride, 64)) return 1;
+    if (make_map(&tb, q.W, q.N, kext, 1, q.ldw, 0, 64)) return 1;
+    Params pm{};
+    pm.M = q.M; pm.N = q.N; pm.K = q.K; pm.k_chunk = q.K; pm.b_box_rows = 64;
+    pm.C = q.C; pm.ldc = q.ldc; pm.out_dtype = q.out_dtype; pm.act = q.act; pm.alpha = 1.f;
+    pm.rows_per_group = 1 << 30; pm.group_stride_rows = 0;
+    pm.z_slices = q.z_slices > 0 ? q.z_slices : 1; pm.z_a_k = q.z_a_k; pm.z_b_k = q.z_b_k; pm.z_c_rows = q.z_c_rows;
+    pm.c_batch_rows = q.c_batch_rows; pm.b_shared = 1; pm.guard = q.guard;
+    dim3 gm((q.N + 255) / 256, (q.M + BM - 1) / BM, nb * pm.z_slices);
+    return launch<256, true, true, EPI_LINEAR, 2>(ta, tb, pm, gm, stream);
+  }
   if (make_map(&ta, q.A, kext, q.M, 1, q.lda, 0, BM)) return 1;
   if (q.w_is_kn) {  // W given as (K, N) row-major: MN-major B operand, boxes of 64 n x 64 k
     if (make_map(&tb, q.W, q.N, kext, 1, q.ldw, 0, 64)) return 1;
@@ -876,8 +902,16 @@ static GlobalWs global_ws(int B, int T, int H, int W, int d, int J, int splits) 
   return w;
 }
 
+struct GlobalWs3;
+static size_t global_ws3_total(int B, int T, int H, int W, int d, int J, int splits);
+static bool global_v3_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HICOM_GLOBAL_V3"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+
 size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits) {
-  return global_ws(B, T, H, W, d, J, splits).total;
+  return global_v3_enabled() ? global_ws3_total(B, T, H, W, d, J, splits) : global_ws(B, T, H, W, d, J, splits).total;
 }
 
 namespace tc {
@@ -934,10 +968,281 @@ __global__ void repair_margT_kernel(float* margT, long long n, const int* flag) 
 }
 }  // namespace tc
 
+// =================================================================================================
+// v3 pipeline: token-major probabilities, no padded MMA rows, no atomics, marginals from one GEMM
+// =================================================================================================
+struct GlobalWs3 {
+  size_t p2, mg, lsum, stab, flag, pe_t, pe2, ind, qext, tq, peq_t, margf, marg, total;
+  long long pld, ild, tq_ld;
+  int Tk, ke2, mslices;
+};
+static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits) {
+  (void)splits; (void)H; (void)W;
+  const size_t N = (size_t)T * H * W;
+  GlobalWs3 w;
+  w.pld = (J + 63) / 64 * 64;
+  w.Tk = (T + 7) / 8 * 8;
+  w.ke2 = kKe + (T + 63) / 64 * 64;      // marginal columns: [h | w | .. | ones] + absolute frame one-hot
+  w.ild = w.ke2 + 64;                    // + relative-frame one-hot block for the score GEMM
+  w.tq_ld = (T + 64 + 7) / 8 * 8;
+  const int mt = (J + tc::BM - 1) / tc::BM;
+  int ms = (296 + B * mt - 1) / (B * mt);
+  w.mslices = ms < 1 ? 1 : (ms > 8 ? 8 : ms);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
+  w.p2 = take((size_t)B * N * w.pld * 2);
+  w.mg = take((size_t)B * J * 4);
+  w.lsum = take((size_t)B * J * 4);
+  w.stab = take((size_t)B * J * 4);
+  w.flag = take(256);
+  w.pe_t = take((size_t)w.Tk * d * 2);
+  w.pe2 = take((size_t)w.ke2 * d * 2);
+  w.ind = take(N * w.ild * 2);
+  w.qext = take((size_t)B * J * kKe * 2);
+  w.tq = take((size_t)B * J * w.tq_ld * 2);
+  w.peq_t = take((size_t)T * B * J * 4);
+  w.margf = take((size_t)B * w.mslices * J * w.ke2 * 4);
+  w.marg = take((size_t)B * J * w.ke2 * 2);
+  w.total = off;
+  return w;
+}
+
+static size_t global_ws3_total(int B, int T, int H, int W, int d, int J, int splits) {
+  return global_ws3(B, T, H, W, d, J, splits).total;
+}
+
+namespace tc {
+// pe_t (Tk x d) and pe2 = [pos_h ; pos_w ; 0 (row 63 multiplies the ones column) | pos_t ; 0] (ke2 x d), bf16
+__global__ void build_pe3_kernel(const float* pt, const float* ph, const float* pw, __nv_bfloat16* pe_t,
+                                 __nv_bfloat16* pe2, int T, int Tk, int ke2, int H, int W, int d) {
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    if (r < Tk) {
+      pe_t[(size_t)r * d + c] = __float2bfloat16_rn(r < T ? pt[(size_t)r * d + c] : 0.f);
+    } else {
+      const int s = r - Tk;
+      float v = 0.f;
+      if (s < H) v = ph[(size_t)s * d + c];
+      else if (s < H + W) v = pw[(size_t)(s - H) * d + c];
+      else if (s >= kKe && s - kKe < T) v = pt[(size_t)(s - kKe) * d + c];
+      pe2[(size_t)s * d + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+// ind[n] = [ one-hot(h), one-hot(H+w), .., 1 (col 63) | one-hot(frame) (ke2-64 cols) | one-hot(frame - first frame of
+//            the 128-token tile, rounded down to a multiple of 8) (64 cols) ]
+__global__ void build_ind3_kernel(__nv_bfloat16* ind, long long N, int H, int W, int ke2, int ild) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * ild) return;
+  const long long n = i / ild;
+  const int c = (int)(i % ild);
+  const int hw = H * W;
+  const int w = (int)(n % W), h = (int)((n / W) % H), t = (int)(n / hw);
+  float v = 0.f;
+  if (c < kKe) v = (c == h || c == H + w || c == kKe - 1) ? 1.f : 0.f;
+  else if (c < ke2) v = (c - kKe == t) ? 1.f : 0.f;
+  else v = (c - ke2 == t - ((int)(((n / BM) * BM) / hw) & ~7)) ? 1.f : 0.f;  // same 8-aligned base as the TMA coordinate
+  ind[i] = __float2bfloat16_rn(v);
+}
+__global__ void zero_bf16_kernel(__nv_bfloat16* p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = __float2bfloat16_rn(0.f);
+}
+__global__ void reset_max_kernel(float* mg, int n, const int* flag) {
+  if (flag != nullptr && *flag == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mg[i] = -INFINITY;
+}
+// stabiliser = bf16(max + margin): it rides into the GEMM as the extension row -stab against the ones column, so the
+// value reported to the merge must be the rounded one that was actually applied
+__global__ void make_stab3_kernel(const float* mg, float* stab, __nv_bfloat16* qext, int n, float margin,
+                                  const int* flag) {
+  if (flag != nullptr && *flag == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const __nv_bfloat16 sb = __float2bfloat16_rn(mg[i] + margin);
+  stab[i] = __bfloat162float(sb);
+  qext[(size_t)i * kKe + kKe - 1] = __float2bfloat16_rn(-__bfloat162float(sb));
+}
+// marg (B*J, ke2) bf16 = sum over K slices of margf; column 63 is the softmax denominator.  A denominator that is not a
+// positive finite number means exp() left the exponent range: raise the flag for the exact-max re-run.
+// exact re-run only: remove the previous stabiliser row so the max pass sees the raw scores again
+__global__ void clear_stab3_kernel(__nv_bfloat16* qext, int n, const int* flag) {
+  if (*flag == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) qext[(size_t)i * kKe + kKe - 1] = __float2bfloat16_rn(0.f);
+}
+__global__ void marg_reduce_kernel(const float* margf, __nv_bfloat16* marg, float* lsum, int B, int S, int J, int ke2,
+                                   int* flag, int guarded) {
+  if (guarded && *flag == 0) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * J * ke2) return;
+  const int c = (int)(i % ke2);
+  const long long bj = i / ke2;
+  const int j = (int)(bj % J), b = (int)(bj / J);
+  float acc = 0.f;
+  for (int s2 = 0; s2 < S; ++s2) acc += margf[(((size_t)b * S + s2) * J + j) * ke2 + c];
+  marg[i] = __float2bfloat16_rn(acc);
+  if (c == kKe - 1) {
+    lsum[bj] = acc;
+    if (!guarded && !(acc > 0.f && acc < 3.0e38f)) atomicExch(flag, 1);
+  }
+}
+__global__ void spread3_kernel(const float* stab, const float* lsum, float* m, float* l, int B, int S, int J) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * S * J) return;
+  const int j = i % J, s2 = (i / J) % S, b = i / (J * S);
+  m[i] = stab[b * J + j];
+  l[i] = s2 == 0 ? lsum[b * J + j] : 0.f;
+}
+}  // namespace tc
+
+static int launch_tc_global_v3(const void* X, const float* pos_t, const float* pos_h, const float* pos_w,
+                               const void* qfold, float* m, float* l, float* o, int B, int T, int H, int W, int d, int J,
+                               int splits, void* workspace, cudaStream_t stream) {
+  using namespace tc;
+  const int N = T * H * W;
+  const GlobalWs3 w = global_ws3(B, T, H, W, d, J, splits);
+  char* ws = static_cast<char*>(workspace);
+  __nv_bfloat16* P2 = reinterpret_cast<__nv_bfloat16*>(ws + w.p2);
+  float* mg = reinterpret_cast<float*>(ws + w.mg);
+  float* lsum = reinterpret_cast<float*>(ws + w.lsum);
+  float* stab = reinterpret_cast<float*>(ws + w.stab);
+  int* flag = reinterpret_cast<int*>(ws + w.flag);
+  __nv_bfloat16* pe_t = reinterpret_cast<__nv_bfloat16*>(ws + w.pe_t);
+  __nv_bfloat16* pe2 = reinterpret_cast<__nv_bfloat16*>(ws + w.pe2);
+  __nv_bfloat16* ind = reinterpret_cast<__nv_bfloat16*>(ws + w.ind);
+  __nv_bfloat16* qext = reinterpret_cast<__nv_bfloat16*>(ws + w.qext);
+  __nv_bfloat16* tq = reinterpret_cast<__nv_bfloat16*>(ws + w.tq);
+  float* peq_t = reinterpret_cast<float*>(ws + w.peq_t);
+  float* margf = reinterpret_cast<float*>(ws + w.margf);
+  __nv_bfloat16* marg = reinterpret_cast<__nv_bfloat16*>(ws + w.marg);
+  const long long BJ = (long long)B * J;
+  const bool narrow = J <= 64;
+  const uint32_t jbox = narrow ? 64 : 96;
+  auto blocks = [](long long n) { return (unsigned)((n + 255) / 256); };
+
+  // 0. tables and indicator matrices
+  build_pe3_kernel<<<w.Tk + w.ke2, 256, 0, stream>>>(pos_t, pos_h, pos_w, pe_t, pe2, T, w.Tk, w.ke2, H, W, d);
+  if (check_launch("build_pe3_kernel")) return 1;
+  build_ind3_kernel<<<blocks((long long)N * w.ild), 256, 0, stream>>>(ind, N, H, W, w.ke2, (int)w.ild);
+  if (check_launch("build_ind3_kernel")) return 1;
+  init_stats_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, lsum, (int)BJ, flag);
+  if (check_launch("init_stats_kernel")) return 1;
+  zero_bf16_kernel<<<blocks(BJ * w.tq_ld), 256, 0, stream>>>(tq, BJ * w.tq_ld);
+  if (check_launch("zero_bf16_kernel")) return 1;
+  {  // qext (B*J, 64) = qfold · [pos_h ; pos_w ; 0]ᵀ ; tq (B*J, T) = qfold · pos_tᵀ ; peq_t (T, B*J) fp32 for the max pass
+    TcLinearParams a{};
+    a.A = qfold; a.W = pe2; a.C = qext; a.lda = d; a.ldw = d; a.ldc = kKe; a.M = (int)BJ; a.N = kKe; a.K = d;
+    a.act = HICOM_ACT_NONE; a.out_dtype = HICOM_BF16; a.rows_per_group = 1 << 30;
+    if (launch_tc_linear(a, stream)) return 1;
+    TcLinearParams c{};
+    c.A = qfold; c.W = pe_t; c.C = tq; c.lda = d; c.ldw = d; c.ldc = w.tq_ld; c.M = (int)BJ; c.N = T; c.K = d;
+    c.act = HICOM_ACT_NONE; c.out_dtype = HICOM_BF16; c.rows_per_group = 1 << 30;
+    if (launch_tc_linear(c, stream)) return 1;
+    TcLinearParams b{};
+    b.A = pe_t; b.W = qfold; b.C = peq_t; b.lda = d; b.ldw = d; b.ldc = BJ; b.M = T; b.N = (int)BJ; b.K = d;
+    b.act = HICOM_ACT_NONE; b.out_dtype = HICOM_F32; b.rows_per_group = 1 << 30;
+    if (launch_tc_linear(b, stream)) return 1;
+  }
+
+  // ---- sampled / exact max pass (rows = score columns, as in v2) -------------------------------------------------
+  CUtensorMap tq128, tx256, tqe128, tind256;
+  if (make_map(&tq128, qfold, d, J, B, d, (uint64_t)J * d, BM)) return 1;
+  if (make_map(&tx256, X, d, N, B, d, (uint64_t)N * d, 256)) return 1;
+  if (make_map(&tqe128, qext, kKe, J, B, kKe, (uint64_t)J * kKe, BM)) return 1;
+  if (make_map(&tind256, ind, kKe, N, 1, w.ild, 0, 256)) return 1;
+  Params pmx{};
+  pmx.M = J; pmx.N = N; pmx.K = d; pmx.k_chunk = d; pmx.b_box_rows = 256;
+  pmx.mg = mg; pmx.k_ext_blocks = 1; pmx.HW = H * W; pmx.T = T; pmx.peq_t = peq_t; pmx.peq_ld = BJ;
+  const int n_tiles256 = (N + 255) / 256;
+  const int mj_tiles = (J + BM - 1) / BM;
+
+  // ---- probabilities: P2[b] (tokens x J) = exp([X | ind0 | indrel] · [qfold | qext | tq(f0..)]ᵀ) --------------------
+  CUtensorMap tx128, tqj, ti0, ti1, tqej, ttq;
+  if (make_map(&tx128, X, d, N, B, d, (uint64_t)N * d, BM)) return 1;
+  if (make_map(&tqj, qfold, d, J, B, d, (uint64_t)J * d, jbox)) return 1;
+  if (make_map(&ti0, ind, kKe, N, 1, w.ild, 0, BM)) return 1;
+  if (make_map(&ti1, ind + w.ke2, kKe, N, 1, w.ild, 0, BM)) return 1;
+  if (make_map(&tqej, qext, kKe, J, B, kKe, (uint64_t)J * kKe, jbox)) return 1;
+  if (make_map(&ttq, tq, w.tq_ld, J, B, w.tq_ld, (uint64_t)J * w.tq_ld, jbox)) return 1;
+  Params pp{};
+  pp.M = N; pp.N = J; pp.K = d; pp.k_chunk = d; pp.b_box_rows = (int)jbox;
+  pp.k_ext_blocks = 2; pp.HW = H * W; pp.T = T; pp.P2 = P2; pp.p2_ld = w.pld;
+  dim3 gprob(1, (N + BM - 1) / BM, B);
+
+  // ---- marginals: margf[b, s] (J x ke2) = P2[b, tokens of s]ᵀ · ind[:, 0:ke2] ----------------------------------------
+  TcLinearParams mm{};
+  const int kslice = ((N + w.mslices - 1) / w.mslices + BK - 1) / BK * BK;
+  mm.A = P2; mm.W = ind; mm.C = margf; mm.lda = w.pld; mm.ldw = w.ild; mm.ldc = w.ke2;
+  mm.M = J; mm.N = w.ke2; mm.K = kslice; mm.k_total = N; mm.act = HICOM_ACT_NONE; mm.out_dtype = HICOM_F32;
+  mm.rows_per_group = 1 << 30; mm.w_is_kn = 1; mm.a_is_km = 1;
+  mm.batch = B; mm.a_batch_stride = (long long)N * w.pld; mm.c_batch_rows = (long long)w.mslices * J;
+  mm.z_slices = w.mslices; mm.z_a_k = kslice; mm.z_b_k = kslice; mm.z_c_rows = J;
+
+  // ---- pooling: O[b,s] (d x J) = [X[b, tokens of s] ; pe2]ᵀ · [P2 ; marg] ------------------------------------------------
+  CUtensorMap txa, tp2, tpe, tmg;
+  if (make_map(&txa, X, d, N, B, d, (uint64_t)N * d, 64)) return 1;
+  if (make_map(&tp2, P2, w.pld, N, B, w.pld, (uint64_t)N * w.pld, 64)) return 1;
+  if (make_map(&tpe, pe2, d, w.ke2, 1, d, 0, 64)) return 1;
+  if (make_map(&tmg, marg, w.ke2, J, B, w.ke2, (uint64_t)J * w.ke2, jbox)) return 1;
+  Params g{};
+  g.M = d; g.N = J; g.K = N;
+  int chunk = (N + splits - 1) / splits;
+  chunk = (chunk + BK - 1) / BK * BK;
+  g.k_chunk = chunk; g.b_box_rows = (int)jbox;
+  g.o = o; g.splits = splits; g.k_ext_blocks = w.ke2 / BK;
+  dim3 gp(splits, d / BM, B);
+
+  auto run = [&](const int* guard, float margin) -> int {
+    // stabiliser -> probabilities -> marginals -> pooling (the exact re-run passes guard = flag)
+    make_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, stab, qext, (int)BJ, margin, guard);
+    if (check_launch("make_stab3_kernel")) return 1;
+    Params p1 = pp; p1.guard = guard;
+    if (narrow ? launch<64, false, false, EPI_PROB2>(tx128, tqj, p1, gprob, stream, &ti0, &tqej, &ti1, &ttq)
+               : launch<288, false, false, EPI_PROB2>(tx128, tqj, p1, gprob, stream, &ti0, &tqej, &ti1, &ttq)) return 1;
+    TcLinearParams m1 = mm; m1.guard = guard;
+    if (launch_tc_linear(m1, stream)) return 1;
+    marg_reduce_kernel<<<blocks(BJ * w.ke2), 256, 0, stream>>>(margf, marg, lsum, B, w.mslices, J, w.ke2, flag,
+                                                               guard != nullptr);
+    if (check_launch("marg_reduce_kernel")) return 1;
+    Params g1 = g; g1.guard = guard;
+    if (narrow ? launch<64, true, true, EPI_POOL>(txa, tp2, g1, gp, stream, &tpe, &tmg)
+               : launch<288, true, true, EPI_POOL>(txa, tp2, g1, gp, stream, &tpe, &tmg)) return 1;
+    return 0;
+  };
+
+  // 1. sampled max over a few evenly spaced token tiles, 2. everything with stab = sampled max + margin
+  {
+    Params ps = pmx;
+    const int n_sample = n_tiles256 < 4 ? n_tiles256 : 4;
+    ps.n_tile_stride = n_tiles256 / n_sample;
+    if (launch<256, false, false, EPI_MAX>(tq128, tx256, ps, dim3(n_sample, mj_tiles, B), stream, &tqe128, &tind256))
+      return 1;
+  }
+  if (run(nullptr, kStabMargin)) return 1;
+  // 3. guarded exact fallback: the denominator check in marg_reduce raised the flag -> exact max over all tiles, margin 0
+  {
+    reset_max_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, (int)BJ, flag);
+    if (check_launch("reset_max_kernel")) return 1;
+    // the max pass must not see the previous stabiliser row: clear it first (guarded)
+    Params pf = pmx; pf.guard = flag;
+    clear_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(qext, (int)BJ, flag);
+    if (check_launch("clear_stab3_kernel")) return 1;
+    if (launch<256, false, false, EPI_MAX>(tq128, tx256, pf, dim3(n_tiles256, mj_tiles, B), stream, &tqe128, &tind256))
+      return 1;
+    if (run(flag, 0.f)) return 1;
+  }
+  spread3_kernel<<<blocks(BJ * splits), 256, 0, stream>>>(stab, lsum, m, l, B, splits, J);
+  return check_launch("spread3_kernel");
+}
+
 int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, const float* pos_w, const void* qfold,
                      float* m, float* l, float* o, int B, int T, int H, int W, int d, int J, int splits,
                      void* workspace, cudaStream_t stream) {
   using namespace tc;
+  if (global_v3_enabled())
+    return launch_tc_global_v3(X, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace, stream);
   const int N = T * H * W;
   const GlobalWs w = global_ws(B, T, H, W, d, J, splits);
   char* ws = static_cast<char*>(workspace);

@@ -15,6 +15,8 @@ struct TcLinearParams {
   int z_slices = 0, z_a_k = 0, z_b_k = 0; long long z_c_rows = 0;  // K slices on the tile z axis (one head / one range)
   int z_c_cols = 0; long long k_total = 0;                           // per-slice output column shift; true K extent
   int accumulate = 0;       // C += result (fp32 C, w_is_kn, no activation)
+  int a_is_km = 0;          // A stored (K, M) row-major per batch entry (with w_is_kn): batched, K-sliced, fp32 C
+  int batch = 0; long long a_batch_stride = 0, c_batch_rows = 0;
   const int* guard = nullptr;  // device flag: the launch is a no-op unless *guard != 0
 };
 
