@@ -906,7 +906,8 @@ struct GlobalWs3;
 static size_t global_ws3_total(int B, int T, int H, int W, int d, int J, int splits);
 static bool global_v3_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("HICOM_GLOBAL_V3"); on = (e && e[0] == '1') ? 1 : 0; }
+  // default: the v3 pipeline; HICOM_GLOBAL_V3=0 selects the older column-major-probability pipeline (kept as a cross-check)
+  if (on < 0) { const char* e = getenv("HICOM_GLOBAL_V3"); on = (e && e[0] == '0') ? 0 : 1; }
   return on == 1;
 }
 
@@ -974,7 +975,7 @@ __global__ void repair_margT_kernel(float* margT, long long n, const int* flag) 
 struct GlobalWs3 {
   size_t p2, mg, lsum, stab, flag, pe_t, pe2, ind, qext, tq, peq_t, margf, marg, total;
   long long pld, ild, tq_ld;
-  int Tk, ke2, mslices;
+  int Tk, ke2, mslices, kslice;
 };
 static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits) {
   (void)splits; (void)H; (void)W;
@@ -982,12 +983,18 @@ static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits
   GlobalWs3 w;
   w.pld = (J + 63) / 64 * 64;
   w.Tk = (T + 7) / 8 * 8;
-  w.ke2 = kKe + (T + 63) / 64 * 64;      // marginal columns: [h | w | .. | ones] + absolute frame one-hot
-  w.ild = w.ke2 + 64;                    // + relative-frame one-hot block for the score GEMM
+  w.ke2 = kKe + (T + 63) / 64 * 64;      // pooled-PE columns: [h | w | .. | ones] + absolute frame one-hot
+  w.ild = 3 * kKe;                       // indicator row: [spatial | frame rel. to K slice | frame rel. to 128-token tile]
   w.tq_ld = (T + 64 + 7) / 8 * 8;
+  // K slices of the marginal GEMM: enough (video, row tile, slice) CTAs for two waves, each slice >= 512 tokens, and
+  // few enough frames per slice (<= 48 + rounding) that a 64-wide relative one-hot covers them whatever T is
   const int mt = (J + tc::BM - 1) / tc::BM;
   int ms = (296 + B * mt - 1) / (B * mt);
-  w.mslices = ms < 1 ? 1 : (ms > 8 ? 8 : ms);
+  const int ms_cap = (int)(N / 512) < 1 ? 1 : ((int)(N / 512) > 128 ? 128 : (int)(N / 512));
+  ms = ms < 1 ? 1 : (ms > ms_cap ? ms_cap : ms);
+  const int ms_min = (T + 47) / 48;
+  w.mslices = ms < ms_min ? ms_min : ms;
+  w.kslice = (int)(((N + w.mslices - 1) / w.mslices + tc::BK - 1) / tc::BK * tc::BK);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
   w.p2 = take((size_t)B * N * w.pld * 2);
@@ -1001,7 +1008,7 @@ static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits
   w.qext = take((size_t)B * J * kKe * 2);
   w.tq = take((size_t)B * J * w.tq_ld * 2);
   w.peq_t = take((size_t)T * B * J * 4);
-  w.margf = take((size_t)B * w.mslices * J * w.ke2 * 4);
+  w.margf = take((size_t)B * w.mslices * J * 2 * kKe * 4);
   w.marg = take((size_t)B * J * w.ke2 * 2);
   w.total = off;
   return w;
@@ -1029,20 +1036,29 @@ __global__ void build_pe3_kernel(const float* pt, const float* ph, const float* 
     }
   }
 }
-// ind[n] = [ one-hot(h), one-hot(H+w), .., 1 (col 63) | one-hot(frame) (ke2-64 cols) | one-hot(frame - first frame of
-//            the 128-token tile, rounded down to a multiple of 8) (64 cols) ]
-__global__ void build_ind3_kernel(__nv_bfloat16* ind, long long N, int H, int W, int ke2, int ild) {
+// ind[n] = [ one-hot(h), one-hot(H+w), .., 1 (col 63) | one-hot(frame - base of n's K slice) | one-hot(frame - base of
+//            n's 128-token tile) ], 3 x 64 columns; a base is the first frame of the range rounded down to a multiple of
+//            8 (the same 16-byte-aligned coordinate the TMA producer uses).  One thread writes 8 columns (16 bytes).
+__global__ void build_ind3_kernel(__nv_bfloat16* ind, int N, int H, int W, int kslice) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * ild) return;
-  const long long n = i / ild;
-  const int c = (int)(i % ild);
+  constexpr int G = 3 * kKe / 8;
+  if (i >= (long long)N * G) return;
+  const int n = (int)(i / G), g = (int)(i % G);
   const int hw = H * W;
-  const int w = (int)(n % W), h = (int)((n / W) % H), t = (int)(n / hw);
-  float v = 0.f;
-  if (c < kKe) v = (c == h || c == H + w || c == kKe - 1) ? 1.f : 0.f;
-  else if (c < ke2) v = (c - kKe == t) ? 1.f : 0.f;
-  else v = (c - ke2 == t - ((int)(((n / BM) * BM) / hw) & ~7)) ? 1.f : 0.f;  // same 8-aligned base as the TMA coordinate
-  ind[i] = __float2bfloat16_rn(v);
+  const int w = n % W, h = (n / W) % H, t = n / hw;
+  int hot0 = -1, hot1 = -1, hot2 = -1;  // columns of this row that hold a one
+  if (g < kKe / 8) { hot0 = h; hot1 = H + w; hot2 = kKe - 1; }
+  else if (g < 2 * kKe / 8) hot0 = kKe + t - ((((n / kslice) * kslice) / hw) & ~7);
+  else hot0 = 2 * kKe + t - ((((n / BM) * BM) / hw) & ~7);
+  uint32_t v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c = g * 8 + 2 * q;
+    const uint32_t lo = (c == hot0 || c == hot1 || c == hot2) ? 0x3f80u : 0u;
+    const uint32_t hi = (c + 1 == hot0 || c + 1 == hot1 || c + 1 == hot2) ? 0x3f80u : 0u;
+    v[q] = lo | (hi << 16);
+  }
+  *reinterpret_cast<uint4*>(ind + (size_t)n * (3 * kKe) + g * 8) = make_uint4(v[0], v[1], v[2], v[3]);
 }
 __global__ void zero_bf16_kernel(__nv_bfloat16* p, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1073,15 +1089,25 @@ __global__ void clear_stab3_kernel(__nv_bfloat16* qext, int n, const int* flag) 
   if (i < n) qext[(size_t)i * kKe + kKe - 1] = __float2bfloat16_rn(0.f);
 }
 __global__ void marg_reduce_kernel(const float* margf, __nv_bfloat16* marg, float* lsum, int B, int S, int J, int ke2,
-                                   int* flag, int guarded) {
+                                   int kslice, int hw, int* flag, int guarded) {
   if (guarded && *flag == 0) return;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * J * ke2) return;
   const int c = (int)(i % ke2);
   const long long bj = i / ke2;
   const int j = (int)(bj % J), b = (int)(bj / J);
+  const float* src = margf + ((size_t)b * S * J + j) * (2 * kKe);
+  const size_t sstride = (size_t)J * 2 * kKe;
   float acc = 0.f;
-  for (int s2 = 0; s2 < S; ++s2) acc += margf[(((size_t)b * S + s2) * J + j) * ke2 + c];
+  if (c < kKe) {
+    for (int s2 = 0; s2 < S; ++s2) acc += src[s2 * sstride + c];
+  } else {  // frame c - 64: slices store it relative to their own base
+    const int t = c - kKe;
+    for (int s2 = 0; s2 < S; ++s2) {
+      const int rel = t - ((int)(((long long)s2 * kslice) / hw) & ~7);
+      if (rel >= 0 && rel < kKe) acc += src[s2 * sstride + kKe + rel];
+    }
+  }
   marg[i] = __float2bfloat16_rn(acc);
   if (c == kKe - 1) {
     lsum[bj] = acc;
@@ -1125,7 +1151,7 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   // 0. tables and indicator matrices
   build_pe3_kernel<<<w.Tk + w.ke2, 256, 0, stream>>>(pos_t, pos_h, pos_w, pe_t, pe2, T, w.Tk, w.ke2, H, W, d);
   if (check_launch("build_pe3_kernel")) return 1;
-  build_ind3_kernel<<<blocks((long long)N * w.ild), 256, 0, stream>>>(ind, N, H, W, w.ke2, (int)w.ild);
+  build_ind3_kernel<<<blocks((long long)N * (w.ild / 8)), 256, 0, stream>>>(ind, N, H, W, w.kslice);
   if (check_launch("build_ind3_kernel")) return 1;
   init_stats_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, lsum, (int)BJ, flag);
   if (check_launch("init_stats_kernel")) return 1;
@@ -1163,7 +1189,7 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   if (make_map(&tx128, X, d, N, B, d, (uint64_t)N * d, BM)) return 1;
   if (make_map(&tqj, qfold, d, J, B, d, (uint64_t)J * d, jbox)) return 1;
   if (make_map(&ti0, ind, kKe, N, 1, w.ild, 0, BM)) return 1;
-  if (make_map(&ti1, ind + w.ke2, kKe, N, 1, w.ild, 0, BM)) return 1;
+  if (make_map(&ti1, ind + 2 * kKe, kKe, N, 1, w.ild, 0, BM)) return 1;
   if (make_map(&tqej, qext, kKe, J, B, kKe, (uint64_t)J * kKe, jbox)) return 1;
   if (make_map(&ttq, tq, w.tq_ld, J, B, w.tq_ld, (uint64_t)J * w.tq_ld, jbox)) return 1;
   Params pp{};
@@ -1171,11 +1197,11 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   pp.k_ext_blocks = 2; pp.HW = H * W; pp.T = T; pp.P2 = P2; pp.p2_ld = w.pld;
   dim3 gprob(1, (N + BM - 1) / BM, B);
 
-  // ---- marginals: margf[b, s] (J x ke2) = P2[b, tokens of s]ᵀ · ind[:, 0:ke2] ----------------------------------------
+  // ---- marginals: margf[b, s] (J x 128) = P2[b, tokens of s]ᵀ · ind[:, 0:128] ---------------------------------------
   TcLinearParams mm{};
-  const int kslice = ((N + w.mslices - 1) / w.mslices + BK - 1) / BK * BK;
-  mm.A = P2; mm.W = ind; mm.C = margf; mm.lda = w.pld; mm.ldw = w.ild; mm.ldc = w.ke2;
-  mm.M = J; mm.N = w.ke2; mm.K = kslice; mm.k_total = N; mm.act = HICOM_ACT_NONE; mm.out_dtype = HICOM_F32;
+  const int kslice = w.kslice;
+  mm.A = P2; mm.W = ind; mm.C = margf; mm.lda = w.pld; mm.ldw = w.ild; mm.ldc = 2 * kKe;
+  mm.M = J; mm.N = 2 * kKe; mm.K = kslice; mm.k_total = N; mm.act = HICOM_ACT_NONE; mm.out_dtype = HICOM_F32;
   mm.rows_per_group = 1 << 30; mm.w_is_kn = 1; mm.a_is_km = 1;
   mm.batch = B; mm.a_batch_stride = (long long)N * w.pld; mm.c_batch_rows = (long long)w.mslices * J;
   mm.z_slices = w.mslices; mm.z_a_k = kslice; mm.z_b_k = kslice; mm.z_c_rows = J;
@@ -1203,8 +1229,8 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
                : launch<288, false, false, EPI_PROB2>(tx128, tqj, p1, gprob, stream, &ti0, &tqej, &ti1, &ttq)) return 1;
     TcLinearParams m1 = mm; m1.guard = guard;
     if (launch_tc_linear(m1, stream)) return 1;
-    marg_reduce_kernel<<<blocks(BJ * w.ke2), 256, 0, stream>>>(margf, marg, lsum, B, w.mslices, J, w.ke2, flag,
-                                                               guard != nullptr);
+    marg_reduce_kernel<<<blocks(BJ * w.ke2), 256, 0, stream>>>(margf, marg, lsum, B, w.mslices, J, w.ke2, kslice,
+                                                               H * W, flag, guard != nullptr);
     if (check_launch("marg_reduce_kernel")) return 1;
     Params g1 = g; g1.guard = guard;
     if (narrow ? launch<64, true, true, EPI_POOL>(txa, tp2, g1, gp, stream, &tpe, &tmg)

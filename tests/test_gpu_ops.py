@@ -237,3 +237,44 @@ def test_softmax_reduce_then_merge_equals_merge(built_library):
     parts = [ops.softmax_reduce(m[:, a:b], l[:, a:b], o[:, a:b]) for a, b in ((0, 2), (2, 3), (3, 6))]
     got = ops.softmax_merge(*(torch.cat([p[i] for p in parts], 1) for i in range(3)), False)
     assert O.rel_err(got.cpu(), want.cpu()) <= 1e-5
+
+
+@pytest.mark.parametrize("T,H,W,splits", [(130, 6, 6, 2), (61, 8, 5, 1), (200, 7, 9, 3)])
+def test_global_partial_long_video(T, H, W, splits, built_library):
+    """Many frames: the marginal GEMM's K slices each carry their own frame base (slice-relative one-hot columns), the
+    score tiles theirs; the pooled position-embedding term must still land on the absolute frame (projector.py:636-640)."""
+    from hicom_b200 import ops
+    from hicom_b200.projector import _axis_table
+    dtype = torch.bfloat16
+    B, d, Q, heads = 1, 1152, 32, 9
+    X = _rand(B, T, H, W, d, seed=11, dtype=dtype)
+    Qg = _rand(B, Q, d, seed=12, dtype=dtype)
+    Wq, Wk, Wv = (_rand(d, d, seed=s, std=0.02, dtype=dtype) for s in (13, 14, 15))
+    bq, bk, bv = (_rand(d, seed=s, std=0.02, dtype=dtype) for s in (16, 17, 18))
+    tabs = [torch.from_numpy(_axis_table(n, d)).float() for n in (T, H, W)]
+    q = ops.linear(Qg.cuda(), Wq.cuda(), bq.cuda(), None, 0, False, ops.IMPL_AUTO)
+    qf = ops.global_fold_query(q, Wk.cuda(), heads, 128 ** -0.5)
+    m, l, o = ops.global_attend_partial(X.cuda(), tabs[0].cuda(), tabs[1].cuda(), tabs[2].cuda(), qf, splits,
+                                        ops.IMPL_AUTO)
+    pooled = ops.softmax_merge(m, l, o, True)
+    got = ops.global_value_proj(pooled, Wv.cuda(), bv.cuda(), Q, heads).float().cpu()
+    xp = (X[0].float() + O.pos_embed_3d(T, H, W, d)).reshape(-1, d)
+    qq = F.linear(Qg[0].float(), Wq.float(), bq.float()).view(Q, heads, 128).transpose(0, 1)
+    kk = F.linear(xp, Wk.float(), bk.float()).view(-1, heads, 128).transpose(0, 1)
+    vv = F.linear(xp, Wv.float(), bv.float()).view(-1, heads, 128).transpose(0, 1)
+    want = (torch.softmax(qq @ kk.transpose(1, 2) * 128 ** -0.5, -1) @ vv).transpose(0, 1).reshape(Q, d)
+    assert O.rel_err(got[0], want) <= 8e-3
+
+
+def test_global_v2_pipeline_still_matches(built_library):
+    """HICOM_GLOBAL_V3=0 selects the older global pipeline (read once per process): run its op tests in a child."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HICOM_GLOBAL_V3="0")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_ops.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "global_partial and not v2_pipeline", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
