@@ -183,13 +183,14 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 // two MUFU ops).  Only used where the result is rounded to bf16 (eps 4e-3); the fp32 path keeps erff.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;  // rcp.approx: __frcp_rn carries a per-element slow-path branch that serialises the unrolled epilogue
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float erf_abs = 1.0f - poly * __expf(-z * z);
+  const float erf_abs = 1.0f - poly * ex2_approx(-z * z * kLog2e);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
