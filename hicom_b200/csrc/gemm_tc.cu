@@ -97,6 +97,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// one lane of a CONVERGED warp (elect.sync): code under it stays on the uniform datapath, so tcgen05/TMA instructions
+// are issued directly instead of through the compiler's per-lane "waterfall" loop that `if (lane == 0)` produces
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -281,7 +292,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===== TMA producer: runs ahead across tiles through the C::STAGES-deep ring =====
-    if (lane == 0) {
+    {  // the whole warp walks the loops; one elected lane arms the barrier and issues the copies
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileInfo t = decode_tile<EPI>(p, tile);
@@ -289,6 +300,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int s = it % C::STAGES;
           const uint32_t ph = (it / C::STAGES) & 1;
           mbar_wait_relaxed(&empty_bar[s], ph ^ 1);
+          if (elect_one()) {
           uint8_t* sa = smem + s * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           const int k0 = t.k_begin + kb * BK;
@@ -339,12 +351,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int r = 0; r < BN; r += p.b_box_rows)
               tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0 + t.zslice * p.z_b_k, t.n_tile * BN + r, t.batch);
           }
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the loops (uniform control flow), one elected lane issues =====
+    {
       constexpr int N_MAIN = BN > 256 ? 256 : BN, N_TAIL = BN > 256 ? BN - 256 : 8;
       // an MN-major operand is made of whole 64-wide swizzle blocks: its tail instruction covers the full fifth block
       // (columns 288..319 are padding whose results the epilogue never reads)
@@ -370,6 +384,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool b_mn_now = B_MN && !(EPI == EPI_POOL && kb >= t.nkb_main);
           const uint32_t idesc_main = b_mn_now ? idesc_main_mn : idesc_main_k;
           const uint32_t idesc_tail = b_mn_now ? idesc_tail_mn : idesc_tail_k;
+          if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk) {
             // K-major: +32 B per 16-element K slice inside the 128 B swizzle row (SBO = 8 rows x 128 B).
@@ -388,8 +403,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
+          }
+          __syncwarp();
         }
-        umma_commit(&tmem_full_bar[buf]);  // accumulator of this tile complete
+        if (elect_one()) umma_commit(&tmem_full_bar[buf]);  // accumulator of this tile complete
+        __syncwarp();
       }
     }
   } else {
