@@ -26,7 +26,10 @@ namespace tc {
 constexpr int BM = 128;  // UMMA M (rows of the accumulator = TMEM lanes)
 constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UK = 16;   // K per tcgen05.mma for 16-bit inputs
-constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+// warp 0 TMA, warp 1 MMA, then the epilogue warps: two per TMEM lane quarter, four for the probability pass (its
+// 288-column accumulator cannot be double-buffered in 512 TMEM columns, so its epilogue is on the critical path)
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == 4 /*EPI_PROB2*/ ? 16 : 8; }
+__host__ __device__ constexpr int num_threads(int epi) { return 64 + 32 * epi_warps(epi); }
 
 enum { EPI_LINEAR = 0, EPI_MAX = 1, EPI_PROB = 2, EPI_POOL = 3, EPI_PROB2 = 4 };
 
@@ -210,6 +213,30 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// Epilogue store coalescing.  After tcgen05.ld each lane owns one output row: 32 bf16 columns = four 16-byte pieces
+// d[4*piece + word].  Storing them directly makes every warp store touch 32 different lines.  Two butterfly exchanges
+// (lane bit 4 <-> piece bit 1, lane bit 3 <-> piece bit 0) leave lane l holding, in slot s, piece (l >> 3) of row
+// 8*s + (l & 7): lanes {r, r+8, r+16, r+24} then write the 64 contiguous bytes of one row, 8 rows per instruction.
+__device__ __forceinline__ void transpose_pieces(uint32_t (&d)[16], int lane) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t send = b4 ? d[4 * k + w] : d[4 * (k + 2) + w];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 16);
+      if (b4) d[4 * k + w] = recv; else d[4 * (k + 2) + w] = recv;
+    }
+#pragma unroll
+  for (int k = 0; k < 4; k += 2)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t send = b3 ? d[4 * k + w] : d[4 * (k + 1) + w];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 8);
+      if (b3) d[4 * k + w] = recv; else d[4 * (k + 1) + w] = recv;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
@@ -252,7 +279,7 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
 
 // FLAGS (EPI_LINEAR only): bit 0 = GELU, bit 1 = fp32 output
 template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(EPI), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB3, const Params p) {
@@ -280,7 +307,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int b = 0; b < C::NBUF; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 8);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], epi_warps(EPI));  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -413,7 +440,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 32-column chunks =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;  // which of the EW/4 warps of this lane quarter
+    constexpr int CSTEP = epi_warps(EPI) / 4;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
     const TileInfo t = decode_tile<EPI>(p, tile);
@@ -442,11 +470,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       orow += (long long)zslice * p.z_c_rows + (long long)batch * p.c_batch_rows;
       const bool has_bias = p.bias != nullptr, has_res = p.R != nullptr;
       const int n_chunks = (p.N - n_tile * BN + 31) / 32 < BN / 32 ? (p.N - n_tile * BN + 31) / 32 : BN / 32;
-      for (int c = half; c < n_chunks; c += 2) {  // warp-uniform trip count: tcgen05.ld needs the whole warp
+      // coalesced bf16 stores (transpose_pieces): warp-uniform conditions only, the shuffles need every lane
+      const bool tr_ok = !kOutF32 && p.diag_heads == 0 && p.ldc % 8 == 0 && (zslice * p.z_c_cols) % 8 == 0 &&
+                         (reinterpret_cast<uintptr_t>(p.C) & 15) == 0;
+      long long orow_s[4];
+      bool ok_s[4];
+      if (tr_ok) {
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+          const int r2 = t.m_tile * BM + q * 32 + 8 * s2 + (lane & 7);
+          ok_s[s2] = r2 < p.M;
+          orow_s[s2] = (ok_s[s2] ? (long long)(r2 / p.rows_per_group) * p.group_stride_rows + (r2 % p.rows_per_group) : 0) +
+                       (long long)zslice * p.z_c_rows + (long long)batch * p.c_batch_rows;
+        }
+      }
+      for (int c = half; c < n_chunks; c += CSTEP) {  // warp-uniform trip count: tcgen05.ld needs the whole warp
         const int n0 = n_tile * BN + c * 32;
         tmem_ld32(taddr + c * 32, v);
+        const bool tr = tr_ok && p.N - n0 >= 32;
         const bool keep = row_ok && (p.diag_heads == 0 || n0 / p.diag_cols == my_head);
-        if (keep) {
+        if (keep || tr) {
           const int nvalid = p.N - n0 < 32 ? p.N - n0 : 32;
           const bool full = nvalid == 32;
 #pragma unroll
@@ -474,7 +517,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
           }
-          if (has_res) {
+          if (has_res && row_ok) {
             const __nv_bfloat16* rp = p.R + (long long)row * p.ldr + n0;
             if (full && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
 #pragma unroll
@@ -493,7 +536,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (i < nvalid) v[i] += __bfloat162float(rp[i]);
             }
           }
-          if (!kOutF32) {
+          if (tr) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) pk[i / 2] = pack_bf16(v[i], v[i + 1]);
+            transpose_pieces(pk, lane);
+            __nv_bfloat16* cb = static_cast<__nv_bfloat16*>(p.C) + n0 + zslice * p.z_c_cols + (lane >> 3) * 8;
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2)
+              if (ok_s[s2])
+                *reinterpret_cast<uint4*>(cb + orow_s[s2] * p.ldc) =
+                    make_uint4(pk[s2 * 4], pk[s2 * 4 + 1], pk[s2 * 4 + 2], pk[s2 * 4 + 3]);
+          } else if (!kOutF32) {
             __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n0 + zslice * p.z_c_cols;
             if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -537,20 +591,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (EPI == EPI_PROB2) {
       // rows = tokens (M), columns = score columns j (N).  The accumulator already holds S - stab in natural units
       // (position terms and the stabiliser ride on extension K blocks), so the epilogue is exp2 + pack + 16-byte stores.
-      const bool row_ok = row < p.M;
-      __nv_bfloat16* prow = p.P2 + ((size_t)batch * p.M + (row_ok ? row : 0)) * p.p2_ld + (size_t)n_tile * BN;
+      // after transpose_pieces this lane stores piece (lane >> 3) of rows 8*s + (lane & 7), s = 0..3, of its quarter
+      const int row0 = t.m_tile * BM + q * 32 + (lane & 7);
+      __nv_bfloat16* pbase = p.P2 + ((size_t)batch * p.M + row0) * p.p2_ld + (size_t)n_tile * BN + (lane >> 3) * 8;
       const int ncols = (int)p.p2_ld - n_tile * BN;  // columns of this tile that exist in memory (multiple of 32)
-      for (int c = half; c < (BN + 31) / 32; c += 2) {
+      for (int c = half; c < (BN + 31) / 32; c += CSTEP) {
         if (c * 32 >= ncols) break;  // warp-uniform
         tmem_ld32(taddr + c * 32, v);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) pk[i / 2] = pack_bf16(ex2_approx(v[i] * kLog2e), ex2_approx(v[i + 1] * kLog2e));
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(prow + c * 32);
+        transpose_pieces(pk, lane);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-        }
+        for (int s2 = 0; s2 < 4; ++s2)
+          if (row0 + 8 * s2 < p.M)
+            *reinterpret_cast<uint4*>(pbase + (size_t)(8 * s2) * p.p2_ld + c * 32) =
+                make_uint4(pk[s2 * 4], pk[s2 * 4 + 1], pk[s2 * 4 + 2], pk[s2 * 4 + 3]);
       }
     } else if (EPI == EPI_MAX && t.m_tile * BM + q * 32 >= p.M) {
       // every row of this warp is padding (J = 288 fills 2.25 M tiles): nothing to read, just release the buffer
@@ -561,7 +617,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const float* peq = p.peq_t + (size_t)batch * p.M + (row_ok ? row : 0);
       float mx = -INFINITY;
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < BN / 32; c += CSTEP) {
         const int t0 = n_tile * BN + c * 32;
         if (t0 >= p.N) break;
         tmem_ld32(taddr + c * 32, v);
@@ -584,7 +640,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float sum = 0.f, mx = -INFINITY, fsum = 0.f;
       int fcur = -1;
       __nv_bfloat16* prow = p.Pt + col * p.pt_ld + (size_t)n_tile * BN;
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < BN / 32; c += CSTEP) {
         const int t0 = n_tile * BN + c * 32;
         const bool any = t0 < p.N;  // warp-uniform
         uint32_t pk[16];
@@ -659,7 +715,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     } else {  // EPI_POOL: rows = channels d (M), columns = score columns j (N = J)
       float* obase = p.o + (((size_t)batch * p.splits + split) * p.N) * p.M + row;
-      for (int c = half; c < (BN + 31) / 32; c += 2) {
+      for (int c = half; c < (BN + 31) / 32; c += CSTEP) {
         if (nkb > 0) tmem_ld32(taddr + c * 32, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -783,7 +839,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   snprintf(label, sizeof(label), "%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI], (FLAGS & 1) ? "+gelu" : "", p.M, p.N,
            p.K, total, p.guard ? " guarded" : "");
   KernelTimer timer(label, stream);
-  kern<<<ctas, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, ta3 ? *ta3 : ta,
+  kern<<<ctas, num_threads(EPI), Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, ta3 ? *ta3 : ta,
                                                            tb3 ? *tb3 : tb, pp);
   char what[160];
   snprintf(what, sizeof(what), "tc_gemm_kernel<%d,%d,%d> %s", BN, (int)A_MN, (int)B_MN, label);
