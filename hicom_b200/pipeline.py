@@ -6,9 +6,40 @@ device->host copy of the tokens on two CUDA streams so PCIe transfers overlap th
 """
 from __future__ import annotations
 
+import contextlib
+import os
 from typing import Optional
 
 import torch
+
+
+@contextlib.contextmanager
+def host_affinity(device=None):
+    """Pin the calling thread to the CPUs NVML reports as local to ``device`` for the duration of the block.
+
+    Pinned host buffers allocated inside land on the GPU's NUMA node; a buffer on the far socket can cut the
+    host->device rate by 2-3x.  Best effort: without NVML, or when the container's cpuset forbids it, nothing changes.
+    """
+    old = None
+    try:
+        import pynvml
+        index = torch.device(device if device is not None else torch.cuda.current_device()).index or 0
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:
+            index = int(visible.split(",")[index])
+        pynvml.nvmlInit()
+        old = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        old = None
+    try:
+        yield
+    finally:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except Exception:
+                pass
 
 
 @torch.no_grad()
