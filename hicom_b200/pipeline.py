@@ -42,31 +42,54 @@ def host_affinity(device=None):
                 pass
 
 
+# Device staging buffers (two slots per input, one per copy/compute stream), kept across calls: a serving process
+# streams many batches of the same shape, and re-allocating 200 MB blocks per chunk makes the caching allocator
+# stall for hundreds of milliseconds during its first dozen calls.
+_STAGING = {}
+
+
+def release_staging() -> None:
+    """Drop the cached device staging buffers and streams of ``compress_from_host``."""
+    _STAGING.clear()
+
+
+def _staging(device, chunk, tensors):
+    key = (str(device), chunk) + tuple((tuple(t.shape[1:]), t.dtype) if t is not None else None for t in tensors)
+    st = _STAGING.get(key)
+    if st is None:
+        st = {"streams": [torch.cuda.Stream(device), torch.cuda.Stream(device)],
+              "slots": [[None if t is None else torch.empty((chunk,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
+                         for t in tensors] for _ in range(2)]}
+        _STAGING[key] = st
+    return st
+
+
 @torch.no_grad()
 def compress_from_host(projector, frames_feature: torch.Tensor, frames_embed: Optional[torch.Tensor],
                        guide_embed: Optional[torch.Tensor], modal: str = "video", out: Optional[torch.Tensor] = None,
-                       chunk: int = 8, device=None) -> torch.Tensor:
+                       chunk: int = 4, device=None) -> torch.Tensor:
     """``frames_feature`` (B,T,H,W,d) [+ ``frames_embed``] and ``guide_embed`` (B,…) on the HOST (pinned for
     async copies) -> tokens (B, n_tokens, Dh) on the host (``out`` if given, else a new pinned tensor)."""
     device = torch.device(device if device is not None else torch.cuda.current_device())
     B = frames_feature.shape[0]
-    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+    chunk = max(1, min(chunk, B))
+    host = (frames_feature, frames_embed, guide_embed)
+    st = _staging(device, chunk, host)
+    streams = st["streams"]
     main = torch.cuda.current_stream(device)
     for s in streams:
         s.wait_stream(main)
-    pending = []
     for i, b0 in enumerate(range(0, B, chunk)):
         b1 = min(B, b0 + chunk)
         s = streams[i % 2]
         with torch.cuda.stream(s):
-            x = frames_feature[b0:b1].to(device, non_blocking=True)
-            e = None if frames_embed is None else frames_embed[b0:b1].to(device, non_blocking=True)
-            g = None if guide_embed is None else guide_embed[b0:b1].to(device, non_blocking=True)
+            # stream order protects the slot: this copy is queued behind the compute that last read it
+            x, e, g = (None if h is None else d[:b1 - b0].copy_(h[b0:b1], non_blocking=True)
+                       for h, d in zip(host, st["slots"][i % 2]))
             tok = projector.forward_batched(x, e, g, modal)
             if out is None:
                 out = torch.empty((B,) + tuple(tok.shape[1:]), dtype=tok.dtype).pin_memory()
             out[b0:b1].copy_(tok, non_blocking=True)
-            pending.append((x, e, g, tok))  # keep device buffers alive until the stream drains
     for s in streams:
         main.wait_stream(s)
     main.synchronize()
