@@ -397,6 +397,7 @@ class OracleProjector:
     state: Dict[str, Tensor] = field(default_factory=dict)
     local_logit: Optional[tuple] = None  # (logit_scale, logit_bias) tensors when use_clip_scale has 'local'
     global_logit: Optional[tuple] = None
+    qk_dim: int = 1152  # 768 for the CLIP-L tower (projector.py:407-414)
 
     def __post_init__(self):
         self.spec = parse_projector_type(self.projector_type)
@@ -410,7 +411,7 @@ class OracleProjector:
     def _local(self, X, E, g, modal):
         ls, lb = self.local_logit if self.local_logit else (None, None)
         return local_compress(self.spec.local, self._mode(self.spec.local), self.state,
-                              "local_compressor", X, E, g, modal, ls, lb)
+                              "local_compressor", X, E, g, modal, ls, lb, qk_dim=self.qk_dim)
 
     def _global(self, X, g, t0=0):
         ls, lb = self.global_logit if self.global_logit else (None, None)
@@ -512,7 +513,7 @@ def param_shapes(projector_type: str, use_guide, hidden: int, d: int = 1152) -> 
 
 
 def synth_state_dict(projector_type: str, use_guide, hidden: int, seed: int = 0,
-                     dtype=torch.float32) -> Dict[str, Tensor]:
+                     dtype=torch.float32, d: int = 1152) -> Dict[str, Tensor]:
     """Seeded weights independent of module construction order (fixtures regenerate them).
 
     Linear weights N(0, .02²) — the reference uses trunc_normal_(std=.02) (:157,464,625); biases
@@ -522,7 +523,7 @@ def synth_state_dict(projector_type: str, use_guide, hidden: int, seed: int = 0,
     """
     g = torch.Generator().manual_seed(seed)
     sd = {}
-    for name, shape in sorted(param_shapes(projector_type, use_guide, hidden).items()):
+    for name, shape in sorted(param_shapes(projector_type, use_guide, hidden, d).items()):
         if name.endswith("_alpha"):
             v = torch.full(shape, 0.5)
         elif "norm.weight" in name:

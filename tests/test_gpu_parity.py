@@ -238,3 +238,61 @@ def test_fp16_inference_dtype(name, built_library):
     truth = truth_fp32(case)
     assert out.shape == truth.shape
     assert O.rel_err(out.float().cpu(), truth) <= 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("guide", ["coarse", "fine", None])
+def test_clip_l_tower_dims(guide, dtype, built_library):
+    """CLIP-L tower: qk_dim 768, 6 heads of 128, 24x24 patches (projector.py:407-414, 577-579) — 192 score columns."""
+    import hicom_b200
+    from util import Cfg
+    ptype, hidden, T, H, W, d = "local43_global32", 128, 8, 24, 24, 768
+    sd = O.synth_state_dict(ptype, guide, hidden, seed=3, dtype=dtype, d=d)
+    X, E, g = O.synth_inputs(T, H, W, O.guide_kind_for(guide), seed=4, d=d, dtype=dtype)
+    m = hicom_b200.build_vision_projector(Cfg(mm_vision_tower="openai/clip-vit-large-patch14-336", mm_hidden_size=d,
+                                              hidden_size=hidden, use_guide=guide, mm_projector_type=ptype,
+                                              max_num_frames=8))
+    m.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+    m = m.to(dtype).cuda().eval()
+    f = lambda t: None if t is None else t.float()
+    orc = O.OracleProjector(ptype, guide, state={k: v.float() for k, v in sd.items()}, qk_dim=d)
+    with torch.no_grad():
+        want = orc.forward(f(X), f(E), f(g), "video")
+        got = m(to_dev(X), to_dev(E), to_dev(g), "video").float().cpu()
+    assert got.shape == want.shape == (2 * 64 + 32, hidden)
+    if dtype == torch.float32:
+        assert O.rel_err(got, want) <= 1e-4
+    else:
+        assert O.cosine(got, want) >= 0.999 and O.rel_err(got, want) <= 1e-2
+
+
+@pytest.mark.parametrize("name", ["coarse_T8", "direct_T8", "fine_T8", "bf16_coarse_T8"])
+def test_local_clip_scale(name, built_library):
+    """use_clip_scale='local' (projector.py:527-529, 547-549): L2-normalised keys and guide, exp(logit_scale) logits.
+    The SigLIP scalars are set on the module directly (the reference pulls them from the hub, :661-663)."""
+    case = CASES_BY_NAME[name]
+    sd, X, E, g, nl = materialise(case)
+    m = cuda_module_for(case, sd)
+    ls, lb = torch.tensor(2.0), torch.tensor(-5.0)
+    m.local_logit_scale, m.local_logit_bias = ls.cuda(), lb.cuda()
+    f = lambda t: None if t is None else t.float()
+    orc = oracle_for(case, sd, torch.float32)
+    orc.local_logit = (ls, lb)
+    with torch.no_grad():
+        want = orc.forward(f(X), f(E), f(g), case.modal, f(nl))
+        got = m(to_dev(X), to_dev(E), to_dev(g), case.modal, to_dev(nl)).float().cpu()
+    if case.dtype == "float32":
+        assert O.rel_err(got, want) <= FP32_TOL
+    else:
+        assert O.cosine(got, want) >= BF16_COS and O.rel_err(got, want) <= BF16_REL
+
+
+def test_global_clip_scale_is_refused_loudly(built_library):
+    """The reassociated global attention cannot L2-normalise projected keys (projector.py:184-188): it must raise, not
+    silently compute something else."""
+    case = CASES_BY_NAME["coarse_T8"]
+    sd, X, E, g, nl = materialise(case)
+    m = cuda_module_for(case, sd)
+    m.global_logit_scale, m.global_logit_bias = torch.tensor(2.0).cuda(), torch.tensor(-5.0).cuda()
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        m(to_dev(X), to_dev(E), to_dev(g), case.modal, to_dev(nl))

@@ -58,3 +58,43 @@ def test_reference_dict_branch_anyres():
         want = m(feats, embeds, g, "image", nl)
         got = oracle_for(case, sd).forward(feats, embeds, g, "image", nl)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("use_guide", [None, "coarse", "fine"])
+def test_live_reference_clip_l_dims(use_guide):
+    """CLIP-L tower: qk_dim 768, 6 heads (projector.py:407-414, 577-579); pins the oracle's ``qk_dim``/``d`` knobs."""
+    from util import Cfg
+    ref = load_reference()
+    ptype, hidden, d = "local43_global32", 64, 768
+    sd = O.synth_state_dict(ptype, use_guide, hidden, seed=3, d=d)
+    X, E, g = O.synth_inputs(8, 6, 6, O.guide_kind_for(use_guide), seed=4, d=d)
+    m = ref.build_vision_projector(Cfg(mm_vision_tower="openai/clip-vit-large-patch14-336", mm_hidden_size=d,
+                                       hidden_size=hidden, use_guide=use_guide, mm_projector_type=ptype,
+                                       max_num_frames=8))
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        want = m.eval()(X, E, g, "video")
+        got = O.OracleProjector(ptype, use_guide, state=sd, qk_dim=d).forward(X, E, g, "video")
+    assert got.shape == want.shape
+    assert O.rel_err(got, want) <= 2e-6
+
+
+@pytest.mark.parametrize("use_guide", ["coarse", "direct", "fine"])
+def test_live_reference_clip_scale(use_guide):
+    """use_clip_scale='local,global' (projector.py:527-529, 547-549, 184-188) with the SigLIP scalars passed in
+    (the hub weights are unavailable offline)."""
+    from oracle.cases import CASES_BY_NAME
+    ref = load_reference()
+    case = CASES_BY_NAME[f"{use_guide}_T8"]
+    sd, X, E, g, nl = materialise(case)
+    m = ref.build_vision_projector(cfg_for(case))
+    m.load_state_dict(sd, strict=True)
+    ls, lb = torch.tensor(2.0), torch.tensor(-5.0)
+    m.local_logit_scale, m.local_logit_bias = ls, lb
+    m.global_logit_scale, m.global_logit_bias = ls.clone(), lb.clone()
+    orc = oracle_for(case, sd)
+    orc.local_logit, orc.global_logit = (ls, lb), (ls, lb)
+    with torch.no_grad():
+        want = m.eval()(X, E, g, case.modal, nl)
+        got = orc.forward(X, E, g, case.modal, nl)
+    assert O.rel_err(got, want) <= 2e-6
