@@ -16,9 +16,10 @@ import torch
 class GraphedCompressor:
     def __init__(self, projector, frames_feature: torch.Tensor, frames_embed: Optional[torch.Tensor],
                  guide_embed: Optional[torch.Tensor], modal: str = "video", frame_shard_t0: Optional[int] = None,
-                 group=None, warmup: int = 3):
+                 group=None, warmup: int = 3, image_newline: Optional[torch.Tensor] = None):
         self.projector = projector
         self.modal = modal
+        self.image_newline = image_newline  # read in place at replay (a parameter of the parent model)
         self.frames_feature = frames_feature.clone()
         self.frames_embed = None if frames_embed is None else frames_embed.clone()
         self.guide_embed = None if guide_embed is None else guide_embed.clone()
@@ -44,7 +45,8 @@ class GraphedCompressor:
             from . import dist as hdist
             return hdist.forward_frame_sharded(self.projector, self.frames_feature, self.frames_embed,
                                                self.guide_embed, t0=self._t0, group=self._group, modal=self.modal)
-        return self.projector.forward_batched(self.frames_feature, self.frames_embed, self.guide_embed, self.modal)
+        return self.projector.forward_batched(self.frames_feature, self.frames_embed, self.guide_embed, self.modal,
+                                              self.image_newline)
 
     def replay(self):
         self.graph.replay()

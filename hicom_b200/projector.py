@@ -16,6 +16,7 @@ PyTorch/CPU fallback: tensors must live on a B200.  ``forward_batched`` is the a
 from __future__ import annotations
 
 import contextlib
+import collections
 import math
 import os
 import re
@@ -492,7 +493,11 @@ class HIComProjector(nn.Module):
         if cached is None or cached[0] != key:
             import copy
             self.__dict__.pop("_shadow", None)
-            clone = copy.deepcopy(self)
+            saved = {k: self.__dict__.pop(k) for k in ("_graphs", "_graphs_max") if k in self.__dict__}
+            try:  # captured graphs are not copyable and belong to this module's parameters
+                clone = copy.deepcopy(self)
+            finally:
+                self.__dict__.update(saved)
             clone.float()
             clone.eval()
             self.__dict__["_shadow"] = (key, clone)
@@ -616,7 +621,46 @@ class HIComProjector(nn.Module):
         return out.view(B, total, Dh)
 
     # -- reference signature -----------------------------------------------------------------------
+    # -- optional CUDA-graph replay for the reference's per-video call pattern -----------------------
+    def enable_cuda_graphs(self, max_entries: int = 8):
+        """Replay a captured CUDA graph for repeated ``forward`` shapes (hicom_arch.py:167-178 calls the projector
+        once per video: ~37 kernel launches whose host cost exceeds their device time).  Inputs are copied into
+        static buffers, the result is returned as a fresh tensor; entries are keyed by shapes/dtypes and by the
+        parameter storage, least-recently-used eviction.  ``disable_cuda_graphs()`` drops them."""
+        self.__dict__["_graphs"] = collections.OrderedDict()
+        self.__dict__["_graphs_max"] = int(max_entries)
+        return self
+
+    def disable_cuda_graphs(self):
+        self.__dict__.pop("_graphs", None)
+        return self
+
+    def _graphed_forward(self, frames_feature, frames_embed, guide_embed, modal, image_newline):
+        cache = self.__dict__["_graphs"]
+        sig = lambda t: None if t is None else (tuple(t.shape), t.dtype, t.device)
+        key = (sig(frames_feature), sig(frames_embed), sig(guide_embed), modal,
+               None if image_newline is None else image_newline.data_ptr(),
+               tuple(p.data_ptr() for p in self.parameters()))
+        g = cache.get(key)
+        if g is None:
+            from .graph import GraphedCompressor
+            E = None if frames_embed is None else frames_embed.unsqueeze(0)
+            G = None if guide_embed is None else guide_embed.unsqueeze(0)
+            g = GraphedCompressor(self, frames_feature.unsqueeze(0), E, G, modal, image_newline=image_newline)
+            cache[key] = g
+            while len(cache) > self.__dict__["_graphs_max"]:
+                cache.popitem(last=False)
+        else:
+            cache.move_to_end(key)
+        out = g(frames_feature.unsqueeze(0), None if frames_embed is None else frames_embed.unsqueeze(0),
+                None if guide_embed is None else guide_embed.unsqueeze(0))
+        return out[0].clone()
+
     def forward(self, frames_feature, frames_embed, guide_embed, modal, image_newline=None):
+        if ("_graphs" in self.__dict__ and torch.is_tensor(frames_feature) and frames_feature.is_cuda
+                and frames_feature.dtype in (torch.float32, torch.bfloat16) and not torch.is_grad_enabled()
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._graphed_forward(frames_feature, frames_embed, guide_embed, modal, image_newline)
         g = None if guide_embed is None else guide_embed.unsqueeze(0)
         if isinstance(frames_feature, dict):  # any-res images: {"base": (H,W,d)|None, "patch": (H',W',d)}
             base_tokens = None

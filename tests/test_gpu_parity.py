@@ -296,3 +296,27 @@ def test_global_clip_scale_is_refused_loudly(built_library):
     m.global_logit_scale, m.global_logit_bias = torch.tensor(2.0).cuda(), torch.tensor(-5.0).cuda()
     with torch.no_grad(), pytest.raises(NotImplementedError):
         m(to_dev(X), to_dev(E), to_dev(g), case.modal, to_dev(nl))
+
+
+def test_forward_with_cuda_graph_cache(built_library):
+    """enable_cuda_graphs(): the reference's per-video call pattern replays cached graphs; results equal the eager
+    path, outputs are fresh tensors, entries are keyed by shape and evicted least-recently-used."""
+    case = CASES_BY_NAME["bf16_coarse_T8"]
+    sd, X, E, g, nl = materialise(case)
+    m = cuda_module_for(case, sd)
+    Xd, Ed, gd = to_dev(X), to_dev(E), to_dev(g)
+    with torch.no_grad():
+        want8 = m(Xd, Ed, gd, "video").clone()
+        want4 = m(Xd[:4].contiguous(), Ed[:4].contiguous(), gd, "video").clone()
+        m.enable_cuda_graphs(max_entries=1)
+        a = m(Xd, Ed, gd, "video")
+        b = m(Xd, Ed, gd, "video")                       # replay of the cached graph
+        assert a.data_ptr() != b.data_ptr() and len(m.__dict__["_graphs"]) == 1
+        c = m(Xd[:4].contiguous(), Ed[:4].contiguous(), gd, "video")   # second shape evicts the first
+        assert len(m.__dict__["_graphs"]) == 1
+        d = m(Xd * 0.5, Ed, gd, "video")                 # new values through the static buffers of a re-captured graph
+        m.disable_cuda_graphs()
+        want_half = m(Xd * 0.5, Ed, gd, "video")
+    for got, want in ((a, want8), (b, want8), (c, want4), (d, want_half)):
+        assert got.shape == want.shape
+        assert O.rel_err(got.float().cpu(), want.float().cpu()) <= 1e-5
