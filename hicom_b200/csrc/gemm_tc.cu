@@ -153,6 +153,60 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---- CTA pair (cta_group::2) helpers: one MMA spans two SMs (M = 256), each CTA stages its own 128 rows of A and
+// HALF of the B tile; the leader (cluster rank 0) issues the MMAs and owns the "full" barriers ------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in the CTA with rank `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose byte count is credited to a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
+                                                 int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane_base+i), columns col..col+31
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -183,9 +237,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: bf16 x bf16 -> fp32, M=128.
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major, int m = BM) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
@@ -240,12 +294,14 @@ __device__ __forceinline__ void transpose_pieces(uint32_t (&d)[16], int lane) {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool CTA2 = false>
 struct Cfg {
-  // 128x64 tiles are for small problems (few tiles): more CTAs, deeper ring, so more weight bytes are in flight
-  static constexpr int STAGES = BN == 64 ? 8 : 4;
+  // 128x64 tiles are for small problems (few tiles): more CTAs, deeper ring, so more weight bytes are in flight.
+  // A CTA pair stages half of B per CTA: six stages fit where four did.
+  static constexpr int STAGES = BN == 64 ? 8 : (CTA2 ? 6 : 4);
   static constexpr uint32_t A_BYTES = BM * BK * 2;
-  static constexpr uint32_t B_BYTES = ((BN + 63) / 64) * 64 * BK * 2;  // whole 64-wide blocks (MN-major B needs them)
+  // whole 64-wide blocks (MN-major B needs them); a pair member holds BN/2 K-major rows
+  static constexpr uint32_t B_BYTES = CTA2 ? (BN / 2) * BK * 2 : ((BN + 63) / 64) * 64 * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NBUF = BN <= 256 ? 2 : 1;          // accumulator buffers in TMEM (epilogue/mainloop overlap)
   static constexpr uint32_t ACC_COLS = BN <= 256 ? 256 : 512;
@@ -257,13 +313,14 @@ struct TileInfo { int n_tile, m_tile, batch, zslice, split, k_begin, nkb, nkb_ma
 
 // Static tile schedule: persistent CTA c handles tiles c, c+grid, c+2*grid, ... of the (x fastest, y, z) tile space.
 // x = N tile (or K split for EPI_POOL), y = M tile, z = tensor batch (or per-head K slice).
+// pair_rank >= 0: tiles_y counts PAIRS of M tiles and this CTA takes M tile 2*y + pair_rank
 template <int EPI>
-__device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
+__device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile, int pair_rank = -1) {
   TileInfo t;
   const int x = tile % p.tiles_x;
   const int y = (tile / p.tiles_x) % p.tiles_y;
   const int z = tile / (p.tiles_x * p.tiles_y);
-  t.m_tile = y;
+  t.m_tile = pair_rank < 0 ? y : 2 * y + pair_rank;
   t.zslice = p.z_slices > 0 ? z % p.z_slices : 0;
   t.batch = p.z_slices > 0 ? z / p.z_slices : z;
   t.n_tile = (EPI == EPI_POOL) ? 0 : x * (p.n_tile_stride > 0 ? p.n_tile_stride : 1);
@@ -278,12 +335,13 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile) {
 }
 
 // FLAGS (EPI_LINEAR only): bit 0 = GELU, bit 1 = fp32 output
-template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS>
+template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS, bool CTA2 = false>
 __global__ void __launch_bounds__(num_threads(EPI), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB3, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CTA2>;
+  static_assert(!CTA2 || (!A_MN && !B_MN && (EPI == EPI_LINEAR || EPI == EPI_PROB2)), "pairs: K-major operands only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -295,6 +353,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.guard != nullptr && *p.guard == 0) return;  // guarded fallback launch: nothing to repair
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_z;
+  // pair mode: CTAs 2i and 2i+1 form a cluster; both walk the same tile sequence, rank r takes M tile 2y + r
+  const int pair_rank = CTA2 ? (int)cluster_ctarank() : -1;
+  const int tile_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -307,13 +369,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int b = 0; b < C::NBUF; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], epi_warps(EPI));  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], (CTA2 ? 2 : 1) * epi_warps(EPI));  // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc_pair<C::TMEM_COLS>(tmem_slot); else tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -321,8 +386,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== TMA producer: runs ahead across tiles through the C::STAGES-deep ring =====
     {  // the whole warp walks the loops; one elected lane arms the barrier and issues the copies
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileInfo t = decode_tile<EPI>(p, tile);
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        const TileInfo t = decode_tile<EPI>(p, tile, pair_rank);
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
           const int s = it % C::STAGES;
           const uint32_t ph = (it / C::STAGES) & 1;
@@ -333,6 +398,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int k0 = t.k_begin + kb * BK;
           const bool ext = (EPI != EPI_LINEAR) && kb >= t.nkb_main;
           const int ke = ext ? kb - t.nkb_main : 0;  // which extension block
+          if constexpr (CTA2) {
+            // Pair mode (K-major A and B).  The leader's barrier collects the bytes of BOTH CTAs; this CTA copies its
+            // own 128 rows of A and its half of every MMA instruction's B rows into its own shared memory.
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+            if (pair_rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+            constexpr int HALF = BN > 256 ? BN / 4 : BN / 2;   // rows of this CTA per MMA instruction (72 or 128)
+            constexpr int NINST = BN > 256 ? 2 : 1;
+            const int brow = t.n_tile * BN + pair_rank * HALF;
+            if (ext && EPI == EPI_PROB2) {
+              if (ke == 0) tma_load_3d_pair(sa, &tmA2, bar, 0, t.m_tile * BM, 0);
+              else tma_load_3d_pair(sa, &tmA3, bar, 0, t.m_tile * BM, 0);
+              // the time table is read at the first frame of the PAIR's 256 tokens (8-aligned), like the one-hot
+              const int f0 = (((t.m_tile & ~1) * BM) / p.HW) & ~7;
+#pragma unroll
+              for (int i = 0; i < NINST; ++i) {
+                if (ke == 0) tma_load_3d_pair(sb + i * HALF * 128, &tmB2, bar, 0, brow + i * 2 * HALF, t.batch);
+                else tma_load_3d_pair(sb + i * HALF * 128, &tmB3, bar, f0, brow + i * 2 * HALF, t.batch);
+              }
+            } else {
+              tma_load_3d_pair(sa, &tmA, bar, k0 + t.zslice * p.z_a_k, t.m_tile * BM, t.batch);
+#pragma unroll
+              for (int i = 0; i < NINST; ++i)
+                tma_load_3d_pair(sb + i * HALF * 128, &tmB, bar, k0 + t.zslice * p.z_b_k, brow + i * 2 * HALF, t.batch);
+            }
+          } else {
           // MN-major B arrives as whole 64-wide blocks; K-major B as BN rows
           const bool b_mn_now = B_MN && !(EPI == EPI_POOL && ext);
           mbar_expect_tx(&full_bar[s], C::A_BYTES + (b_mn_now ? C::B_BYTES : (uint32_t)BN * BK * 2));
@@ -378,6 +468,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int r = 0; r < BN; r += p.b_box_rows)
               tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0 + t.zslice * p.z_b_k, t.n_tile * BN + r, t.batch);
           }
+          }  // !CTA2
           }
           __syncwarp();
         }
@@ -385,7 +476,46 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the loops (uniform control flow), one elected lane issues =====
-    {
+    if constexpr (CTA2) {
+      // pair mode: only the leader issues; one instruction covers 256 rows (128 per CTA) and reads half of its B rows
+      // from each CTA.  BN = 288 -> two instructions of 144 columns (72 rows per CTA each), BN = 256 -> one.
+      if (pair_rank == 0) {
+        constexpr int NI = BN > 256 ? BN / 2 : BN;          // columns per instruction
+        constexpr int HALF = NI / 2;                        // B rows per CTA per instruction
+        constexpr uint32_t idesc = make_idesc(NI, false, false, 2 * BM);
+        uint32_t it = 0, tcount = 0;
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
+          const TileInfo t = decode_tile<EPI>(p, tile, pair_rank);
+          const uint32_t buf = tcount % C::NBUF;
+          const uint32_t bph = (tcount / C::NBUF) & 1;
+          mbar_wait(&tmem_empty_bar[buf], bph ^ 1);  // both CTAs' epilogues have drained this accumulator buffer
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
+          for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+            const int s = it % C::STAGES;
+            const uint32_t ph = (it / C::STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
+            const uint32_t sb = sa + C::A_BYTES;
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < BK / UK; ++kk) {
+                const uint64_t adesc = make_smem_desc(sa + kk * 32, 16, 1024);
+                const uint32_t acc = (kb > 0 || kk > 0) ? 1u : 0u;
+                umma_bf16_pair(d_tmem, adesc, make_smem_desc(sb + kk * 32, 16, 1024), idesc, acc);
+                if (BN > 256)
+                  umma_bf16_pair(d_tmem + NI, adesc, make_smem_desc(sb + HALF * 128 + kk * 32, 16, 1024), idesc, acc);
+              }
+              umma_commit_pair(&empty_bar[s]);  // frees the stage in both CTAs
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit_pair(&tmem_full_bar[buf]);  // both CTAs' epilogues may read their 128 rows
+          __syncwarp();
+        }
+      }
+    } else {
       constexpr int N_MAIN = BN > 256 ? 256 : BN, N_TAIL = BN > 256 ? BN - 256 : 8;
       // an MN-major operand is made of whole 64-wide swizzle blocks: its tail instruction covers the full fifth block
       // (columns 288..319 are padding whose results the epilogue never reads)
@@ -393,8 +523,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc_main_mn = make_idesc(N_MAIN, A_MN, true), idesc_main_k = make_idesc(N_MAIN, A_MN, false);
       constexpr uint32_t idesc_tail_mn = make_idesc(N_TAIL_MN, A_MN, true), idesc_tail_k = make_idesc(N_TAIL, A_MN, false);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        const TileInfo t = decode_tile<EPI>(p, tile);
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
+        const TileInfo t = decode_tile<EPI>(p, tile, pair_rank);
         const uint32_t buf = tcount % C::NBUF;
         const uint32_t bph = (tcount / C::NBUF) & 1;
         mbar_wait(&tmem_empty_bar[buf], bph ^ 1);  // the epilogue has drained this accumulator buffer
@@ -443,8 +573,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 2) >> 2;  // which of the EW/4 warps of this lane quarter
     constexpr int CSTEP = epi_warps(EPI) / 4;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-    const TileInfo t = decode_tile<EPI>(p, tile);
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
+    const TileInfo t = decode_tile<EPI>(p, tile, pair_rank);
     const uint32_t buf = tcount % C::NBUF;
     const uint32_t bph = (tcount / C::NBUF) & 1;
     const int n_tile = t.n_tile, batch = t.batch, zslice = t.zslice, split = t.split, nkb = t.nkb;
@@ -727,13 +857,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // all tcgen05.ld of this tile have completed (tcgen05.wait::ld): hand the accumulator buffer back to the MMA warp
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    if (lane == 0) {
+      if (CTA2 && pair_rank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[buf]), 0));
+      else mbar_arrive(&tmem_empty_bar[buf]);
+    }
     }  // tile loop
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  if (CTA2) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it
+  if (warp == 1) {
+    if (CTA2) tmem_dealloc_pair<C::TMEM_COLS>(tmem_base); else tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -811,14 +947,15 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS = 0>
+template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS = 0, bool CTA2 = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t stream,
                   const CUtensorMap* ta2 = nullptr, const CUtensorMap* tb2 = nullptr,
                   const CUtensorMap* ta3 = nullptr, const CUtensorMap* tb3 = nullptr) {
   static bool configured = false;
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI, FLAGS>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, EPI, FLAGS, CTA2>;
+  constexpr size_t kSmem = Cfg<BN, CTA2>::SMEM_BYTES;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     HICOM_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
@@ -830,20 +967,42 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     if (num_sms <= 0) num_sms = 148;
   }
   Params pp = p;
-  pp.tiles_x = (int)grid.x; pp.tiles_y = (int)grid.y; pp.tiles_z = (int)grid.z;
-  const long long total = (long long)grid.x * grid.y * grid.z;
+  // pair mode: grid.y counts M tiles; two of them (one per CTA of a pair) make one scheduled tile
+  pp.tiles_x = (int)grid.x; pp.tiles_y = CTA2 ? (int)(grid.y + 1) / 2 : (int)grid.y; pp.tiles_z = (int)grid.z;
+  const long long total = (long long)pp.tiles_x * pp.tiles_y * pp.tiles_z;
   if (total == 0) return 0;
-  const unsigned ctas = (unsigned)(total < num_sms ? total : num_sms);  // persistent: one CTA per SM at most
+  // persistent: one CTA per SM at most (one pair per two SMs)
+  const unsigned ctas = CTA2 ? 2u * (unsigned)(total < num_sms / 2 ? total : num_sms / 2)
+                             : (unsigned)(total < num_sms ? total : num_sms);
   char label[96];
   static const char* names[] = {"tc_linear", "tc_scores_max", "tc_scores_prob", "tc_pool", "tc_scores_prob2"};
-  snprintf(label, sizeof(label), "%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI], (FLAGS & 1) ? "+gelu" : "", p.M, p.N,
-           p.K, total, p.guard ? " guarded" : "");
+  snprintf(label, sizeof(label), "%s%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI], (FLAGS & 1) ? "+gelu" : "",
+           CTA2 ? "/pair" : "", p.M, p.N, p.K, total, p.guard ? " guarded" : "");
   KernelTimer timer(label, stream);
-  kern<<<ctas, num_threads(EPI), Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, ta3 ? *ta3 : ta,
-                                                           tb3 ? *tb3 : tb, pp);
+  if (CTA2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(num_threads(EPI)); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, ta3 ? *ta3 : ta,
+                                       tb3 ? *tb3 : tb, pp);
+    HICOM_REQUIRE(e == cudaSuccess, "cudaLaunchKernelEx(%s): %s", label, cudaGetErrorString(e));
+  } else {
+    kern<<<ctas, num_threads(EPI), kSmem, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, ta3 ? *ta3 : ta,
+                                                    tb3 ? *tb3 : tb, pp);
+  }
   char what[160];
   snprintf(what, sizeof(what), "tc_gemm_kernel<%d,%d,%d> %s", BN, (int)A_MN, (int)B_MN, label);
   return check_launch(what);
+}
+
+static bool pair_mode_enabled() {
+  static int on = -1;
+  // default on; HICOM_CTA2=0 keeps every GEMM on single-CTA tiles (cross-check, tested in a child process)
+  if (on < 0) { const char* e = getenv("HICOM_CTA2"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
 }
 
 }  // namespace tc
@@ -916,6 +1075,18 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
       case 1: return launch<64, false, false, EPI_LINEAR, 1>(ta, tb64, p, g64, stream);
       case 2: return launch<64, false, false, EPI_LINEAR, 2>(ta, tb64, p, g64, stream);
       case 3: return launch<64, false, false, EPI_LINEAR, 3>(ta, tb64, p, g64, stream);
+    }
+  }
+  // large plain K-major GEMMs: CTA pairs (cta_group::2), each CTA stages half of the weight tile
+  if (pair_mode_enabled() && !q.w_is_kn && q.z_slices == 0 && q.diag_heads == 0 &&
+      (long long)grid.x * grid.y >= 296) {
+    CUtensorMap tb128;
+    if (make_map(&tb128, q.W, kext, q.N, 1, q.ldw, 0, 128)) return 1;
+    switch (flags) {
+      case 0: return launch<256, false, false, EPI_LINEAR, 0, true>(ta, tb128, p, grid, stream);
+      case 1: return launch<256, false, false, EPI_LINEAR, 1, true>(ta, tb128, p, grid, stream);
+      case 2: return launch<256, false, false, EPI_LINEAR, 2, true>(ta, tb128, p, grid, stream);
+      case 3: return launch<256, false, false, EPI_LINEAR, 3, true>(ta, tb128, p, grid, stream);
     }
   }
 #define HICOM_TC_LINEAR_CASE(F)                                                                  \
@@ -1112,9 +1283,9 @@ __global__ void build_pe3_kernel(const float* pt, const float* ph, const float* 
   }
 }
 // ind[n] = [ one-hot(h), one-hot(H+w), .., 1 (col 63) | one-hot(frame - base of n's K slice) | one-hot(frame - base of
-//            n's 128-token tile) ], 3 x 64 columns; a base is the first frame of the range rounded down to a multiple of
+//            n's score tile: 128 tokens, or the 256 of a CTA pair) ], 3 x 64 columns; a base is the first frame of the range rounded down to a multiple of
 //            8 (the same 16-byte-aligned coordinate the TMA producer uses).  One thread writes 8 columns (16 bytes).
-__global__ void build_ind3_kernel(__nv_bfloat16* ind, int N, int H, int W, int kslice) {
+__global__ void build_ind3_kernel(__nv_bfloat16* ind, int N, int H, int W, int kslice, int rel_tile) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   constexpr int G = 3 * kKe / 8;
   if (i >= (long long)N * G) return;
@@ -1124,7 +1295,7 @@ __global__ void build_ind3_kernel(__nv_bfloat16* ind, int N, int H, int W, int k
   int hot0 = -1, hot1 = -1, hot2 = -1;  // columns of this row that hold a one
   if (g < kKe / 8) { hot0 = h; hot1 = H + w; hot2 = kKe - 1; }
   else if (g < 2 * kKe / 8) hot0 = kKe + t - ((((n / kslice) * kslice) / hw) & ~7);
-  else hot0 = 2 * kKe + t - ((((n / BM) * BM) / hw) & ~7);
+  else hot0 = 2 * kKe + t - ((((n / rel_tile) * rel_tile) / hw) & ~7);
   uint32_t v[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -1226,7 +1397,9 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   // 0. tables and indicator matrices
   build_pe3_kernel<<<w.Tk + w.ke2, 256, 0, stream>>>(pos_t, pos_h, pos_w, pe_t, pe2, T, w.Tk, w.ke2, H, W, d);
   if (check_launch("build_pe3_kernel")) return 1;
-  build_ind3_kernel<<<blocks((long long)N * (w.ild / 8)), 256, 0, stream>>>(ind, N, H, W, w.kslice);
+  // the probability pass runs on CTA pairs (256-token tiles) when enabled and the tile's frames fit the 64-wide one-hot
+  const bool pair = pair_mode_enabled() && J > 64;  // H*W >= 32 (tc_global_selected): 256 tokens span <= 9 frames
+  build_ind3_kernel<<<blocks((long long)N * (w.ild / 8)), 256, 0, stream>>>(ind, N, H, W, w.kslice, pair ? 2 * BM : BM);
   if (check_launch("build_ind3_kernel")) return 1;
   init_stats_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, lsum, (int)BJ, flag);
   if (check_launch("init_stats_kernel")) return 1;
@@ -1267,6 +1440,12 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   if (make_map(&ti1, ind + 2 * kKe, kKe, N, 1, w.ild, 0, BM)) return 1;
   if (make_map(&tqej, qext, kKe, J, B, kKe, (uint64_t)J * kKe, jbox)) return 1;
   if (make_map(&ttq, tq, w.tq_ld, J, B, w.tq_ld, (uint64_t)J * w.tq_ld, jbox)) return 1;
+  CUtensorMap tqj72, tqej72, ttq72;  // pair mode: each CTA stages 72 of the 144 rows of an MMA instruction's B operand
+  if (pair) {
+    if (make_map(&tqj72, qfold, d, J, B, d, (uint64_t)J * d, 72)) return 1;
+    if (make_map(&tqej72, qext, kKe, J, B, kKe, (uint64_t)J * kKe, 72)) return 1;
+    if (make_map(&ttq72, tq, w.tq_ld, J, B, w.tq_ld, (uint64_t)J * w.tq_ld, 72)) return 1;
+  }
   Params pp{};
   pp.M = N; pp.N = J; pp.K = d; pp.k_chunk = d; pp.b_box_rows = (int)jbox;
   pp.k_ext_blocks = 2; pp.HW = H * W; pp.T = T; pp.P2 = P2; pp.p2_ld = w.pld;
@@ -1300,6 +1479,10 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
     make_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, stab, qext, (int)BJ, margin, guard);
     if (check_launch("make_stab3_kernel")) return 1;
     Params p1 = pp; p1.guard = guard;
+    if (pair) {
+      if (launch<288, false, false, EPI_PROB2, 0, true>(tx128, tqj72, p1, gprob, stream, &ti0, &tqej72, &ti1, &ttq72))
+        return 1;
+    } else
     if (narrow ? launch<64, false, false, EPI_PROB2>(tx128, tqj, p1, gprob, stream, &ti0, &tqej, &ti1, &ttq)
                : launch<288, false, false, EPI_PROB2>(tx128, tqj, p1, gprob, stream, &ti0, &tqej, &ti1, &ttq)) return 1;
     TcLinearParams m1 = mm; m1.guard = guard;

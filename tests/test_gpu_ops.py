@@ -278,3 +278,33 @@ def test_global_v2_pipeline_still_matches(built_library):
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+def test_single_cta_tiles_still_match(built_library):
+    """HICOM_CTA2=0 turns the CTA-pair (cta_group::2) variants off (read once per process): run the GEMM-heavy op tests
+    on single-CTA tiles in a child."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HICOM_CTA2="0")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_ops.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "(linear or global_partial) and not pipeline and not single_cta", "-p",
+                        "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
+
+
+@pytest.mark.parametrize("M,N,K,act", [(40000, 512, 256, 0), (10300, 3584, 1152, 1), (38000, 300, 64, 0)])
+def test_linear_cta_pairs_large(M, N, K, act, built_library):
+    """Large plain GEMMs run on CTA pairs (M = 256 per MMA, half of the weight tile per CTA): odd M-tile counts, ragged
+    N, short K."""
+    from hicom_b200 import ops
+    A = _rand(M, K, seed=21, dtype=torch.bfloat16).cuda()
+    W = _rand(N, K, seed=22, std=0.03, dtype=torch.bfloat16).cuda()
+    b = _rand(N, seed=23, dtype=torch.bfloat16).cuda()
+    got = ops.linear(A, W, b, None, act, False, ops.IMPL_AUTO).float()
+    ref = A.float() @ W.float().t() + b.float()
+    if act:
+        ref = F.gelu(ref)
+    assert O.rel_err(got.cpu(), ref.cpu()) <= 6e-3
