@@ -28,8 +28,11 @@ constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UK = 16;   // K per tcgen05.mma for 16-bit inputs
 // warp 0 TMA, warp 1 MMA, then the epilogue warps: two per TMEM lane quarter, four for the probability pass (its
 // 288-column accumulator cannot be double-buffered in 512 TMEM columns, so its epilogue is on the critical path)
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == 4 /*EPI_PROB2*/ ? 16 : 8; }
-__host__ __device__ constexpr int num_threads(int epi) { return 64 + 32 * epi_warps(epi); }
+// ... and for the GELU linear, whose epilogue (two MUFU + ~15 FP32 ops per element) outlasts a K = 1152 mainloop
+__host__ __device__ constexpr int epi_warps(int epi, int flags = 0) {
+  return (epi == 4 /*EPI_PROB2*/ || (epi == 0 /*EPI_LINEAR*/ && (flags & 1))) ? 16 : 8;
+}
+__host__ __device__ constexpr int num_threads(int epi, int flags = 0) { return 64 + 32 * epi_warps(epi, flags); }
 
 enum { EPI_LINEAR = 0, EPI_MAX = 1, EPI_PROB = 2, EPI_POOL = 3, EPI_PROB2 = 4 };
 
@@ -170,7 +173,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default .release.cta semantics (as CUTLASS' ClusterBarrier::arrive): the TMEM reads this orders were completed by
+  // tcgen05.wait::ld already; a cluster-scope release would also drain the epilogue's global stores (MEMBAR.ALL.GPU)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose byte count is credited to a barrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
@@ -298,7 +303,7 @@ template <int BN, bool CTA2 = false>
 struct Cfg {
   // 128x64 tiles are for small problems (few tiles): more CTAs, deeper ring, so more weight bytes are in flight.
   // A CTA pair stages half of B per CTA: six stages fit where four did.
-  static constexpr int STAGES = BN == 64 ? 8 : (CTA2 ? 6 : 4);
+  static constexpr int STAGES = BN == 64 ? 8 : (CTA2 ? (BN <= 144 ? 8 : 6) : 4);
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   // whole 64-wide blocks (MN-major B needs them); a pair member holds BN/2 K-major rows
   static constexpr uint32_t B_BYTES = CTA2 ? (BN / 2) * BK * 2 : ((BN + 63) / 64) * 64 * BK * 2;
@@ -336,7 +341,7 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile, int p
 
 // FLAGS (EPI_LINEAR only): bit 0 = GELU, bit 1 = fp32 output
 template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS, bool CTA2 = false>
-__global__ void __launch_bounds__(num_threads(EPI), 1)
+__global__ void __launch_bounds__(num_threads(EPI, FLAGS), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB3, const Params p) {
@@ -369,7 +374,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int b = 0; b < C::NBUF; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], (CTA2 ? 2 : 1) * epi_warps(EPI));  // one arrival per epilogue warp (of both CTAs)
+      mbar_init(&tmem_empty_bar[b], (CTA2 ? 2 : 1) * epi_warps(EPI, FLAGS));  // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
@@ -571,7 +576,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== epilogue warps: TMEM lane quarter = warp % 4; the two warps of a quarter take alternate 32-column chunks =====
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;  // which of the EW/4 warps of this lane quarter
-    constexpr int CSTEP = epi_warps(EPI) / 4;
+    constexpr int CSTEP = epi_warps(EPI, FLAGS) / 4;
     uint32_t tcount = 0;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
     const TileInfo t = decode_tile<EPI>(p, tile, pair_rank);
@@ -724,7 +729,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // after transpose_pieces this lane stores piece (lane >> 3) of rows 8*s + (lane & 7), s = 0..3, of its quarter
       const int row0 = t.m_tile * BM + q * 32 + (lane & 7);
       __nv_bfloat16* pbase = p.P2 + ((size_t)batch * p.M + row0) * p.p2_ld + (size_t)n_tile * BN + (lane >> 3) * 8;
-      const int ncols = (int)p.p2_ld - n_tile * BN;  // columns of this tile that exist in memory (multiple of 32)
+      // columns this tile may write (multiple of 8): a single N tile also fills the row's padding up to p2_ld, one of
+      // several must leave its neighbour's columns alone
+      const int ncols = p.tiles_x == 1 ? (int)p.p2_ld : min(BN, (int)p.p2_ld - n_tile * BN);
       for (int c = half; c < (BN + 31) / 32; c += CSTEP) {
         if (c * 32 >= ncols) break;  // warp-uniform
         tmem_ld32(taddr + c * 32, v);
@@ -734,7 +741,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         transpose_pieces(pk, lane);
 #pragma unroll
         for (int s2 = 0; s2 < 4; ++s2)
-          if (row0 + 8 * s2 < p.M)
+          if (row0 + 8 * s2 < p.M && c * 32 + (lane >> 3) * 8 < ncols)
             *reinterpret_cast<uint4*>(pbase + (size_t)(8 * s2) * p.p2_ld + c * 32) =
                 make_uint4(pk[s2 * 4], pk[s2 * 4 + 1], pk[s2 * 4 + 2], pk[s2 * 4 + 3]);
       }
@@ -981,7 +988,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   KernelTimer timer(label, stream);
   if (CTA2) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(num_threads(EPI)); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(num_threads(EPI, FLAGS)); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -990,7 +997,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
                                        tb3 ? *tb3 : tb, pp);
     HICOM_REQUIRE(e == cudaSuccess, "cudaLaunchKernelEx(%s): %s", label, cudaGetErrorString(e));
   } else {
-    kern<<<ctas, num_threads(EPI), kSmem, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, ta3 ? *ta3 : ta,
+    kern<<<ctas, num_threads(EPI, FLAGS), kSmem, stream>>>(ta, tb, ta2 ? *ta2 : ta, tb2 ? *tb2 : tb, ta3 ? *ta3 : ta,
                                                     tb3 ? *tb3 : tb, pp);
   }
   char what[160];
@@ -1479,7 +1486,12 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
     make_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, stab, qext, (int)BJ, margin, guard);
     if (check_launch("make_stab3_kernel")) return 1;
     Params p1 = pp; p1.guard = guard;
-    if (pair) {
+    static const bool halves = [] { const char* e = getenv("HICOM_PROB_HALVES"); return !(e && e[0] == '0'); }();
+    if (pair && halves && J == 288) {
+      // two 144-column N tiles per 256-token pair tile: accumulators double-buffered, the token tile is fetched twice
+      if (launch<144, false, false, EPI_PROB2, 0, true>(tx128, tqj72, p1, dim3(2, gprob.y, gprob.z), stream, &ti0,
+                                                        &tqej72, &ti1, &ttq72)) return 1;
+    } else if (pair) {
       if (launch<288, false, false, EPI_PROB2, 0, true>(tx128, tqj72, p1, gprob, stream, &ti0, &tqej72, &ti1, &ttq72))
         return 1;
     } else
