@@ -415,7 +415,7 @@ def run_ours(args):
     roof["peak_source"] = pk["source"] + (" (sustained bf16)" if kind != "hbm" else " (copy)")
     roof["traffic"] = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if args.workload == "c2" and os.path.exists(tpath):  # DRAM bytes per launch from the committed ncu --set full capture
+    if args.workload == "c2" and USE_GUIDE == "coarse" and os.path.exists(tpath):  # DRAM bytes per launch, committed ncu capture
         roof["traffic"] = json.load(open(tpath)).get(dname.split()[0])
     exec_flops = videos_per_step * (w["flops_scores"] + w["flops_pool"] + w["flops_local_readout"])
     ops_table = {k: {"calls": c, "ms_per_step": ms / op_steps} for k, (c, ms) in

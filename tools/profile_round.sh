@@ -14,6 +14,6 @@ timeout 300 python tools/latency_b1.py > $O/latency_b1.txt 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_final.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-  -k "regex:local_attend_v2|tc_gemm_kernel<.int.288" -s 3 -c 3 -o $O/prof_final \
+  -k "regex:local_attend_v2|tc_gemm_kernel<.int.288|tc_gemm_kernel<.int.144" -s 0 -c 5 -o $O/prof_final \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graph > $O/ncu_final.log 2>&1
 ls -la $O/*.ncu-rep
