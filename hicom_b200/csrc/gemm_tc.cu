@@ -1,17 +1,24 @@
 // tcgen05 / TMEM / TMA GEMM family for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
 //
 // One warp-specialised PERSISTENT kernel template (grid <= #SMs, static tile schedule, 128 x BN output tiles,
-// two accumulator buffers in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1):
+// two accumulator buffers in TMEM when BN <= 256 so the epilogue of tile i overlaps the mainloop of tile i+1):
 //   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B boxes) into a STAGES-deep smem ring
 //   warp 1      MMA issuer     one elected lane issues tcgen05.mma (M=128, N<=256, K=16) per 32-byte K slice,
 //                              tcgen05.commit releases smem stages and finally publishes the accumulator
-//   warps 2..5  epilogue       tcgen05.ld of the 128 x BN fp32 accumulator (one TMEM lane = one output row
-//                              per thread), fused epilogue, stores
+//   warps 2..   epilogue       8 warps (16 for the probability pass and the GELU linear): tcgen05.ld of the
+//                              128 x BN fp32 accumulator (one TMEM lane = one output row per thread), fused
+//                              epilogue, coalesced stores
+// CTA2 variants (large K-major GEMMs): two CTAs of a cluster form a pair, tcgen05.mma.cta_group::2 covers 256 rows,
+// each CTA stages its own 128 rows of A and half of the B rows (see the "CTA pair" helpers below).
 // Uses:
 //   EPI_LINEAR  C = act(A·Wᵀ + bias) + R                 nn.Linear stages / readouts   (projector.py:307-312)
-//   EPI_MAX     column max of S = qfold·X'ᵀ               global scores, pass 1         (projector.py:197,213)
-//   EPI_PROB    P = exp(S - max) (bf16) and its row sums  global scores, pass 2
-//   EPI_POOL    O = X'ᵀ·P (A operand MN-major)            global P·V in reassociated form (projector.py:215)
+//   EPI_MAX     column max of S = qfold·X'ᵀ               sampled / exact stabiliser    (projector.py:197,213)
+//   EPI_PROB2   P2 = exp(S - stab), tokens on M           global scores -> probabilities (default pipeline)
+//   EPI_PROB    P = exp(S - stab), score columns on M     same, older pipeline (HICOM_GLOBAL_V3=0)
+//   EPI_POOL    O = [X ; tables]ᵀ·[P ; marginals]         global P·V in reassociated form (projector.py:215)
+// Environment switches (read once per process; defaults are the fast paths, the others are kept as cross-checks and
+// exercised by child-process tests): HICOM_CTA2=0 single-CTA tiles only; HICOM_PROB_HALVES=0 one 288-column pair tile
+// instead of two 144-column halves; HICOM_GLOBAL_V3=0 the older global pipeline.
 #include <cuda.h>
 #include <stdlib.h>
 
