@@ -450,12 +450,15 @@ class GlobalCompressor(nn.Module):
         return out
 
 
-def default_splits(B: int, N: int, d: int = 1152) -> int:
-    """Token ranges per video for the pooling GEMM's split-K: (d/128) row tiles x B videos x splits CTAs should
-    cover the 148 SMs about twice; each range keeps >= 512 tokens.  Fewer splits = fewer fp32 partials to merge."""
-    tiles = max(1, d // 128) * max(B, 1)
-    want = max(1, -(-296 // tiles))
-    return max(1, min(want, N // 512 if N >= 512 else 1))
+def default_splits(B: int, N: int, d: int = 1152, sms: int = 148) -> int:
+    """Token ranges per video for the pooling GEMM's split-K.  The persistent kernel walks (d/128) row tiles x B videos
+    x splits tiles in waves of ``sms`` CTAs, so the time is ~ ceil(tiles / sms) / splits: take the smallest split count
+    within 5 % of the best (fewer splits = fewer fp32 partials to write and merge), each range >= 512 tokens."""
+    base = max(1, d // 128) * max(B, 1)
+    cap = max(1, min(64, N // 512 if N >= 512 else 1))
+    cost = lambda s: -(-(base * s) // sms) / s
+    best = min(cost(s) for s in range(1, cap + 1))
+    return next(s for s in range(1, cap + 1) if cost(s) <= 1.05 * best)
 
 
 class HIComProjector(nn.Module):
