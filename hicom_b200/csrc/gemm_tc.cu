@@ -1246,14 +1246,19 @@ static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits
   w.ke2 = kKe + (T + 63) / 64 * 64;      // pooled-PE columns: [h | w | .. | ones] + absolute frame one-hot
   w.ild = 3 * kKe;                       // indicator row: [spatial | frame rel. to K slice | frame rel. to 128-token tile]
   w.tq_ld = (T + 64 + 7) / 8 * 8;
-  // K slices of the marginal GEMM: enough (video, row tile, slice) CTAs for two waves, each slice >= 512 tokens, and
-  // few enough frames per slice (<= 48 + rounding) that a 64-wide relative one-hot covers them whatever T is
+  // K slices of the marginal GEMM.  The persistent kernel walks B x (row tiles) x slices tiles in waves of ~148
+  // CTAs, so its time goes like ceil(tiles / 148) / slices: take the smallest slice count within 5 % of the best.
+  // Each slice keeps >= 512 tokens and spans few enough frames (<= 48 + rounding) that a 64-wide relative one-hot
+  // covers them whatever T is.
   const int mt = (J + tc::BM - 1) / tc::BM;
-  int ms = (296 + B * mt - 1) / (B * mt);
   const int ms_cap = (int)(N / 512) < 1 ? 1 : ((int)(N / 512) > 128 ? 128 : (int)(N / 512));
-  ms = ms < 1 ? 1 : (ms > ms_cap ? ms_cap : ms);
   const int ms_min = (T + 47) / 48;
-  w.mslices = ms < ms_min ? ms_min : ms;
+  auto cost = [&](int s2) { return (double)(((long long)B * mt * s2 + 147) / 148) / s2; };
+  double best = 1e30;
+  for (int s2 = ms_min; s2 <= (ms_cap > ms_min ? ms_cap : ms_min); ++s2) best = cost(s2) < best ? cost(s2) : best;
+  w.mslices = ms_min;
+  for (int s2 = ms_min; s2 <= (ms_cap > ms_min ? ms_cap : ms_min); ++s2)
+    if (cost(s2) <= 1.05 * best) { w.mslices = s2; break; }
   w.kslice = (int)(((N + w.mslices - 1) / w.mslices + tc::BK - 1) / tc::BK * tc::BK);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
@@ -1518,7 +1523,13 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   // 1. sampled max over a few evenly spaced token tiles, 2. everything with stab = sampled max + margin
   {
     Params ps = pmx;
-    const int n_sample = n_tiles256 < 4 ? n_tiles256 : 4;
+    // 2..4 evenly spaced 256-token tiles per video: the count that needs the fewest waves of 148 CTAs (ties: more)
+    int n_sample = n_tiles256 < 4 ? n_tiles256 : 4;
+    {
+      auto waves = [&](int n) { return ((long long)n * mj_tiles * B + 147) / 148; };
+      for (int n = n_sample - 1; n >= 2; --n)
+        if (waves(n) < waves(n_sample)) n_sample = n;
+    }
     ps.n_tile_stride = n_tiles256 / n_sample;
     if (launch<256, false, false, EPI_MAX>(tq128, tx256, ps, dim3(n_sample, mj_tiles, B), stream, &tqe128, &tind256))
       return 1;
