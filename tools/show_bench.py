@@ -1,3 +1,4 @@
+"""Print value, ms/step and the largest kernels of a bench.py JSON line read from stdin:  python bench.py ... | python tools/show_bench.py TAG [kernel-substring]"""
 import json, sys
 tag = sys.argv[1]; pat = sys.argv[2] if len(sys.argv) > 2 else ""
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
