@@ -71,6 +71,7 @@ struct Params {
   int b_shared;                    // B operand has no batch axis (coordinate 0 for every batch entry)
   __nv_bfloat16* P2; long long p2_ld;  // EPI_PROB2: probabilities (B, tokens, p2_ld), token-major
   const float* peq_t; long long peq_ld;  // (T, B*J) time term of the scores: pos_t[t]·qfold[b,j]
+  const __nv_bfloat16* tqm; long long tqm_ld;  // if set: the same term as (B*J, tqm_ld) bf16 rows (EPI_MAX, default pipeline)
   float* margT; int margT_ld;      // (B*J, margT_ld) sum of probabilities per frame (EPI_PROB accumulates)
 
 };
@@ -759,7 +760,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (EPI == EPI_MAX) {
       // rows = score columns j (M = J), columns = tokens of this tile
       const bool row_ok = row < p.M;
-      const float* peq = p.peq_t + (size_t)batch * p.M + (row_ok ? row : 0);
+      const size_t col = (size_t)batch * p.M + (row_ok ? row : 0);
+      const float* peq = p.peq_t != nullptr ? p.peq_t + col : nullptr;
+      const __nv_bfloat16* tqr = p.tqm != nullptr ? p.tqm + col * p.tqm_ld : nullptr;
       float mx = -INFINITY;
       for (int c = half; c < BN / 32; c += CSTEP) {
         const int t0 = n_tile * BN + c * 32;
@@ -768,8 +771,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // time term of the position embedding: a 32-token chunk touches at most two frames (HW >= 32)
         const int f0 = t0 / p.HW;
         const int nb = (f0 + 1) * p.HW - t0;
-        const float pt0 = peq[(size_t)f0 * p.peq_ld];
-        const float pt1 = (f0 + 1 < p.T) ? peq[(size_t)(f0 + 1) * p.peq_ld] : 0.f;
+        float pt0, pt1;
+        if (p.tqm != nullptr) {
+          pt0 = __bfloat162float(tqr[f0]);
+          pt1 = (f0 + 1 < p.T) ? __bfloat162float(tqr[f0 + 1]) : 0.f;
+        } else {
+          pt0 = peq[(size_t)f0 * p.peq_ld];
+          pt1 = (f0 + 1 < p.T) ? peq[(size_t)(f0 + 1) * p.peq_ld] : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (t0 + i < p.N) mx = fmaxf(mx, v[i] + (i < nb ? pt0 : pt1));
@@ -1233,19 +1242,17 @@ __global__ void repair_margT_kernel(float* margT, long long n, const int* flag) 
 // v3 pipeline: token-major probabilities, no padded MMA rows, no atomics, marginals from one GEMM
 // =================================================================================================
 struct GlobalWs3 {
-  size_t p2, mg, lsum, stab, flag, pe_t, pe2, ind, qext, tq, peq_t, margf, marg, total;
-  long long pld, ild, tq_ld;
-  int Tk, ke2, mslices, kslice;
+  size_t p2, mg, lsum, stab, flag, pe2, ind, qt, margf, marg, total;
+  long long pld, ild;
+  int ke2, mslices, kslice;
 };
 static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits) {
   (void)splits; (void)H; (void)W;
   const size_t N = (size_t)T * H * W;
   GlobalWs3 w;
   w.pld = (J + 63) / 64 * 64;
-  w.Tk = (T + 7) / 8 * 8;
   w.ke2 = kKe + (T + 63) / 64 * 64;      // pooled-PE columns: [h | w | .. | ones] + absolute frame one-hot
   w.ild = 3 * kKe;                       // indicator row: [spatial | frame rel. to K slice | frame rel. to 128-token tile]
-  w.tq_ld = (T + 64 + 7) / 8 * 8;
   // K slices of the marginal GEMM.  The persistent kernel walks B x (row tiles) x slices tiles in waves of ~148
   // CTAs, so its time goes like ceil(tiles / 148) / slices: take the smallest slice count within 5 % of the best.
   // Each slice keeps >= 512 tokens and spans few enough frames (<= 48 + rounding) that a 64-wide relative one-hot
@@ -1267,12 +1274,9 @@ static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits
   w.lsum = take((size_t)B * J * 4);
   w.stab = take((size_t)B * J * 4);
   w.flag = take(256);
-  w.pe_t = take((size_t)w.Tk * d * 2);
   w.pe2 = take((size_t)w.ke2 * d * 2);
   w.ind = take(N * w.ild * 2);
-  w.qext = take((size_t)B * J * kKe * 2);
-  w.tq = take((size_t)B * J * w.tq_ld * 2);
-  w.peq_t = take((size_t)T * B * J * 4);
+  w.qt = take((size_t)B * J * w.ke2 * 2);         // qfold · pe2ᵀ = [spatial term, col 63 = -stabiliser | time term per frame]
   w.margf = take((size_t)B * w.mslices * J * 2 * kKe * 4);
   w.marg = take((size_t)B * J * w.ke2 * 2);
   w.total = off;
@@ -1284,28 +1288,11 @@ static size_t global_ws3_total(int B, int T, int H, int W, int d, int J, int spl
 }
 
 namespace tc {
-// pe_t (Tk x d) and pe2 = [pos_h ; pos_w ; 0 (row 63 multiplies the ones column) | pos_t ; 0] (ke2 x d), bf16
-__global__ void build_pe3_kernel(const float* pt, const float* ph, const float* pw, __nv_bfloat16* pe_t,
-                                 __nv_bfloat16* pe2, int T, int Tk, int ke2, int H, int W, int d) {
-  const int r = blockIdx.x;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    if (r < Tk) {
-      pe_t[(size_t)r * d + c] = __float2bfloat16_rn(r < T ? pt[(size_t)r * d + c] : 0.f);
-    } else {
-      const int s = r - Tk;
-      float v = 0.f;
-      if (s < H) v = ph[(size_t)s * d + c];
-      else if (s < H + W) v = pw[(size_t)(s - H) * d + c];
-      else if (s >= kKe && s - kKe < T) v = pt[(size_t)(s - kKe) * d + c];
-      pe2[(size_t)s * d + c] = __float2bfloat16_rn(v);
-    }
-  }
-}
 // ind[n] = [ one-hot(h), one-hot(H+w), .., 1 (col 63) | one-hot(frame - base of n's K slice) | one-hot(frame - base of
 //            n's score tile: 128 tokens, or the 256 of a CTA pair) ], 3 x 64 columns; a base is the first frame of the range rounded down to a multiple of
 //            8 (the same 16-byte-aligned coordinate the TMA producer uses).  One thread writes 8 columns (16 bytes).
-__global__ void build_ind3_kernel(__nv_bfloat16* ind, int N, int H, int W, int kslice, int rel_tile) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void build_ind3_row(__nv_bfloat16* ind, long long i, int N, int H, int W, int kslice,
+                                               int rel_tile) {
   constexpr int G = 3 * kKe / 8;
   if (i >= (long long)N * G) return;
   const int n = (int)(i / G), g = (int)(i % G);
@@ -1325,34 +1312,50 @@ __global__ void build_ind3_kernel(__nv_bfloat16* ind, int N, int H, int W, int k
   }
   *reinterpret_cast<uint4*>(ind + (size_t)n * (3 * kKe) + g * 8) = make_uint4(v[0], v[1], v[2], v[3]);
 }
-__global__ void zero_bf16_kernel(__nv_bfloat16* p, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = __float2bfloat16_rn(0.f);
-}
-__global__ void reset_max_kernel(float* mg, int n, const int* flag) {
-  if (flag != nullptr && *flag == 0) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) mg[i] = -INFINITY;
+// ONE launch prepares everything that does not depend on the scores: blocks [0, nb_ind) the indicator matrix, the next
+// ke2 blocks the bf16 table pe2 = [pos_h ; pos_w ; 0 (row 63 multiplies the ones column) | pos_t ; 0] (ke2 x d), the rest
+// reset the running max / denominators / fallback flag.
+__global__ void prep3_kernel(__nv_bfloat16* ind, int N, int H, int W, int kslice, int rel_tile, unsigned nb_ind,
+                             const float* pt, const float* ph, const float* pw, __nv_bfloat16* pe2, int T, int ke2, int d,
+                             float* mg, float* lsum, int n_stats, int* flag) {
+  const unsigned bid = blockIdx.x;
+  if (bid < nb_ind) {
+    build_ind3_row(ind, (long long)bid * blockDim.x + threadIdx.x, N, H, W, kslice, rel_tile);
+  } else if (bid < nb_ind + (unsigned)ke2) {
+    const int s = (int)(bid - nb_ind);
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float v = 0.f;
+      if (s < H) v = ph[(size_t)s * d + c];
+      else if (s < H + W) v = pw[(size_t)(s - H) * d + c];
+      else if (s >= kKe && s - kKe < T) v = pt[(size_t)(s - kKe) * d + c];
+      pe2[(size_t)s * d + c] = __float2bfloat16_rn(v);
+    }
+  } else {
+    const int i = (int)(bid - nb_ind - (unsigned)ke2) * blockDim.x + threadIdx.x;
+    if (i < n_stats) { mg[i] = -INFINITY; lsum[i] = 0.f; }
+    if (i == 0) *flag = 0;
+  }
 }
 // stabiliser = bf16(max + margin): it rides into the GEMM as the extension row -stab against the ones column, so the
 // value reported to the merge must be the rounded one that was actually applied
-__global__ void make_stab3_kernel(const float* mg, float* stab, __nv_bfloat16* qext, int n, float margin,
+__global__ void make_stab3_kernel(const float* mg, float* stab, __nv_bfloat16* qt, int ld, int n, float margin,
                                   const int* flag) {
   if (flag != nullptr && *flag == 0) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const __nv_bfloat16 sb = __float2bfloat16_rn(mg[i] + margin);
   stab[i] = __bfloat162float(sb);
-  qext[(size_t)i * kKe + kKe - 1] = __float2bfloat16_rn(-__bfloat162float(sb));
+  qt[(size_t)i * ld + kKe - 1] = __float2bfloat16_rn(-__bfloat162float(sb));
+}
+// exact re-run only: forget the sampled max and remove the previous stabiliser (column 63 of qt) so the max pass sees
+// the raw scores again
+__global__ void reset_for_exact3_kernel(float* mg, __nv_bfloat16* qt, int ld, int n, const int* flag) {
+  if (*flag == 0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { mg[i] = -INFINITY; qt[(size_t)i * ld + kKe - 1] = __float2bfloat16_rn(0.f); }
 }
 // marg (B*J, ke2) bf16 = sum over K slices of margf; column 63 is the softmax denominator.  A denominator that is not a
 // positive finite number means exp() left the exponent range: raise the flag for the exact-max re-run.
-// exact re-run only: remove the previous stabiliser row so the max pass sees the raw scores again
-__global__ void clear_stab3_kernel(__nv_bfloat16* qext, int n, const int* flag) {
-  if (*flag == 0) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) qext[(size_t)i * kKe + kKe - 1] = __float2bfloat16_rn(0.f);
-}
 __global__ void marg_reduce_kernel(const float* margf, __nv_bfloat16* marg, float* lsum, int B, int S, int J, int ke2,
                                    int kslice, int hw, int* flag, int guarded) {
   if (guarded && *flag == 0) return;
@@ -1400,12 +1403,14 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   float* lsum = reinterpret_cast<float*>(ws + w.lsum);
   float* stab = reinterpret_cast<float*>(ws + w.stab);
   int* flag = reinterpret_cast<int*>(ws + w.flag);
-  __nv_bfloat16* pe_t = reinterpret_cast<__nv_bfloat16*>(ws + w.pe_t);
   __nv_bfloat16* pe2 = reinterpret_cast<__nv_bfloat16*>(ws + w.pe2);
   __nv_bfloat16* ind = reinterpret_cast<__nv_bfloat16*>(ws + w.ind);
-  __nv_bfloat16* qext = reinterpret_cast<__nv_bfloat16*>(ws + w.qext);
-  __nv_bfloat16* tq = reinterpret_cast<__nv_bfloat16*>(ws + w.tq);
-  float* peq_t = reinterpret_cast<float*>(ws + w.peq_t);
+  // qt (B*J, ke2): columns 0..63 = spatial position term of every score column (63 = -stabiliser, against the ones
+  // column of `ind`), columns 64.. = time term per frame; `qext` and `tq` are views of it
+  __nv_bfloat16* qt = reinterpret_cast<__nv_bfloat16*>(ws + w.qt);
+  __nv_bfloat16* qext = qt;
+  __nv_bfloat16* tq = qt + kKe;
+  const uint64_t qld = (uint64_t)w.ke2, tcols = (uint64_t)w.ke2 - kKe;
   float* margf = reinterpret_cast<float*>(ws + w.margf);
   __nv_bfloat16* marg = reinterpret_cast<__nv_bfloat16*>(ws + w.marg);
   const long long BJ = (long long)B * J;
@@ -1413,41 +1418,31 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   const uint32_t jbox = narrow ? 64 : 96;
   auto blocks = [](long long n) { return (unsigned)((n + 255) / 256); };
 
-  // 0. tables and indicator matrices
-  build_pe3_kernel<<<w.Tk + w.ke2, 256, 0, stream>>>(pos_t, pos_h, pos_w, pe_t, pe2, T, w.Tk, w.ke2, H, W, d);
-  if (check_launch("build_pe3_kernel")) return 1;
-  // the probability pass runs on CTA pairs (256-token tiles) when enabled and the tile's frames fit the 64-wide one-hot
+  // 0. indicator matrix, position tables, statistics: one launch
+  // the probability pass runs on CTA pairs (256-token tiles) when enabled
   const bool pair = pair_mode_enabled() && J > 64;  // H*W >= 32 (tc_global_selected): 256 tokens span <= 9 frames
-  build_ind3_kernel<<<blocks((long long)N * (w.ild / 8)), 256, 0, stream>>>(ind, N, H, W, w.kslice, pair ? 2 * BM : BM);
-  if (check_launch("build_ind3_kernel")) return 1;
-  init_stats_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, lsum, (int)BJ, flag);
-  if (check_launch("init_stats_kernel")) return 1;
-  zero_bf16_kernel<<<blocks(BJ * w.tq_ld), 256, 0, stream>>>(tq, BJ * w.tq_ld);
-  if (check_launch("zero_bf16_kernel")) return 1;
-  {  // qext (B*J, 64) = qfold · [pos_h ; pos_w ; 0]ᵀ ; tq (B*J, T) = qfold · pos_tᵀ ; peq_t (T, B*J) fp32 for the max pass
+  {
+    const unsigned nb_ind = blocks((long long)N * (w.ild / 8));
+    prep3_kernel<<<nb_ind + (unsigned)w.ke2 + blocks(BJ), 256, 0, stream>>>(
+        ind, N, H, W, w.kslice, pair ? 2 * BM : BM, nb_ind, pos_t, pos_h, pos_w, pe2, T, w.ke2, d, mg, lsum, (int)BJ, flag);
+    if (check_launch("prep3_kernel")) return 1;
+  }
+  {  // qt = qfold · pe2ᵀ: [pos_h·q | pos_w·q | 0 ... | pos_t[0]·q, pos_t[1]·q, ...] in one GEMM
     TcLinearParams a{};
-    a.A = qfold; a.W = pe2; a.C = qext; a.lda = d; a.ldw = d; a.ldc = kKe; a.M = (int)BJ; a.N = kKe; a.K = d;
+    a.A = qfold; a.W = pe2; a.C = qt; a.lda = d; a.ldw = d; a.ldc = w.ke2; a.M = (int)BJ; a.N = w.ke2; a.K = d;
     a.act = HICOM_ACT_NONE; a.out_dtype = HICOM_BF16; a.rows_per_group = 1 << 30;
     if (launch_tc_linear(a, stream)) return 1;
-    TcLinearParams c{};
-    c.A = qfold; c.W = pe_t; c.C = tq; c.lda = d; c.ldw = d; c.ldc = w.tq_ld; c.M = (int)BJ; c.N = T; c.K = d;
-    c.act = HICOM_ACT_NONE; c.out_dtype = HICOM_BF16; c.rows_per_group = 1 << 30;
-    if (launch_tc_linear(c, stream)) return 1;
-    TcLinearParams b{};
-    b.A = pe_t; b.W = qfold; b.C = peq_t; b.lda = d; b.ldw = d; b.ldc = BJ; b.M = T; b.N = (int)BJ; b.K = d;
-    b.act = HICOM_ACT_NONE; b.out_dtype = HICOM_F32; b.rows_per_group = 1 << 30;
-    if (launch_tc_linear(b, stream)) return 1;
   }
 
   // ---- sampled / exact max pass (rows = score columns, as in v2) -------------------------------------------------
   CUtensorMap tq128, tx256, tqe128, tind256;
   if (make_map(&tq128, qfold, d, J, B, d, (uint64_t)J * d, BM)) return 1;
   if (make_map(&tx256, X, d, N, B, d, (uint64_t)N * d, 256)) return 1;
-  if (make_map(&tqe128, qext, kKe, J, B, kKe, (uint64_t)J * kKe, BM)) return 1;
+  if (make_map(&tqe128, qext, kKe, J, B, qld, (uint64_t)J * qld, BM)) return 1;
   if (make_map(&tind256, ind, kKe, N, 1, w.ild, 0, 256)) return 1;
   Params pmx{};
   pmx.M = J; pmx.N = N; pmx.K = d; pmx.k_chunk = d; pmx.b_box_rows = 256;
-  pmx.mg = mg; pmx.k_ext_blocks = 1; pmx.HW = H * W; pmx.T = T; pmx.peq_t = peq_t; pmx.peq_ld = BJ;
+  pmx.mg = mg; pmx.k_ext_blocks = 1; pmx.HW = H * W; pmx.T = T; pmx.tqm = tq; pmx.tqm_ld = (long long)qld;
   const int n_tiles256 = (N + 255) / 256;
   const int mj_tiles = (J + BM - 1) / BM;
 
@@ -1457,13 +1452,14 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   if (make_map(&tqj, qfold, d, J, B, d, (uint64_t)J * d, jbox)) return 1;
   if (make_map(&ti0, ind, kKe, N, 1, w.ild, 0, BM)) return 1;
   if (make_map(&ti1, ind + 2 * kKe, kKe, N, 1, w.ild, 0, BM)) return 1;
-  if (make_map(&tqej, qext, kKe, J, B, kKe, (uint64_t)J * kKe, jbox)) return 1;
-  if (make_map(&ttq, tq, w.tq_ld, J, B, w.tq_ld, (uint64_t)J * w.tq_ld, jbox)) return 1;
+  if (make_map(&tqej, qext, kKe, J, B, qld, (uint64_t)J * qld, jbox)) return 1;
+  // frames past T read as zero (zero rows of pe2 up to the padded extent, TMA zero fill beyond it)
+  if (make_map(&ttq, tq, tcols, J, B, qld, (uint64_t)J * qld, jbox)) return 1;
   CUtensorMap tqj72, tqej72, ttq72;  // pair mode: each CTA stages 72 of the 144 rows of an MMA instruction's B operand
   if (pair) {
     if (make_map(&tqj72, qfold, d, J, B, d, (uint64_t)J * d, 72)) return 1;
-    if (make_map(&tqej72, qext, kKe, J, B, kKe, (uint64_t)J * kKe, 72)) return 1;
-    if (make_map(&ttq72, tq, w.tq_ld, J, B, w.tq_ld, (uint64_t)J * w.tq_ld, 72)) return 1;
+    if (make_map(&tqej72, qext, kKe, J, B, qld, (uint64_t)J * qld, 72)) return 1;
+    if (make_map(&ttq72, tq, tcols, J, B, qld, (uint64_t)J * qld, 72)) return 1;
   }
   Params pp{};
   pp.M = N; pp.N = J; pp.K = d; pp.k_chunk = d; pp.b_box_rows = (int)jbox;
@@ -1495,7 +1491,7 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
 
   auto run = [&](const int* guard, float margin) -> int {
     // stabiliser -> probabilities -> marginals -> pooling (the exact re-run passes guard = flag)
-    make_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, stab, qext, (int)BJ, margin, guard);
+    make_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, stab, qt, w.ke2, (int)BJ, margin, guard);
     if (check_launch("make_stab3_kernel")) return 1;
     Params p1 = pp; p1.guard = guard;
     static const bool halves = [] { const char* e = getenv("HICOM_PROB_HALVES"); return !(e && e[0] == '0'); }();
@@ -1537,12 +1533,9 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   if (run(nullptr, kStabMargin)) return 1;
   // 3. guarded exact fallback: the denominator check in marg_reduce raised the flag -> exact max over all tiles, margin 0
   {
-    reset_max_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, (int)BJ, flag);
-    if (check_launch("reset_max_kernel")) return 1;
-    // the max pass must not see the previous stabiliser row: clear it first (guarded)
+    reset_for_exact3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, qt, w.ke2, (int)BJ, flag);
+    if (check_launch("reset_for_exact3_kernel")) return 1;
     Params pf = pmx; pf.guard = flag;
-    clear_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(qext, (int)BJ, flag);
-    if (check_launch("clear_stab3_kernel")) return 1;
     if (launch<256, false, false, EPI_MAX>(tq128, tx256, pf, dim3(n_tiles256, mj_tiles, B), stream, &tqe128, &tind256))
       return 1;
     if (run(flag, 0.f)) return 1;
