@@ -2,7 +2,7 @@
 # usage: tools/scale_run.sh "<gpu counts>" ; runs both bench arms for each N (driver-style launch), prints compact lines
 python -m hicom_b200.build 2>/dev/null
 for N in $1; do
-  for wl in c2 c4; do
+  for wl in ${WL:-c2 c4}; do
     if [ "$N" = "1" ]; then
       timeout 300 python bench.py --gpus 1 --steps 50 --warmup 5 --workload $wl --no-cpu-baseline 2>gpurun_out/scale_${wl}_$N.err | tail -1 > gpurun_out/scale_${wl}_$N.json
     else
