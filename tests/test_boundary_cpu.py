@@ -106,3 +106,18 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+def test_default_splits_follow_cta_waves():
+    """Split-K of the pooling GEMM: tiles = 9 x B x splits walk 148 persistent CTAs in waves; fewest splits within 5 %
+    of the best wave count, every range >= 512 tokens."""
+    from hicom_b200.projector import default_splits
+    assert default_splits(32, 11664) == 1       # 288 tiles = two full waves, no partials to merge
+    assert default_splits(16, 11664) == 1       # 144 tiles = one wave
+    assert default_splits(1, 373248) == 16      # 144 tiles, not 297 (three waves)
+    assert default_splits(1, 729) == 1          # a single frame cannot be cut below 512 tokens
+    for B, N in [(1, 11664), (3, 5832), (7, 46656), (24, 11664), (100, 23328)]:
+        s = default_splits(B, N)
+        assert 1 <= s <= max(1, N // 512)
+        cost = lambda k: -(-(9 * B * k) // 148) / k
+        assert cost(s) <= 1.05 * min(cost(k) for k in range(1, max(1, min(64, N // 512)) + 1))
