@@ -311,7 +311,7 @@ template <int BN, bool CTA2 = false>
 struct Cfg {
   // 128x64 tiles are for small problems (few tiles): more CTAs, deeper ring, so more weight bytes are in flight.
   // A CTA pair stages half of B per CTA: six stages fit where four did.
-  static constexpr int STAGES = BN == 64 ? 8 : (CTA2 ? (BN <= 144 ? 8 : 6) : 4);
+  static constexpr int STAGES = BN == 64 ? 8 : (CTA2 ? (BN <= 144 ? 8 : 6) : (BN <= 128 ? 6 : 4));
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   // whole 64-wide blocks (MN-major B needs them); a pair member holds BN/2 K-major rows
   static constexpr uint32_t B_BYTES = CTA2 ? (BN / 2) * BK * 2 : ((BN + 63) / 64) * 64 * BK * 2;
@@ -1062,6 +1062,10 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
     pm.rows_per_group = 1 << 30; pm.group_stride_rows = 0;
     pm.z_slices = q.z_slices > 0 ? q.z_slices : 1; pm.z_a_k = q.z_a_k; pm.z_b_k = q.z_b_k; pm.z_c_rows = q.z_c_rows;
     pm.c_batch_rows = q.c_batch_rows; pm.b_shared = 1; pm.guard = q.guard;
+    if (q.N <= 128) {  // the probability marginals: 128-column tiles leave room for a six-stage ring (bandwidth-bound)
+      dim3 gm128((q.N + 127) / 128, (q.M + BM - 1) / BM, nb * pm.z_slices);
+      return launch<128, true, true, EPI_LINEAR, 2>(ta, tb, pm, gm128, stream);
+    }
     dim3 gm((q.N + 255) / 256, (q.M + BM - 1) / BM, nb * pm.z_slices);
     return launch<256, true, true, EPI_LINEAR, 2>(ta, tb, pm, gm, stream);
   }
