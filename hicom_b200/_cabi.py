@@ -30,6 +30,9 @@ PROTOTYPES = {
     "hicom_global_fold_query": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_float, c_int, c_void_p]),
     "hicom_global_attend_workspace_bytes": (c_size_t, [c_int] * 9),
     "hicom_global_attend_partial": (c_int, [c_void_p] * 8 + [c_int] * 8 + [c_void_p, c_size_t, c_int, c_void_p]),
+    "hicom_global_attend_partial_keys": (c_int, [c_void_p] * 9 + [c_int] * 8 + [c_void_p, c_size_t, c_int, c_void_p]),
+    "hicom_posadd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
+    "hicom_l2norm_rows": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p]),
     "hicom_softmax_merge": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_int, c_void_p]),
     "hicom_softmax_reduce": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 4),
     "hicom_global_value_proj": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),

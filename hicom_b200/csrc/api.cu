@@ -252,10 +252,12 @@ extern "C" size_t hicom_global_attend_workspace_bytes(int B, int T, int H, int W
   return align256((size_t)B * N * d * elem_size(dtype)) + align256((size_t)B * N * J * sizeof(float));
 }
 
-extern "C" int hicom_global_attend_partial(const void* X, const float* pos_t, const float* pos_h,
-                                           const float* pos_w, const void* qfold, float* m, float* l, float* o,
-                                           int B, int T, int H, int W, int d, int J, int splits, int dtype,
-                                           void* workspace, size_t workspace_bytes, int impl, void* stream) {
+// Kscore != nullptr: the scores are Kscore·qfoldᵀ (no position terms: the caller's keys already contain them) while the
+// pooled operand stays x' = X + pos_embed (hicom_global_attend_partial_keys, the clip-scale variant).
+static int global_attend_partial_impl(const void* X, const void* Kscore, const float* pos_t, const float* pos_h,
+                                      const float* pos_w, const void* qfold, float* m, float* l, float* o,
+                                      int B, int T, int H, int W, int d, int J, int splits, int dtype,
+                                      void* workspace, size_t workspace_bytes, int impl, void* stream) {
   HICOM_REQUIRE(X && qfold && m && l && o && workspace, "global_attend_partial: null pointer");
   HICOM_REQUIRE(pos_t && pos_h && pos_w, "global_attend_partial: position tables required");
   HICOM_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && d > 0 && d % 128 == 0 && J > 0 && splits > 0,
@@ -270,7 +272,7 @@ extern "C" int hicom_global_attend_partial(const void* X, const float* pos_t, co
   if (impl == HICOM_IMPL_TCGEN05)
     HICOM_REQUIRE(tc_global_selected(dtype, impl, d, J, T, H, W), "global_attend_partial: tcgen05 path needs bf16, d%%128==0");
   if (tc_global_selected(dtype, impl, d, J, T, H, W))
-    return launch_tc_global(X, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace, s);
+    return launch_tc_global(X, Kscore, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace, s);
 
   const int rows_per_split = (N + splits - 1) / splits;
   char* ws = static_cast<char*>(workspace);
@@ -279,7 +281,7 @@ extern "C" int hicom_global_attend_partial(const void* X, const float* pos_t, co
   if (launch_posadd(X, Xp, pos_t, pos_h, pos_w, B, T, H, W, d, dtype, s)) return 1;
   {  // S[b] (N,J) = X'[b] (N,d) · qfold[b]ᵀ (d,J)
     GemmParams g = plain_gemm();
-    g.A = Xp; g.B = qfold; g.C = S;
+    g.A = Kscore != nullptr ? Kscore : Xp; g.B = qfold; g.C = S;
     g.M = N; g.N = J; g.K = d;
     g.sAm = d; g.sAk = 1; g.sAb1 = (long long)N * d;
     g.sBk = 1; g.sBn = d; g.sBb1 = (long long)J * d;
@@ -303,3 +305,22 @@ extern "C" int hicom_global_attend_partial(const void* X, const float* pos_t, co
   }
   return 0;
 }
+
+extern "C" int hicom_global_attend_partial(const void* X, const float* pos_t, const float* pos_h,
+                                           const float* pos_w, const void* qfold, float* m, float* l, float* o,
+                                           int B, int T, int H, int W, int d, int J, int splits, int dtype,
+                                           void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  return global_attend_partial_impl(X, nullptr, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, dtype,
+                                    workspace, workspace_bytes, impl, stream);
+}
+
+extern "C" int hicom_global_attend_partial_keys(const void* X, const void* Kscore, const float* pos_t,
+                                                const float* pos_h, const float* pos_w, const void* qfold, float* m,
+                                                float* l, float* o, int B, int T, int H, int W, int d, int J,
+                                                int splits, int dtype, void* workspace, size_t workspace_bytes,
+                                                int impl, void* stream) {
+  HICOM_REQUIRE(Kscore != nullptr, "global_attend_partial_keys: null key operand");
+  return global_attend_partial_impl(X, Kscore, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, dtype,
+                                    workspace, workspace_bytes, impl, stream);
+}
+

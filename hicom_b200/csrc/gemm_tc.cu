@@ -1316,6 +1316,10 @@ __device__ __forceinline__ void build_ind3_row(__nv_bfloat16* ind, long long i, 
   }
   *reinterpret_cast<uint4*>(ind + (size_t)n * (3 * kKe) + g * 8) = make_uint4(v[0], v[1], v[2], v[3]);
 }
+__global__ void zero_bf16_kernel(__nv_bfloat16* p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = __float2bfloat16_rn(0.f);
+}
 // ONE launch prepares everything that does not depend on the scores: blocks [0, nb_ind) the indicator matrix, the next
 // ke2 blocks the bf16 table pe2 = [pos_h ; pos_w ; 0 (row 63 multiplies the ones column) | pos_t ; 0] (ke2 x d), the rest
 // reset the running max / denominators / fallback flag.
@@ -1395,7 +1399,8 @@ __global__ void spread3_kernel(const float* stab, const float* lsum, float* m, f
 }
 }  // namespace tc
 
-static int launch_tc_global_v3(const void* X, const float* pos_t, const float* pos_h, const float* pos_w,
+static int launch_tc_global_v3(const void* X, const void* Kscore, const float* pos_t, const float* pos_h,
+                               const float* pos_w,
                                const void* qfold, float* m, float* l, float* o, int B, int T, int H, int W, int d, int J,
                                int splits, void* workspace, cudaStream_t stream) {
   using namespace tc;
@@ -1431,7 +1436,10 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
         ind, N, H, W, w.kslice, pair ? 2 * BM : BM, nb_ind, pos_t, pos_h, pos_w, pe2, T, w.ke2, d, mg, lsum, (int)BJ, flag);
     if (check_launch("prep3_kernel")) return 1;
   }
-  {  // qt = qfold · pe2ᵀ: [pos_h·q | pos_w·q | 0 ... | pos_t[0]·q, pos_t[1]·q, ...] in one GEMM
+  if (Kscore != nullptr) {  // the caller's keys already carry their position terms: no score-side tables
+    zero_bf16_kernel<<<blocks(BJ * w.ke2), 256, 0, stream>>>(qt, BJ * w.ke2);
+    if (check_launch("zero_bf16_kernel")) return 1;
+  } else {  // qt = qfold · pe2ᵀ: [pos_h·q | pos_w·q | 0 ... | pos_t[0]·q, pos_t[1]·q, ...] in one GEMM
     TcLinearParams a{};
     a.A = qfold; a.W = pe2; a.C = qt; a.lda = d; a.ldw = d; a.ldc = w.ke2; a.M = (int)BJ; a.N = w.ke2; a.K = d;
     a.act = HICOM_ACT_NONE; a.out_dtype = HICOM_BF16; a.rows_per_group = 1 << 30;
@@ -1441,7 +1449,8 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   // ---- sampled / exact max pass (rows = score columns, as in v2) -------------------------------------------------
   CUtensorMap tq128, tx256, tqe128, tind256;
   if (make_map(&tq128, qfold, d, J, B, d, (uint64_t)J * d, BM)) return 1;
-  if (make_map(&tx256, X, d, N, B, d, (uint64_t)N * d, 256)) return 1;
+  const void* Xs = Kscore != nullptr ? Kscore : X;  // score operand of the max / probability passes
+  if (make_map(&tx256, Xs, d, N, B, d, (uint64_t)N * d, 256)) return 1;
   if (make_map(&tqe128, qext, kKe, J, B, qld, (uint64_t)J * qld, BM)) return 1;
   if (make_map(&tind256, ind, kKe, N, 1, w.ild, 0, 256)) return 1;
   Params pmx{};
@@ -1452,7 +1461,7 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
 
   // ---- probabilities: P2[b] (tokens x J) = exp([X | ind0 | indrel] · [qfold | qext | tq(f0..)]ᵀ) --------------------
   CUtensorMap tx128, tqj, ti0, ti1, tqej, ttq;
-  if (make_map(&tx128, X, d, N, B, d, (uint64_t)N * d, BM)) return 1;
+  if (make_map(&tx128, Xs, d, N, B, d, (uint64_t)N * d, BM)) return 1;
   if (make_map(&tqj, qfold, d, J, B, d, (uint64_t)J * d, jbox)) return 1;
   if (make_map(&ti0, ind, kKe, N, 1, w.ild, 0, BM)) return 1;
   if (make_map(&ti1, ind + 2 * kKe, kKe, N, 1, w.ild, 0, BM)) return 1;
@@ -1548,12 +1557,15 @@ static int launch_tc_global_v3(const void* X, const float* pos_t, const float* p
   return check_launch("spread3_kernel");
 }
 
-int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, const float* pos_w, const void* qfold,
+int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, const float* pos_h, const float* pos_w,
+                     const void* qfold,
                      float* m, float* l, float* o, int B, int T, int H, int W, int d, int J, int splits,
                      void* workspace, cudaStream_t stream) {
   using namespace tc;
   if (global_v3_enabled())
-    return launch_tc_global_v3(X, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace, stream);
+    return launch_tc_global_v3(X, Kscore, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace,
+                               stream);
+  HICOM_REQUIRE(Kscore == nullptr, "global_attend_partial_keys needs the default global pipeline (HICOM_GLOBAL_V3 != 0)");
   const int N = T * H * W;
   const GlobalWs w = global_ws(B, T, H, W, d, J, splits);
   char* ws = static_cast<char*>(workspace);

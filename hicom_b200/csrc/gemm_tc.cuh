@@ -26,7 +26,7 @@ int launch_tc_linear(const TcLinearParams& p, cudaStream_t stream);
 
 bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W);
 size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits);
-int launch_tc_global(const void* X, const float* pos_t, const float* pos_h, const float* pos_w,
+int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, const float* pos_h, const float* pos_w,
                      const void* qfold, float* m, float* l, float* o, int B, int T, int H, int W, int d, int J,
                      int splits, void* workspace, cudaStream_t stream);
 

@@ -130,6 +130,34 @@ int launch_posadd(const void* X, void* Y, const float* pt, const float* ph, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row-wise L2 normalisation: y = x / ||x||_2 (the clip-scale attention variant, projector.py:184-186).
+// One warp per row, any d % 4 == 0; in place allowed.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(const T* __restrict__ X, T* __restrict__ Y, long long rows,
+                                                          int d) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* x = X + row * d;
+  T* y = Y + row * d;
+  float ss = 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    float v[4];
+    Vec4<T>::load(x + c, v);
+    ss += v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+  }
+  const float inv = 1.f / sqrtf(warp_sum(ss));
+  for (int c = lane * 4; c < d; c += 128) {
+    float v[4];
+    Vec4<T>::load(x + c, v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] *= inv;
+    Vec4<T>::store(y + c, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Split-softmax column statistics.  S (B,N,J) fp32 scores -> in place P = exp(S - m[b,s,j]) with
 // m the max over the split's token range, l the sum of P.   (projector.py:213, per split)
 // grid (J/32, splits, B), block (32, 8).
@@ -331,4 +359,22 @@ extern "C" int hicom_softmax_reduce(const float* m, const float* l, const float*
   dim3 grid(J, B);
   softmax_merge_kernel<float, true><<<grid, 128, 0, as_stream(stream)>>>(m, l, o, o_out, m_out, l_out, P, J, d);
   return check_launch("softmax_reduce_kernel");
+}
+
+extern "C" int hicom_posadd(const void* X, void* Y, const float* pos_t, const float* pos_h, const float* pos_w, int B,
+                            int T, int H, int W, int d, int dtype, void* stream) {
+  HICOM_REQUIRE(X && Y && pos_t && pos_h && pos_w, "posadd: null pointer");
+  HICOM_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && d > 0 && d % 128 == 0, "posadd: bad shape");
+  return hicom::launch_posadd(X, Y, pos_t, pos_h, pos_w, B, T, H, W, d, dtype, as_stream(stream));
+}
+
+extern "C" int hicom_l2norm_rows(const void* X, void* Y, long long rows, int d, int dtype, void* stream) {
+  HICOM_REQUIRE(X && Y, "l2norm_rows: null pointer");
+  HICOM_REQUIRE(rows >= 0 && d > 0 && d % 4 == 0, "l2norm_rows: bad shape");
+  if (rows == 0) return 0;
+  const long long blocks = (rows + 7) / 8;
+  HICOM_REQUIRE(blocks < (1ll << 31), "l2norm_rows: too many rows");
+  HICOM_DISPATCH_DTYPE(dtype, E, (hicom::l2norm_rows_kernel<E><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      static_cast<const E*>(X), static_cast<E*>(Y), rows, d)));
+  return check_launch("l2norm_rows_kernel");
 }

@@ -83,7 +83,8 @@ def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, 
         local_tokens = local_tokens.view(B, att.shape[1], Dh)
     if gc is not None:
         Qg = gc.injected_query(guide_embed, B, X.dtype)
-        m, l, o = gc.partials(X, gc.fold(Qg, projector.global_logit_scale), t0=t0)
+        m, l, o = gc.partials(X, gc.fold(Qg, projector.global_logit_scale), t0=t0,
+                              logit_scale=projector.global_logit_scale)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             from . import ops
             if m.shape[1] > 1:  # reduce this rank's token splits first: one J*(d+2) fp32 message per video

@@ -289,6 +289,63 @@ def _impl_global_attend_partial(X: Tensor, pos_t: Tensor, pos_h: Tensor, pos_w: 
     return m, l, o
 
 
+def _impl_global_attend_partial_keys(X: Tensor, Kscore: Tensor, pos_t: Tensor, pos_h: Tensor, pos_w: Tensor,
+                                     qfold: Tensor, splits: int, impl: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """global_attend_partial whose scores come from explicit (normalised) keys ``Kscore`` (B,T,H,W,d) while the pooled
+    operand stays X + pos_embed — the use_clip_scale variant, projector.py:184-188."""
+    dev = _need_cuda(X, Kscore, pos_t, pos_h, pos_w, qfold)
+    X, Kscore, qfold = X.contiguous(), Kscore.contiguous(), qfold.contiguous()
+    B, T, H, W, d = X.shape
+    J = qfold.shape[1]
+    if Kscore.shape != X.shape or Kscore.dtype != X.dtype:
+        raise ValueError("global_attend_partial_keys: Kscore must match X in shape and dtype")
+    for name, tab, n in (("pos_t", pos_t, T), ("pos_h", pos_h, H), ("pos_w", pos_w, W)):
+        if tab.dtype != torch.float32 or tab.shape != (n, d) or not tab.is_contiguous():
+            raise ValueError(f"global_attend_partial_keys: {name} must be contiguous fp32 ({n},{d})")
+    if qfold.shape != (B, J, d) or qfold.dtype != X.dtype:
+        raise ValueError("global_attend_partial_keys: qfold must be (B,J,d) in the feature dtype")
+    lib = _cabi.load()
+    ws_bytes = lib.hicom_global_attend_workspace_bytes(B, T, H, W, d, J, splits, _dt(X), impl)
+    ws = torch.empty((max(ws_bytes, 256),), dtype=torch.uint8, device=dev)
+    m = torch.empty((B, splits, J), dtype=torch.float32, device=dev)
+    l = torch.empty((B, splits, J), dtype=torch.float32, device=dev)
+    o = torch.empty((B, splits, J, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.hicom_global_attend_partial_keys(_ptr(X), _ptr(Kscore), _ptr(pos_t), _ptr(pos_h), _ptr(pos_w),
+                                                  _ptr(qfold), _ptr(m), _ptr(l), _ptr(o), B, T, H, W, d, J, splits,
+                                                  _dt(X), _ptr(ws), ws.numel(), impl, _stream(dev))
+    _cabi.check(rc, "hicom_global_attend_partial_keys")
+    return m, l, o
+
+
+def _impl_posadd(X: Tensor, pos_t: Tensor, pos_h: Tensor, pos_w: Tensor) -> Tensor:
+    """X (B,T,H,W,d) + pos_t[t] + pos_h[h] + pos_w[w] (fp32 per-axis tables) — projector.py:636-640, separable form."""
+    dev = _need_cuda(X, pos_t, pos_h, pos_w)
+    X = X.contiguous()
+    B, T, H, W, d = X.shape
+    for name, tab, n in (("pos_t", pos_t, T), ("pos_h", pos_h, H), ("pos_w", pos_w, W)):
+        if tab.dtype != torch.float32 or tab.shape != (n, d) or not tab.is_contiguous():
+            raise ValueError(f"posadd: {name} must be contiguous fp32 ({n},{d})")
+    out = torch.empty_like(X)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_posadd(_ptr(X), _ptr(out), _ptr(pos_t), _ptr(pos_h), _ptr(pos_w), B, T, H, W, d,
+                                       _dt(X), _stream(dev))
+    _cabi.check(rc, "hicom_posadd")
+    return out
+
+
+def _impl_l2norm_rows(X: Tensor) -> Tensor:
+    """Rows of X (…, d) divided by their L2 norm — projector.py:184-186, :527-529."""
+    dev = _need_cuda(X)
+    X = X.contiguous()
+    out = torch.empty_like(X)
+    d = X.shape[-1]
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_l2norm_rows(_ptr(X), _ptr(out), X.numel() // d, d, _dt(X), _stream(dev))
+    _cabi.check(rc, "hicom_l2norm_rows")
+    return out
+
+
 def _impl_softmax_merge(m: Tensor, l: Tensor, o: Tensor, out_bf16: bool) -> Tensor:
     """Combine (m,l,o) partials over dim 1 (token splits and/or frame shards) -> pooled (B,J,d)."""
     dev = _need_cuda(m, l, o)
@@ -479,6 +536,10 @@ guide_attend = _wrap("guide_attend", _impl_guide_attend, (), lambda *a: "guide_a
 global_fold_query = _wrap("global_fold_query", _impl_global_fold_query, (), lambda *a: "global_fold_query")
 global_attend_partial = _wrap("global_attend_partial", _impl_global_attend_partial, (),
                               lambda *a: "global_attend_partial")
+global_attend_partial_keys = _wrap("global_attend_partial_keys", _impl_global_attend_partial_keys, (),
+                                   lambda *a: "global_attend_partial_keys")
+posadd = _wrap("posadd", _impl_posadd, (), lambda *a: "posadd")
+l2norm_rows = _wrap("l2norm_rows", _impl_l2norm_rows, (), lambda *a: "l2norm_rows")
 softmax_merge = _wrap("softmax_merge", _impl_softmax_merge, (), lambda *a: "softmax_merge")
 softmax_reduce = _wrap("softmax_reduce", _impl_softmax_reduce, (), lambda *a: "softmax_reduce")
 global_value_proj = _wrap("global_value_proj", _impl_global_value_proj, (), lambda *a: "global_value_proj")

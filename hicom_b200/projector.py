@@ -407,7 +407,7 @@ class GlobalCompressor(nn.Module):
             return rows
         return self.guide_injector(rows, guide)
 
-    def partials(self, X, qfold, t0=0, splits=None):
+    def partials(self, X, qfold, t0=0, splits=None, logit_scale=None):
         """(m,l,o) split-softmax partials of this block of frames (projector.py:636-640,197,213,215)."""
         B, T, H, W, d = X.shape
         if not self.use_pos_emb:
@@ -415,7 +415,17 @@ class GlobalCompressor(nn.Module):
         pt, ph, pw = self.pos_tables(t0, T, H, W, X.device)
         if splits is None:
             splits = default_splits(B, T * H * W, d)
-        return ops.global_attend_partial(X, pt, ph, pw, qfold, splits, _IMPL)
+        if logit_scale is None:
+            return ops.global_attend_partial(X, pt, ph, pw, qfold, splits, _IMPL)
+        # use_clip_scale (projector.py:184-188): keys are L2-normalised over all d channels, so they are needed
+        # explicitly: k = Wk·x + bk + Wk·PE (the position term through the same separable tables), then row norms.
+        attn = self.attn_layer
+        Wk = attn.k_proj.weight
+        K = ops.linear(X.reshape(B * T * H * W, d), Wk, attn.k_proj.bias, None, ops.ACT_NONE, False, _IMPL)
+        kt, kh, kw = (ops.linear(tab.to(X.dtype), Wk, None, None, ops.ACT_NONE, False, _IMPL).float().contiguous()
+                      for tab in (pt, ph, pw))
+        K = ops.l2norm_rows(ops.posadd(K.view(B, T, H, W, d), kt, kh, kw))
+        return ops.global_attend_partial_keys(X, K, pt, ph, pw, qfold, splits, _IMPL)
 
     def finish(self, Qg, m, l, o, out, row_offset, group_stride):
         """merge -> v_proj -> out_proj + residual -> readout, written into rows of ``out`` (projector.py:215-226,646)."""
@@ -431,20 +441,28 @@ class GlobalCompressor(nn.Module):
             view[:, row_offset + 1:row_offset + nq] = view[:, row_offset:row_offset + 1]
 
     def fold(self, Qg, logit_scale=None):
+        """Score operand per (head, query) column: Wk folded into the queries (reassociation), or — with
+        use_clip_scale — exp(logit_scale) x the L2-normalised query restricted to its head's channels, to be applied
+        to explicit normalised keys (`partials(..., logit_scale=...)`)."""
         attn = self.attn_layer
-        if logit_scale is not None:
-            raise NotImplementedError(
-                "use_clip_scale for the global compressor (L2-normalised keys, projector.py:184-188) is not "
-                "supported by the reassociated kernels yet")
         q = ops.linear(Qg, attn.q_proj.weight, attn.q_proj.bias, None, ops.ACT_NONE, False, _IMPL)
-        return ops.global_fold_query(q, attn.k_proj.weight, attn.num_heads, attn.scale)
+        if logit_scale is None:
+            return ops.global_fold_query(q, attn.k_proj.weight, attn.num_heads, attn.scale)
+        B, Q, d = q.shape
+        heads, hd = attn.num_heads, d // attn.num_heads
+        scale = torch.as_tensor(logit_scale, device=q.device).exp().to(q.dtype)   # a tensor: no host sync (graphs)
+        qn = ops.l2norm_rows(q) * scale                                           # projector.py:184-188
+        qfold = torch.zeros((B, heads, Q, heads, hd), dtype=q.dtype, device=q.device)
+        idx = torch.arange(heads, device=q.device)
+        qfold[:, idx, :, idx, :] = qn.view(B, Q, heads, hd).permute(2, 0, 1, 3)  # column (h,i) keeps head h's channels
+        return qfold.view(B, heads * Q, d)
 
     def forward(self, frames_feature, frames_embed, guide_embed, modal, logit_scale, logit_bias):
         """Reference signature (projector.py:634): one video, returns (Q, Dh)."""
         X = frames_feature.unsqueeze(0)
         g = None if guide_embed is None else guide_embed.unsqueeze(0)
         Qg = self.injected_query(g, 1, X.dtype)
-        m, l, o = self.partials(X, self.fold(Qg, logit_scale))
+        m, l, o = self.partials(X, self.fold(Qg, logit_scale), logit_scale=logit_scale)
         out = torch.empty((self.query.shape[0], self.readout[-1].out_features), dtype=X.dtype, device=X.device)
         self.finish(Qg, m, l, o, out, 0, 0)
         return out
@@ -617,7 +635,7 @@ class HIComProjector(nn.Module):
                 self._emit_local(att, grid, plan, image_newline, out, n_base, total)
         if gc is not None:
             Qg = gc.injected_query(guide_embed, B, X.dtype)
-            m, l, o = gc.partials(X, gc.fold(Qg, self.global_logit_scale))
+            m, l, o = gc.partials(X, gc.fold(Qg, self.global_logit_scale), logit_scale=self.global_logit_scale)
             gc.finish(Qg, m, l, o, out, n_base + n_local, total)
         if side is not None:
             main.wait_stream(side)

@@ -141,6 +141,29 @@ int hicom_global_attend_partial(const void* X, const float* pos_t, const float* 
                                 int B, int T, int H, int W, int d, int J, int splits, int dtype,
                                 void* workspace, size_t workspace_bytes, int impl, void* stream);
 
+/* hicom_global_attend_partial_keys: the clip-scale variant (use_clip_scale has 'global', projector.py:184-188):
+ *   q and k are L2-normalised over all d channels BEFORE the head split and the logits are scaled by
+ *   exp(logit_scale) (+ logit_bias, which cancels in the softmax).  The per-token key norm cannot be folded into the
+ *   queries, so the caller supplies explicit normalised keys
+ *     Kscore (B,T,H,W,d) = l2norm_rows(Wk·x' + bk)   [hicom_linear, hicom_posadd with Wk-transformed tables,
+ *                                                      hicom_l2norm_rows]
+ *   and qfold (B,J,d) = exp(logit_scale) * blockdiag_h(l2norm(q)); the scores are Kscore·qfoldᵀ, while the pooled
+ *   operand remains x' = X + pos_embed, so the value side stays reassociated (v_proj after pooling).
+ *   Same outputs and workspace contract as hicom_global_attend_partial.
+ */
+int hicom_global_attend_partial_keys(const void* X, const void* Kscore, const float* pos_t,
+                                     const float* pos_h, const float* pos_w, const void* qfold, float* m,
+                                     float* l, float* o, int B, int T, int H, int W, int d, int J, int splits,
+                                     int dtype, void* workspace, size_t workspace_bytes, int impl, void* stream);
+
+/* hicom_posadd: Y[b,t,h,w,:] = X[b,t,h,w,:] + pos_t[t] + pos_h[h] + pos_w[w]  (the separable form of the
+ *   position-embedding add, projector.py:636-640; fp32 tables, X/Y in dtype, in place allowed). */
+int hicom_posadd(const void* X, void* Y, const float* pos_t, const float* pos_h, const float* pos_w, int B,
+                 int T, int H, int W, int d, int dtype, void* stream);
+
+/* hicom_l2norm_rows: Y[r,:] = X[r,:] / ||X[r,:]||_2  (projector.py:184-186, :527-529); in place allowed. */
+int hicom_l2norm_rows(const void* X, void* Y, long long rows, int d, int dtype, void* stream);
+
 /* hicom_softmax_merge: combine P partials per (video, column) — across token splits and, after an
  *   all-gather, across frame shards on other GPUs:
  *     M = max_p m_p;  L = sum_p l_p e^{m_p-M};  pooled = sum_p o_p e^{m_p-M} / L

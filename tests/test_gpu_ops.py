@@ -308,3 +308,19 @@ def test_linear_cta_pairs_large(M, N, K, act, built_library):
     if act:
         ref = F.gelu(ref)
     assert O.rel_err(got.cpu(), ref.cpu()) <= 6e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_posadd_and_l2norm_rows(dtype, built_library):
+    """The two helpers of the clip-scale variant: separable position add (projector.py:636-640) and row L2 norms
+    (:184-186)."""
+    from hicom_b200 import ops
+    B, T, H, W, d = 2, 3, 5, 4, 1152
+    X = _rand(B, T, H, W, d, seed=31, dtype=dtype)
+    pt, ph, pw = (_rand(n, d, seed=s2) for n, s2 in ((T, 32), (H, 33), (W, 34)))
+    got = ops.posadd(X.cuda(), pt.cuda(), ph.cuda(), pw.cuda()).float().cpu()
+    want = X.float() + pt[None, :, None, None] + ph[None, None, :, None] + pw[None, None, None, :]
+    assert O.rel_err(got, want.to(dtype).float()) <= (1e-6 if dtype == torch.float32 else 8e-3)
+    got = ops.l2norm_rows(X.cuda()).float().cpu()
+    want = X.float() / X.float().norm(dim=-1, keepdim=True)
+    assert O.rel_err(got, want) <= (1e-6 if dtype == torch.float32 else 8e-3)
