@@ -582,11 +582,14 @@ class HIComProjector(nn.Module):
 
     # -- batched entry (additive) ------------------------------------------------------
     def forward_batched(self, frames_feature, frames_embed, guide_embed, modal, image_newline=None,
-                        is_anyres=False, base=None, with_global=True):
+                        is_anyres=False, base=None, with_global=True, out=None, out_row_offset=0):
         """``frames_feature`` (B,T,H,W,d) [+ ``frames_embed`` same shape] and ``guide_embed`` (B,d) / (B,L,d)
         -> (B, n_tokens, Dh), equal to stacking ``forward`` over the batch (hicom_arch.py:167-178).
         ``base`` (B,n,Dh) tokens are copied in front (any-res base image); ``with_global=False`` skips the
-        global compressor (the any-res base image only feeds the local one, projector.py:680-684)."""
+        global compressor (the any-res base image only feeds the local one, projector.py:680-684).
+        ``out`` (B, L, Dh), contiguous: write the tokens straight into rows ``out_row_offset ..`` of every sample of a
+        caller-owned buffer — the padded ``inputs_embeds`` of hicom_arch.py:283-373 — instead of a new tensor; the
+        readout epilogues store there directly, the returned tensor is the view ``out[:, off:off+n_tokens]``."""
         X = frames_feature
         if X.dim() != 5:
             raise ValueError(f"forward_batched expects (B,T,H,W,d), got {tuple(X.shape)}")
@@ -599,9 +602,12 @@ class HIComProjector(nn.Module):
             # superset of fp16, fp32 CUDA kernels) and round the tokens back once.
             f32 = lambda t: None if t is None else t.float()
             shadow = self._fp32_shadow()
-            out = shadow.forward_batched(X.float(), f32(frames_embed), f32(guide_embed), modal, f32(image_newline),
+            res = shadow.forward_batched(X.float(), f32(frames_embed), f32(guide_embed), modal, f32(image_newline),
                                          is_anyres=is_anyres, base=f32(base), with_global=with_global)
-            return None if out is None else out.to(torch.float16)
+            if res is None or out is None:
+                return None if res is None else res.to(torch.float16)
+            out[:, out_row_offset:out_row_offset + res.shape[1]] = res.to(out.dtype)
+            return out[:, out_row_offset:out_row_offset + res.shape[1]]
         B, T, H, W, d = X.shape
         lc = self.local_compressor
         gc = self.global_compressor if with_global else None
@@ -619,9 +625,20 @@ class HIComProjector(nn.Module):
         if gc is not None:
             n_global = gc.query.shape[0]
         total = n_base + n_local + n_global
-        out = torch.empty((B * total, Dh), dtype=X.dtype, device=X.device)
+        dest, off0, stride = out, 0, total
+        if dest is None:
+            out = torch.empty((B * total, Dh), dtype=X.dtype, device=X.device)
+        else:  # rows [off0, off0 + total) of every sample of the caller's (B, L, Dh) buffer
+            if (dest.dim() != 3 or dest.shape[0] != B or dest.shape[2] != Dh or dest.dtype != X.dtype
+                    or dest.device != X.device or not dest.is_contiguous()):
+                raise ValueError(f"out must be a contiguous ({B}, L, {Dh}) {X.dtype} tensor on {X.device}")
+            off0, stride = int(out_row_offset), dest.shape[1]
+            if off0 < 0 or off0 + total > stride:
+                raise ValueError(f"out has {stride} rows per sample, need {off0} + {total}")
+            out = dest.view(B * stride, Dh)
+        n_base += off0  # every row offset below is relative to the sample's first row
         if base is not None:
-            out.view(B, total, Dh)[:, :n_base] = base
+            out.view(B, stride, Dh)[:, off0:n_base] = base
         # The local chain (HBM-bound window attention + readout) and the global chain (tensor-bound score / pooling
         # GEMMs) are independent and write disjoint rows of `out`: run them on two streams so they overlap.
         side = None
@@ -632,14 +649,14 @@ class HIComProjector(nn.Module):
         if lc is not None:
             with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
                 att = lc.attend(X, frames_embed, guide_embed, modal, self.local_logit_scale, self.local_logit_bias)
-                self._emit_local(att, grid, plan, image_newline, out, n_base, total)
+                self._emit_local(att, grid, plan, image_newline, out, n_base, stride)
         if gc is not None:
             Qg = gc.injected_query(guide_embed, B, X.dtype)
             m, l, o = gc.partials(X, gc.fold(Qg, self.global_logit_scale), logit_scale=self.global_logit_scale)
-            gc.finish(Qg, m, l, o, out, n_base + n_local, total)
+            gc.finish(Qg, m, l, o, out, n_base + n_local, stride)
         if side is not None:
             main.wait_stream(side)
-        return out.view(B, total, Dh)
+        return out.view(B, stride, Dh)[:, off0:off0 + total]
 
     # -- reference signature -----------------------------------------------------------------------
     # -- optional CUDA-graph replay for the reference's per-video call pattern -----------------------

@@ -338,3 +338,25 @@ def test_forward_with_cuda_graph_cache(built_library):
     for got, want in ((a, want8), (b, want8), (c, want4), (d, want_half)):
         assert got.shape == want.shape
         assert O.rel_err(got.float().cpu(), want.float().cpu()) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["bf16_coarse_T8", "video_grid_newline", "direct_T8", "video_one_token"])
+def test_forward_batched_writes_into_padded_buffer(name, built_library):
+    """Token splice (hicom_arch.py:283-373): the tokens are stored straight into rows [off, off+n) of every sample of a
+    caller-owned padded (B, L, Dh) buffer; all other rows stay untouched."""
+    case = CASES_BY_NAME[name]
+    sd, X, E, g, nl = materialise(case)
+    m = cuda_module_for(case, sd)
+    B = 3
+    st = lambda t: None if t is None else torch.stack([to_dev(t)] * B)
+    with torch.no_grad():
+        want = m.forward_batched(st(X), st(E), st(g), case.modal, to_dev(nl))
+        n, Dh = want.shape[1], want.shape[2]
+        off, L = 11, n + 37
+        buf = torch.full((B, L, Dh), 7.0, dtype=want.dtype, device="cuda")
+        got = m.forward_batched(st(X), st(E), st(g), case.modal, to_dev(nl), out=buf, out_row_offset=off)
+    assert got.data_ptr() == buf[:, off:].data_ptr() and got.shape == want.shape
+    assert torch.equal(buf[:, off:off + n], want)
+    assert bool((buf[:, :off] == 7.0).all()) and bool((buf[:, off + n:] == 7.0).all())
+    with torch.no_grad(), pytest.raises(ValueError):
+        m.forward_batched(st(X), st(E), st(g), case.modal, to_dev(nl), out=buf, out_row_offset=L - n + 1)
