@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhicom_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU = 0, 1
+ACT_NONE, ACT_GELU, ACT_GELU_TANH = 0, 1, 2
 Q_POOLED, Q_FILM_LN, Q_VECTOR, Q_EXPLICIT = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 
@@ -23,6 +23,7 @@ PROTOTYPES = {
     "hicom_local_attend": (c_int, [c_void_p] * 8 + [c_int] * 8 + [c_float, c_int, c_int, c_void_p]),
     "hicom_linear": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, c_void_p]),
+    "hicom_layernorm": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_void_p]),
     "hicom_film_layernorm": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "hicom_add_layernorm": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     "hicom_mix_layernorm": (c_int, [c_void_p] * 6 + [c_int64, c_int, c_int, c_void_p]),

@@ -141,7 +141,7 @@ extern "C" int hicom_linear(const void* A, int64_t lda, const void* W, int64_t l
   HICOM_REQUIRE(M >= 0 && N > 0 && K > 0, "linear: bad shape M=%d N=%d K=%d", M, N, K);
   HICOM_REQUIRE(lda >= K && ldw >= K && ldc >= N, "linear: leading dimension too small");
   HICOM_REQUIRE(rows_per_group > 0, "linear: rows_per_group must be positive");
-  HICOM_REQUIRE(act == HICOM_ACT_NONE || act == HICOM_ACT_GELU, "linear: bad activation %d", act);
+  HICOM_REQUIRE(act == HICOM_ACT_NONE || act == HICOM_ACT_GELU || act == HICOM_ACT_GELU_TANH, "linear: bad activation %d", act);
   if (M == 0) return 0;
   // skinny problems (M <= 32): warp-per-column kernel, all SMs stream the weights (see skinny.cu)
   if (impl == HICOM_IMPL_AUTO && !(in_dtype == HICOM_F32 && out_dtype == HICOM_BF16) &&

@@ -109,6 +109,14 @@ __device__ __forceinline__ float warp_max(float v) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// tanh form ("gelu_pytorch_tanh", the SigLIP MLP activation): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+__device__ __forceinline__ float gelu_tanh(float x) {
+  return 0.5f * x * (1.0f + tanhf(0.7978845608028654f * fmaf(0.044715f * x * x, x, x)));
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  return act == HICOM_ACT_GELU ? gelu_erf(v) : (act == HICOM_ACT_GELU_TANH ? gelu_tanh(v) : v);
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLnEps = 1e-6f;  // projector.py:318,403,565
 

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmParams p) {
       if (n >= p.N) continue;
       float v = acc[i][j] * p.alpha;
       if (bias) v += to_f32<TB>(bias[n]);
-      if (p.act == HICOM_ACT_GELU) v = gelu_erf(v);
+      v = apply_act(v, p.act);
       if (R) v += to_f32<TB>(R[m * p.ldr + n]);
       C[orow * p.ldc + n] = from_f32<TC>(v);
     }

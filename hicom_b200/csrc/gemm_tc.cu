@@ -37,7 +37,7 @@ constexpr int UK = 16;   // K per tcgen05.mma for 16-bit inputs
 // 288-column accumulator cannot be double-buffered in 512 TMEM columns, so its epilogue is on the critical path)
 // ... and for the GELU linear, whose epilogue (two MUFU + ~15 FP32 ops per element) outlasts a K = 1152 mainloop
 __host__ __device__ constexpr int epi_warps(int epi, int flags = 0) {
-  return (epi == 4 /*EPI_PROB2*/ || (epi == 0 /*EPI_LINEAR*/ && (flags & 1))) ? 16 : 8;
+  return (epi == 4 /*EPI_PROB2*/ || (epi == 0 /*EPI_LINEAR*/ && (flags & 9))) ? 16 : 8;
 }
 __host__ __device__ constexpr int num_threads(int epi, int flags = 0) { return 64 + 32 * epi_warps(epi, flags); }
 
@@ -275,6 +275,15 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// tanh-form GELU (SigLIP head MLP, encoder.py:285): 0.5 x (1 + tanh(u)) = x / (1 + exp(-2u)),
+// u = sqrt(2/pi) (x + 0.044715 x^3); two MUFU ops, branch-free.  exp -> inf gives x * 0 = 0 for large negative x.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(-2.0f * kLog2e * u)));
+  return x * r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -347,7 +356,7 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile, int p
   return t;
 }
 
-// FLAGS (EPI_LINEAR only): bit 0 = GELU, bit 1 = fp32 output
+// FLAGS (EPI_LINEAR only): bit 0 = GELU (erf), bit 1 = fp32 output, bit 2 = accumulate into C, bit 3 = GELU (tanh)
 template <int BN, bool A_MN, bool B_MN, int EPI, int FLAGS, bool CTA2 = false>
 __global__ void __launch_bounds__(num_threads(EPI, FLAGS), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -600,6 +609,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (EPI == EPI_LINEAR) {
       constexpr bool kGelu = (FLAGS & 1) != 0;
+      constexpr bool kGeluTanh = (FLAGS & 8) != 0;
       constexpr bool kOutF32 = (FLAGS & 2) != 0;
       constexpr bool kAccum = (FLAGS & 4) != 0;  // C += result (fp32 C only)
       const bool row_ok = row < p.M;
@@ -659,6 +669,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (kGelu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          }
+          if (kGeluTanh) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fast(v[i]);
           }
           if (has_res && row_ok) {
             const __nv_bfloat16* rp = p.R + (long long)row * p.ldr + n0;
@@ -999,7 +1013,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
                              : (unsigned)(total < num_sms ? total : num_sms);
   char label[96];
   static const char* names[] = {"tc_linear", "tc_scores_max", "tc_scores_prob", "tc_pool", "tc_scores_prob2"};
-  snprintf(label, sizeof(label), "%s%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI], (FLAGS & 1) ? "+gelu" : "",
+  snprintf(label, sizeof(label), "%s%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI],
+           (FLAGS & 1) ? "+gelu" : ((FLAGS & 8) ? "+gelu_tanh" : ""),
            CTA2 ? "/pair" : "", p.M, p.N, p.K, total, p.guard ? " guarded" : "");
   KernelTimer timer(label, stream);
   if (CTA2) {
@@ -1090,7 +1105,10 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
                   "tcgen05 linear: accumulate is only built for fp32 C, (K,N) weights, no activation");
     return launch<256, false, true, EPI_LINEAR, 6>(ta, tb, p, grid, stream);
   }
-  const int flags = (q.act == HICOM_ACT_GELU ? 1 : 0) | (q.out_dtype == HICOM_F32 ? 2 : 0);
+  const int flags = (q.act == HICOM_ACT_GELU ? 1 : 0) | (q.out_dtype == HICOM_F32 ? 2 : 0) |
+                    (q.act == HICOM_ACT_GELU_TANH ? 8 : 0);
+  HICOM_REQUIRE(q.act != HICOM_ACT_GELU_TANH || (!q.w_is_kn && q.out_dtype == HICOM_BF16),
+                "tcgen05 linear: the tanh GELU is only built for bf16 C and (N,K) weights");
   // small problems: 128x64 tiles spread over 4x more CTAs with an 8-deep ring (latency-bound otherwise)
   if (!q.w_is_kn && q.z_slices == 0 && (long long)grid.x * grid.y < 74 && q.N >= 64) {
     CUtensorMap tb64;
@@ -1102,6 +1120,7 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
       case 1: return launch<64, false, false, EPI_LINEAR, 1>(ta, tb64, p, g64, stream);
       case 2: return launch<64, false, false, EPI_LINEAR, 2>(ta, tb64, p, g64, stream);
       case 3: return launch<64, false, false, EPI_LINEAR, 3>(ta, tb64, p, g64, stream);
+      case 8: return launch<64, false, false, EPI_LINEAR, 8>(ta, tb64, p, g64, stream);
     }
   }
   // large plain K-major GEMMs: CTA pairs (cta_group::2), each CTA stages half of the weight tile
@@ -1114,6 +1133,7 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
       case 1: return launch<256, false, false, EPI_LINEAR, 1, true>(ta, tb128, p, grid, stream);
       case 2: return launch<256, false, false, EPI_LINEAR, 2, true>(ta, tb128, p, grid, stream);
       case 3: return launch<256, false, false, EPI_LINEAR, 3, true>(ta, tb128, p, grid, stream);
+      case 8: return launch<256, false, false, EPI_LINEAR, 8, true>(ta, tb128, p, grid, stream);
     }
   }
 #define HICOM_TC_LINEAR_CASE(F)                                                                  \
@@ -1125,6 +1145,7 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
     HICOM_TC_LINEAR_CASE(1)
     HICOM_TC_LINEAR_CASE(2)
     HICOM_TC_LINEAR_CASE(3)
+    case 8: return launch<256, false, false, EPI_LINEAR, 8>(ta, tb, p, grid, stream);
   }
 #undef HICOM_TC_LINEAR_CASE
   return 1;

@@ -9,7 +9,7 @@ namespace hicom {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm family: one warp per row, lane owns chunks {lane, lane+32, ...} (d = 128*CPL).
 // ------------------------------------------------------------------------------------------------
-enum { LN_FILM = 0, LN_ADD = 1, LN_MIX = 2 };
+enum { LN_FILM = 0, LN_ADD = 1, LN_MIX = 2, LN_PLAIN = 3 };
 
 struct LnParams {
   const void* a; const void* b; const float* film; const void* w; const void* bias; const void* alpha;
@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(256) rowwise_ln_kernel(const LnParams p) {
       Vec4<T>::load(static_cast<const T*>(p.b) + row * d + off, y);
 #pragma unroll
       for (int e = 0; e < 4; ++e) u[c][e] = x[e] + y[e];
+    } else if (MODE == LN_PLAIN) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) u[c][e] = x[e];
     } else {  // LN_MIX: normalise b (=y), keep a (=x)
       float y[4];
       Vec4<T>::load(static_cast<const T*>(p.b) + row * d + off, y);
@@ -297,6 +300,14 @@ __global__ void __launch_bounds__(256) guide_attend_kernel(const T* __restrict__
 }  // namespace hicom
 
 using namespace hicom;
+
+extern "C" int hicom_layernorm(const void* x, const void* ln_w, const void* ln_b, void* out, int64_t rows, int d,
+                               int dtype, void* stream) {
+  HICOM_REQUIRE(x && ln_w && ln_b && out, "layernorm: null pointer");
+  HICOM_REQUIRE(rows >= 0 && d > 0 && d % 128 == 0, "layernorm: bad shape");
+  LnParams p{}; p.a = x; p.w = ln_w; p.bias = ln_b; p.out = out; p.rows = rows; p.d = d; p.rows_per_group = 1;
+  HICOM_DISPATCH_DTYPE(dtype, E, return (launch_ln<E, LN_PLAIN>(p, as_stream(stream))));
+}
 
 extern "C" int hicom_film_layernorm(const void* x, const float* film, const void* ln_w, const void* ln_b,
                                     void* out, int rows, int d, int rows_per_group, int dtype, void* stream) {

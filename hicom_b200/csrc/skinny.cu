@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const SkinnyParams p
       if (lane < M) {
         float v = mine * p.alpha;
         if (p.bias) v += to_f32<TI>(static_cast<const TI*>(p.bias)[n]);
-        if (p.act == HICOM_ACT_GELU) v = gelu_erf(v);
+        v = apply_act(v, p.act);
         if (p.R) v += to_f32<TI>(static_cast<const TI*>(p.R)[(size_t)lane * p.ldr + n]);
         const long long orow = (long long)(lane / p.rows_per_group) * p.group_stride_rows + (lane % p.rows_per_group);
         static_cast<TO*>(p.C)[orow * p.ldc + n] = from_f32<TO>(v);

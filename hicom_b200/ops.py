@@ -16,7 +16,7 @@ import torch
 from torch import Tensor
 
 from . import _cabi
-from ._cabi import ACT_GELU, ACT_NONE, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05  # noqa: F401 (re-exported)
+from ._cabi import ACT_GELU, ACT_GELU_TANH, ACT_NONE, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05  # noqa: F401 (re-exported)
 from ._cabi import Q_EXPLICIT, Q_FILM_LN, Q_POOLED, Q_VECTOR  # noqa: F401
 
 _DT = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
@@ -180,6 +180,22 @@ def _impl_linear_into(A: Tensor, W: Tensor, bias: Optional[Tensor], residual: Op
     Cview = out[row_offset:]
     _linear_call(A2, W, _c(bias), R2, Cview, out.stride(0), M, N, K, act, _dt(out), rows_per_group,
                  group_stride_rows, impl, dev)
+
+
+def _impl_layernorm(x: Tensor, ln_w: Tensor, ln_b: Tensor) -> Tensor:
+    """LN(x) over the last dim, eps 1e-6 — the SigLIP head's layernorm in front of the frames_embed MLP
+    (encoder.py:284)."""
+    dev = _need_cuda(x, ln_w, ln_b)
+    x = x.contiguous()
+    d = x.shape[-1]
+    if ln_w.shape != (d,) or ln_b.shape != (d,) or ln_w.dtype != x.dtype or ln_b.dtype != x.dtype:
+        raise ValueError("layernorm: weight/bias must be (d,) in the input dtype")
+    out = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_layernorm(_ptr(x), _ptr(_c(ln_w)), _ptr(_c(ln_b)), _ptr(out), x.numel() // d, d,
+                                          _dt(x), _stream(dev))
+    _cabi.check(rc, "hicom_layernorm")
+    return out
 
 
 def _impl_film_layernorm(x: Tensor, film: Tensor, ln_w: Tensor, ln_b: Tensor, rows_per_group: int) -> Tensor:
@@ -529,6 +545,7 @@ grid_pool = _wrap("grid_pool", _impl_grid_pool, (), lambda *a: "grid_pool")
 local_attend = _wrap("local_attend", _impl_local_attend, (), lambda *a: "local_attend")
 linear = _wrap("linear", _impl_linear, (), _lin_label)
 linear_into = _wrap("linear_into", _impl_linear_into, ("out",), _lin_label)
+layernorm = _wrap("layernorm", _impl_layernorm, (), lambda *a: "layernorm")
 film_layernorm = _wrap("film_layernorm", _impl_film_layernorm, (), lambda *a: "film_layernorm")
 add_layernorm = _wrap("add_layernorm", _impl_add_layernorm, (), lambda *a: "add_layernorm")
 mix_layernorm = _wrap("mix_layernorm", _impl_mix_layernorm, (), lambda *a: "mix_layernorm")

@@ -25,7 +25,9 @@ extern "C" {
 #define HICOM_ABI_VERSION 1
 
 enum { HICOM_F32 = 0, HICOM_BF16 = 1 };
-enum { HICOM_ACT_NONE = 0, HICOM_ACT_GELU = 1 }; /* GELU = exact erf form (nn.GELU(), projector.py:310) */
+/* GELU = exact erf form (nn.GELU(), projector.py:310); GELU_TANH = the tanh form ("gelu_pytorch_tanh") of the SigLIP
+ * pooling-head MLP that produces frames_embed (encoder.py:284-285) */
+enum { HICOM_ACT_NONE = 0, HICOM_ACT_GELU = 1, HICOM_ACT_GELU_TANH = 2 };
 enum {
   HICOM_Q_POOLED = 0,   /* query = grid-pooled feature                 (use_guide None/off)        */
   HICOM_Q_FILM_LN = 1,  /* query = LN(pooled*(1+scale)+shift)           (coarse, projector.py:369-372) */
@@ -96,7 +98,11 @@ int hicom_linear(const void* A, int64_t lda, const void* W, int64_t ldw, const v
  *                    film (G,2d) fp32, row r uses film[r / rows_per_group]
  *   add_layernorm  : out = LN(a + b)                 fine injector residual (:392)
  *   mix_layernorm  : out = (1-alpha)*x + alpha*LN(y) adapters (:365,533-534,541); alpha read from device
+ *   layernorm      : out = LN(x)                     producer side: the SigLIP head's layernorm in front of the MLP
+ *                    that makes frames_embed (encoder.py:284; eps 1e-6 = SigLIP's layer_norm_eps)
  */
+int hicom_layernorm(const void* x, const void* ln_w, const void* ln_b, void* out, int64_t rows, int d, int dtype,
+                    void* stream);
 int hicom_film_layernorm(const void* x, const float* film, const void* ln_w, const void* ln_b,
                          void* out, int rows, int d, int rows_per_group, int dtype, void* stream);
 int hicom_add_layernorm(const void* a, const void* b, const void* ln_w, const void* ln_b, void* out,
