@@ -37,6 +37,12 @@ PROTOTYPES = {
     "hicom_softmax_merge": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_int, c_void_p]),
     "hicom_softmax_reduce": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 4),
     "hicom_global_value_proj": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
+    "hicom_gemm": (c_int, [c_void_p] + [c_int64] * 4 + [c_void_p] + [c_int64] * 4 + [c_void_p] + [c_int64] * 3 +
+                   [c_int] * 5 + [c_float] + [c_int] * 3 + [c_void_p]),
+    "hicom_act_backward": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_int, c_void_p]),
+    "hicom_softmax_backward": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_int, c_void_p]),
+    "hicom_local_attend_backward_query": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_int, c_int, c_void_p]),
+    "hicom_film_layernorm_backward": (c_int, [c_void_p] * 8 + [c_int64, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,370 @@
+"""Training path of the compressor: autograd for the custom ops.
+
+The reference trains ``mm_projector`` in all three stages (train.py:704-738, ``mm_tunable_parts``) through PyTorch
+autograd; the SigLIP tower and the guide encoder are frozen (encoder.py:235,247), so gradients are needed for the
+projector's PARAMETERS only — never for ``frames_feature``, ``frames_embed`` or the instruction embedding.
+
+``forward_batched_train`` is the differentiable twin of ``HIComProjector.forward_batched``.  Its forward runs the same
+sm_100a kernels as inference; every op that has a trainable parameter upstream is wrapped in a
+``torch.autograd.Function`` whose backward is composed from the C-ABI blocks of ``csrc/backward.cu``
+(``hicom_gemm`` for every contraction, ``hicom_act_backward``, ``hicom_softmax_backward``,
+``hicom_local_attend_backward_query``, ``hicom_film_layernorm_backward``).  PyTorch only supplies plumbing: views,
+``cat``/``expand`` of token rows, dtype casts, and reductions over tensors of a few hundred rows.
+
+Global attention backward in the reassociated form (forward: projector.py:180-226 as ``pooled = softmax(x'·qfold)ᵀ x'``):
+    dP = x'·dpooledᵀ,   delta_j = pooled_j·dpooled_j,   dS = P ∘ (dP − delta),   dqfold = dSᵀ·x'
+so no gradient is ever formed for the N x 1152 keys/values the reference materialises.
+
+Status: first correct CUDA path (SIMT GEMMs, fp32 accumulation).  Supported: ``use_guide`` None/off/direct/coarse,
+no adapters (``adaptq/k/v/g``), no ``use_clip_scale``; ``fine`` and the adapters raise ``NotImplementedError``.
+Opt-in (``HICOM_AUTOGRAD=1`` or ``hicom_b200.autograd.enable()``) until it has been validated on a B200; without the
+switch a forward under autograd keeps failing loudly (``projector._require_no_grad``).
+"""
+from __future__ import annotations
+
+import math
+import os
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import ops
+
+ENABLED = os.environ.get("HICOM_AUTOGRAD", "0") == "1"
+
+
+def enable(on: bool = True) -> None:
+    """Route grad-enabled projector forwards through ``forward_batched_train`` instead of raising."""
+    global ENABLED
+    ENABLED = bool(on)
+
+
+def _impl():
+    from . import projector
+    return projector._IMPL
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+def _gemm_to(A: torch.Tensor, B: torch.Tensor, want: torch.dtype, alpha: float = 1.0) -> torch.Tensor:
+    """alpha * A @ B on hicom_gemm (strided views, fp32 accumulation), result cast to ``want``."""
+    if A.dtype == torch.bfloat16 and B.dtype == torch.float32:
+        A = A.float()
+    out_fp32 = A.dtype != B.dtype or (A.dtype == torch.bfloat16 and want == torch.float32)
+    C = ops.gemm(A, B, None, out_fp32, alpha)
+    return C if C.dtype == want else C.to(want)
+
+
+def _colsum_to(x2: torch.Tensor, want: torch.dtype) -> torch.Tensor:
+    """Column sums of (M, N) as 1ᵀ·x on hicom_gemm — bias gradients."""
+    ones = torch.ones((1, x2.shape[0]), dtype=x2.dtype, device=x2.device)
+    return _gemm_to(ones, x2, want).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------
+# nn.Linear / build_mlp stage                                           projector.py:307-312
+# ------------------------------------------------------------------------------------------
+class LinearFn(Function):
+    """y = act(A·Wᵀ + bias) [+ residual]; backward: dpre = dy ∘ act'(pre), dA = dpre·W, dW = dpreᵀ·A, db = 1ᵀ·dpre."""
+
+    @staticmethod
+    def forward(ctx, A, W, bias, residual, act, out_fp32):
+        ctx.save_for_backward(A, W, bias)
+        ctx.act = act
+        ctx.res_dtype = None if residual is None else residual.dtype
+        return ops.linear(A, W, bias, residual, act, out_fp32, _impl())
+
+    @staticmethod
+    def backward(ctx, dY):
+        A, W, bias = ctx.saved_tensors
+        N, K = W.shape
+        A2 = A.reshape(-1, K)
+        M = A2.shape[0]
+        dY2 = dY.reshape(M, N)
+        need_A, need_W, need_b, need_R = ctx.needs_input_grad[:4]
+        dR = dY.to(ctx.res_dtype) if (need_R and ctx.res_dtype is not None) else None
+        if ctx.act != ops.ACT_NONE:
+            pre = ops.linear(A2, W, bias, None, ops.ACT_NONE, True, _impl())  # fp32 pre-activations, recomputed
+            dpre = ops.act_backward(pre, dY2, ctx.act)
+        else:
+            dpre = dY2
+        dA = _gemm_to(dpre, W, A.dtype).reshape(A.shape) if need_A else None
+        dW = _gemm_to(dpre.t(), A2, W.dtype) if need_W else None
+        db = _colsum_to(dpre, bias.dtype) if (need_b and bias is not None) else None
+        return dA, dW, db, dR, None, None
+
+
+def linear(A, W, bias=None, residual=None, act=ops.ACT_NONE, out_fp32=False):
+    return LinearFn.apply(A, W, bias, residual, act, out_fp32)
+
+
+def mlp(seq: nn.Sequential, x: torch.Tensor, out_fp32: bool = False):
+    """build_mlp Sequential (projector.py:307-312) on differentiable linears (GELU fused in all but the last)."""
+    linears = [m for m in seq if isinstance(m, nn.Linear)]
+    for i, lin in enumerate(linears):
+        last = i == len(linears) - 1
+        x = linear(x, lin.weight, lin.bias, None, ops.ACT_NONE if last else ops.ACT_GELU, out_fp32 and last)
+    return x
+
+
+# ------------------------------------------------------------------------------------------
+# global attention, reassociated                                         projector.py:180-226
+# ------------------------------------------------------------------------------------------
+class FoldQueryFn(Function):
+    """qfold[b, h*Q+i, :] = alpha * q[b, i, head h] · Wk[head h rows, :]  (ops.global_fold_query).
+    ``bk`` (k_proj.bias) shifts every score of a column by one constant, which the softmax cancels: it takes no part in
+    the forward and its gradient is exactly zero — returned as zeros (not None) so that every trainable parameter
+    receives a gradient, as under the reference's autograd (DDP / ZeRO reducers expect that)."""
+
+    @staticmethod
+    def forward(ctx, q, Wk, bk, heads, alpha):
+        ctx.save_for_backward(q, Wk)
+        ctx.heads, ctx.alpha = heads, alpha
+        ctx.bk_meta = None if bk is None else (bk.shape, bk.dtype, bk.device)
+        return ops.global_fold_query(q, Wk, heads, alpha)
+
+    @staticmethod
+    def backward(ctx, dqfold):
+        q, Wk = ctx.saved_tensors
+        heads, alpha = ctx.heads, ctx.alpha
+        B, Q, d = q.shape
+        hd = d // heads
+        dqf = dqfold.contiguous().view(B, heads, Q, d)                      # [b, h, i, k]
+        dq = dWk = None
+        if ctx.needs_input_grad[0]:
+            dq = torch.empty_like(q)
+            wk_t = Wk.view(heads, hd, d).transpose(1, 2)                    # [h, k, c]
+            dq_view = dq.view(B, Q, heads, hd).permute(0, 2, 1, 3)          # [b, h, i, c]
+            if dqf.dtype != wk_t.dtype:
+                dqf_op, wk_t = dqf.float(), wk_t.float()
+                tmp = ops.gemm(dqf_op, wk_t, None, True, alpha)
+                dq_view.copy_(tmp)
+            else:
+                ops.gemm(dqf, wk_t, dq_view, False, alpha)
+        if ctx.needs_input_grad[1]:
+            q_h = q.contiguous().view(B * Q, heads, hd).permute(1, 2, 0)    # [h, c, (b,i)]
+            dqf_h = dqf.permute(1, 0, 2, 3).reshape(heads, B * Q, d)        # [h, (b,i), k]  (small copy)
+            dWk = _gemm_to(q_h, dqf_h, Wk.dtype, alpha).reshape(d, d)
+        dbk = None
+        if ctx.needs_input_grad[2] and ctx.bk_meta is not None:
+            shape, dtype, device = ctx.bk_meta
+            dbk = torch.zeros(shape, dtype=dtype, device=device)
+        return dq, dWk, dbk, None, None
+
+
+class ValueProjFn(Function):
+    """attn[b, i, head h] = Wv[head h rows] · pooled[b, h*Q+i] + bv  (ops.global_value_proj)."""
+
+    @staticmethod
+    def forward(ctx, pooled, Wv, bv, Q, heads):
+        ctx.save_for_backward(pooled, Wv, bv)
+        ctx.Q, ctx.heads = Q, heads
+        return ops.global_value_proj(pooled, Wv, bv, Q, heads)
+
+    @staticmethod
+    def backward(ctx, dattn):
+        pooled, Wv, bv = ctx.saved_tensors
+        Q, heads = ctx.Q, ctx.heads
+        B, J, d = pooled.shape
+        hd = d // heads
+        da = dattn.contiguous()
+        dpooled = dWv = dbv = None
+        if ctx.needs_input_grad[0]:
+            da_h = da.view(B, Q, heads, hd).permute(0, 2, 1, 3)             # [b, h, i, c]
+            wv_h = Wv.view(heads, hd, d)                                    # [h, c, k]
+            if da_h.dtype != wv_h.dtype:
+                da_h, wv_h = da_h.float(), wv_h.float()
+            dpooled = ops.gemm(da_h, wv_h, None, False, 1.0).reshape(B, J, d).to(pooled.dtype)
+        if ctx.needs_input_grad[1]:
+            da_t = da.view(B * Q, heads, hd).permute(1, 2, 0)               # [h, c, (b,i)]
+            p_h = pooled.view(B, heads, Q, d).permute(1, 0, 2, 3).reshape(heads, B * Q, d)
+            dWv = _gemm_to(da_t, p_h, Wv.dtype).reshape(d, d)
+        if ctx.needs_input_grad[2] and bv is not None:
+            dbv = _colsum_to(da.view(B * Q, d), bv.dtype)
+        return dpooled, dWv, dbv, None, None
+
+
+class GlobalPoolFn(Function):
+    """pooled[b, j, :] = sum_n softmax_n(x'_n · qfold[b, j]) x'_n,  x' = X + pos_embed  (split-softmax kernels + merge).
+    X comes from the frozen tower: the only differentiable input is ``qfold``."""
+
+    @staticmethod
+    def forward(ctx, X, qfold, gc, t0, splits):
+        m, l, o = gc.partials(X, qfold, t0, splits)
+        pooled = ops.softmax_merge(m, l, o, X.dtype == torch.bfloat16)
+        mo, lo, _ = ops.softmax_reduce(m, l, o)
+        lse = mo[:, 0] + torch.log(lo[:, 0])                                # (B, J) fp32
+        ctx.save_for_backward(X, qfold, pooled, lse)
+        ctx.gc, ctx.t0 = gc, t0
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        X, qfold, pooled, lse = ctx.saved_tensors
+        if not ctx.needs_input_grad[1]:
+            return None, None, None, None, None
+        B, T, H, W, d = X.shape
+        N = T * H * W
+        pt, ph, pw = ctx.gc.pos_tables(ctx.t0, T, H, W, X.device)
+        Xp = ops.posadd(X, pt, ph, pw).view(B, N, d)                        # explicit x' (projector.py:636-640)
+        dpl = dpooled.contiguous().to(X.dtype)
+        S = ops.gemm(Xp, qfold.transpose(1, 2), None, True, 1.0)            # (B, N, J) fp32 scores
+        dP = ops.gemm(Xp, dpl.transpose(1, 2), None, True, 1.0)             # (B, N, J) fp32
+        delta = (pooled.float() * dpl.float()).sum(-1)                      # (B, J)
+        dS = ops.softmax_backward(S, dP, lse, delta, X.dtype == torch.bfloat16)
+        dqfold = _gemm_to(dS.transpose(1, 2), Xp, qfold.dtype)              # (B, J, d)
+        return None, dqfold, None, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# coarse injector and window attention                          projector.py:369-372, 546-553
+# ------------------------------------------------------------------------------------------
+class FilmLayerNormFn(Function):
+    """LN(x*(1+scale)+shift)*w + b with film = [scale | shift] (G, 2d) fp32, row r using film[r // rows_per_group]."""
+
+    @staticmethod
+    def forward(ctx, x, film, ln_w, ln_b, rows_per_group):
+        ctx.save_for_backward(x, film, ln_w)
+        ctx.rpg = rows_per_group
+        ctx.b_dtype = ln_b.dtype
+        return ops.film_layernorm(x, film, ln_w, ln_b, rows_per_group)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, film, ln_w = ctx.saved_tensors
+        need_x = ctx.needs_input_grad[0]
+        dx, dfilm, dw, db = ops.film_layernorm_backward(x, film, ln_w, dy.contiguous().to(x.dtype), ctx.rpg, need_x)
+        return (dx.view(x.shape) if need_x else None, dfilm if ctx.needs_input_grad[1] else None,
+                dw.to(ln_w.dtype) if ctx.needs_input_grad[2] else None,
+                db.to(ctx.b_dtype) if ctx.needs_input_grad[3] else None, None)
+
+
+class LocalAttendQueryFn(Function):
+    """Window attention on explicit query rows (ops.local_attend, Q_EXPLICIT); differentiable in the rows only."""
+
+    @staticmethod
+    def forward(ctx, K, V, X, Qrows, kt, ks, scale, k_l2norm):
+        ctx.save_for_backward(K, V, Qrows)
+        ctx.geom = (kt, ks, scale, k_l2norm)
+        return ops.local_attend(K, V, X, Qrows, None, None, None, kt, ks, ops.Q_EXPLICIT, scale, k_l2norm)
+
+    @staticmethod
+    def backward(ctx, dO):
+        K, V, Qrows = ctx.saved_tensors
+        kt, ks, scale, k_l2norm = ctx.geom
+        dQ = None
+        if ctx.needs_input_grad[3]:
+            dQ = ops.local_attend_backward_query(K, V, Qrows, dO.contiguous().to(Qrows.dtype), kt, ks, scale, k_l2norm)
+        return None, None, None, dQ, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# the differentiable forward
+# ------------------------------------------------------------------------------------------
+def _is_param(x) -> bool:
+    return isinstance(x, torch.Tensor)
+
+
+def check_supported(proj, X, E, G) -> None:
+    for name, t in (("frames_feature", X), ("frames_embed", E), ("guide_embed", G)):
+        if t is not None and t.requires_grad:
+            raise NotImplementedError(
+                f"hicom_b200.autograd: {name} requires grad, but the kernels only produce parameter gradients (the "
+                "reference freezes the SigLIP tower and the guide encoder, encoder.py:235,247)")
+    if X.dtype not in (torch.float32, torch.bfloat16):
+        raise NotImplementedError(f"hicom_b200.autograd: dtype {X.dtype} (train in fp32 or bf16)")
+    if proj.local_logit_scale is not None or proj.global_logit_scale is not None:
+        raise NotImplementedError("hicom_b200.autograd: use_clip_scale is not differentiable yet")
+    for comp in (proj.local_compressor, proj.global_compressor):
+        if comp is None:
+            continue
+        if comp.use_guide not in (None, "off", "direct", "coarse"):
+            raise NotImplementedError(f"hicom_b200.autograd: use_guide={comp.use_guide!r} is not differentiable yet "
+                                      "(supported: None, 'off', 'direct', 'coarse')")
+        inj = comp.guide_injector
+        if _is_param(getattr(inj, "guide_alpha", 0)) or isinstance(getattr(inj, "text2qk_proj", None), nn.Sequential):
+            raise NotImplementedError("hicom_b200.autograd: guide adapters (adaptg / text2qk_proj) are not "
+                                      "differentiable yet")
+    lc = proj.local_compressor
+    if lc is not None and any(_is_param(a) for a in (lc.q_alpha, lc.k_alpha, lc.v_alpha)):
+        raise NotImplementedError("hicom_b200.autograd: adaptq/adaptk/adaptv are not differentiable yet")
+
+
+def _local_tokens(proj, X, E, G, modal, image_newline, is_anyres):
+    lc = proj.local_compressor
+    B, T, H, W, d = X.shape
+    tk, grid = lc.output_grid(T, H, W, modal)
+    sk = lc.spatial_kernel_size
+    n_local, plan = proj._local_rows(grid, modal, image_newline, is_anyres)
+    if plan != "plain" and image_newline is None:
+        raise ValueError("this mm_newline_position needs image_newline")
+    if lc.use_guide == "coarse":
+        inj = lc.guide_injector
+        inj.check_guide(G, 0)
+        film = mlp(inj.coarse_proj, inj.prepared_guide(G), out_fp32=True)          # (B, 2d) fp32, projector.py:370-371
+        with torch.no_grad():
+            q0 = ops.grid_pool(X, tk, sk)                                          # projector.py:539-540 (no parameter)
+        rows = FilmLayerNormFn.apply(q0, film, inj.coarse_norm.weight, inj.coarse_norm.bias, q0.shape[1])
+        K = X if E is None else E
+        att = LocalAttendQueryFn.apply(K, X, X, rows, tk, sk, 1.0 / math.sqrt(lc.qk_dim), False)
+    else:  # None / off / direct: nothing trainable in front of the readout — the fused inference kernel, as a constant
+        with torch.no_grad():
+            att = lc.attend(X, E, G, modal, None, None)
+    tokens = mlp(lc.readout, att)                                                  # (B, Nw, Dh), projector.py:559
+    Dh = tokens.shape[-1]
+    t1, h1, w1 = grid
+    if plan == "plain":
+        return tokens
+    nl = image_newline.to(tokens.dtype)
+    if plan == "tail":                                                             # mm_utils.py:115-117
+        return torch.cat([tokens, nl.expand(B, 1, Dh)], dim=1)
+    if plan == "grid":                                                             # mm_utils.py:101-107
+        blk = torch.cat([tokens.view(B, t1 * h1, w1, Dh), nl.expand(B, t1 * h1, 1, Dh)], dim=2)
+    else:                                                                          # "frame", mm_utils.py:108-114
+        blk = torch.cat([tokens.view(B, t1, h1 * w1, Dh), nl.expand(B, t1, 1, Dh)], dim=2)
+    return blk.reshape(B, n_local, Dh)
+
+
+def _global_tokens(proj, X, G, splits=None, t0=0):
+    gc = proj.global_compressor
+    attn = gc.attn_layer
+    B = X.shape[0]
+    nq, d = gc.query.shape
+    if gc.use_guide == "direct":          # projector.py:367-368: every query row is the guide — one distinct row
+        gc.guide_injector.check_guide(G, 0)
+        Qg = gc.guide_injector.prepared_guide(G).unsqueeze(1).contiguous()          # (B, 1, d), no parameter
+    else:
+        rows = gc.query.to(X.dtype).unsqueeze(0).expand(B, nq, d).contiguous()      # autograd sums over the batch
+        if gc.use_guide == "coarse":
+            inj = gc.guide_injector
+            inj.check_guide(G, 0)
+            film = mlp(inj.coarse_proj, inj.prepared_guide(G), out_fp32=True)
+            Qg = FilmLayerNormFn.apply(rows, film, inj.coarse_norm.weight, inj.coarse_norm.bias, nq)
+        else:
+            Qg = rows
+    nrows = Qg.shape[1]
+    q = linear(Qg, attn.q_proj.weight, attn.q_proj.bias)                            # projector.py:180
+    qfold = FoldQueryFn.apply(q, attn.k_proj.weight, attn.k_proj.bias, attn.num_heads, attn.scale)  # :181 + :197
+    pooled = GlobalPoolFn.apply(X, qfold, gc, t0, splits)                           # :197-215
+    a = ValueProjFn.apply(pooled, attn.v_proj.weight, attn.v_proj.bias, nrows, attn.num_heads)  # :182, :223-224
+    x = linear(a, attn.out_proj.weight, attn.out_proj.bias, Qg)                     # :226 + residual of :646
+    tokens = mlp(gc.readout, x)                                                     # (B, nrows, Dh)
+    if nrows != nq:
+        tokens = tokens.expand(B, nq, tokens.shape[-1])
+    return tokens
+
+
+def forward_batched_train(proj, X, E, G, modal, image_newline=None, is_anyres=False, base=None, with_global=True):
+    """Differentiable ``HIComProjector.forward_batched``: same arguments, same ``(B, n_tokens, Dh)`` result, with an
+    autograd graph reaching every projector parameter (and ``image_newline`` / ``base``)."""
+    check_supported(proj, X, E, G)
+    ops._need_cuda(X, E, G)  # raises for CPU tensors: there is no CPU fallback
+    parts = [] if base is None else [base]
+    if proj.local_compressor is not None:
+        parts.append(_local_tokens(proj, X, E, G, modal, image_newline, is_anyres))
+    if proj.global_compressor is not None and with_global:
+        parts.append(_global_tokens(proj, X, G))
+    if not parts:
+        return None
+    return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhicom_b200.so")
 OBJ_DIR = os.path.join(ROOT, "build", "obj")
-SOURCES = ["api.cu", "local_attend.cu", "gemm_simt.cu", "rowwise.cu", "gemm_tc.cu", "skinny.cu"]
+SOURCES = ["api.cu", "local_attend.cu", "gemm_simt.cu", "rowwise.cu", "gemm_tc.cu", "skinny.cu", "backward.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
@@ -69,11 +69,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     want = "\n".join(objs)
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == want:
         return LIB_PATH
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs,
+    tmp = LIB_PATH + f".tmp{os.getpid()}"  # link beside the target, then rename: readers never see a half-written library
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs,
            "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
     with open(stamp, "w") as f:
         f.write(want)
     if verbose:

@@ -1,0 +1,410 @@
+// Backward pass building blocks (stages 1-3 of the reference TRAIN the projector, train.py:704-738).
+//
+// First correct CUDA path, same progression as the forward one: every contraction of the backward formulas runs on the
+// generic strided SIMT GEMM (fp32 accumulation) through hicom_gemm; the element-wise pieces around them live here.
+//   hicom_gemm              C = alpha * A·B over arbitrary element strides, two batch levels
+//   hicom_act_backward      dx = dy * act'(pre)                      (GELU erf / tanh, projector.py:310, encoder.py:285)
+//   hicom_softmax_backward  dS = exp(S - lse) * (dP - delta)         (softmax of projector.py:213 in reassociated form)
+//   hicom_local_attend_backward_query   d(query) of the window attention (projector.py:546-553)
+//   hicom_film_layernorm_backward       backward of LN(x*(1+scale)+shift) (projector.py:369-372)
+#include "gemm_simt.cuh"
+
+namespace hicom {
+
+// ------------------------------------------------------------------------------------------------
+// dx = dy * act'(pre)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  // d/dx [x Phi(x)] = Phi(x) + x phi(x)
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float c = 0.7978845608028654f, a = 0.044715f;
+  const float t = tanhf(c * fmaf(a * x * x, x, x));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * c * fmaf(3.0f * a * x, x, 1.0f);
+}
+
+template <typename TP, typename T>
+__global__ void __launch_bounds__(256) act_backward_kernel(const TP* __restrict__ pre, const T* __restrict__ dy,
+                                                           T* __restrict__ dx, long long n, int act) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = to_f32<TP>(pre[i]);
+    const float g = act == HICOM_ACT_GELU ? gelu_erf_grad(x) : (act == HICOM_ACT_GELU_TANH ? gelu_tanh_grad(x) : 1.0f);
+    dx[i] = from_f32<T>(to_f32<T>(dy[i]) * g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dS[b,n,j] = exp(S[b,n,j] - lse[b,j]) * (dP[b,n,j] - delta[b,j])
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_backward_kernel(const float* __restrict__ S, const float* __restrict__ dP,
+                                                               const float* __restrict__ lse,
+                                                               const float* __restrict__ delta, T* __restrict__ dS,
+                                                               long long NJ, int J, long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long b = i / NJ;
+    const int j = (int)(i % J);  // NJ is a multiple of J, so i % J is the column
+    const float p = __expf(S[i] - lse[b * J + j]);
+    dS[i] = from_f32<T>(p * (dP[i] - delta[b * J + j]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Window attention, gradient with respect to the query rows (projector.py:546-553):
+//   s_k = scale * q·k_k,  p = softmax_k(s),  o = sum_k p_k v_k
+//   dp_k = dO·v_k,  ds_k = p_k (dp_k - sum_k p_k dp_k),  dq = scale * sum_k ds_k k_k
+// One warp per window; lane L owns channels {4(L + 32c)}.  Two passes over the window members (statistics, then the
+// gradient), members addressed with the reference's balanced-window starts (common.cuh).  Keys/values are read with
+// plain vector loads: this runs once per training step, next to three GEMMs over the same tokens.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) local_attend_bwd_q_kernel(const T* __restrict__ Ksrc, const T* __restrict__ Vsrc,
+                                                                 const T* __restrict__ Q, const T* __restrict__ dO,
+                                                                 T* __restrict__ dQ, int B, int T_, int H, int W, int d,
+                                                                 AxisWin at, AxisWin ah, AxisWin aw, float scale,
+                                                                 int k_l2norm) {
+  const int lane = threadIdx.x & 31;
+  const int h1 = ah.count, w1 = aw.count;
+  const long long nw = (long long)at.count * h1 * w1;
+  const long long win = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (win >= (long long)B * nw) return;
+  const int b = (int)(win / nw);
+  const int r = (int)(win % nw);
+  const int wt = r / (h1 * w1), wh = (r / w1) % h1, ww = r % w1;
+  const int ts = axis_win_start(at, wt), hs = axis_win_start(ah, wh), ws = axis_win_start(aw, ww);
+  const int nt = at.len, nh = ah.len, nwid = aw.len;
+
+  float q[CPL][4], go[CPL][4];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) {
+    const int off = (lane + 32 * c) * 4;
+    Vec4<T>::load(Q + win * d + off, q[c]);
+    Vec4<T>::load(dO + win * d + off, go[c]);
+  }
+  const int members = nt * nh * nwid;
+  // pass 1: softmax statistics and sum_k p_k dp_k
+  float m = -INFINITY, l = 0.f, pd = 0.f;
+  for (int e = 0; e < members; ++e) {
+    const int t = ts + e / (nh * nwid), h = hs + (e / nwid) % nh, w = ws + e % nwid;
+    const long long tok = (((long long)b * T_ + t) * H + h) * W + w;
+    float s = 0.f, dp = 0.f, kk = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int off = (lane + 32 * c) * 4;
+      float k4[4], v4[4];
+      Vec4<T>::load(Ksrc + tok * d + off, k4);
+      Vec4<T>::load(Vsrc + tok * d + off, v4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        s = fmaf(q[c][i], k4[i], s);
+        dp = fmaf(go[c][i], v4[i], dp);
+        kk = fmaf(k4[i], k4[i], kk);
+      }
+    }
+    s = warp_sum(s); dp = warp_sum(dp);
+    if (k_l2norm) s *= rsqrtf(warp_sum(kk));
+    s *= scale;
+    const float mn = fmaxf(m, s);
+    const float corr = __expf(m - mn), p = __expf(s - mn);
+    l = l * corr + p;
+    pd = pd * corr + p * dp;
+    m = mn;
+  }
+  const float inv_l = 1.f / l;
+  const float delta = pd * inv_l;
+  // pass 2: dq = scale * sum_k p_k (dp_k - delta) k_k   (k normalised when k_l2norm)
+  float acc[CPL][4];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[c][i] = 0.f;
+  for (int e = 0; e < members; ++e) {
+    const int t = ts + e / (nh * nwid), h = hs + (e / nwid) % nh, w = ws + e % nwid;
+    const long long tok = (((long long)b * T_ + t) * H + h) * W + w;
+    float k[CPL][4];
+    float s = 0.f, dp = 0.f, kk = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int off = (lane + 32 * c) * 4;
+      float v4[4];
+      Vec4<T>::load(Ksrc + tok * d + off, k[c]);
+      Vec4<T>::load(Vsrc + tok * d + off, v4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        s = fmaf(q[c][i], k[c][i], s);
+        dp = fmaf(go[c][i], v4[i], dp);
+        kk = fmaf(k[c][i], k[c][i], kk);
+      }
+    }
+    s = warp_sum(s); dp = warp_sum(dp);
+    const float rn = k_l2norm ? rsqrtf(warp_sum(kk)) : 1.f;
+    s *= rn * scale;
+    const float ds = __expf(s - m) * inv_l * (dp - delta) * scale * rn;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[c][i] = fmaf(ds, k[c][i], acc[c][i]);
+  }
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) Vec4<T>::store(dQ + win * d + (lane + 32 * c) * 4, acc[c]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of y = LN(u) * w + bias, u = x * (1 + scale_g) + shift_g  (coarse injector, projector.py:369-372), one warp
+// per row, group g = row / rows_per_group:
+//   g_hat = dy * w;  du = rstd * (g_hat - mean(g_hat) - u_hat * mean(g_hat * u_hat))
+//   dx = du * (1 + scale);  dscale_g += du * x;  dshift_g += du;  dw += dy * u_hat;  dbias += dy     (fp32 atomics)
+// dx may be null (x = pooled features of a frozen tower).  dfilm (G, 2d), dw, dbias (d) are fp32 and must be zeroed
+// by the caller.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) film_ln_backward_kernel(const T* __restrict__ x, const float* __restrict__ film,
+                                                               const T* __restrict__ w, const T* __restrict__ dy,
+                                                               T* __restrict__ dx, float* __restrict__ dfilm,
+                                                               float* __restrict__ dw, float* __restrict__ dbias,
+                                                               long long rows, int d, int rows_per_group) {
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  // a block walks a contiguous range of rows (of ONE group when rows_per_group is a multiple of the range) so that
+  // the per-channel sums are accumulated in registers and flushed with one atomic per channel per warp and group
+  const long long rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r_begin = (long long)blockIdx.x * rows_per_block;
+  long long r_end = r_begin + rows_per_block;
+  if (r_end > rows) r_end = rows;
+  float aw[CPL][4], ab[CPL][4], asc[CPL][4], ash[CPL][4];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) aw[c][i] = ab[c][i] = asc[c][i] = ash[c][i] = 0.f;
+  long long cur_group = -1;
+  auto flush_film = [&]() {
+    if (cur_group < 0) return;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ch = (lane + 32 * c) * 4 + i;
+        atomicAdd(dfilm + cur_group * 2 * d + ch, asc[c][i]);
+        atomicAdd(dfilm + cur_group * 2 * d + d + ch, ash[c][i]);
+        asc[c][i] = ash[c][i] = 0.f;
+      }
+  };
+  for (long long row = r_begin + wib; row < r_end; row += wpb) {
+    const long long g = row / rows_per_group;
+    if (g != cur_group) { flush_film(); cur_group = g; }
+    const float* sc = film + g * 2 * d;
+    float xv[CPL][4], u[CPL][4], gy[CPL][4], s1[CPL][4];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int off = (lane + 32 * c) * 4;
+      float h4[4];
+      Vec4<T>::load(x + row * d + off, xv[c]);
+      Vec4<T>::load(dy + row * d + off, gy[c]);
+      Vec4<float>::load(sc + off, s1[c]);
+      Vec4<float>::load(sc + d + off, h4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { u[c][i] = fmaf(xv[c][i], 1.f + s1[c][i], h4[i]); sum += u[c][i]; }
+    }
+    const float mean = warp_sum(sum) / (float)d;
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float dv = u[c][i] - mean; var = fmaf(dv, dv, var); }
+    const float rstd = rsqrtf(warp_sum(var) / (float)d + kLnEps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int off = (lane + 32 * c) * 4;
+      float w4[4];
+      Vec4<T>::load(w + off, w4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float uh = (u[c][i] - mean) * rstd;
+        aw[c][i] = fmaf(gy[c][i], uh, aw[c][i]);
+        ab[c][i] += gy[c][i];
+        const float gh = gy[c][i] * w4[i];
+        u[c][i] = uh;      // keep u_hat
+        gy[c][i] = gh;     // keep g_hat
+        m1 += gh;
+        m2 = fmaf(gh, uh, m2);
+      }
+    }
+    m1 = warp_sum(m1) / (float)d;
+    m2 = warp_sum(m2) / (float)d;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      float o4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float du = rstd * (gy[c][i] - m1 - u[c][i] * m2);
+        asc[c][i] = fmaf(du, xv[c][i], asc[c][i]);
+        ash[c][i] += du;
+        o4[i] = du * (1.f + s1[c][i]);
+      }
+      if (dx) Vec4<T>::store(dx + row * d + (lane + 32 * c) * 4, o4);
+    }
+  }
+  flush_film();
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ch = (lane + 32 * c) * 4 + i;
+      atomicAdd(dw + ch, aw[c][i]);
+      atomicAdd(dbias + ch, ab[c][i]);
+    }
+}
+
+}  // namespace hicom
+
+using namespace hicom;
+
+extern "C" int hicom_gemm(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, int64_t sAb2, const void* B,
+                          int64_t sBk, int64_t sBn, int64_t sBb1, int64_t sBb2, void* C, int64_t ldc, int64_t sCb1,
+                          int64_t sCb2, int M, int N, int K, int nb1, int nb2, float alpha, int a_dtype, int b_dtype,
+                          int c_dtype, void* stream) {
+  HICOM_REQUIRE(A && B && C, "gemm: null pointer");
+  HICOM_REQUIRE(M >= 0 && N >= 0 && K >= 0 && nb1 >= 0 && nb2 >= 0, "gemm: bad shape M=%d N=%d K=%d batch=%dx%d", M, N, K,
+                nb1, nb2);
+  HICOM_REQUIRE(ldc >= N, "gemm: ldc too small");
+  if (M == 0 || N == 0 || nb1 * nb2 == 0) return 0;
+  GemmParams g{};
+  g.A = A; g.B = B; g.C = C;
+  g.M = M; g.N = N; g.K = K;
+  g.sAm = sAm; g.sAk = sAk; g.sAb1 = sAb1; g.sAb2 = sAb2;
+  g.sBk = sBk; g.sBn = sBn; g.sBb1 = sBb1; g.sBb2 = sBb2;
+  g.ldc = ldc; g.sCb1 = sCb1; g.sCb2 = sCb2;
+  g.nb1 = nb1; g.nb2 = nb2;
+  g.alpha = alpha; g.act = HICOM_ACT_NONE;
+  g.rows_per_group = 1 << 30; g.group_stride_rows = 0;
+  cudaStream_t s = as_stream(stream);
+  const int key = a_dtype * 100 + b_dtype * 10 + c_dtype;
+  switch (key) {
+    case HICOM_F32 * 100 + HICOM_F32 * 10 + HICOM_F32: return launch_gemm_simt<float, float, float>(g, s);
+    case HICOM_F32 * 100 + HICOM_F32 * 10 + HICOM_BF16: return launch_gemm_simt<float, float, __nv_bfloat16>(g, s);
+    case HICOM_BF16 * 100 + HICOM_BF16 * 10 + HICOM_BF16:
+      return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(g, s);
+    case HICOM_BF16 * 100 + HICOM_BF16 * 10 + HICOM_F32: return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, float>(g, s);
+    case HICOM_F32 * 100 + HICOM_BF16 * 10 + HICOM_F32: return launch_gemm_simt<float, __nv_bfloat16, float>(g, s);
+    default: break;
+  }
+  set_error("gemm: dtype combination A=%d B=%d C=%d is not built", a_dtype, b_dtype, c_dtype);
+  return 1;
+}
+
+extern "C" int hicom_act_backward(const void* pre, const void* dy, void* dx, int64_t n, int act, int pre_dtype,
+                                  int dtype, void* stream) {
+  HICOM_REQUIRE(pre && dy && dx, "act_backward: null pointer");
+  HICOM_REQUIRE(n >= 0, "act_backward: bad size");
+  HICOM_REQUIRE(act == HICOM_ACT_NONE || act == HICOM_ACT_GELU || act == HICOM_ACT_GELU_TANH,
+                "act_backward: bad activation %d", act);
+  if (n == 0) return 0;
+  const long long want = (n + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  cudaStream_t s = as_stream(stream);
+  if (pre_dtype == HICOM_F32 && dtype == HICOM_F32)
+    act_backward_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)pre, (const float*)dy, (float*)dx, n, act);
+  else if (pre_dtype == HICOM_F32 && dtype == HICOM_BF16)
+    act_backward_kernel<float, __nv_bfloat16><<<blocks, 256, 0, s>>>((const float*)pre, (const __nv_bfloat16*)dy,
+                                                                     (__nv_bfloat16*)dx, n, act);
+  else if (pre_dtype == HICOM_BF16 && dtype == HICOM_BF16)
+    act_backward_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, s>>>(
+        (const __nv_bfloat16*)pre, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, n, act);
+  else {
+    set_error("act_backward: dtype combination pre=%d dy=%d is not built", pre_dtype, dtype);
+    return 1;
+  }
+  return check_launch("act_backward_kernel");
+}
+
+extern "C" int hicom_softmax_backward(const float* S, const float* dP, const float* lse, const float* delta, void* dS,
+                                      int B, int64_t N, int J, int out_dtype, void* stream) {
+  HICOM_REQUIRE(S && dP && lse && delta && dS, "softmax_backward: null pointer");
+  HICOM_REQUIRE(B >= 0 && N >= 0 && J > 0, "softmax_backward: bad shape");
+  const long long total = (long long)B * N * J;
+  if (total == 0) return 0;
+  const long long want = (total + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  cudaStream_t s = as_stream(stream);
+  if (out_dtype == HICOM_F32)
+    softmax_backward_kernel<float><<<blocks, 256, 0, s>>>(S, dP, lse, delta, (float*)dS, N * J, J, total);
+  else if (out_dtype == HICOM_BF16)
+    softmax_backward_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(S, dP, lse, delta, (__nv_bfloat16*)dS, N * J, J, total);
+  else {
+    set_error("softmax_backward: unknown dtype code %d", out_dtype);
+    return 1;
+  }
+  return check_launch("softmax_backward_kernel");
+}
+
+template <typename T>
+static int launch_local_bwd_q(const void* K, const void* V, const void* Q, const void* dO, void* dQ, int B, int T_, int H,
+                              int W, int d, const AxisWin& at, const AxisWin& ah, const AxisWin& aw, float scale,
+                              int k_l2norm, cudaStream_t s) {
+  const long long wins = (long long)B * at.count * ah.count * aw.count;
+  if (wins == 0) return 0;
+  const long long blocks = (wins + 7) / 8;
+  HICOM_REQUIRE(blocks < (1ll << 31), "local_attend_backward_query: too many windows");
+#define HICOM_LBQ(CPL)                                                                                              \
+  local_attend_bwd_q_kernel<T, CPL><<<(unsigned)blocks, 256, 0, s>>>((const T*)K, (const T*)V, (const T*)Q,          \
+                                                                     (const T*)dO, (T*)dQ, B, T_, H, W, d, at, ah,  \
+                                                                     aw, scale, k_l2norm)
+  switch (d / 128) {
+    case 9: HICOM_LBQ(9); break;
+    case 6: HICOM_LBQ(6); break;
+    case 1: HICOM_LBQ(1); break;
+    default: set_error("local_attend_backward_query: d=%d unsupported", d); return 1;
+  }
+#undef HICOM_LBQ
+  return check_launch("local_attend_bwd_q_kernel");
+}
+
+extern "C" int hicom_local_attend_backward_query(const void* Ksrc, const void* Vsrc, const void* Q, const void* dO,
+                                                 void* dQ, int B, int T, int H, int W, int d, int kt, int ks,
+                                                 float logit_scale, int k_l2norm, int dtype, void* stream) {
+  HICOM_REQUIRE(Ksrc && Vsrc && Q && dO && dQ, "local_attend_backward_query: null pointer");
+  HICOM_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && d > 0 && d % 128 == 0 && kt > 0 && ks > 0,
+                "local_attend_backward_query: bad shape");
+  AxisWin at, ah, aw;
+  HICOM_REQUIRE(make_axis_win(T, kt, &at) && make_axis_win(H, ks, &ah) && make_axis_win(W, ks, &aw),
+                "local_attend_backward_query: the reference cannot stack these windows (T=%d H=%d W=%d, kernel %d/%d)", T,
+                H, W, kt, ks);
+  HICOM_DISPATCH_DTYPE(dtype, E, return (launch_local_bwd_q<E>(Ksrc, Vsrc, Q, dO, dQ, B, T, H, W, d, at, ah, aw,
+                                                                logit_scale, k_l2norm, as_stream(stream))));
+}
+
+template <typename T>
+static int launch_film_ln_bwd(const void* x, const float* film, const void* w, const void* dy, void* dx, float* dfilm,
+                              float* dw, float* dbias, long long rows, int d, int rows_per_group, cudaStream_t s) {
+  if (rows == 0) return 0;
+  // blocks of 8 warps over contiguous row ranges; ranges never straddle more groups than necessary
+  long long blocks = (rows + 63) / 64;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+#define HICOM_FLB(CPL)                                                                                          \
+  film_ln_backward_kernel<T, CPL><<<(unsigned)blocks, 256, 0, s>>>((const T*)x, film, (const T*)w, (const T*)dy, \
+                                                                   (T*)dx, dfilm, dw, dbias, rows, d, rows_per_group)
+  switch (d / 128) {
+    case 9: HICOM_FLB(9); break;
+    case 6: HICOM_FLB(6); break;
+    case 1: HICOM_FLB(1); break;
+    default: set_error("film_layernorm_backward: d=%d unsupported", d); return 1;
+  }
+#undef HICOM_FLB
+  return check_launch("film_ln_backward_kernel");
+}
+
+extern "C" int hicom_film_layernorm_backward(const void* x, const float* film, const void* ln_w, const void* dy,
+                                             void* dx, float* dfilm, float* dw, float* dbias, int64_t rows, int d,
+                                             int rows_per_group, int dtype, void* stream) {
+  HICOM_REQUIRE(x && film && ln_w && dy && dfilm && dw && dbias, "film_layernorm_backward: null pointer");
+  HICOM_REQUIRE(rows >= 0 && d > 0 && d % 128 == 0 && rows_per_group > 0, "film_layernorm_backward: bad shape");
+  HICOM_DISPATCH_DTYPE(dtype, E, return (launch_film_ln_bwd<E>(x, film, ln_w, dy, dx, dfilm, dw, dbias, rows, d,
+                                                                rows_per_group, as_stream(stream))));
+}

@@ -411,6 +411,129 @@ def _impl_global_value_proj(pooled: Tensor, Wv: Tensor, bv: Optional[Tensor], Q:
     return out
 
 
+# ------------------------------------------------------------------------------------------
+# backward building blocks (composed by hicom_b200/autograd.py)
+# ------------------------------------------------------------------------------------------
+_GEMM_TRIPLES = {(torch.float32, torch.float32, torch.float32), (torch.float32, torch.float32, torch.bfloat16),
+                 (torch.bfloat16, torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.bfloat16, torch.float32),
+                 (torch.float32, torch.bfloat16, torch.float32)}
+
+
+def _impl_gemm(A: Tensor, B: Tensor, out: Optional[Tensor], out_fp32: bool, alpha: float) -> Tensor:
+    """C = alpha * A @ B over strided VIEWS (no copies): A (..., M, K), B (..., K, N) with up to two leading batch
+    dims each (broadcast dims may have stride 0, e.g. from ``expand``), any element strides; ``out`` (..., M, N) may
+    be a strided view with unit inner stride (written in place), else a new contiguous tensor in A's dtype (fp32 when
+    ``out_fp32``).  The contraction behind every backward formula (dA = dY·W, dW = dYᵀ·A, per-head folds, …)."""
+    dev = _need_cuda(A, B, out)
+    if A.dim() < 2 or B.dim() < 2 or A.dim() > 4 or B.dim() > 4:
+        raise ValueError("gemm: operands must have 2 to 4 dims")
+    M, K = A.shape[-2:]
+    K2, N = B.shape[-2:]
+    if K != K2:
+        raise ValueError(f"gemm: inner dims differ ({K} vs {K2})")
+    batch = torch.broadcast_shapes(A.shape[:-2], B.shape[:-2])
+    batch = (1,) * (2 - len(batch)) + tuple(batch)
+    A4, B4 = A.expand(*batch, M, K), B.expand(*batch, K, N)
+    if out is None:
+        odt = torch.float32 if out_fp32 else A.dtype
+        out = torch.empty((*batch, M, N), dtype=odt, device=dev)
+        ret = out.reshape(*torch.broadcast_shapes(A.shape[:-2], B.shape[:-2]), M, N)
+    else:
+        ret = out
+        if tuple(out.shape[-2:]) != (M, N) or (N > 1 and out.stride(-1) != 1):
+            raise ValueError("gemm: out must be (..., M, N) with unit inner stride")
+    C4 = out.expand(*batch, M, N) if out.dim() < 4 else out
+    if tuple(C4.shape) != (*batch, M, N) or any(C4.stride(i) == 0 and batch[i] > 1 for i in (0, 1)):
+        raise ValueError("gemm: out batch dims do not match the operands")
+    if (A.dtype, B.dtype, out.dtype) not in _GEMM_TRIPLES:
+        raise TypeError(f"gemm: dtype combination {A.dtype}, {B.dtype} -> {out.dtype} is not built")
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_gemm(_ptr(A4), A4.stride(2), A4.stride(3), A4.stride(0), A4.stride(1),
+                                     _ptr(B4), B4.stride(2), B4.stride(3), B4.stride(0), B4.stride(1),
+                                     _ptr(C4), C4.stride(2) if M > 1 else max(C4.stride(2), N), C4.stride(0),
+                                     C4.stride(1), M, N, K, batch[0], batch[1], float(alpha), _dt(A), _dt(B),
+                                     _dt(out), _stream(dev))
+    _cabi.check(rc, "hicom_gemm")
+    return ret
+
+
+def _impl_act_backward(pre: Tensor, dy: Tensor, act: int) -> Tensor:
+    """dy * act'(pre) — backward of the GELU between the layers of build_mlp (projector.py:310)."""
+    dev = _need_cuda(pre, dy)
+    pre, dy = pre.contiguous(), dy.contiguous()
+    if pre.shape != dy.shape:
+        raise ValueError("act_backward: shape mismatch")
+    out = torch.empty_like(dy)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_act_backward(_ptr(pre), _ptr(dy), _ptr(out), dy.numel(), act, _dt(pre), _dt(dy),
+                                             _stream(dev))
+    _cabi.check(rc, "hicom_act_backward")
+    return out
+
+
+def _impl_softmax_backward(S: Tensor, dP: Tensor, lse: Tensor, delta: Tensor, out_bf16: bool) -> Tensor:
+    """dS = exp(S - lse) * (dP - delta): S, dP (B,N,J) fp32, lse/delta (B,J) fp32 — softmax of projector.py:213."""
+    dev = _need_cuda(S, dP, lse, delta)
+    S, dP, lse, delta = S.contiguous(), dP.contiguous(), lse.contiguous(), delta.contiguous()
+    B, N, J = S.shape
+    if dP.shape != S.shape or lse.shape != (B, J) or delta.shape != (B, J):
+        raise ValueError("softmax_backward: shape mismatch")
+    if any(t.dtype != torch.float32 for t in (S, dP, lse, delta)):
+        raise TypeError("softmax_backward: fp32 inputs expected")
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+    out = torch.empty((B, N, J), dtype=odt, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_softmax_backward(_ptr(S), _ptr(dP), _ptr(lse), _ptr(delta), _ptr(out), B, N, J,
+                                                 _DT[odt], _stream(dev))
+    _cabi.check(rc, "hicom_softmax_backward")
+    return out
+
+
+def _impl_local_attend_backward_query(K: Tensor, V: Tensor, Q: Tensor, dO: Tensor, kt: int, ks: int,
+                                      logit_scale: float, k_l2norm: bool) -> Tensor:
+    """d(query rows) of local_attend — projector.py:546-553; K, V (B,T,H,W,d), Q, dO (B,Nw,d)."""
+    dev = _need_cuda(K, V, Q, dO)
+    V = V.contiguous()
+    K = V if K.data_ptr() == V.data_ptr() else K.contiguous()
+    Q, dO = Q.contiguous(), dO.contiguous()
+    B, T, H, W, d = V.shape
+    nw = num_windows(T, H, W, kt, ks)
+    if K.shape != V.shape or Q.shape != (B, nw, d) or dO.shape != (B, nw, d):
+        raise ValueError("local_attend_backward_query: shape mismatch")
+    if not (K.dtype == V.dtype == Q.dtype == dO.dtype):
+        raise TypeError("local_attend_backward_query: dtypes differ")
+    out = torch.empty_like(Q)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_local_attend_backward_query(_ptr(K), _ptr(V), _ptr(Q), _ptr(dO), _ptr(out), B, T, H,
+                                                            W, d, kt, ks, float(logit_scale), int(k_l2norm),
+                                                            _dt(V), _stream(dev))
+    _cabi.check(rc, "hicom_local_attend_backward_query")
+    return out
+
+
+def _impl_film_layernorm_backward(x: Tensor, film: Tensor, ln_w: Tensor, dy: Tensor, rows_per_group: int,
+                                  need_dx: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Backward of film_layernorm: returns (dx | empty, dfilm (G,2d) fp32, dw (d) fp32, dbias (d) fp32)."""
+    dev = _need_cuda(x, film, ln_w, dy)
+    x, film, dy = x.contiguous(), film.contiguous(), dy.contiguous()
+    d = x.shape[-1]
+    rows = x.numel() // d
+    if dy.shape != x.shape or dy.dtype != x.dtype or ln_w.dtype != x.dtype:
+        raise ValueError("film_layernorm_backward: operands differ")
+    if film.dtype != torch.float32 or film.shape[-1] != 2 * d or rows > film.shape[0] * rows_per_group:
+        raise ValueError("film_layernorm_backward: film must be fp32 (G, 2d) covering every row")
+    dx = torch.empty_like(x) if need_dx else torch.empty((0,), dtype=x.dtype, device=dev)
+    dfilm = torch.zeros_like(film)
+    dw = torch.zeros((d,), dtype=torch.float32, device=dev)
+    db = torch.zeros((d,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_film_layernorm_backward(_ptr(x), _ptr(film), _ptr(_c(ln_w)), _ptr(dy),
+                                                        _ptr(dx) if need_dx else None, _ptr(dfilm), _ptr(dw),
+                                                        _ptr(db), rows, d, rows_per_group, _dt(x), _stream(dev))
+    _cabi.check(rc, "hicom_film_layernorm_backward")
+    return dx, dfilm, dw, db
+
+
 def kernel_launch_count() -> int:
     """Kernels enqueued by libhicom_b200 since load (bench.py's ``gpu_launches``)."""
     return int(_cabi.load().hicom_kernel_launch_count())
@@ -560,3 +683,7 @@ l2norm_rows = _wrap("l2norm_rows", _impl_l2norm_rows, (), lambda *a: "l2norm_row
 softmax_merge = _wrap("softmax_merge", _impl_softmax_merge, (), lambda *a: "softmax_merge")
 softmax_reduce = _wrap("softmax_reduce", _impl_softmax_reduce, (), lambda *a: "softmax_reduce")
 global_value_proj = _wrap("global_value_proj", _impl_global_value_proj, (), lambda *a: "global_value_proj")
+# backward blocks are called directly (``gemm`` writes into strided views, which torch.library cannot describe)
+gemm, act_backward, softmax_backward = _impl_gemm, _impl_act_backward, _impl_softmax_backward
+local_attend_backward_query = _impl_local_attend_backward_query
+film_layernorm_backward = _impl_film_layernorm_backward

@@ -123,12 +123,18 @@ def _require_no_grad(module, *tensors):
     """The kernels are forward-only.  Fail loudly instead of silently returning tensors cut off from autograd
     (SURVEY §8b): run under ``torch.no_grad()`` / ``torch.inference_mode()`` (as ``mm_infer`` does,
     hicom/__init__.py:107) or freeze the projector."""
-    if not torch.is_grad_enabled():
-        return
-    if any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in module.parameters()):
+    if _grad_needed(module, *tensors):
         raise RuntimeError(
             "hicom_b200 compressor kernels are forward-only: call under torch.no_grad()/torch.inference_mode(), "
-            "or set requires_grad_(False) on the projector and its inputs (backward is not implemented)")
+            "or set requires_grad_(False) on the projector and its inputs (the training path of "
+            "hicom_b200/autograd.py is opt-in: HICOM_AUTOGRAD=1 or hicom_b200.autograd.enable())")
+
+
+def _grad_needed(module, *tensors) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    return (any(t is not None and t.requires_grad for t in tensors)
+            or any(p.requires_grad for p in module.parameters()))
 
 
 class IdentityMap(nn.Module):
@@ -593,7 +599,14 @@ class HIComProjector(nn.Module):
         X = frames_feature
         if X.dim() != 5:
             raise ValueError(f"forward_batched expects (B,T,H,W,d), got {tuple(X.shape)}")
-        _require_no_grad(self, X, frames_embed, guide_embed)
+        if _grad_needed(self, X, frames_embed, guide_embed, image_newline, base):
+            from . import autograd as _ag
+            if not _ag.ENABLED:
+                _require_no_grad(self, X, frames_embed, guide_embed, image_newline, base)
+            if out is not None:
+                raise NotImplementedError("forward_batched(out=...) writes in place and is inference-only")
+            return _ag.forward_batched_train(self, X, frames_embed, guide_embed, modal, image_newline,
+                                             is_anyres=is_anyres, base=base, with_global=with_global)
         if not X.is_cuda:
             raise RuntimeError("hicom_b200 ops run on CUDA tensors only (no CPU fallback)")
         if X.dtype == torch.float16:

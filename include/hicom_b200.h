@@ -191,6 +191,48 @@ int hicom_softmax_reduce(const float* m, const float* l, const float* o, int B, 
 int hicom_global_value_proj(const void* pooled, const void* Wv, const void* bv, void* attn, int B,
                             int Q, int d, int heads, int dtype, void* stream);
 
+/* ---- backward building blocks --------------------------------------------
+ * The reference trains the projector in all three stages (train.py:704-738) through PyTorch autograd; these entry
+ * points are what `hicom_b200/autograd.py` composes into the backward of each forward op above.  The SigLIP tower and
+ * the guide encoder are frozen (encoder.py:235,247), so no gradient flows to X, E or the instruction embedding.
+ *
+ * hicom_gemm: C[b1,b2] = alpha * A[b1,b2] · B[b1,b2] with arbitrary ELEMENT strides — A[m,k] at m*sAm + k*sAk,
+ *   B[k,n] at k*sBk + n*sBn, C rows ldc apart, unit inner stride — and two batch levels (strides may be 0 to
+ *   broadcast).  Every contraction of the backward formulas: dA = dY·W, dW = dYᵀ·A, db = 1ᵀ·dY (nn.Linear,
+ *   projector.py:307-312), dP = X'·dpooledᵀ and dqfold = dSᵀ·X' (global attention, :197-215), the per-head products
+ *   of the query fold and the value projection.  fp32 accumulation.  Built dtype triples (A,B,C): (f32,f32,f32),
+ *   (f32,f32,bf16), (bf16,bf16,bf16), (bf16,bf16,f32), (f32,bf16,f32).
+ */
+int hicom_gemm(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, int64_t sAb2, const void* B, int64_t sBk,
+               int64_t sBn, int64_t sBb1, int64_t sBb2, void* C, int64_t ldc, int64_t sCb1, int64_t sCb2, int M, int N,
+               int K, int nb1, int nb2, float alpha, int a_dtype, int b_dtype, int c_dtype, void* stream);
+
+/* hicom_act_backward: dx[i] = dy[i] * act'(pre[i]) for HICOM_ACT_* (exact erf GELU of projector.py:310, tanh GELU of the
+ *   SigLIP head); pre in pre_dtype (fp32 pre-activations recomputed by hicom_linear), dy/dx in dtype; in place allowed. */
+int hicom_act_backward(const void* pre, const void* dy, void* dx, int64_t n, int act, int pre_dtype, int dtype,
+                       void* stream);
+
+/* hicom_softmax_backward: backward of the column softmax of the global attention (projector.py:213) in the
+ *   reassociated form: with P[b,n,j] = exp(S[b,n,j] - lse[b,j]) and pooled[b,j] = sum_n P x'_n,
+ *     dS[b,n,j] = P[b,n,j] * (dP[b,n,j] - delta[b,j]),  dP = x'_n·dpooled[b,j],  delta[b,j] = pooled[b,j]·dpooled[b,j].
+ *   S, dP (B,N,J) fp32; lse, delta (B,J) fp32; dS (B,N,J) in out_dtype (may alias S or dP when fp32). */
+int hicom_softmax_backward(const float* S, const float* dP, const float* lse, const float* delta, void* dS, int B,
+                           int64_t N, int J, int out_dtype, void* stream);
+
+/* hicom_local_attend_backward_query: gradient of hicom_local_attend's output with respect to its query rows
+ *   (projector.py:546-553; the keys/values come from frozen towers).  Ksrc, Vsrc (B,T,H,W,d); Q, dO, dQ (B,Nw,d) with
+ *   Q the injected query rows actually used by the forward; same window rule, logit_scale and k_l2norm as the forward. */
+int hicom_local_attend_backward_query(const void* Ksrc, const void* Vsrc, const void* Q, const void* dO, void* dQ,
+                                      int B, int T, int H, int W, int d, int kt, int ks, float logit_scale,
+                                      int k_l2norm, int dtype, void* stream);
+
+/* hicom_film_layernorm_backward: backward of hicom_film_layernorm, y = LN(x*(1+scale)+shift)*w + b (coarse injector,
+ *   projector.py:369-372).  x, dy (rows,d) and ln_w (d) in dtype; film (G,2d) fp32.  Outputs: dx (rows,d) in dtype or
+ *   NULL; dfilm (G,2d), dw (d), dbias (d) fp32, ACCUMULATED into (zero them first). */
+int hicom_film_layernorm_backward(const void* x, const float* film, const void* ln_w, const void* dy, void* dx,
+                                  float* dfilm, float* dw, float* dbias, int64_t rows, int d, int rows_per_group,
+                                  int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE: torch-CPU stand-ins for the ``hicom_b200.ops`` entry points used by the training path.
+
+``tests/test_autograd_cpu.py`` patches them into ``hicom_b200.ops`` so that the backward FORMULAS and index plumbing of
+``hicom_b200/autograd.py`` (which op is called with which strided view) can be checked on a machine without a GPU
+against PyTorch autograd through the oracle.  The kernels themselves are checked on the GPU
+(``tests/test_gpu_autograd.py``).  Each stand-in restates the contract written in ``include/hicom_b200.h``."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from oracle import hicom_oracle as O
+
+ACT_NONE, ACT_GELU, ACT_GELU_TANH = 0, 1, 2
+Q_POOLED, Q_FILM_LN, Q_VECTOR, Q_EXPLICIT = 0, 1, 2, 3
+calls = []  # (name, ...) log so tests can assert which kernels the path would have launched
+
+
+def _act(x, act):
+    return F.gelu(x) if act == ACT_GELU else (F.gelu(x, approximate="tanh") if act == ACT_GELU_TANH else x)
+
+
+def linear(A, W, bias, residual, act, out_fp32, impl):
+    calls.append(("linear", tuple(A.shape), tuple(W.shape), act))
+    y = _act(F.linear(A.float(), W.float(), None if bias is None else bias.float()), act)
+    if residual is not None:
+        y = y + residual.float().reshape(y.shape)
+    return y if out_fp32 else y.to(A.dtype)
+
+
+def gemm(A, B, out, out_fp32, alpha):
+    calls.append(("gemm", tuple(A.shape), tuple(B.shape)))
+    C = alpha * torch.matmul(A.float(), B.float())
+    if out is None:
+        return C if (out_fp32 or A.dtype == torch.float32) else C.to(A.dtype)
+    assert out.stride(-1) == 1 or out.shape[-1] == 1
+    out.copy_(C.reshape(out.shape))
+    return out
+
+
+def act_backward(pre, dy, act):
+    calls.append(("act_backward", act))
+    x = pre.detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        (g,) = torch.autograd.grad(_act(x, act), x, dy.float())
+    return g.to(dy.dtype)
+
+
+def softmax_backward(S, dP, lse, delta, out_bf16):
+    calls.append(("softmax_backward",))
+    dS = torch.exp(S - lse[:, None, :]) * (dP - delta[:, None, :])
+    return dS.bfloat16() if out_bf16 else dS
+
+
+def global_fold_query(q, Wk, heads, alpha):
+    B, Q, d = q.shape
+    hd = d // heads
+    qf = torch.einsum("bihc,hck->bhik", q.float().view(B, Q, heads, hd), Wk.float().view(heads, hd, d)) * alpha
+    return qf.reshape(B, heads * Q, d).to(q.dtype)
+
+
+def posadd(X, pt, ph, pw):
+    return (X.float() + pt[None, :, None, None, :] + ph[None, None, :, None, :] + pw[None, None, None, :, :]).to(X.dtype)
+
+
+def global_attend_partial(X, pt, ph, pw, qfold, splits, impl):
+    calls.append(("global_attend_partial", splits))
+    B, T, H, W, d = X.shape
+    N = T * H * W
+    Xp = posadd(X, pt, ph, pw).float().view(B, N, d)
+    S = torch.matmul(Xp, qfold.float().transpose(1, 2))  # (B,N,J)
+    chunk = -(-N // splits)
+    ms, ls, os_ = [], [], []
+    for s in range(splits):
+        a, b = s * chunk, min(N, (s + 1) * chunk)
+        m = S[:, a:b].max(dim=1).values
+        p = torch.exp(S[:, a:b] - m[:, None, :])
+        ms.append(m); ls.append(p.sum(1)); os_.append(torch.einsum("bnj,bnd->bjd", p, Xp[:, a:b]))
+    return torch.stack(ms, 1), torch.stack(ls, 1), torch.stack(os_, 1)
+
+
+def softmax_reduce(m, l, o):
+    M = m.max(dim=1, keepdim=True).values
+    w = torch.exp(m - M)
+    return M, (l * w).sum(1, keepdim=True), (o * w[..., None]).sum(1, keepdim=True)
+
+
+def softmax_merge(m, l, o, out_bf16):
+    M, L, Osum = softmax_reduce(m, l, o)
+    pooled = (Osum / L[..., None])[:, 0]
+    return pooled.bfloat16() if out_bf16 else pooled
+
+
+def global_value_proj(pooled, Wv, bv, Q, heads):
+    B, J, d = pooled.shape
+    hd = d // heads
+    a = torch.einsum("bhik,hck->bihc", pooled.float().view(B, heads, Q, d), Wv.float().view(heads, hd, d))
+    a = a.reshape(B, Q, d)
+    if bv is not None:
+        a = a + bv.float()
+    return a.to(pooled.dtype)
+
+
+def grid_pool(X, kt, ks):
+    B, T, H, W, d = X.shape
+    ds = (math.ceil(T / kt), math.ceil(H / ks), math.ceil(W / ks))
+    q = F.interpolate(X.float().permute(0, 4, 1, 2, 3), size=ds, mode="trilinear")
+    return q.permute(0, 2, 3, 4, 1).reshape(B, -1, d).to(X.dtype)
+
+
+def film_layernorm(x, film, ln_w, ln_b, rows_per_group):
+    d = x.shape[-1]
+    rows = x.reshape(-1, d).float()
+    g = torch.arange(rows.shape[0]) // rows_per_group
+    u = rows * (1 + film[g, :d]) + film[g, d:]
+    return F.layer_norm(u, (d,), ln_w.float(), ln_b.float(), 1e-6).to(x.dtype).reshape(x.shape)
+
+
+def film_layernorm_backward(x, film, ln_w, dy, rows_per_group, need_dx):
+    calls.append(("film_layernorm_backward",))
+    xx = x.detach().float().requires_grad_(True)
+    ff = film.detach().clone().requires_grad_(True)
+    ww = ln_w.detach().float().requires_grad_(True)
+    bb = torch.zeros_like(ww).requires_grad_(True)
+    with torch.enable_grad():
+        y = film_layernorm(xx, ff, ww, bb, rows_per_group)
+        dx, dfilm, dw, db = torch.autograd.grad(y, (xx, ff, ww, bb), dy.float())
+    return (dx.to(x.dtype) if need_dx else x.new_empty(0)), dfilm, dw, db
+
+
+def local_attend(K, V, P, q_aux, film, ln_w, ln_b, kt, ks, qmode, logit_scale, k_l2norm):
+    calls.append(("local_attend", qmode))
+    B, T, H, W, d = V.shape
+    if qmode == Q_POOLED:
+        Q = grid_pool(P, kt, ks).float()
+    elif qmode == Q_VECTOR:
+        nw = math.ceil(T / kt) * math.ceil(H / ks) * math.ceil(W / ks)
+        Q = q_aux.float()[:, None, :].expand(B, nw, d)
+    elif qmode == Q_EXPLICIT:
+        Q = q_aux.float()
+    else:
+        q0 = grid_pool(P, kt, ks)
+        Q = film_layernorm(q0, film, ln_w, ln_b, q0.shape[1]).float()
+    outs = []
+    for b in range(B):
+        k = K[b].float()
+        if k_l2norm:
+            k = k / k.norm(dim=-1, keepdim=True)
+        rk = O.window_gather(k, (min(kt, T), min(ks, H), min(ks, W)) if False else (kt, ks, ks))
+        rv = O.window_gather(V[b].float(), (kt, ks, ks))
+        s = torch.einsum("nd,nmd->nm", Q[b], rk) * logit_scale
+        outs.append(torch.einsum("nm,nmd->nd", torch.softmax(s, dim=-1), rv))
+    return torch.stack(outs).to(V.dtype)
+
+
+def local_attend_backward_query(K, V, Q, dO, kt, ks, logit_scale, k_l2norm):
+    calls.append(("local_attend_backward_query",))
+    q = Q.detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        o = local_attend(K.float(), V.float(), V.float(), q, None, None, None, kt, ks, Q_EXPLICIT, logit_scale, k_l2norm)
+        (dq,) = torch.autograd.grad(o, q, dO.float())
+    return dq.to(Q.dtype)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None:
+            return t.device
+    return None
+
+
+ALL = ["linear", "gemm", "act_backward", "softmax_backward", "global_fold_query", "posadd", "global_attend_partial",
+       "softmax_reduce", "softmax_merge", "global_value_proj", "grid_pool", "film_layernorm", "film_layernorm_backward",
+       "local_attend", "local_attend_backward_query", "_need_cuda"]
+
+
+def install(monkeypatch):
+    """Patch every stand-in into hicom_b200.ops (the modules look ops up by attribute at call time)."""
+    import sys
+    from hicom_b200 import ops
+    me = sys.modules[__name__]
+    for name in ALL:
+        monkeypatch.setattr(ops, name, getattr(me, name))
+    calls.clear()

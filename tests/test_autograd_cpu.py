@@ -1,0 +1,138 @@
+"""CPU: the backward FORMULAS and view plumbing of hicom_b200/autograd.py, with every kernel replaced
+by its torch-CPU stand-in (tests/cpu_ops.py), against PyTorch autograd through the oracle — i.e. against what the
+reference's training step computes (train.py:704-738 trains mm_projector through autograd).  The kernels themselves
+are compared with the same stand-ins on the GPU (tests/test_gpu_autograd.py)."""
+import dataclasses
+
+import pytest
+import torch
+
+import cpu_ops
+from oracle import hicom_oracle as O
+from oracle.cases import CASES_BY_NAME, materialise
+from util import cfg_for
+
+TRAIN_CASES = ["none_T8", "direct_T8", "coarse_T8", "off_T4", "coarse_T7", "coarse_nondiv_7x8", "global_only_coarse_T8",
+               "local22_global8_T8", "forced_guide", "video_grid_newline", "video_frame_newline", "video_one_token",
+               "image_T1_newline", "none_T2_short_window"]
+
+
+def _module(case, sd):
+    import hicom_b200
+    m = hicom_b200.build_vision_projector(cfg_for(case))
+    m.load_state_dict(sd, strict=True)
+    return m.train()
+
+
+def _oracle_grads(case, sd, X, E, g, nl, probe):
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    nl_leaf = None if nl is None else nl.clone().requires_grad_(True)
+    orc = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf)
+    out = orc.forward(X, E, g, case.modal, nl_leaf)
+    (out * probe).sum().backward()
+    grads = {k: v.grad for k, v in leaf.items()}
+    return out.detach(), grads, (None if nl_leaf is None else nl_leaf.grad)
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_parameter_gradients_match_reference_autograd(name, monkeypatch):
+    from hicom_b200 import autograd as ag
+    case = CASES_BY_NAME[name]
+    sd, X, E, g, nl = materialise(case)
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, sd)
+    nl_leaf = None if nl is None else nl.clone().requires_grad_(True)
+    out = m(X, E, g, case.modal, nl_leaf)                       # the reference's per-video forward signature
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    want_out, want, want_nl = _oracle_grads(case, sd, X, E, g, nl, probe)
+    assert out.shape == want_out.shape
+    assert O.rel_err(out.detach(), want_out) <= 2e-5
+    (out * probe).sum().backward()
+    got = {k: p.grad for k, p in m.named_parameters()}
+    assert set(got) == set(want)
+    for k in sorted(want):
+        if want[k] is None or float(want[k].abs().max()) == 0.0:   # parameter unused by this mode (direct: query)
+            assert got[k] is None or float(got[k].abs().max()) == 0.0, k
+            continue
+        assert got[k] is not None, f"no gradient reached {k}"
+        if k.endswith("attn_layer.k_proj.bias") and "guide_injector" not in k:
+            # a per-column constant of the scores: the softmax cancels it, the reference's autograd leaves rounding noise
+            assert float(want[k].abs().max()) <= 1e-6 and float(got[k].abs().max()) == 0.0
+            continue
+        assert O.rel_err(got[k], want[k]) <= 2e-4, (k, O.rel_err(got[k], want[k]))
+    if nl is not None:
+        assert O.rel_err(nl_leaf.grad, want_nl) <= 1e-5
+    kinds = {c[0] for c in cpu_ops.calls}
+    assert "gemm" in kinds and "softmax_backward" in kinds or m.global_compressor is None
+
+
+def test_batched_gradients_sum_over_videos(monkeypatch):
+    """forward_batched under autograd == the per-video loop (hicom_arch.py:167-178): gradients add up over the batch."""
+    from hicom_b200 import autograd as ag
+    case = CASES_BY_NAME["coarse_T4"]
+    sd, X, E, g, _ = materialise(case)
+    X2, E2, g2 = (torch.stack([t, t.flip(0) * 0.9]) for t in (X, E, g))
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, sd)
+    out = m.forward_batched(X2, E2, g2, "video")
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+    (out * probe).sum().backward()
+    got = {k: p.grad.clone() for k, p in m.named_parameters()}
+    total = None
+    for b in range(2):
+        _, gr, _ = _oracle_grads(case, sd, X2[b], E2[b], g2[b], None, probe[b])
+        total = gr if total is None else {k: total[k] + gr[k] for k in gr}
+    for k in sorted(total):
+        if k == "global_compressor.attn_layer.k_proj.bias":     # exactly zero here, rounding noise in the reference
+            assert float(total[k].abs().max()) <= 1e-6 and float(got[k].abs().max()) == 0.0
+            continue
+        assert O.rel_err(got[k], total[k]) <= 2e-4, k
+
+
+def test_opt_in_and_unsupported_configs_fail_loudly(monkeypatch):
+    from hicom_b200 import autograd as ag
+    case = CASES_BY_NAME["fine_T8"]
+    sd, X, E, g, _ = materialise(case)
+    cpu_ops.install(monkeypatch)
+    m = _module(case, sd)
+    monkeypatch.setattr(ag, "ENABLED", False)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        m(X, E, g, "video")
+    monkeypatch.setattr(ag, "ENABLED", True)
+    with pytest.raises(NotImplementedError, match="fine"):
+        m(X, E, g, "video")
+    case = CASES_BY_NAME["adaptkv_coarse_T8"]
+    sd, X, E, g, _ = materialise(case)
+    with pytest.raises(NotImplementedError, match="adapt"):
+        _module(case, sd)(X, E, g, "video")
+    case = CASES_BY_NAME["coarse_T4"]
+    sd, X, E, g, _ = materialise(case)
+    with pytest.raises(NotImplementedError, match="frames_feature requires grad"):
+        _module(case, sd)(X.clone().requires_grad_(True), E, g, "video")
+    # frozen projector under grad mode: nothing needs a graph -> the plain inference path (which refuses CPU tensors)
+    m = _module(case, sd).requires_grad_(False)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        m(X, E, g, "video")
+
+
+def test_bf16_parameter_gradients_have_parameter_dtype(monkeypatch):
+    from hicom_b200 import autograd as ag
+    case = dataclasses.replace(CASES_BY_NAME["coarse_T4"], dtype="bfloat16")
+    sd, X, E, g, _ = materialise(case)
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, {k: v.float() for k, v in sd.items()}).to(torch.bfloat16)
+    out = m(X, E, g, "video")
+    assert out.dtype == torch.bfloat16
+    out.float().sum().backward()
+    for k, p in m.named_parameters():
+        assert p.grad is not None and p.grad.dtype == torch.bfloat16 and bool(torch.isfinite(p.grad.float()).all()), k
+    f32 = {k: v.float() for k, v in sd.items()}
+    _, want, _ = _oracle_grads(dataclasses.replace(case, dtype="float32"), f32, X.float(), E.float(), g.float(), None,
+                               torch.ones(out.shape))
+    for k in ("local_compressor.readout.2.weight", "global_compressor.attn_layer.k_proj.weight",
+              "global_compressor.query", "local_compressor.guide_injector.coarse_proj.0.weight"):
+        got = dict(m.named_parameters())[k].grad.float()
+        assert O.cosine(got, want[k]) >= 0.99, (k, O.cosine(got, want[k]))
