@@ -15,10 +15,11 @@ Global attention backward in the reassociated form (forward: projector.py:180-22
     dP = x'·dpooledᵀ,   delta_j = pooled_j·dpooled_j,   dS = P ∘ (dP − delta),   dqfold = dSᵀ·x'
 so no gradient is ever formed for the N x 1152 keys/values the reference materialises.
 
-Status: first correct CUDA path (SIMT GEMMs, fp32 accumulation).  Supported: ``use_guide`` None/off/direct/coarse,
-no adapters (``adaptq/k/v/g``), no ``use_clip_scale``; ``fine`` and the adapters raise ``NotImplementedError``.
-Opt-in (``HICOM_AUTOGRAD=1`` or ``hicom_b200.autograd.enable()``) until it has been validated on a B200; without the
-switch a forward under autograd keeps failing loudly (``projector._require_no_grad``).
+Status: first correct CUDA path (SIMT GEMMs, fp32 accumulation), validated on a B200 against PyTorch autograd through
+the oracle (tests/test_gpu_autograd.py).  Supported: ``use_guide`` None/off/direct/coarse, no adapters
+(``adaptq/k/v/g``), no ``use_clip_scale``; ``fine`` and the adapters raise ``NotImplementedError`` — nothing ever
+returns a tensor silently cut off from the graph.  ``HICOM_AUTOGRAD=0`` / ``hicom_b200.autograd.enable(False)`` restores
+the forward-only behaviour (a forward that needs gradients raises, ``projector._require_no_grad``).
 """
 from __future__ import annotations
 
@@ -30,7 +31,7 @@ from torch.autograd import Function
 
 from . import ops
 
-ENABLED = os.environ.get("HICOM_AUTOGRAD", "0") == "1"
+ENABLED = os.environ.get("HICOM_AUTOGRAD", "1") == "1"
 
 
 def enable(on: bool = True) -> None:

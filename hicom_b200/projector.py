@@ -126,8 +126,8 @@ def _require_no_grad(module, *tensors):
     if _grad_needed(module, *tensors):
         raise RuntimeError(
             "hicom_b200 compressor kernels are forward-only: call under torch.no_grad()/torch.inference_mode(), "
-            "or set requires_grad_(False) on the projector and its inputs (the training path of "
-            "hicom_b200/autograd.py is opt-in: HICOM_AUTOGRAD=1 or hicom_b200.autograd.enable())")
+            "or set requires_grad_(False) on the module and its inputs (the compressor's training path, "
+            "hicom_b200/autograd.py, has been switched off with HICOM_AUTOGRAD=0 / autograd.enable(False))")
 
 
 def _grad_needed(module, *tensors) -> bool:

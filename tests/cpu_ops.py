@@ -146,7 +146,7 @@ def local_attend(K, V, P, q_aux, film, ln_w, ln_b, kt, ks, qmode, logit_scale, k
         k = K[b].float()
         if k_l2norm:
             k = k / k.norm(dim=-1, keepdim=True)
-        rk = O.window_gather(k, (min(kt, T), min(ks, H), min(ks, W)) if False else (kt, ks, ks))
+        rk = O.window_gather(k, (kt, ks, ks))
         rv = O.window_gather(V[b].float(), (kt, ks, ks))
         s = torch.einsum("nd,nmd->nm", Q[b], rk) * logit_scale
         outs.append(torch.einsum("nm,nmd->nd", torch.softmax(s, dim=-1), rv))

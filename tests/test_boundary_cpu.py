@@ -95,8 +95,15 @@ def test_no_cpu_fallback(built_library):
     m = hicom_b200.build_vision_projector(Cfg(hidden_size=64))
     with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA tensors only"):
         m(torch.randn(4, 6, 6, 1152), None, None, "video")
-    with pytest.raises(RuntimeError, match="forward-only"):
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):   # training path (autograd on): same refusal
         m(torch.randn(4, 6, 6, 1152), None, None, "video")
+    from hicom_b200 import autograd as ag
+    ag.enable(False)
+    try:
+        with pytest.raises(RuntimeError, match="forward-only"):
+            m(torch.randn(4, 6, 6, 1152), None, None, "video")
+    finally:
+        ag.enable(True)
 
 
 def test_product_never_imports_oracle():

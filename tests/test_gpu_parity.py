@@ -108,9 +108,16 @@ def test_reference_failures_are_loud(built_library):
             m(X.cuda(), E.cuda(), torch.randn(4, 1152, device="cuda"), "video")  # coarse wants a (d,) vector
         with pytest.raises(ValueError):
             m(X.cuda(), E.cuda(), None, "video")
-    # forward-only kernels: autograd-enabled calls on trainable parameters fail loudly, not silently
-    with pytest.raises(RuntimeError, match="forward-only"):
-        m(X.cuda(), E.cuda(), g.cuda(), "video")
+    # autograd-enabled calls on trainable parameters: gradients (hicom_b200/autograd.py), or — with the training path
+    # switched off — a loud failure; never a tensor silently cut off from the graph
+    assert m(X.cuda(), E.cuda(), g.cuda(), "video").requires_grad
+    from hicom_b200 import autograd as ag
+    ag.enable(False)
+    try:
+        with pytest.raises(RuntimeError, match="forward-only"):
+            m(X.cuda(), E.cuda(), g.cuda(), "video")
+    finally:
+        ag.enable(True)
     with torch.inference_mode():
         assert m(X.cuda(), E.cuda(), g.cuda(), "video").shape[0] == 40
 
