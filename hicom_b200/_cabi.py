@@ -41,7 +41,7 @@ PROTOTYPES = {
                    [c_int] * 5 + [c_float] + [c_int] * 3 + [c_void_p]),
     "hicom_act_backward": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "hicom_softmax_backward": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_int, c_void_p]),
-    "hicom_local_attend_backward_query": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_int, c_int, c_void_p]),
+    "hicom_local_attend_backward": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_float, c_int, c_int, c_void_p]),
     "hicom_film_layernorm_backward": (c_int, [c_void_p] * 8 + [c_int64, c_int, c_int, c_int, c_void_p]),
 }
 

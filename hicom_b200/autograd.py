@@ -1,14 +1,16 @@
 """Training path of the compressor: autograd for the custom ops.
 
 The reference trains ``mm_projector`` in all three stages (train.py:704-738, ``mm_tunable_parts``) through PyTorch
-autograd; the SigLIP tower and the guide encoder are frozen (encoder.py:235,247), so gradients are needed for the
-projector's PARAMETERS only — never for ``frames_feature``, ``frames_embed`` or the instruction embedding.
+autograd.  ``frames_feature`` always comes from the frozen SigLIP body (encoder.py:235) and never needs a gradient; stage
+3 of the release recipe additionally tunes ``vision_model_head`` and ``guide_encoder`` (train.py:717-726), so
+``frames_embed`` (the keys of the local attention, made by the head: ``hicom_b200.producer``) and the instruction
+embedding may require gradients too — both are supported.
 
 ``forward_batched_train`` is the differentiable twin of ``HIComProjector.forward_batched``.  Its forward runs the same
 sm_100a kernels as inference; every op that has a trainable parameter upstream is wrapped in a
 ``torch.autograd.Function`` whose backward is composed from the C-ABI blocks of ``csrc/backward.cu``
 (``hicom_gemm`` for every contraction, ``hicom_act_backward``, ``hicom_softmax_backward``,
-``hicom_local_attend_backward_query``, ``hicom_film_layernorm_backward``).  PyTorch only supplies plumbing: views,
+``hicom_local_attend_backward``, ``hicom_film_layernorm_backward``).  PyTorch only supplies plumbing: views,
 ``cat``/``expand`` of token rows, dtype casts, and reductions over tensors of a few hundred rows.
 
 Global attention backward in the reassociated form (forward: projector.py:180-226 as ``pooled = softmax(x'·qfold)ᵀ x'``):
@@ -241,23 +243,50 @@ class FilmLayerNormFn(Function):
                 db.to(ctx.b_dtype) if ctx.needs_input_grad[3] else None, None)
 
 
-class LocalAttendQueryFn(Function):
-    """Window attention on explicit query rows (ops.local_attend, Q_EXPLICIT); differentiable in the rows only."""
+class LocalAttendFn(Function):
+    """Window attention on explicit query rows (ops.local_attend, Q_EXPLICIT); differentiable in the query rows and in
+    the keys (``frames_embed``) — the values are ``frames_feature`` of the frozen SigLIP body."""
 
     @staticmethod
-    def forward(ctx, K, V, X, Qrows, kt, ks, scale, k_l2norm):
+    def forward(ctx, K, V, Qrows, kt, ks, scale, k_l2norm):
         ctx.save_for_backward(K, V, Qrows)
         ctx.geom = (kt, ks, scale, k_l2norm)
-        return ops.local_attend(K, V, X, Qrows, None, None, None, kt, ks, ops.Q_EXPLICIT, scale, k_l2norm)
+        return ops.local_attend(K, V, V, Qrows, None, None, None, kt, ks, ops.Q_EXPLICIT, scale, k_l2norm)
 
     @staticmethod
     def backward(ctx, dO):
         K, V, Qrows = ctx.saved_tensors
         kt, ks, scale, k_l2norm = ctx.geom
-        dQ = None
-        if ctx.needs_input_grad[3]:
-            dQ = ops.local_attend_backward_query(K, V, Qrows, dO.contiguous().to(Qrows.dtype), kt, ks, scale, k_l2norm)
-        return None, None, None, dQ, None, None, None, None
+        need_k, _, need_q = ctx.needs_input_grad[:3]
+        dQ = dK = None
+        if need_q or need_k:
+            dQ, dK, _ = ops.local_attend_backward(K, V, Qrows, dO.contiguous().to(Qrows.dtype), kt, ks, scale,
+                                                  k_l2norm, need_q, need_k, False)
+            if dK is not None and dK.dtype != K.dtype:
+                dK = dK.to(K.dtype)
+        return dK, None, dQ, None, None, None, None
+
+
+class LayerNormFn(Function):
+    """LN(x)*w + b (ops.layernorm, eps 1e-6) — the SigLIP head's layernorm in the producer (encoder.py:284).  Backward
+    on hicom_film_layernorm_backward with a zero FiLM (scale = shift = 0 leaves u = x)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.b_dtype = b.dtype
+        return ops.layernorm(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        d = x.shape[-1]
+        rows = x.numel() // d
+        film = torch.zeros((1, 2 * d), dtype=torch.float32, device=x.device)
+        need_x = ctx.needs_input_grad[0]
+        dx, _, dw, db = ops.film_layernorm_backward(x, film, w, dy.contiguous().to(x.dtype), max(rows, 1), need_x)
+        return (dx.view(x.shape) if need_x else None, dw.to(w.dtype) if ctx.needs_input_grad[1] else None,
+                db.to(ctx.b_dtype) if ctx.needs_input_grad[2] else None)
 
 
 # ------------------------------------------------------------------------------------------
@@ -268,11 +297,10 @@ def _is_param(x) -> bool:
 
 
 def check_supported(proj, X, E, G) -> None:
-    for name, t in (("frames_feature", X), ("frames_embed", E), ("guide_embed", G)):
-        if t is not None and t.requires_grad:
-            raise NotImplementedError(
-                f"hicom_b200.autograd: {name} requires grad, but the kernels only produce parameter gradients (the "
-                "reference freezes the SigLIP tower and the guide encoder, encoder.py:235,247)")
+    if X.requires_grad:
+        raise NotImplementedError(
+            "hicom_b200.autograd: frames_feature requires grad — gradients into the SigLIP body (mm_tunable_parts "
+            "'pure_vision_model', train.py:712-715) are not built; the release recipe keeps it frozen (encoder.py:235)")
     if X.dtype not in (torch.float32, torch.bfloat16):
         raise NotImplementedError(f"hicom_b200.autograd: dtype {X.dtype} (train in fp32 or bf16)")
     if proj.local_logit_scale is not None or proj.global_logit_scale is not None:
@@ -307,8 +335,14 @@ def _local_tokens(proj, X, E, G, modal, image_newline, is_anyres):
         with torch.no_grad():
             q0 = ops.grid_pool(X, tk, sk)                                          # projector.py:539-540 (no parameter)
         rows = FilmLayerNormFn.apply(q0, film, inj.coarse_norm.weight, inj.coarse_norm.bias, q0.shape[1])
-        K = X if E is None else E
-        att = LocalAttendQueryFn.apply(K, X, X, rows, tk, sk, 1.0 / math.sqrt(lc.qk_dim), False)
+        att = LocalAttendFn.apply(X if E is None else E, X, rows, tk, sk, 1.0 / math.sqrt(lc.qk_dim), False)
+    elif lc.use_guide == "direct" and (G.requires_grad or (E is not None and E.requires_grad)):
+        # stage 3 (train.py:717-726): the guide encoder and the SigLIP head that makes frames_embed are tuned, so the
+        # query (= the instruction vector for every window, projector.py:367-368) and the keys carry gradients
+        lc.guide_injector.check_guide(G, 0)
+        nw = ops.num_windows(T, H, W, tk, sk)
+        rows = lc.guide_injector.prepared_guide(G).unsqueeze(1).expand(B, nw, d)   # autograd sums dq over the windows
+        att = LocalAttendFn.apply(X if E is None else E, X, rows, tk, sk, 1.0 / math.sqrt(lc.qk_dim), False)
     else:  # None / off / direct: nothing trainable in front of the readout — the fused inference kernel, as a constant
         with torch.no_grad():
             att = lc.attend(X, E, G, modal, None, None)

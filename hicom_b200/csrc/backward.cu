@@ -5,7 +5,7 @@
 //   hicom_gemm              C = alpha * A·B over arbitrary element strides, two batch levels
 //   hicom_act_backward      dx = dy * act'(pre)                      (GELU erf / tanh, projector.py:310, encoder.py:285)
 //   hicom_softmax_backward  dS = exp(S - lse) * (dP - delta)         (softmax of projector.py:213 in reassociated form)
-//   hicom_local_attend_backward_query   d(query) of the window attention (projector.py:546-553)
+//   hicom_local_attend_backward         d(query), d(keys), d(values) of the window attention (projector.py:546-553)
 //   hicom_film_layernorm_backward       backward of LN(x*(1+scale)+shift) (projector.py:369-372)
 #include "gemm_simt.cuh"
 
@@ -55,17 +55,23 @@ __global__ void __launch_bounds__(256) softmax_backward_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// Window attention, gradient with respect to the query rows (projector.py:546-553):
+// Window attention backward (projector.py:546-553):
 //   s_k = scale * q·k_k,  p = softmax_k(s),  o = sum_k p_k v_k
-//   dp_k = dO·v_k,  ds_k = p_k (dp_k - sum_k p_k dp_k),  dq = scale * sum_k ds_k k_k
+//   dp_k = dO·v_k,  ds_k = p_k (dp_k - sum_k p_k dp_k)
+//   dq = scale * sum_k ds_k k_k        (query rows: FiLM / instruction parameters upstream)
+//   dk_k = scale * ds_k q              (keys = frames_embed: stage 3 tunes the SigLIP head that makes it, train.py:717-721)
+//   dv_k = p_k dO                      (values: only with a trainable value adapter)
 // One warp per window; lane L owns channels {4(L + 32c)}.  Two passes over the window members (statistics, then the
-// gradient), members addressed with the reference's balanced-window starts (common.cuh).  Keys/values are read with
-// plain vector loads: this runs once per training step, next to three GEMMs over the same tokens.
+// gradients), members addressed with the reference's balanced-window starts (common.cuh).  dK / dV are fp32 and
+// ACCUMULATED with atomics: balanced windows of non-divisible grids overlap by one element, so a token can belong to
+// two windows per axis.  Keys/values are read with plain vector loads: this runs once per training step, next to
+// GEMMs over the same tokens.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CPL>
 __global__ void __launch_bounds__(256) local_attend_bwd_q_kernel(const T* __restrict__ Ksrc, const T* __restrict__ Vsrc,
                                                                  const T* __restrict__ Q, const T* __restrict__ dO,
-                                                                 T* __restrict__ dQ, int B, int T_, int H, int W, int d,
+                                                                 T* __restrict__ dQ, float* __restrict__ dK,
+                                                                 float* __restrict__ dV, int B, int T_, int H, int W, int d,
                                                                  AxisWin at, AxisWin ah, AxisWin aw, float scale,
                                                                  int k_l2norm) {
   const int lane = threadIdx.x & 31;
@@ -144,14 +150,29 @@ __global__ void __launch_bounds__(256) local_attend_bwd_q_kernel(const T* __rest
     s = warp_sum(s); dp = warp_sum(dp);
     const float rn = k_l2norm ? rsqrtf(warp_sum(kk)) : 1.f;
     s *= rn * scale;
-    const float ds = __expf(s - m) * inv_l * (dp - delta) * scale * rn;
+    const float p = __expf(s - m) * inv_l;
+    const float ds = p * (dp - delta) * scale * rn;
 #pragma unroll
     for (int c = 0; c < CPL; ++c)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[c][i] = fmaf(ds, k[c][i], acc[c][i]);
-  }
+    if (dK != nullptr) {  // (host refuses k_l2norm together with dK: the normalisation is not differentiated)
 #pragma unroll
-  for (int c = 0; c < CPL; ++c) Vec4<T>::store(dQ + win * d + (lane + 32 * c) * 4, acc[c]);
+      for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(dK + tok * d + (lane + 32 * c) * 4 + i, ds * q[c][i]);
+    }
+    if (dV != nullptr) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(dV + tok * d + (lane + 32 * c) * 4 + i, p * go[c][i]);
+    }
+  }
+  if (dQ != nullptr) {
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) Vec4<T>::store(dQ + win * d + (lane + 32 * c) * 4, acc[c]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -345,38 +366,40 @@ extern "C" int hicom_softmax_backward(const float* S, const float* dP, const flo
 }
 
 template <typename T>
-static int launch_local_bwd_q(const void* K, const void* V, const void* Q, const void* dO, void* dQ, int B, int T_, int H,
-                              int W, int d, const AxisWin& at, const AxisWin& ah, const AxisWin& aw, float scale,
+static int launch_local_bwd_q(const void* K, const void* V, const void* Q, const void* dO, void* dQ, float* dK, float* dV,
+                              int B, int T_, int H, int W, int d, const AxisWin& at, const AxisWin& ah, const AxisWin& aw, float scale,
                               int k_l2norm, cudaStream_t s) {
   const long long wins = (long long)B * at.count * ah.count * aw.count;
   if (wins == 0) return 0;
   const long long blocks = (wins + 7) / 8;
-  HICOM_REQUIRE(blocks < (1ll << 31), "local_attend_backward_query: too many windows");
+  HICOM_REQUIRE(blocks < (1ll << 31), "local_attend_backward: too many windows");
 #define HICOM_LBQ(CPL)                                                                                              \
   local_attend_bwd_q_kernel<T, CPL><<<(unsigned)blocks, 256, 0, s>>>((const T*)K, (const T*)V, (const T*)Q,          \
-                                                                     (const T*)dO, (T*)dQ, B, T_, H, W, d, at, ah,  \
-                                                                     aw, scale, k_l2norm)
+                                                                     (const T*)dO, (T*)dQ, dK, dV, B, T_, H, W, d,  \
+                                                                     at, ah, aw, scale, k_l2norm)
   switch (d / 128) {
     case 9: HICOM_LBQ(9); break;
     case 6: HICOM_LBQ(6); break;
     case 1: HICOM_LBQ(1); break;
-    default: set_error("local_attend_backward_query: d=%d unsupported", d); return 1;
+    default: set_error("local_attend_backward: d=%d unsupported", d); return 1;
   }
 #undef HICOM_LBQ
-  return check_launch("local_attend_bwd_q_kernel");
+  return check_launch("local_attend_bwd_kernel");
 }
 
-extern "C" int hicom_local_attend_backward_query(const void* Ksrc, const void* Vsrc, const void* Q, const void* dO,
-                                                 void* dQ, int B, int T, int H, int W, int d, int kt, int ks,
-                                                 float logit_scale, int k_l2norm, int dtype, void* stream) {
-  HICOM_REQUIRE(Ksrc && Vsrc && Q && dO && dQ, "local_attend_backward_query: null pointer");
+extern "C" int hicom_local_attend_backward(const void* Ksrc, const void* Vsrc, const void* Q, const void* dO, void* dQ,
+                                           float* dK, float* dV, int B, int T, int H, int W, int d, int kt, int ks,
+                                           float logit_scale, int k_l2norm, int dtype, void* stream) {
+  HICOM_REQUIRE(Ksrc && Vsrc && Q && dO, "local_attend_backward: null pointer");
+  HICOM_REQUIRE(dQ || dK || dV, "local_attend_backward: no output requested");
   HICOM_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && d > 0 && d % 128 == 0 && kt > 0 && ks > 0,
-                "local_attend_backward_query: bad shape");
+                "local_attend_backward: bad shape");
+  HICOM_REQUIRE(!(dK && k_l2norm), "local_attend_backward: key gradients through the L2 normalisation are not built");
   AxisWin at, ah, aw;
   HICOM_REQUIRE(make_axis_win(T, kt, &at) && make_axis_win(H, ks, &ah) && make_axis_win(W, ks, &aw),
-                "local_attend_backward_query: the reference cannot stack these windows (T=%d H=%d W=%d, kernel %d/%d)", T,
-                H, W, kt, ks);
-  HICOM_DISPATCH_DTYPE(dtype, E, return (launch_local_bwd_q<E>(Ksrc, Vsrc, Q, dO, dQ, B, T, H, W, d, at, ah, aw,
+                "local_attend_backward: the reference cannot stack these windows (T=%d H=%d W=%d, kernel %d/%d)", T, H, W,
+                kt, ks);
+  HICOM_DISPATCH_DTYPE(dtype, E, return (launch_local_bwd_q<E>(Ksrc, Vsrc, Q, dO, dQ, dK, dV, B, T, H, W, d, at, ah, aw,
                                                                 logit_scale, k_l2norm, as_stream(stream))));
 }
 

@@ -489,9 +489,10 @@ def _impl_softmax_backward(S: Tensor, dP: Tensor, lse: Tensor, delta: Tensor, ou
     return out
 
 
-def _impl_local_attend_backward_query(K: Tensor, V: Tensor, Q: Tensor, dO: Tensor, kt: int, ks: int,
-                                      logit_scale: float, k_l2norm: bool) -> Tensor:
-    """d(query rows) of local_attend — projector.py:546-553; K, V (B,T,H,W,d), Q, dO (B,Nw,d)."""
+def _impl_local_attend_backward(K: Tensor, V: Tensor, Q: Tensor, dO: Tensor, kt: int, ks: int, logit_scale: float,
+                                k_l2norm: bool, need_q: bool, need_k: bool, need_v: bool):
+    """Backward of local_attend (projector.py:546-553): K, V (B,T,H,W,d); Q, dO (B,Nw,d).  Returns
+    (dQ in Q's dtype | None, dK fp32 (B,T,H,W,d) | None, dV fp32 | None)."""
     dev = _need_cuda(K, V, Q, dO)
     V = V.contiguous()
     K = V if K.data_ptr() == V.data_ptr() else K.contiguous()
@@ -499,16 +500,18 @@ def _impl_local_attend_backward_query(K: Tensor, V: Tensor, Q: Tensor, dO: Tenso
     B, T, H, W, d = V.shape
     nw = num_windows(T, H, W, kt, ks)
     if K.shape != V.shape or Q.shape != (B, nw, d) or dO.shape != (B, nw, d):
-        raise ValueError("local_attend_backward_query: shape mismatch")
+        raise ValueError("local_attend_backward: shape mismatch")
     if not (K.dtype == V.dtype == Q.dtype == dO.dtype):
-        raise TypeError("local_attend_backward_query: dtypes differ")
-    out = torch.empty_like(Q)
+        raise TypeError("local_attend_backward: dtypes differ")
+    dQ = torch.empty_like(Q) if need_q else None
+    dK = torch.zeros(V.shape, dtype=torch.float32, device=dev) if need_k else None
+    dV = torch.zeros(V.shape, dtype=torch.float32, device=dev) if need_v else None
     with torch.cuda.device(dev):
-        rc = _cabi.load().hicom_local_attend_backward_query(_ptr(K), _ptr(V), _ptr(Q), _ptr(dO), _ptr(out), B, T, H,
-                                                            W, d, kt, ks, float(logit_scale), int(k_l2norm),
-                                                            _dt(V), _stream(dev))
-    _cabi.check(rc, "hicom_local_attend_backward_query")
-    return out
+        rc = _cabi.load().hicom_local_attend_backward(_ptr(K), _ptr(V), _ptr(Q), _ptr(dO), _ptr(dQ), _ptr(dK),
+                                                      _ptr(dV), B, T, H, W, d, kt, ks, float(logit_scale),
+                                                      int(k_l2norm), _dt(V), _stream(dev))
+    _cabi.check(rc, "hicom_local_attend_backward")
+    return dQ, dK, dV
 
 
 def _impl_film_layernorm_backward(x: Tensor, film: Tensor, ln_w: Tensor, dy: Tensor, rows_per_group: int,
@@ -685,5 +688,5 @@ softmax_reduce = _wrap("softmax_reduce", _impl_softmax_reduce, (), lambda *a: "s
 global_value_proj = _wrap("global_value_proj", _impl_global_value_proj, (), lambda *a: "global_value_proj")
 # backward blocks are called directly (``gemm`` writes into strided views, which torch.library cannot describe)
 gemm, act_backward, softmax_backward = _impl_gemm, _impl_act_backward, _impl_softmax_backward
-local_attend_backward_query = _impl_local_attend_backward_query
+local_attend_backward = _impl_local_attend_backward
 film_layernorm_backward = _impl_film_layernorm_backward

@@ -13,7 +13,9 @@ nine times what the reassociated compressor executes.  The SigLIP tower itself s
 
 Kernels: ``ops.layernorm`` (one warp per row), then the persistent tcgen05 linear twice — ``fc1`` with the tanh GELU
 fused in its epilogue (16 epilogue warps, two MUFU per element), ``fc2`` with bias and the residual ``h`` fused.  No
-PyTorch/CPU fallback; forward only.
+PyTorch/CPU fallback.  Under autograd (stage 3 tunes ``vision_model_head``, train.py:717-721) the same kernels run
+inside the Functions of ``hicom_b200/autograd.py`` (LayerNormFn, LinearFn), so the head's layernorm / MLP parameters
+receive gradients; ``HICOM_AUTOGRAD=0`` restores the forward-only failure.
 """
 from __future__ import annotations
 
@@ -21,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .projector import _IMPL, _require_no_grad
+from .projector import _IMPL, _grad_needed, _require_no_grad
 
 __all__ = ["SiglipHeadEmbed", "text_head_embed"]
 
@@ -68,7 +70,6 @@ class SiglipHeadEmbed(nn.Module):
         h = last_hidden_state
         if h.dim() != 3:
             raise ValueError(f"expected last_hidden_state (b, tokens, d), got {tuple(h.shape)}")
-        _require_no_grad(self, h)
         if h.dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"hicom_b200 supports float32 and bfloat16 tensors, got {h.dtype}")
         b, n, d = h.shape
@@ -76,6 +77,15 @@ class SiglipHeadEmbed(nn.Module):
         if side * side != n:
             raise ValueError(f"{n} tokens are not a {side} x {side} grid")
         h = h.contiguous()
+        if _grad_needed(self, h):
+            from . import autograd as ag
+            if not ag.ENABLED:
+                _require_no_grad(self, h)
+            ops._need_cuda(h)
+            y = ag.LayerNormFn.apply(h, self.layernorm.weight, self.layernorm.bias)
+            y = ag.linear(y, self.mlp.fc1.weight, self.mlp.fc1.bias, None, self.act)
+            y = ag.linear(y, self.mlp.fc2.weight, self.mlp.fc2.bias, h)
+            return y.view(b, side, side, d)
         y = ops.layernorm(h, self.layernorm.weight, self.layernorm.bias)
         y = ops.linear(y, self.mlp.fc1.weight, self.mlp.fc1.bias, None, self.act, False, _IMPL)
         y = ops.linear(y, self.mlp.fc2.weight, self.mlp.fc2.bias, h, ops.ACT_NONE, False, _IMPL)
@@ -84,5 +94,10 @@ class SiglipHeadEmbed(nn.Module):
 
 def text_head_embed(last_hidden_state: torch.Tensor, head: nn.Linear) -> torch.Tensor:
     """``fine`` guide tokens: ``guide_encoder.text_model.head(last_hidden_state)`` (encoder.py:279-280), (b, L, d)."""
-    _require_no_grad(head, last_hidden_state)
+    if _grad_needed(head, last_hidden_state):
+        from . import autograd as ag
+        if not ag.ENABLED:
+            _require_no_grad(head, last_hidden_state)
+        ops._need_cuda(last_hidden_state)
+        return ag.linear(last_hidden_state, head.weight, head.bias)
     return ops.linear(last_hidden_state, head.weight, head.bias, None, ops.ACT_NONE, False, _IMPL)

@@ -219,12 +219,15 @@ int hicom_act_backward(const void* pre, const void* dy, void* dx, int64_t n, int
 int hicom_softmax_backward(const float* S, const float* dP, const float* lse, const float* delta, void* dS, int B,
                            int64_t N, int J, int out_dtype, void* stream);
 
-/* hicom_local_attend_backward_query: gradient of hicom_local_attend's output with respect to its query rows
- *   (projector.py:546-553; the keys/values come from frozen towers).  Ksrc, Vsrc (B,T,H,W,d); Q, dO, dQ (B,Nw,d) with
- *   Q the injected query rows actually used by the forward; same window rule, logit_scale and k_l2norm as the forward. */
-int hicom_local_attend_backward_query(const void* Ksrc, const void* Vsrc, const void* Q, const void* dO, void* dQ,
-                                      int B, int T, int H, int W, int d, int kt, int ks, float logit_scale,
-                                      int k_l2norm, int dtype, void* stream);
+/* hicom_local_attend_backward: gradients of hicom_local_attend's output (projector.py:546-553) with respect to
+ *   dQ (B,Nw,d) in dtype   the query rows actually used by the forward (Q, same shape) — FiLM / instruction parameters;
+ *   dK (B,T,H,W,d) fp32    the keys (frames_embed: stage 3 tunes the SigLIP head that produces it, train.py:717-721);
+ *   dV (B,T,H,W,d) fp32    the values (trainable value adapter only).
+ *   Any of the three may be NULL.  dK / dV are ACCUMULATED with atomics (overlapping balanced windows): zero them first.
+ *   Same window rule, logit_scale and k_l2norm as the forward; dK is refused together with k_l2norm. */
+int hicom_local_attend_backward(const void* Ksrc, const void* Vsrc, const void* Q, const void* dO, void* dQ, float* dK,
+                                float* dV, int B, int T, int H, int W, int d, int kt, int ks, float logit_scale,
+                                int k_l2norm, int dtype, void* stream);
 
 /* hicom_film_layernorm_backward: backward of hicom_film_layernorm, y = LN(x*(1+scale)+shift)*w + b (coarse injector,
  *   projector.py:369-372).  x, dy (rows,d) and ln_w (d) in dtype; film (G,2d) fp32.  Outputs: dx (rows,d) in dtype or

@@ -153,13 +153,19 @@ def local_attend(K, V, P, q_aux, film, ln_w, ln_b, kt, ks, qmode, logit_scale, k
     return torch.stack(outs).to(V.dtype)
 
 
-def local_attend_backward_query(K, V, Q, dO, kt, ks, logit_scale, k_l2norm):
-    calls.append(("local_attend_backward_query",))
+def local_attend_backward(K, V, Q, dO, kt, ks, logit_scale, k_l2norm, need_q, need_k, need_v):
+    calls.append(("local_attend_backward", need_q, need_k, need_v))
     q = Q.detach().float().requires_grad_(True)
+    k = K.detach().float().requires_grad_(True)
+    v = V.detach().float().requires_grad_(True)
     with torch.enable_grad():
-        o = local_attend(K.float(), V.float(), V.float(), q, None, None, None, kt, ks, Q_EXPLICIT, logit_scale, k_l2norm)
-        (dq,) = torch.autograd.grad(o, q, dO.float())
-    return dq.to(Q.dtype)
+        o = local_attend(k, v, v, q, None, None, None, kt, ks, Q_EXPLICIT, logit_scale, k_l2norm)
+        dq, dk, dv = torch.autograd.grad(o, (q, k, v), dO.float())
+    return (dq.to(Q.dtype) if need_q else None), (dk if need_k else None), (dv if need_v else None)
+
+
+def layernorm(x, w, b):
+    return F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), 1e-6).to(x.dtype)
 
 
 def _need_cuda(*ts):
@@ -171,7 +177,7 @@ def _need_cuda(*ts):
 
 ALL = ["linear", "gemm", "act_backward", "softmax_backward", "global_fold_query", "posadd", "global_attend_partial",
        "softmax_reduce", "softmax_merge", "global_value_proj", "grid_pool", "film_layernorm", "film_layernorm_backward",
-       "local_attend", "local_attend_backward_query", "_need_cuda"]
+       "local_attend", "local_attend_backward", "layernorm", "_need_cuda"]
 
 
 def install(monkeypatch):

@@ -136,3 +136,49 @@ def test_bf16_parameter_gradients_have_parameter_dtype(monkeypatch):
               "global_compressor.query", "local_compressor.guide_injector.coarse_proj.0.weight"):
         got = dict(m.named_parameters())[k].grad.float()
         assert O.cosine(got, want[k]) >= 0.99, (k, O.cosine(got, want[k]))
+
+
+@pytest.mark.parametrize("name", ["direct_T8", "coarse_T8", "coarse_nondiv_7x8", "video_one_token"])
+def test_stage3_gradients_reach_frames_embed_and_guide(name, monkeypatch):
+    """Stage 3 of the release recipe tunes vision_model_head and guide_encoder (train.py:717-726): frames_embed (the
+    local keys) and the instruction embedding then require gradients."""
+    from hicom_b200 import autograd as ag
+    case = CASES_BY_NAME[name]
+    sd, X, E, g, nl = materialise(case)
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, sd)
+    E1, g1 = E.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    out = m(X, E1, g1, case.modal, nl)
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    (out * probe).sum().backward()
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    E2, g2 = E.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    want = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf).forward(X, E2, g2, case.modal, nl)
+    (want * probe).sum().backward()
+    assert O.rel_err(E1.grad, E2.grad) <= 2e-4 and O.rel_err(g1.grad, g2.grad) <= 2e-4
+    for k, p in m.named_parameters():
+        if leaf[k].grad is not None and float(leaf[k].grad.abs().max()) > 1e-6:
+            assert O.rel_err(p.grad, leaf[k].grad) <= 2e-4, k
+    assert ("local_attend_backward", True, True, False) in cpu_ops.calls
+
+
+def test_producer_head_gradients(monkeypatch):
+    """vision_model_head in mm_tunable_parts: layernorm / fc1 / fc2 of the SigLIP head receive gradients through
+    frames_embed = h + mlp(layernorm(h)) (encoder.py:284-285)."""
+    from hicom_b200 import autograd as ag
+    from hicom_b200.producer import SiglipHeadEmbed
+    from oracle import siglip_head as SH
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    sd = SH.synth_head_state(3, hidden=128, inter=256)
+    m = SiglipHeadEmbed(128, 256)
+    m.load_state_dict(sd, strict=True)
+    h = SH.synth_hidden(2, 16, seed=2, hidden=128)
+    out = m(h)
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(6))
+    (out * probe).sum().backward()
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    (SH.image_embeds(leaf, h, side=4) * probe).sum().backward()
+    for k, p in m.named_parameters():
+        assert O.rel_err(p.grad, leaf[k].grad) <= 2e-4, k

@@ -75,7 +75,8 @@ def test_softmax_backward(out_bf16, built_library):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(8, 6, 6, 4, 3, False), (7, 7, 8, 4, 3, False), (1, 6, 6, 1, 3, True), (2, 6, 6, 4, 2, False)])
-def test_local_attend_backward_query(shape, dtype, built_library):
+def test_local_attend_backward(shape, dtype, built_library):
+    """dQ, dK, dV of the window attention; (7,7,8) has overlapping balanced windows (tokens in two windows: atomics)."""
     from hicom_b200 import ops
     T, H, W, kt, ks, l2 = shape
     B, d = 2, 1152
@@ -83,9 +84,22 @@ def test_local_attend_backward_query(shape, dtype, built_library):
     nw = ops.num_windows(T, H, W, kt, ks)
     Q, dO = _r(B, nw, d, seed=3, std=0.5).to(dtype), _r(B, nw, d, seed=4).to(dtype)
     scale = 1.0 / d ** 0.5 if not l2 else 10.0
-    got = ops.local_attend_backward_query(K.cuda(), V.cuda(), Q.cuda(), dO.cuda(), kt, ks, scale, l2).float().cpu()
-    want = cpu_ops.local_attend_backward_query(K.float(), V.float(), Q.float(), dO.float(), kt, ks, scale, l2)
-    assert O.rel_err(got, want) <= (2e-5 if dtype == torch.float32 else 8e-3)
+    dq, dk, dv = ops.local_attend_backward(K.cuda(), V.cuda(), Q.cuda(), dO.cuda(), kt, ks, scale, l2, True, not l2, True)
+    wq, wk, wv = cpu_ops.local_attend_backward(K.float(), V.float(), Q.float(), dO.float(), kt, ks, scale, l2,
+                                               True, True, True)
+    tol = 2e-5 if dtype == torch.float32 else 8e-3
+    assert O.rel_err(dq.float().cpu(), wq) <= tol
+    assert dv.dtype == torch.float32 and O.rel_err(dv.cpu(), wv) <= tol
+    if l2:
+        assert dk is None
+        with pytest.raises(RuntimeError, match="L2 normalisation"):
+            ops.local_attend_backward(K.cuda(), V.cuda(), Q.cuda(), dO.cuda(), kt, ks, scale, True, False, True, False)
+    else:
+        assert dk.dtype == torch.float32 and O.rel_err(dk.cpu(), wk) <= tol
+    only_k = ops.local_attend_backward(K.cuda(), V.cuda(), Q.cuda(), dO.cuda(), kt, ks, scale, False, False, True, False)
+    assert only_k[0] is None and only_k[2] is None and O.rel_err(
+        only_k[1].cpu(), cpu_ops.local_attend_backward(K.float(), V.float(), Q.float(), dO.float(), kt, ks, scale,
+                                                       False, False, True, False)[1]) <= tol
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -196,3 +210,50 @@ def test_switch_off_restores_forward_only(built_library):
     sd, X, E, g, _ = materialise(fine)
     with pytest.raises(NotImplementedError, match="fine"):
         _train_module(fine, sd)(X.cuda(), E.cuda(), g.cuda(), "video")
+
+
+@pytest.mark.parametrize("name,dtype", [("direct_T8", "float32"), ("coarse_nondiv_7x8", "float32"),
+                                        ("direct_T8", "bfloat16")])
+def test_stage3_gradients_reach_frames_embed_and_guide(name, dtype, built_library, autograd_on):
+    """vision_model_head + guide_encoder tuned (train.py:717-726): frames_embed and the instruction embedding carry
+    gradients, compared with PyTorch autograd through the oracle."""
+    case = dataclasses.replace(CASES_BY_NAME[name], dtype=dtype)
+    sd, X, E, g, nl = materialise(case)
+    m = _train_module(case, sd)
+    E1, g1 = E.cuda().requires_grad_(True), g.cuda().requires_grad_(True)
+    out = m(X.cuda(), E1, g1, case.modal, None)
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    (out.float() * probe.cuda()).sum().backward()
+    leaf = {k: v.float().clone().requires_grad_(True) for k, v in sd.items()}
+    E2, g2 = E.float().clone().requires_grad_(True), g.float().clone().requires_grad_(True)
+    want = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf).forward(X.float(), E2, g2,
+                                                                                               case.modal, None)
+    (want * probe).sum().backward()
+    assert E1.grad.dtype == E1.dtype and g1.grad.dtype == g1.dtype
+    if dtype == "float32":
+        assert O.rel_err(E1.grad.cpu(), E2.grad) <= 1e-3 and O.rel_err(g1.grad.cpu(), g2.grad) <= 1e-3
+    else:
+        assert O.cosine(E1.grad.float().cpu(), E2.grad) >= 0.99 and O.cosine(g1.grad.float().cpu(), g2.grad) >= 0.99
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_producer_head_gradients(dtype, built_library, autograd_on):
+    from hicom_b200.producer import SiglipHeadEmbed
+    from oracle import siglip_head as SH
+    sd = SH.synth_head_state(3)
+    m = SiglipHeadEmbed()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dtype).cuda().train()
+    h = SH.synth_hidden(2, 36, seed=2).to(dtype)
+    out = m(h.cuda())
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(6))
+    (out.float() * probe.cuda()).sum().backward()
+    leaf = {k: v.to(dtype).float().clone().requires_grad_(True) for k, v in sd.items()}
+    (SH.image_embeds(leaf, h.float(), side=6) * probe).sum().backward()
+    for k, p in m.named_parameters():
+        got = p.grad.float().cpu()
+        assert p.grad.dtype == dtype
+        if dtype == torch.float32:
+            assert O.rel_err(got, leaf[k].grad) <= 1e-3, k
+        else:
+            assert O.cosine(got, leaf[k].grad) >= 0.99, k

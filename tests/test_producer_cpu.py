@@ -64,8 +64,15 @@ def test_no_cpu_fallback_and_bad_inputs():
             m(torch.zeros(1, 5, 128))                    # 5 tokens are not a square grid
         with pytest.raises(TypeError):
             m(torch.zeros(1, 4, 128, dtype=torch.float16))
-    with pytest.raises(RuntimeError, match="forward-only"):
-        m(torch.zeros(1, 4, 128))                        # autograd on: fail loudly
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 4, 128))                        # autograd on: the training path, same refusal of CPU tensors
+    from hicom_b200 import autograd as ag
+    ag.enable(False)
+    try:
+        with pytest.raises(RuntimeError, match="forward-only"):
+            m(torch.zeros(1, 4, 128))                    # training path switched off: fail loudly, never drop gradients
+    finally:
+        ag.enable(True)
     with pytest.raises(NotImplementedError):
         SiglipHeadEmbed(128, 256, layer_norm_eps=1e-5)
     with pytest.raises(NotImplementedError):
