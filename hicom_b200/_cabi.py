@@ -43,6 +43,7 @@ PROTOTYPES = {
     "hicom_softmax_backward": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_int, c_void_p]),
     "hicom_local_attend_backward": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_float, c_int, c_int, c_void_p]),
     "hicom_film_layernorm_backward": (c_int, [c_void_p] * 8 + [c_int64, c_int, c_int, c_int, c_void_p]),
+    "hicom_mix_layernorm_backward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -10,7 +10,7 @@ embedding may require gradients too — both are supported.
 sm_100a kernels as inference; every op that has a trainable parameter upstream is wrapped in a
 ``torch.autograd.Function`` whose backward is composed from the C-ABI blocks of ``csrc/backward.cu``
 (``hicom_gemm`` for every contraction, ``hicom_act_backward``, ``hicom_softmax_backward``,
-``hicom_local_attend_backward``, ``hicom_film_layernorm_backward``).  PyTorch only supplies plumbing: views,
+``hicom_local_attend_backward``, ``hicom_film_layernorm_backward``, ``hicom_mix_layernorm_backward``).  PyTorch only supplies plumbing: views,
 ``cat``/``expand`` of token rows, dtype casts, and reductions over tensors of a few hundred rows.
 
 Global attention backward in the reassociated form (forward: projector.py:180-226 as ``pooled = softmax(x'·qfold)ᵀ x'``):
@@ -18,9 +18,9 @@ Global attention backward in the reassociated form (forward: projector.py:180-22
 so no gradient is ever formed for the N x 1152 keys/values the reference materialises.
 
 Status: first correct CUDA path (SIMT GEMMs, fp32 accumulation), validated on a B200 against PyTorch autograd through
-the oracle (tests/test_gpu_autograd.py).  Supported: ``use_guide`` None/off/direct/coarse, no adapters
-(``adaptq/k/v/g``), no ``use_clip_scale``; ``fine`` and the adapters raise ``NotImplementedError`` — nothing ever
-returns a tensor silently cut off from the graph.  ``HICOM_AUTOGRAD=0`` / ``hicom_b200.autograd.enable(False)`` restores
+the oracle (tests/test_gpu_autograd.py).  Supported: every ``use_guide`` mode (None/off/direct/coarse/fine) and every
+adapter (``adaptq/k/v/g``); ``use_clip_scale`` and a ``frames_feature`` that requires grad raise
+``NotImplementedError`` — nothing ever returns a tensor silently cut off from the graph.  ``HICOM_AUTOGRAD=0`` / ``hicom_b200.autograd.enable(False)`` restores
 the forward-only behaviour (a forward that needs gradients raises, ``projector._require_no_grad``).
 """
 from __future__ import annotations
@@ -244,8 +244,9 @@ class FilmLayerNormFn(Function):
 
 
 class LocalAttendFn(Function):
-    """Window attention on explicit query rows (ops.local_attend, Q_EXPLICIT); differentiable in the query rows and in
-    the keys (``frames_embed``) — the values are ``frames_feature`` of the frozen SigLIP body."""
+    """Window attention on explicit query rows (ops.local_attend, Q_EXPLICIT); differentiable in the query rows, the
+    keys (``frames_embed`` / the key adapter's output) and the values (only behind a trainable value adapter — plain
+    values are ``frames_feature`` of the frozen SigLIP body)."""
 
     @staticmethod
     def forward(ctx, K, V, Qrows, kt, ks, scale, k_l2norm):
@@ -257,14 +258,14 @@ class LocalAttendFn(Function):
     def backward(ctx, dO):
         K, V, Qrows = ctx.saved_tensors
         kt, ks, scale, k_l2norm = ctx.geom
-        need_k, _, need_q = ctx.needs_input_grad[:3]
-        dQ = dK = None
-        if need_q or need_k:
-            dQ, dK, _ = ops.local_attend_backward(K, V, Qrows, dO.contiguous().to(Qrows.dtype), kt, ks, scale,
-                                                  k_l2norm, need_q, need_k, False)
-            if dK is not None and dK.dtype != K.dtype:
-                dK = dK.to(K.dtype)
-        return dK, None, dQ, None, None, None, None
+        need_k, need_v, need_q = ctx.needs_input_grad[:3]
+        dQ = dK = dV = None
+        if need_q or need_k or need_v:
+            dQ, dK, dV = ops.local_attend_backward(K, V, Qrows, dO.contiguous().to(Qrows.dtype), kt, ks, scale,
+                                                   k_l2norm, need_q, need_k, need_v)
+            dK = None if dK is None else dK.to(K.dtype)
+            dV = None if dV is None else dV.to(V.dtype)
+        return dK, dV, dQ, None, None, None, None
 
 
 class LayerNormFn(Function):
@@ -289,6 +290,88 @@ class LayerNormFn(Function):
                 db.to(ctx.b_dtype) if ctx.needs_input_grad[2] else None)
 
 
+class MixLayerNormFn(Function):
+    """(1 - alpha) * x + alpha * LN(y) — the adapter mixes (ops.mix_layernorm; projector.py:365,533-534,541)."""
+
+    @staticmethod
+    def forward(ctx, x, y, ln_w, ln_b, alpha):
+        alpha = alpha.to(x.dtype)
+        ctx.save_for_backward(x, y, ln_w, ln_b, alpha)
+        return ops.mix_layernorm(x, y, ln_w, ln_b, alpha)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, ln_w, ln_b, alpha = ctx.saved_tensors
+        need_x = ctx.needs_input_grad[0]
+        dx, dy, dw, db, da = ops.mix_layernorm_backward(x, y, ln_w, ln_b, alpha, dout.contiguous().to(x.dtype), need_x)
+        return (dx, dy if ctx.needs_input_grad[1] else None, dw.to(ln_w.dtype) if ctx.needs_input_grad[2] else None,
+                db.to(ln_b.dtype) if ctx.needs_input_grad[3] else None,
+                da.to(alpha.dtype).reshape(alpha.shape) if ctx.needs_input_grad[4] else None)
+
+
+class AddLayerNormFn(Function):
+    """LN(a + b) — the fine injector's residual (ops.add_layernorm, projector.py:392); backward through the FiLM-LN
+    backward kernel with a zero FiLM."""
+
+    @staticmethod
+    def forward(ctx, a, b, ln_w, ln_b):
+        ctx.save_for_backward(a, b, ln_w)
+        ctx.b_dtype = ln_b.dtype
+        return ops.add_layernorm(a, b, ln_w, ln_b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b, ln_w = ctx.saved_tensors
+        d = a.shape[-1]
+        u = a + b                                                            # small: query rows only
+        film = torch.zeros((1, 2 * d), dtype=torch.float32, device=a.device)
+        du, _, dw, db = ops.film_layernorm_backward(u, film, ln_w, dy.contiguous().to(a.dtype), max(u.numel() // d, 1),
+                                                    True)
+        du = du.view(a.shape)
+        return (du if ctx.needs_input_grad[0] else None, du if ctx.needs_input_grad[1] else None,
+                dw.to(ln_w.dtype) if ctx.needs_input_grad[2] else None,
+                db.to(ctx.b_dtype) if ctx.needs_input_grad[3] else None)
+
+
+class GuideAttendFn(Function):
+    """Multi-head attention of query rows over the L instruction tokens (ops.guide_attend; projector.py:391 ->
+    :193-224).  Backward composed from hicom_gemm over per-head strided views and hicom_softmax_backward (the softmax
+    runs over the L keys: scores are laid out (b*h, L, rows) so that the key axis is the one the kernel normalises)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads, scale):
+        ctx.save_for_backward(q, k, v)
+        ctx.heads, ctx.scale = heads, scale
+        return ops.guide_attend(q, k, v, heads, scale)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v = ctx.saved_tensors
+        heads, scale = ctx.heads, ctx.scale
+        B, n, d = q.shape
+        L = k.shape[1]
+        hd = d // heads
+        split = lambda t, rows: t.contiguous().view(B, rows, heads, hd).permute(0, 2, 1, 3)   # [b, h, row, c] view
+        qh, kh, vh, doh = split(q, n), split(k, L), split(v, L), split(dout.to(q.dtype), n)
+        St = ops.gemm(kh, qh.transpose(-1, -2), None, True, scale).view(B * heads, L, n)      # scale * k_l·q_i
+        dPt = ops.gemm(vh, doh.transpose(-1, -2), None, True, 1.0).view(B * heads, L, n)      # v_l·do_i
+        lse = torch.logsumexp(St, dim=1)                                                       # (b*h, rows), small
+        zero = torch.zeros_like(lse)
+        P = ops.softmax_backward(St, torch.ones_like(St), lse, zero, False)                   # exp(S - lse)
+        delta = (P * dPt).sum(dim=1)
+        dSt = ops.softmax_backward(St, dPt, lse, delta, False).view(B, heads, L, n)
+        P = P.view(B, heads, L, n)
+        merge = lambda t, rows: t.permute(0, 2, 1, 3).reshape(B, rows, d)
+        dq = dk = dv = None
+        if ctx.needs_input_grad[0]:
+            dq = merge(ops.gemm(dSt.transpose(-1, -2), kh, None, True, scale), n).to(q.dtype)
+        if ctx.needs_input_grad[1]:
+            dk = merge(ops.gemm(dSt, qh, None, True, scale), L).to(k.dtype)
+        if ctx.needs_input_grad[2]:
+            dv = merge(ops.gemm(P, doh, None, True, 1.0), L).to(v.dtype)
+        return dq, dk, dv, None, None
+
+
 # ------------------------------------------------------------------------------------------
 # the differentiable forward
 # ------------------------------------------------------------------------------------------
@@ -306,18 +389,44 @@ def check_supported(proj, X, E, G) -> None:
     if proj.local_logit_scale is not None or proj.global_logit_scale is not None:
         raise NotImplementedError("hicom_b200.autograd: use_clip_scale is not differentiable yet")
     for comp in (proj.local_compressor, proj.global_compressor):
-        if comp is None:
-            continue
-        if comp.use_guide not in (None, "off", "direct", "coarse"):
-            raise NotImplementedError(f"hicom_b200.autograd: use_guide={comp.use_guide!r} is not differentiable yet "
-                                      "(supported: None, 'off', 'direct', 'coarse')")
-        inj = comp.guide_injector
-        if _is_param(getattr(inj, "guide_alpha", 0)) or isinstance(getattr(inj, "text2qk_proj", None), nn.Sequential):
-            raise NotImplementedError("hicom_b200.autograd: guide adapters (adaptg / text2qk_proj) are not "
-                                      "differentiable yet")
-    lc = proj.local_compressor
-    if lc is not None and any(_is_param(a) for a in (lc.q_alpha, lc.k_alpha, lc.v_alpha)):
-        raise NotImplementedError("hicom_b200.autograd: adaptq/adaptk/adaptv are not differentiable yet")
+        if comp is not None and comp.use_guide not in (None, "off", "direct", "coarse", "fine"):
+            raise NotImplementedError  # projector.py:350
+
+
+def _mix(x, proj, norm, alpha):
+    """(1-α)x + α·LN(proj(x)) (projector.py:365,533-534,541), differentiable; the identity when not adapting."""
+    if not _is_param(alpha):
+        return x
+    y = mlp(proj, x) if isinstance(proj, nn.Sequential) else linear(x, proj.weight, proj.bias)
+    return MixLayerNormFn.apply(x, y, norm.weight, norm.bias, alpha)
+
+
+def _prepared_guide(inj, G):
+    """GuideInjector.prepared_guide with gradients: text2qk projection + guide adapter (projector.py:364-365,388-389)."""
+    if isinstance(inj.text2qk_proj, nn.Sequential):
+        G = mlp(inj.text2qk_proj, G)
+    return _mix(G, inj.guide_proj, inj.guide_norm, inj.guide_alpha)
+
+
+def _inject(inj, mode, rows, G):
+    """GuideInjector.forward on explicit rows (B, n, d) (projector.py:344-397), differentiable."""
+    if mode in (None, "off"):
+        return rows
+    inj.check_guide(G, 0)
+    B, n, d = rows.shape
+    g = _prepared_guide(inj, G)
+    if mode == "direct":                                                   # :367-368: the rows' content is discarded
+        return g.unsqueeze(1).expand(B, n, d)                              # autograd sums over the rows
+    if mode == "coarse":                                                   # :369-372
+        film = mlp(inj.coarse_proj, g, out_fp32=True)
+        return FilmLayerNormFn.apply(rows.contiguous(), film, inj.coarse_norm.weight, inj.coarse_norm.bias, n)
+    mha = inj.fine_proj                                                    # fine, :374-397
+    q = linear(rows, mha.q_proj.weight, mha.q_proj.bias)
+    k = linear(g, mha.k_proj.weight, mha.k_proj.bias)
+    v = linear(g, mha.v_proj.weight, mha.v_proj.bias)
+    a = GuideAttendFn.apply(q, k, v, mha.num_heads, mha.scale)
+    a = linear(a, mha.out_proj.weight, mha.out_proj.bias)
+    return AddLayerNormFn.apply(rows.contiguous(), a, inj.fine_norm.weight, inj.fine_norm.bias)
 
 
 def _local_tokens(proj, X, E, G, modal, image_newline, is_anyres):
@@ -328,24 +437,27 @@ def _local_tokens(proj, X, E, G, modal, image_newline, is_anyres):
     n_local, plan = proj._local_rows(grid, modal, image_newline, is_anyres)
     if plan != "plain" and image_newline is None:
         raise ValueError("this mm_newline_position needs image_newline")
-    if lc.use_guide == "coarse":
-        inj = lc.guide_injector
-        inj.check_guide(G, 0)
-        film = mlp(inj.coarse_proj, inj.prepared_guide(G), out_fp32=True)          # (B, 2d) fp32, projector.py:370-371
-        with torch.no_grad():
-            q0 = ops.grid_pool(X, tk, sk)                                          # projector.py:539-540 (no parameter)
-        rows = FilmLayerNormFn.apply(q0, film, inj.coarse_norm.weight, inj.coarse_norm.bias, q0.shape[1])
-        att = LocalAttendFn.apply(X if E is None else E, X, rows, tk, sk, 1.0 / math.sqrt(lc.qk_dim), False)
-    elif lc.use_guide == "direct" and (G.requires_grad or (E is not None and E.requires_grad)):
-        # stage 3 (train.py:717-726): the guide encoder and the SigLIP head that makes frames_embed are tuned, so the
-        # query (= the instruction vector for every window, projector.py:367-368) and the keys carry gradients
-        lc.guide_injector.check_guide(G, 0)
-        nw = ops.num_windows(T, H, W, tk, sk)
-        rows = lc.guide_injector.prepared_guide(G).unsqueeze(1).expand(B, nw, d)   # autograd sums dq over the windows
-        att = LocalAttendFn.apply(X if E is None else E, X, rows, tk, sk, 1.0 / math.sqrt(lc.qk_dim), False)
-    else:  # None / off / direct: nothing trainable in front of the readout — the fused inference kernel, as a constant
+    mode = lc.use_guide
+    adapting = any(_is_param(a) for a in (lc.q_alpha, lc.k_alpha, lc.v_alpha))
+    upstream = (mode in ("coarse", "fine") or adapting
+                or (mode == "direct" and (G.requires_grad or _is_param(lc.guide_injector.guide_alpha)))
+                or (E is not None and E.requires_grad))
+    if not upstream:
+        # nothing trainable in front of the readout (query = pooled feature or the frozen instruction vector, keys and
+        # values from frozen towers): the fused inference kernel, as a constant
         with torch.no_grad():
             att = lc.attend(X, E, G, modal, None, None)
+    else:
+        K = _mix(X if E is None else E, lc.k_proj, lc.k_norm, lc.k_alpha)          # projector.py:532-533
+        V = _mix(X, lc.v_proj, lc.v_norm, lc.v_alpha)                              # :534
+        if mode == "direct":
+            rows = torch.empty((B, ops.num_windows(T, H, W, tk, sk), d), dtype=X.dtype, device=X.device)  # shape only
+        else:
+            with torch.no_grad():
+                rows = ops.grid_pool(X, tk, sk)                                    # :539-540 (no parameter)
+            rows = _mix(rows, lc.q_proj, lc.q_norm, lc.q_alpha)                    # :541
+        rows = _inject(lc.guide_injector, mode, rows, G)                           # :542
+        att = LocalAttendFn.apply(K, V, rows, tk, sk, 1.0 / math.sqrt(lc.qk_dim), False)   # :544-558
     tokens = mlp(lc.readout, att)                                                  # (B, Nw, Dh), projector.py:559
     Dh = tokens.shape[-1]
     t1, h1, w1 = grid
@@ -368,16 +480,10 @@ def _global_tokens(proj, X, G, splits=None, t0=0):
     nq, d = gc.query.shape
     if gc.use_guide == "direct":          # projector.py:367-368: every query row is the guide — one distinct row
         gc.guide_injector.check_guide(G, 0)
-        Qg = gc.guide_injector.prepared_guide(G).unsqueeze(1).contiguous()          # (B, 1, d), no parameter
+        Qg = _prepared_guide(gc.guide_injector, G).unsqueeze(1).contiguous()        # (B, 1, d)
     else:
         rows = gc.query.to(X.dtype).unsqueeze(0).expand(B, nq, d).contiguous()      # autograd sums over the batch
-        if gc.use_guide == "coarse":
-            inj = gc.guide_injector
-            inj.check_guide(G, 0)
-            film = mlp(inj.coarse_proj, inj.prepared_guide(G), out_fp32=True)
-            Qg = FilmLayerNormFn.apply(rows, film, inj.coarse_norm.weight, inj.coarse_norm.bias, nq)
-        else:
-            Qg = rows
+        Qg = _inject(gc.guide_injector, gc.use_guide, rows, G)                      # projector.py:642
     nrows = Qg.shape[1]
     q = linear(Qg, attn.q_proj.weight, attn.q_proj.bias)                            # projector.py:180
     qfold = FoldQueryFn.apply(q, attn.k_proj.weight, attn.k_proj.bias, attn.num_heads, attn.scale)  # :181 + :197
@@ -392,7 +498,8 @@ def _global_tokens(proj, X, G, splits=None, t0=0):
 
 def forward_batched_train(proj, X, E, G, modal, image_newline=None, is_anyres=False, base=None, with_global=True):
     """Differentiable ``HIComProjector.forward_batched``: same arguments, same ``(B, n_tokens, Dh)`` result, with an
-    autograd graph reaching every projector parameter (and ``image_newline`` / ``base``)."""
+    autograd graph reaching every projector parameter (and ``image_newline`` / ``base`` / ``frames_embed`` / the
+    instruction embedding when they require grad)."""
     check_supported(proj, X, E, G)
     ops._need_cuda(X, E, G)  # raises for CPU tensors: there is no CPU fallback
     parts = [] if base is None else [base]

@@ -7,6 +7,7 @@
 //   hicom_softmax_backward  dS = exp(S - lse) * (dP - delta)         (softmax of projector.py:213 in reassociated form)
 //   hicom_local_attend_backward         d(query), d(keys), d(values) of the window attention (projector.py:546-553)
 //   hicom_film_layernorm_backward       backward of LN(x*(1+scale)+shift) (projector.py:369-372)
+//   hicom_mix_layernorm_backward        backward of (1-alpha)*x + alpha*LN(y), the adapter mixes (projector.py:365,533-534,541)
 #include "gemm_simt.cuh"
 
 namespace hicom {
@@ -283,6 +284,99 @@ __global__ void __launch_bounds__(256) film_ln_backward_kernel(const T* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of out = (1 - alpha) * x + alpha * (LN(y) * w + bias)   (adapter mixes, projector.py:365,533-534,541), one warp
+// per row, a block walks a contiguous range of rows:
+//   dx = (1 - alpha) * dout;  g = alpha * dout;  g_hat = g * w;
+//   dy = rstd * (g_hat - mean(g_hat) - y_hat * mean(g_hat * y_hat))
+//   dw += g * y_hat;  dbias += g;  dalpha += sum dout * (LN(y)*w + bias - x)                  (fp32 atomics)
+// dx may be null (x from a frozen tower).  dw, dbias (d) and dalpha (1) are fp32 and must be zeroed by the caller.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256) mix_ln_backward_kernel(const T* __restrict__ x, const T* __restrict__ y,
+                                                              const T* __restrict__ w, const T* __restrict__ bias,
+                                                              const T* __restrict__ alpha, const T* __restrict__ dout,
+                                                              T* __restrict__ dx, T* __restrict__ dy,
+                                                              float* __restrict__ dw, float* __restrict__ dbias,
+                                                              float* __restrict__ dalpha, long long rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const long long rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r_begin = (long long)blockIdx.x * rows_per_block;
+  long long r_end = r_begin + rows_per_block;
+  if (r_end > rows) r_end = rows;
+  const float al = to_f32<T>(*alpha);
+  float aw[CPL][4], ab[CPL][4];
+  float aal = 0.f;
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) aw[c][i] = ab[c][i] = 0.f;
+  for (long long row = r_begin + wib; row < r_end; row += wpb) {
+    float u[CPL][4], go[CPL][4];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int off = (lane + 32 * c) * 4;
+      Vec4<T>::load(y + row * d + off, u[c]);
+      Vec4<T>::load(dout + row * d + off, go[c]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sum += u[c][i];
+    }
+    const float mean = warp_sum(sum) / (float)d;
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float dv = u[c][i] - mean; var = fmaf(dv, dv, var); }
+    const float rstd = rsqrtf(warp_sum(var) / (float)d + kLnEps);
+    float m1 = 0.f, m2 = 0.f;
+    float gh[CPL][4];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int off = (lane + 32 * c) * 4;
+      float w4[4], b4[4], x4[4], o4[4];
+      Vec4<T>::load(w + off, w4);
+      Vec4<T>::load(bias + off, b4);
+      Vec4<T>::load(x + row * d + off, x4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float uh = (u[c][i] - mean) * rstd;
+        const float ln = fmaf(uh, w4[i], b4[i]);
+        aal = fmaf(go[c][i], ln - x4[i], aal);
+        const float g = al * go[c][i];
+        aw[c][i] = fmaf(g, uh, aw[c][i]);
+        ab[c][i] += g;
+        gh[c][i] = g * w4[i];
+        u[c][i] = uh;
+        m1 += gh[c][i];
+        m2 = fmaf(gh[c][i], uh, m2);
+        o4[i] = (1.f - al) * go[c][i];
+      }
+      if (dx) Vec4<T>::store(dx + row * d + off, o4);
+    }
+    m1 = warp_sum(m1) / (float)d;
+    m2 = warp_sum(m2) / (float)d;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      float o4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o4[i] = rstd * (gh[c][i] - m1 - u[c][i] * m2);
+      Vec4<T>::store(dy + row * d + (lane + 32 * c) * 4, o4);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ch = (lane + 32 * c) * 4 + i;
+      atomicAdd(dw + ch, aw[c][i]);
+      atomicAdd(dbias + ch, ab[c][i]);
+    }
+  aal = warp_sum(aal);
+  if (lane == 0) atomicAdd(dalpha, aal);
+}
+
 }  // namespace hicom
 
 using namespace hicom;
@@ -430,4 +524,35 @@ extern "C" int hicom_film_layernorm_backward(const void* x, const float* film, c
   HICOM_REQUIRE(rows >= 0 && d > 0 && d % 128 == 0 && rows_per_group > 0, "film_layernorm_backward: bad shape");
   HICOM_DISPATCH_DTYPE(dtype, E, return (launch_film_ln_bwd<E>(x, film, ln_w, dy, dx, dfilm, dw, dbias, rows, d,
                                                                 rows_per_group, as_stream(stream))));
+}
+
+template <typename T>
+static int launch_mix_ln_bwd(const void* x, const void* y, const void* w, const void* bias, const void* alpha,
+                             const void* dout, void* dx, void* dy, float* dw, float* dbias, float* dalpha, long long rows,
+                             int d, cudaStream_t s) {
+  if (rows == 0) return 0;
+  long long blocks = (rows + 63) / 64;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+#define HICOM_MLB(CPL)                                                                                              \
+  mix_ln_backward_kernel<T, CPL><<<(unsigned)blocks, 256, 0, s>>>((const T*)x, (const T*)y, (const T*)w, (const T*)bias, \
+                                                                  (const T*)alpha, (const T*)dout, (T*)dx, (T*)dy, dw,  \
+                                                                  dbias, dalpha, rows, d)
+  switch (d / 128) {
+    case 9: HICOM_MLB(9); break;
+    case 6: HICOM_MLB(6); break;
+    case 1: HICOM_MLB(1); break;
+    default: set_error("mix_layernorm_backward: d=%d unsupported", d); return 1;
+  }
+#undef HICOM_MLB
+  return check_launch("mix_ln_backward_kernel");
+}
+
+extern "C" int hicom_mix_layernorm_backward(const void* x, const void* y, const void* ln_w, const void* ln_b,
+                                            const void* alpha, const void* dout, void* dx, void* dy, float* dw,
+                                            float* dbias, float* dalpha, int64_t rows, int d, int dtype, void* stream) {
+  HICOM_REQUIRE(x && y && ln_w && ln_b && alpha && dout && dy && dw && dbias && dalpha,
+                "mix_layernorm_backward: null pointer");
+  HICOM_REQUIRE(rows >= 0 && d > 0 && d % 128 == 0, "mix_layernorm_backward: bad shape");
+  HICOM_DISPATCH_DTYPE(dtype, E, return (launch_mix_ln_bwd<E>(x, y, ln_w, ln_b, alpha, dout, dx, dy, dw, dbias, dalpha,
+                                                               rows, d, as_stream(stream))));
 }

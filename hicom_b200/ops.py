@@ -537,6 +537,28 @@ def _impl_film_layernorm_backward(x: Tensor, film: Tensor, ln_w: Tensor, dy: Ten
     return dx, dfilm, dw, db
 
 
+def _impl_mix_layernorm_backward(x: Tensor, y: Tensor, ln_w: Tensor, ln_b: Tensor, alpha: Tensor, dout: Tensor,
+                                 need_dx: bool):
+    """Backward of mix_layernorm: returns (dx | None, dy, dw fp32 (d), dbias fp32 (d), dalpha fp32 (1))."""
+    dev = _need_cuda(x, y, ln_w, ln_b, alpha, dout)
+    x, y, dout = x.contiguous(), y.contiguous(), dout.contiguous()
+    d = x.shape[-1]
+    if y.shape != x.shape or dout.shape != x.shape or not (x.dtype == y.dtype == dout.dtype == alpha.dtype == ln_w.dtype):
+        raise ValueError("mix_layernorm_backward: operands differ")
+    dx = torch.empty_like(x) if need_dx else None
+    dy = torch.empty_like(y)
+    dw = torch.zeros((d,), dtype=torch.float32, device=dev)
+    db = torch.zeros((d,), dtype=torch.float32, device=dev)
+    da = torch.zeros((1,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_mix_layernorm_backward(_ptr(x), _ptr(y), _ptr(_c(ln_w)), _ptr(_c(ln_b)),
+                                                       _ptr(alpha.contiguous()), _ptr(dout), _ptr(dx), _ptr(dy),
+                                                       _ptr(dw), _ptr(db), _ptr(da), x.numel() // d, d, _dt(x),
+                                                       _stream(dev))
+    _cabi.check(rc, "hicom_mix_layernorm_backward")
+    return dx, dy, dw, db, da
+
+
 def kernel_launch_count() -> int:
     """Kernels enqueued by libhicom_b200 since load (bench.py's ``gpu_launches``)."""
     return int(_cabi.load().hicom_kernel_launch_count())
@@ -690,3 +712,4 @@ global_value_proj = _wrap("global_value_proj", _impl_global_value_proj, (), lamb
 gemm, act_backward, softmax_backward = _impl_gemm, _impl_act_backward, _impl_softmax_backward
 local_attend_backward = _impl_local_attend_backward
 film_layernorm_backward = _impl_film_layernorm_backward
+mix_layernorm_backward = _impl_mix_layernorm_backward

@@ -236,6 +236,14 @@ int hicom_film_layernorm_backward(const void* x, const float* film, const void* 
                                   float* dfilm, float* dw, float* dbias, int64_t rows, int d, int rows_per_group,
                                   int dtype, void* stream);
 
+/* hicom_mix_layernorm_backward: backward of hicom_mix_layernorm, out = (1-alpha)*x + alpha*(LN(y)*w + b) — the
+ *   adaptq/adaptk/adaptv/adaptg mixes (projector.py:365,533-534,541).  x, y, dout (rows,d), ln_w, ln_b (d), alpha (1) in
+ *   dtype.  Outputs: dx (rows,d) in dtype or NULL (x from a frozen tower); dy (rows,d) in dtype; dw, dbias (d) and
+ *   dalpha (1) fp32, ACCUMULATED into (zero them first). */
+int hicom_mix_layernorm_backward(const void* x, const void* y, const void* ln_w, const void* ln_b, const void* alpha,
+                                 const void* dout, void* dx, void* dy, float* dw, float* dbias, float* dalpha,
+                                 int64_t rows, int d, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

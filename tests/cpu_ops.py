@@ -164,6 +164,33 @@ def local_attend_backward(K, V, Q, dO, kt, ks, logit_scale, k_l2norm, need_q, ne
     return (dq.to(Q.dtype) if need_q else None), (dk if need_k else None), (dv if need_v else None)
 
 
+def mix_layernorm(x, y, ln_w, ln_b, alpha):
+    a = alpha.float()
+    ln = F.layer_norm(y.float(), (y.shape[-1],), ln_w.float(), ln_b.float(), 1e-6)
+    return ((1 - a) * x.float() + a * ln).to(x.dtype)
+
+
+def mix_layernorm_backward(x, y, ln_w, ln_b, alpha, dout, need_dx):
+    calls.append(("mix_layernorm_backward",))
+    leaves = [t.detach().float().requires_grad_(True) for t in (x, y, ln_w, ln_b, alpha)]
+    with torch.enable_grad():
+        out = mix_layernorm(*leaves)
+        dx, dy, dw, db, da = torch.autograd.grad(out, leaves, dout.float())
+    return (dx.to(x.dtype) if need_dx else None), dy.to(y.dtype), dw, db, da.reshape(1)
+
+
+def add_layernorm(a, b, ln_w, ln_b):
+    return F.layer_norm(a.float() + b.float(), (a.shape[-1],), ln_w.float(), ln_b.float(), 1e-6).to(a.dtype)
+
+
+def guide_attend(q, k, v, heads, scale):
+    B, n, d = q.shape
+    hd = d // heads
+    sp = lambda t: t.float().view(B, t.shape[1], heads, hd).transpose(1, 2)
+    p = torch.softmax(torch.matmul(sp(q), sp(k).transpose(2, 3)) * scale, dim=-1)
+    return torch.matmul(p, sp(v)).transpose(1, 2).reshape(B, n, d).to(q.dtype)
+
+
 def layernorm(x, w, b):
     return F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), 1e-6).to(x.dtype)
 
@@ -177,7 +204,8 @@ def _need_cuda(*ts):
 
 ALL = ["linear", "gemm", "act_backward", "softmax_backward", "global_fold_query", "posadd", "global_attend_partial",
        "softmax_reduce", "softmax_merge", "global_value_proj", "grid_pool", "film_layernorm", "film_layernorm_backward",
-       "local_attend", "local_attend_backward", "layernorm", "_need_cuda"]
+       "local_attend", "local_attend_backward", "layernorm", "mix_layernorm", "mix_layernorm_backward", "add_layernorm",
+       "guide_attend", "_need_cuda"]
 
 
 def install(monkeypatch):

@@ -121,6 +121,25 @@ def test_film_layernorm_backward(rows, rpg, need_dx, dtype, built_library):
     assert O.rel_err(dfilm.cpu(), wfilm) <= tol and O.rel_err(dw.cpu(), wdw) <= tol and O.rel_err(db.cpu(), wdb) <= tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,need_dx", [(64, True), (700, False), (5, True)])
+def test_mix_layernorm_backward(rows, need_dx, dtype, built_library):
+    from hicom_b200 import ops
+    d = 1152
+    x, y, dout = (_r(rows, d, seed=s, std=0.5).to(dtype) for s in (1, 2, 3))
+    w, b = (1 + _r(d, seed=4, std=0.1)).to(dtype), _r(d, seed=5, std=0.1).to(dtype)
+    alpha = torch.tensor([0.3]).to(dtype)
+    dx, dy, dw, db, da = ops.mix_layernorm_backward(x.cuda(), y.cuda(), w.cuda(), b.cuda(), alpha.cuda(), dout.cuda(), need_dx)
+    wdx, wdy, wdw, wdb, wda = cpu_ops.mix_layernorm_backward(x.float(), y.float(), w.float(), b.float(), alpha.float(),
+                                                             dout.float(), True)
+    tol = 2e-5 if dtype == torch.float32 else 8e-3
+    assert (dx is None) == (not need_dx)
+    if need_dx:
+        assert O.rel_err(dx.float().cpu(), wdx) <= tol
+    assert O.rel_err(dy.float().cpu(), wdy) <= tol and O.rel_err(dw.cpu(), wdw) <= tol and O.rel_err(db.cpu(), wdb) <= tol
+    assert abs(float(da.cpu()) - float(wda)) <= tol * max(1.0, abs(float(wda)))
+
+
 # ---- the whole training path -------------------------------------------------------------------------------------
 def _oracle_grads(case, sd, X, E, g, nl, probe):
     leaf = {k: v.float().clone().requires_grad_(True) for k, v in sd.items()}
@@ -147,13 +166,19 @@ def autograd_on():
     ag.enable(old)
 
 
+RELEASE_ADAPTKV = dataclasses.replace(CASES_BY_NAME["adaptkv_coarse_T8"], name="adaptkv_direct_T8", use_guide="direct")
+
+
 @pytest.mark.parametrize("name", ["none_T8", "direct_T8", "coarse_T8", "coarse_T7", "coarse_nondiv_7x8",
-                                  "global_only_coarse_T8", "video_grid_newline", "coarse_27x27_T4"])
+                                  "global_only_coarse_T8", "video_grid_newline", "coarse_27x27_T4",
+                                  "fine_T8", "adaptkv_coarse_T8", "adaptqkvg_fine_T8", "adaptkv_direct_T8"])
 @pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
 def test_training_step_gradients(name, dtype, built_library, autograd_on):
-    case = dataclasses.replace(CASES_BY_NAME[name], dtype=dtype)
-    if dtype == "bfloat16" and name not in ("coarse_T8", "direct_T8", "coarse_27x27_T4"):
-        pytest.skip("bf16 is covered on three representative cases")
+    """`adaptkv_direct_T8` is the second release recipe (scripts/qwen2.5_7B/release/directg_local43_adaptkv_global32.sh)."""
+    base = RELEASE_ADAPTKV if name == "adaptkv_direct_T8" else CASES_BY_NAME[name]
+    case = dataclasses.replace(base, dtype=dtype)
+    if dtype == "bfloat16" and name not in ("coarse_T8", "direct_T8", "coarse_27x27_T4", "adaptkv_direct_T8", "fine_T8"):
+        pytest.skip("bf16 is covered on five representative cases")
     sd, X, E, g, nl = materialise(case)
     m = _train_module(case, sd)
     dev = lambda t: None if t is None else t.cuda()
@@ -166,8 +191,8 @@ def test_training_step_gradients(name, dtype, built_library, autograd_on):
     (out.float() * probe.cuda()).sum().backward()
     for k, p in m.named_parameters():
         w = want[k]
-        if w is None or float(w.abs().max()) <= 1e-6:
-            assert p.grad is None or float(p.grad.float().abs().max()) <= 1e-6, k
+        if w is None or float(w.abs().max()) <= 1e-6:   # unused parameter, or a key bias the softmax cancels (noise)
+            assert p.grad is None or float(p.grad.float().abs().max()) <= (1e-6 if fp32 else 1e-3), k
             continue
         assert p.grad is not None and p.grad.dtype == p.dtype, k
         got = p.grad.float().cpu()
