@@ -230,11 +230,13 @@ def test_switch_off_restores_forward_only(built_library):
             m(X.cuda(), E.cuda(), g.cuda(), "video")
     finally:
         ag.enable(old)
-    # unsupported configurations stay loud with the path on
-    fine = CASES_BY_NAME["fine_T8"]
-    sd, X, E, g, _ = materialise(fine)
-    with pytest.raises(NotImplementedError, match="fine"):
-        _train_module(fine, sd)(X.cuda(), E.cuda(), g.cuda(), "video")
+    # what is not differentiable stays loud with the path on: use_clip_scale, gradients into frames_feature
+    m.local_logit_scale, m.local_logit_bias = torch.tensor(2.0, device="cuda"), torch.tensor(-1.0, device="cuda")
+    with pytest.raises(NotImplementedError, match="use_clip_scale"):
+        m(X.cuda(), E.cuda(), g.cuda(), "video")
+    m.local_logit_scale = m.local_logit_bias = None
+    with pytest.raises(NotImplementedError, match="frames_feature requires grad"):
+        m(X.cuda().requires_grad_(True), E.cuda(), g.cuda(), "video")
 
 
 @pytest.mark.parametrize("name,dtype", [("direct_T8", "float32"), ("coarse_nondiv_7x8", "float32"),
