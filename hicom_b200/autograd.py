@@ -54,7 +54,9 @@ def _gemm_to(A: torch.Tensor, B: torch.Tensor, want: torch.dtype, alpha: float =
     """alpha * A @ B on hicom_gemm (strided views, fp32 accumulation), result cast to ``want``."""
     if A.dtype == torch.bfloat16 and B.dtype == torch.float32:
         A = A.float()
-    out_fp32 = A.dtype != B.dtype or (A.dtype == torch.bfloat16 and want == torch.float32)
+    # a transposed A (dW = dYᵀ·A, dqfold = dSᵀ·x') accumulates over thousands of rows into a small result: keep it fp32
+    # (that is also the form the tensor-core path serves) and round once
+    out_fp32 = A.dtype != B.dtype or (A.dtype == torch.bfloat16 and (want == torch.float32 or A.stride(-2) == 1))
     C = ops.gemm(A, B, None, out_fp32, alpha)
     return C if C.dtype == want else C.to(want)
 

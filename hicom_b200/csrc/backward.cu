@@ -8,7 +8,10 @@
 //   hicom_local_attend_backward         d(query), d(keys), d(values) of the window attention (projector.py:546-553)
 //   hicom_film_layernorm_backward       backward of LN(x*(1+scale)+shift) (projector.py:369-372)
 //   hicom_mix_layernorm_backward        backward of (1-alpha)*x + alpha*LN(y), the adapter mixes (projector.py:365,533-534,541)
+#include <stdlib.h>
+
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace hicom {
 
@@ -381,6 +384,56 @@ __global__ void __launch_bounds__(256) mix_ln_backward_kernel(const T* __restric
 
 using namespace hicom;
 
+// Large bf16 contractions of the backward go to the persistent tcgen05 kernel when their strides match one of the
+// operand layouts it already serves in the forward (per batch entry, one launch each):
+//   NT  A (M,K) K-major, B given as (N,K) K-major   S = x'·qfoldᵀ, dP = x'·dpooledᵀ            -> plain linear
+//   NN  A (M,K) K-major, B (K,N) row-major          dA = dpre·W                                 -> MN-major B (w_is_kn)
+//   TN  A stored (K,M),  B (K,N) row-major, fp32 C  dW = dpreᵀ·A, dqfold = dSᵀ·x'               -> MN-major A and B
+// Returns -1 when the problem stays on the SIMT kernel.  HICOM_GEMM_TC=0 keeps everything on SIMT (cross-check).
+static int gemm_tc_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HICOM_GEMM_TC"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on;
+}
+
+static int try_gemm_tc(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, int64_t sAb2, const void* B, int64_t sBk,
+                       int64_t sBn, int64_t sBb1, int64_t sBb2, void* C, int64_t ldc, int64_t sCb1, int64_t sCb2, int M,
+                       int N, int K, int nb1, int nb2, float alpha, int a_dtype, int b_dtype, int c_dtype,
+                       cudaStream_t stream) {
+  if (!gemm_tc_enabled() || a_dtype != HICOM_BF16 || b_dtype != HICOM_BF16) return -1;
+  if (M < 2 || N < 2 || K < 16 || (long long)M * N * K < (1ll << 24)) return -1;  // small: launch-bound either way
+  const long long nb = (long long)nb1 * nb2;
+  if (nb > 64) return -1;
+  const bool a_kmajor = sAk == 1, a_mmajor = sAm == 1 && !a_kmajor;
+  const bool b_kmajor = sBk == 1, b_nmajor = sBn == 1 && !b_kmajor;
+  int mode;  // 0 NT, 1 NN, 2 TN
+  long long lda, ldw;
+  if (a_kmajor && b_kmajor) { mode = 0; lda = sAm; ldw = sBn; }
+  else if (a_kmajor && b_nmajor) { mode = 1; lda = sAm; ldw = sBk; }
+  else if (a_mmajor && b_nmajor) { mode = 2; lda = sAk; ldw = sBk; }
+  else return -1;
+  if (mode == 2 && (c_dtype != HICOM_F32 || alpha != 1.0f)) return -1;
+  if (mode != 2 && K % 8 != 0) return -1;
+  if (lda % 8 != 0 || ldw % 8 != 0) return -1;
+  if (nb > 1 && ((nb1 > 1 && (sAb1 % 8 || sBb1 % 8)) || (nb2 > 1 && (sAb2 % 8 || sBb2 % 8)))) return -1;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -1;
+  const size_t csz = c_dtype == HICOM_F32 ? 4 : 2;
+  for (int b1 = 0; b1 < nb1; ++b1)
+    for (int b2 = 0; b2 < nb2; ++b2) {
+      TcLinearParams t{};
+      t.A = static_cast<const __nv_bfloat16*>(A) + b1 * sAb1 + b2 * sAb2;
+      t.W = static_cast<const __nv_bfloat16*>(B) + b1 * sBb1 + b2 * sBb2;
+      t.C = static_cast<char*>(C) + (size_t)(b1 * sCb1 + b2 * sCb2) * csz;
+      t.bias = nullptr; t.R = nullptr; t.ldr = 0;
+      t.lda = lda; t.ldw = ldw; t.ldc = ldc; t.M = M; t.N = N; t.K = K;
+      t.act = HICOM_ACT_NONE; t.out_dtype = c_dtype; t.rows_per_group = 1 << 30; t.group_stride_rows = 0;
+      t.alpha = alpha;
+      t.w_is_kn = mode >= 1; t.a_is_km = mode == 2;
+      if (launch_tc_linear(t, stream)) return 1;
+    }
+  return 0;
+}
+
 extern "C" int hicom_gemm(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, int64_t sAb2, const void* B,
                           int64_t sBk, int64_t sBn, int64_t sBb1, int64_t sBb2, void* C, int64_t ldc, int64_t sCb1,
                           int64_t sCb2, int M, int N, int K, int nb1, int nb2, float alpha, int a_dtype, int b_dtype,
@@ -390,6 +443,11 @@ extern "C" int hicom_gemm(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1,
                 nb1, nb2);
   HICOM_REQUIRE(ldc >= N, "gemm: ldc too small");
   if (M == 0 || N == 0 || nb1 * nb2 == 0) return 0;
+  {
+    const int rc = try_gemm_tc(A, sAm, sAk, sAb1, sAb2, B, sBk, sBn, sBb1, sBb2, C, ldc, sCb1, sCb2, M, N, K, nb1, nb2,
+                               alpha, a_dtype, b_dtype, c_dtype, as_stream(stream));
+    if (rc >= 0) return rc;
+  }
   GemmParams g{};
   g.A = A; g.B = B; g.C = C;
   g.M = M; g.N = N; g.K = K;

@@ -51,6 +51,28 @@ def test_gemm_strided_views(da, db, mode, built_library):
         assert O.rel_err(dq.float().cpu(), want_h) <= tol
 
 
+@pytest.mark.parametrize("layout", ["NT", "NN", "TN"])
+@pytest.mark.parametrize("M,N,K,batch", [(2916, 288, 1152, 2), (700, 1152, 3584, 1), (1152, 4304, 648, 1), (288, 1152, 2916, 3)])
+def test_gemm_large_bf16_layouts(layout, M, N, K, batch, built_library):
+    """The three operand layouts of the backward's big bf16 contractions (tcgen05 path when HICOM_GEMM_TC is on, SIMT
+    otherwise — same contract): NT S = x'·qfoldᵀ, NN dA = dY·W, TN dW = dYᵀ·A with fp32 output; ragged M/N/K tiles."""
+    from hicom_b200 import ops
+    A = _r(batch, M, K, seed=1, std=0.5, dtype=torch.bfloat16)
+    Bm = _r(batch, K, N, seed=2, std=0.05, dtype=torch.bfloat16)
+    want = torch.matmul(A.float(), Bm.float())
+    if layout == "NT":
+        a_op, b_op = A.cuda(), Bm.transpose(1, 2).contiguous().cuda().transpose(1, 2)     # B stored (N, K)
+    elif layout == "NN":
+        a_op, b_op = A.cuda(), Bm.cuda()
+    else:
+        a_op, b_op = A.transpose(1, 2).contiguous().cuda().transpose(1, 2), Bm.cuda()     # A stored (K, M)
+    got32 = ops.gemm(a_op, b_op, None, True, 1.0)
+    assert got32.dtype == torch.float32 and O.rel_err(got32.cpu(), want) <= 2e-3
+    if layout != "TN":
+        got16 = ops.gemm(a_op, b_op, None, False, 0.5)
+        assert got16.dtype == torch.bfloat16 and O.rel_err(got16.float().cpu(), 0.5 * want) <= 6e-3
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("act", [1, 2])
 def test_act_backward(act, dtype, built_library):
