@@ -252,6 +252,50 @@ def synth_batch(B, T, device, seed):
     return mk(B, T, H, W, D), mk(B, T, H, W, D), mk(B, D)
 
 
+def _timed_ms(fn, warmup, iters):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def measure_next_rows(hidden, T, B, device):
+    """SURVEY §8 'next' rows, reported beside the headline (never part of it): the producer of frames_embed
+    (encoder.py:284-286, hicom_b200.producer) on this step's B*T frames, and one training step (forward + backward,
+    hicom_b200.autograd) of the projector on 8 videos.  CUDA events, inputs resident, bf16."""
+    from hicom_b200.producer import SiglipHeadEmbed
+    out = {}
+    frames = min(B * T, 1024)
+    torch.manual_seed(1)
+    head = SiglipHeadEmbed().to(torch.bfloat16).to(device).eval()
+    h = (0.7 * torch.randn(frames, H * W, D, device=device)).to(torch.bfloat16)
+    with torch.no_grad():
+        ms = _timed_ms(lambda: head(h), 3, 5)
+    out["producer"] = {"what": "frames_embed = h + head.mlp(head.layernorm(h)) (encoder.py:284-286)", "frames": frames,
+                       "ms": ms, "frames_per_s": frames / ms * 1e3,
+                       "tflops": 2.0 * 2 * frames * H * W * D * 4304 / ms / 1e9}
+    del h, head
+    Bt = min(B, 8)
+    m = build_projector(hidden, device).train()
+    X, E, G = synth_batch(Bt, T, device, 99)
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        m.forward_batched(X, E, G, "video").float().square().mean().backward()
+
+    ms = _timed_ms(step, 2, 5)
+    out["train_step"] = {"what": "forward + backward of the projector (parameter gradients, hicom_b200.autograd)",
+                         "videos": Bt, "frames": Bt * T, "use_guide": USE_GUIDE, "ms": ms,
+                         "frames_per_s": Bt * T / ms * 1e3}
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from hicom_b200 import ops
@@ -445,6 +489,13 @@ def run_ours(args):
         except Exception as exc:  # reported, never fatal
             gpu_eager = {"unavailable": repr(exc)[:200]}
 
+    next_rows = None
+    if world == 1 and not args.no_cpu_baseline and not frame_sharded:
+        try:
+            next_rows = measure_next_rows(hidden, T, B, device)
+        except Exception as exc:  # reported, never fatal
+            next_rows = {"unavailable": repr(exc)[:200]}
+
     line = {
         "metric": "frames/s through the HICom compressor", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -463,6 +514,7 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu,
         "gpu_eager_baseline": gpu_eager,
+        "next_rows": next_rows,
         "ops": ops_table,
         "kernels": kernels_table,
     }

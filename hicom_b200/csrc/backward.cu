@@ -1,7 +1,8 @@
 // Backward pass building blocks (stages 1-3 of the reference TRAIN the projector, train.py:704-738).
 //
-// First correct CUDA path, same progression as the forward one: every contraction of the backward formulas runs on the
-// generic strided SIMT GEMM (fp32 accumulation) through hicom_gemm; the element-wise pieces around them live here.
+// Every contraction of the backward formulas goes through hicom_gemm: the generic strided SIMT GEMM (fp32 mode, small
+// problems, odd strides) or — large bf16 problems in the NT / NN / TN layouts — the persistent tcgen05 kernel of
+// gemm_tc.cu (try_gemm_tc below).  The element-wise pieces around them live here.
 //   hicom_gemm              C = alpha * A·B over arbitrary element strides, two batch levels
 //   hicom_act_backward      dx = dy * act'(pre)                      (GELU erf / tanh, projector.py:310, encoder.py:285)
 //   hicom_softmax_backward  dS = exp(S - lse) * (dP - delta)         (softmax of projector.py:213 in reassociated form)
@@ -392,7 +393,7 @@ using namespace hicom;
 // Returns -1 when the problem stays on the SIMT kernel.  HICOM_GEMM_TC=0 keeps everything on SIMT (cross-check).
 static int gemm_tc_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("HICOM_GEMM_TC"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (on < 0) { const char* e = getenv("HICOM_GEMM_TC"); on = (e && e[0] == '0') ? 0 : 1; }
   return on;
 }
 

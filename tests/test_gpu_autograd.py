@@ -306,3 +306,20 @@ def test_producer_head_gradients(dtype, built_library, autograd_on):
             assert O.rel_err(got, leaf[k].grad) <= 1e-3, k
         else:
             assert O.cosine(got, leaf[k].grad) >= 0.99, k
+
+
+def test_simt_cross_check_of_the_backward_gemms(built_library):
+    """HICOM_GEMM_TC=0 keeps every backward contraction on the SIMT GEMM (read once per process): run the layout tests
+    and two whole-step gradient checks in a child process."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("HICOM_GEMM_TC") == "0":
+        pytest.skip("already the SIMT configuration")
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, HICOM_GEMM_TC="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_autograd.py"), "-q", "-x", "-m", "gpu",
+                        "-p", "no:cacheprovider", "-k",
+                        "gemm_large_bf16_layouts or (training_step_gradients and bfloat16 and (coarse_27x27 or adaptkv))"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -82,7 +82,8 @@ def main():
         print(json.dumps(res[-1]), flush=True)
     with open(os.path.join(OUT, "autograd_bench.json"), "w") as f:
         f.write(json.dumps({"what": "forward+backward of the drop-in projector, width 3584, 16 frames per video, bf16, "
-                                    "first CUDA path (SIMT GEMMs in the backward)", "results": res}) + "\n")
+                                    "backward GEMMs on " + ("the SIMT kernel" if os.environ.get("HICOM_GEMM_TC") == "0"
+                                                               else "tcgen05 (large bf16) / SIMT"), "results": res}) + "\n")
 
 
 if __name__ == "__main__":
