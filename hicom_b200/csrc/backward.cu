@@ -404,7 +404,7 @@ static int try_gemm_tc(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, in
   if (!gemm_tc_enabled() || a_dtype != HICOM_BF16 || b_dtype != HICOM_BF16) return -1;
   if (M < 2 || N < 2 || K < 16 || (long long)M * N * K < (1ll << 24)) return -1;  // small: launch-bound either way
   const long long nb = (long long)nb1 * nb2;
-  if (nb > 64) return -1;
+  if (nb > 4096) return -1;  // one launch per batch entry (per video): beyond this the batched SIMT grid is the better deal
   const bool a_kmajor = sAk == 1, a_mmajor = sAm == 1 && !a_kmajor;
   const bool b_kmajor = sBk == 1, b_nmajor = sBn == 1 && !b_kmajor;
   int mode;  // 0 NT, 1 NN, 2 TN
