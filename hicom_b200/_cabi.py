@@ -39,6 +39,7 @@ PROTOTYPES = {
     "hicom_global_value_proj": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "hicom_gemm": (c_int, [c_void_p] + [c_int64] * 4 + [c_void_p] + [c_int64] * 4 + [c_void_p] + [c_int64] * 3 +
                    [c_int] * 5 + [c_float] + [c_int] * 3 + [c_void_p]),
+    "hicom_colsum": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "hicom_act_backward": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "hicom_softmax_backward": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_int, c_void_p]),
     "hicom_local_attend_backward": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_float, c_int, c_int, c_void_p]),

@@ -62,7 +62,10 @@ def _gemm_to(A: torch.Tensor, B: torch.Tensor, want: torch.dtype, alpha: float =
 
 
 def _colsum_to(x2: torch.Tensor, want: torch.dtype) -> torch.Tensor:
-    """Column sums of (M, N) as 1ᵀ·x on hicom_gemm — bias gradients."""
+    """Column sums of (M, N) — bias gradients (db = 1ᵀ·dpre): hicom_colsum, or 1ᵀ·x on hicom_gemm for odd shapes."""
+    if ops.colsum_supported(x2):
+        s = ops.colsum(x2)
+        return s if s.dtype == want else s.to(want)
     ones = torch.ones((1, x2.shape[0]), dtype=x2.dtype, device=x2.device)
     return _gemm_to(ones, x2, want).reshape(-1)
 

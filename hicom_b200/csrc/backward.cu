@@ -43,6 +43,39 @@ __global__ void __launch_bounds__(256) act_backward_kernel(const TP* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// out[n] += sum_m x[m, n]  (bias gradients, db = 1ᵀ·dpre).  Block = 32 column groups of 4 x 8 row lanes; rows strided
+// over gridDim.y; the 8 row lanes are folded in shared memory, blocks of one column range meet in fp32 atomics.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out,
+                                                     long long M, int N) {
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cx) * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+    for (long long r = (long long)blockIdx.y * 8 + ry; r < M; r += (long long)gridDim.y * 8) {
+      float v[4];
+      Vec4<T>::load(x + r * ld + col, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] += v[i];
+    }
+  }
+  __shared__ float red[8][32][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) red[ry][cx][i] = acc[i];
+  __syncthreads();
+  if (ry == 0 && col < N) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][cx][i];
+      atomicAdd(out + col + i, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // dS[b,n,j] = exp(S[b,n,j] - lse[b,j]) * (dP[b,n,j] - delta[b,j])
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -471,6 +504,21 @@ extern "C" int hicom_gemm(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1,
   }
   set_error("gemm: dtype combination A=%d B=%d C=%d is not built", a_dtype, b_dtype, c_dtype);
   return 1;
+}
+
+extern "C" int hicom_colsum(const void* x, int64_t ld, float* out, int64_t M, int N, int dtype, void* stream) {
+  HICOM_REQUIRE(x && out, "colsum: null pointer");
+  HICOM_REQUIRE(M >= 0 && N > 0 && N % 4 == 0 && ld >= N && ld % 4 == 0, "colsum: needs N and ld to be multiples of 4");
+  HICOM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "colsum: x must be 16-byte aligned");
+  if (M == 0) return 0;
+  long long gy = (M + 63) / 64;  // >= 8 rows per row lane
+  if (gy > 64) gy = 64;
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)gy);
+  cudaStream_t s = as_stream(stream);
+  if (dtype == HICOM_F32) colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, ld, out, M, N);
+  else if (dtype == HICOM_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, ld, out, M, N);
+  else { set_error("colsum: unknown dtype code %d", dtype); return 1; }
+  return check_launch("colsum_kernel");
 }
 
 extern "C" int hicom_act_backward(const void* pre, const void* dy, void* dx, int64_t n, int act, int pre_dtype,

@@ -457,6 +457,24 @@ def _impl_gemm(A: Tensor, B: Tensor, out: Optional[Tensor], out_fp32: bool, alph
     return ret
 
 
+def colsum_supported(x2: Tensor) -> bool:
+    return (x2.dim() == 2 and x2.shape[1] % 4 == 0 and x2.stride(1) == 1 and x2.stride(0) % 4 == 0
+            and x2.stride(0) >= x2.shape[1] and x2.data_ptr() % 16 == 0 and x2.dtype in _DT)
+
+
+def _impl_colsum(x2: Tensor) -> Tensor:
+    """Column sums of (M, N) -> fp32 (N) — bias gradients (db = 1ᵀ·dpre)."""
+    dev = _need_cuda(x2)
+    if not colsum_supported(x2):
+        raise ValueError("colsum: needs a 2-D row-major view with N and the row pitch multiples of 4, 16-byte aligned")
+    M, N = x2.shape
+    out = torch.zeros((N,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_colsum(_ptr(x2), x2.stride(0), _ptr(out), M, N, _dt(x2), _stream(dev))
+    _cabi.check(rc, "hicom_colsum")
+    return out
+
+
 def _impl_act_backward(pre: Tensor, dy: Tensor, act: int) -> Tensor:
     """dy * act'(pre) — backward of the GELU between the layers of build_mlp (projector.py:310)."""
     dev = _need_cuda(pre, dy)
@@ -709,7 +727,7 @@ softmax_merge = _wrap("softmax_merge", _impl_softmax_merge, (), lambda *a: "soft
 softmax_reduce = _wrap("softmax_reduce", _impl_softmax_reduce, (), lambda *a: "softmax_reduce")
 global_value_proj = _wrap("global_value_proj", _impl_global_value_proj, (), lambda *a: "global_value_proj")
 # backward blocks are called directly (``gemm`` writes into strided views, which torch.library cannot describe)
-gemm, act_backward, softmax_backward = _impl_gemm, _impl_act_backward, _impl_softmax_backward
+gemm, act_backward, softmax_backward, colsum = _impl_gemm, _impl_act_backward, _impl_softmax_backward, _impl_colsum
 local_attend_backward = _impl_local_attend_backward
 film_layernorm_backward = _impl_film_layernorm_backward
 mix_layernorm_backward = _impl_mix_layernorm_backward

@@ -130,6 +130,22 @@ def _require_no_grad(module, *tensors):
             "hicom_b200/autograd.py, has been switched off with HICOM_AUTOGRAD=0 / autograd.enable(False))")
 
 
+def splice_rows(out: torch.Tensor, tokens: torch.Tensor, offsets) -> torch.Tensor:
+    """``out[b, offsets[b] : offsets[b] + n] = tokens[b]`` for every sample with ONE indexed copy — the token splice of
+    hicom_arch.py:283-373 when every sample's visual tokens start at a different position of the padded embedding
+    buffer.  ``out`` (B, L, Dh), ``tokens`` (B, n, Dh), ``offsets`` B ints (list or tensor).  Returns ``out``."""
+    B, n, Dh = tokens.shape
+    off = torch.as_tensor(offsets, dtype=torch.long, device=out.device).reshape(-1)
+    if out.dim() != 3 or out.shape[0] != B or out.shape[2] != Dh or off.numel() != B:
+        raise ValueError(f"splice_rows: out {tuple(out.shape)} / offsets {off.numel()} do not match tokens {tuple(tokens.shape)}")
+    host = off if off.device.type == "cpu" else None
+    if host is not None and B > 0 and (int(host.min()) < 0 or int(host.max()) + n > out.shape[1]):
+        raise ValueError(f"splice_rows: rows out of range (L={out.shape[1]}, n={n}, offsets {host.tolist()})")
+    rows = (torch.arange(B, device=out.device) * out.shape[1] + off).unsqueeze(1) + torch.arange(n, device=out.device)
+    out.view(B * out.shape[1], Dh).index_copy_(0, rows.reshape(-1), tokens.reshape(B * n, Dh).to(out.dtype))
+    return out
+
+
 def _grad_needed(module, *tensors) -> bool:
     if not torch.is_grad_enabled():
         return False
@@ -595,10 +611,21 @@ class HIComProjector(nn.Module):
         global compressor (the any-res base image only feeds the local one, projector.py:680-684).
         ``out`` (B, L, Dh), contiguous: write the tokens straight into rows ``out_row_offset ..`` of every sample of a
         caller-owned buffer — the padded ``inputs_embeds`` of hicom_arch.py:283-373 — instead of a new tensor; the
-        readout epilogues store there directly, the returned tensor is the view ``out[:, off:off+n_tokens]``."""
+        readout epilogues store there directly, the returned tensor is the view ``out[:, off:off+n_tokens]``.
+        ``out_row_offset`` may also be one offset PER SAMPLE (list / tensor of B ints: the visual tokens follow prompts
+        of different lengths): the tokens are then produced as one block and spliced with one indexed copy
+        (``splice_rows``); the block is returned."""
         X = frames_feature
         if X.dim() != 5:
             raise ValueError(f"forward_batched expects (B,T,H,W,d), got {tuple(X.shape)}")
+        if out is not None and not isinstance(out_row_offset, int):
+            if out.dim() != 3 or not out.is_contiguous():
+                raise ValueError("out must be a contiguous (B, L, Dh) tensor")
+            tokens = self.forward_batched(X, frames_embed, guide_embed, modal, image_newline, is_anyres=is_anyres,
+                                          base=base, with_global=with_global)
+            if tokens is not None:
+                splice_rows(out, tokens.detach() if not torch.is_grad_enabled() else tokens, out_row_offset)
+            return tokens
         if _grad_needed(self, X, frames_embed, guide_embed, image_newline, base):
             from . import autograd as _ag
             if not _ag.ENABLED:

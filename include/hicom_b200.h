@@ -207,6 +207,10 @@ int hicom_gemm(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, int64_t sA
                int64_t sBn, int64_t sBb1, int64_t sBb2, void* C, int64_t ldc, int64_t sCb1, int64_t sCb2, int M, int N,
                int K, int nb1, int nb2, float alpha, int a_dtype, int b_dtype, int c_dtype, void* stream);
 
+/* hicom_colsum: out[n] += sum_m x[m,n] — bias gradients (db = 1ᵀ·dpre of nn.Linear, projector.py:307-312).  x (M,N) in
+ *   dtype with row pitch ld (N and ld multiples of 4, x 16-byte aligned); out (N) fp32, ACCUMULATED into (zero it first). */
+int hicom_colsum(const void* x, int64_t ld, float* out, int64_t M, int N, int dtype, void* stream);
+
 /* hicom_act_backward: dx[i] = dy[i] * act'(pre[i]) for HICOM_ACT_* (exact erf GELU of projector.py:310, tanh GELU of the
  *   SigLIP head); pre in pre_dtype (fp32 pre-activations recomputed by hicom_linear), dy/dx in dtype; in place allowed. */
 int hicom_act_backward(const void* pre, const void* dy, void* dx, int64_t n, int act, int pre_dtype, int dtype,

@@ -38,6 +38,11 @@ def gemm(A, B, out, out_fp32, alpha):
     return out
 
 
+def colsum(x2):
+    calls.append(("colsum",))
+    return x2.float().sum(0)
+
+
 def act_backward(pre, dy, act):
     calls.append(("act_backward", act))
     x = pre.detach().float().requires_grad_(True)
@@ -202,7 +207,7 @@ def _need_cuda(*ts):
     return None
 
 
-ALL = ["linear", "gemm", "act_backward", "softmax_backward", "global_fold_query", "posadd", "global_attend_partial",
+ALL = ["linear", "gemm", "colsum", "act_backward", "softmax_backward", "global_fold_query", "posadd", "global_attend_partial",
        "softmax_reduce", "softmax_merge", "global_value_proj", "grid_pool", "film_layernorm", "film_layernorm_backward",
        "local_attend", "local_attend_backward", "layernorm", "mix_layernorm", "mix_layernorm_backward", "add_layernorm",
        "guide_attend", "_need_cuda"]

@@ -128,3 +128,24 @@ def test_default_splits_follow_cta_waves():
         assert 1 <= s <= max(1, N // 512)
         cost = lambda k: -(-(9 * B * k) // 148) / k
         assert cost(s) <= 1.05 * min(cost(k) for k in range(1, max(1, min(64, N // 512)) + 1))
+
+
+def test_splice_rows_per_sample_offsets():
+    """Token splice with one offset per sample (hicom_arch.py:283-373: visual tokens follow prompts of different lengths)."""
+    from hicom_b200.projector import splice_rows
+    g = torch.Generator().manual_seed(0)
+    out = torch.zeros(3, 12, 8)
+    tokens = torch.randn(3, 4, 8, generator=g)
+    ret = splice_rows(out, tokens, [0, 8, 3])
+    assert ret is out
+    for b, o in enumerate([0, 8, 3]):
+        assert torch.equal(out[b, o:o + 4], tokens[b])
+        mask = torch.ones(12, dtype=torch.bool); mask[o:o + 4] = False
+        assert float(out[b, mask].abs().max()) == 0.0
+    out2 = torch.zeros(3, 12, 8, dtype=torch.bfloat16)
+    splice_rows(out2, tokens, torch.tensor([1, 2, 3]))
+    assert torch.equal(out2[1, 2:6], tokens[1].bfloat16())
+    with pytest.raises(ValueError, match="out of range"):
+        splice_rows(out, tokens, [0, 9, 3])
+    with pytest.raises(ValueError, match="do not match"):
+        splice_rows(out, tokens, [0, 1])

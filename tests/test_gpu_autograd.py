@@ -83,6 +83,33 @@ def test_act_backward(act, dtype, built_library):
     assert O.rel_err(got, want) <= (2e-6 if dtype == torch.float32 else 4e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,pitch", [(2592, 3584, 3584), (5, 8, 8), (1000, 1152, 2304), (70000, 128, 128)])
+def test_colsum(M, N, pitch, dtype, built_library):
+    from hicom_b200 import ops
+    buf = _r(M, pitch, seed=M + N, std=0.5).to(dtype)
+    got = ops.colsum(buf.cuda()[:, :N]).cpu()
+    want = buf[:, :N].double().sum(0).float()
+    assert got.dtype == torch.float32 and O.rel_err(got, want) <= 1e-5
+    assert not ops.colsum_supported(buf.cuda()[:, 1:N - 1])
+
+
+def test_forward_batched_splices_at_per_sample_offsets(built_library):
+    """Token splice with one row offset per sample (hicom_arch.py:283-373) == the one-block result, copied once."""
+    case = CASES_BY_NAME["coarse_T4"]
+    sd, X, E, g, _ = materialise(case)
+    m = _train_module(case, sd).eval()
+    Xb, Eb, gb = torch.stack([X, X.flip(0)]).cuda(), torch.stack([E, E.flip(0)]).cuda(), torch.stack([g, -g]).cuda()
+    with torch.no_grad():
+        block = m.forward_batched(Xb, Eb, gb, "video")
+        n = block.shape[1]
+        buf = torch.zeros(2, n + 9, block.shape[2], device="cuda")
+        ret = m.forward_batched(Xb, Eb, gb, "video", out=buf, out_row_offset=[5, 0])
+    assert O.rel_err(ret.cpu(), block.cpu()) <= 1e-5          # two runs: fp32 atomics may reorder the last bit
+    assert torch.equal(buf[0, 5:5 + n], ret[0]) and torch.equal(buf[1, :n], ret[1])
+    assert float(buf[0, :5].abs().max()) == 0.0 and float(buf[1, n:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("out_bf16", [False, True])
 def test_softmax_backward(out_bf16, built_library):
     from hicom_b200 import ops
