@@ -83,3 +83,53 @@ def test_shard_arithmetic():
     m, l, o = torch.randn(2, 3, 4), torch.rand(2, 3, 4), torch.randn(2, 3, 4, 5)
     m2, l2, o2 = hd.unpack_partials(hd.pack_partials(m, l, o))
     assert torch.equal(m, m2) and torch.equal(l, l2) and torch.equal(o, o2)
+
+
+# ---- data-parallel training through the drop-in module (train.py launches one process per GPU with torchrun) ----------
+def _ddp_worker(rank, world, port, results):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cpu_ops
+    import hicom_b200
+    from hicom_b200 import autograd as ag, ops
+    from oracle.cases import CASES_BY_NAME, materialise
+    from util import cfg_for
+    for name in cpu_ops.ALL:  # torch-CPU stand-ins for the kernels (tests/cpu_ops.py): this test is about the plumbing
+        setattr(ops, name, getattr(cpu_ops, name))
+    ag.enable(True)
+    case = CASES_BY_NAME["coarse_T4"]
+    sd, X, E, g, _ = materialise(case)
+    m = hicom_b200.build_vision_projector(cfg_for(case))
+    m.load_state_dict(sd, strict=True)
+    # find_unused_parameters stays False: every trainable parameter must receive a gradient (k_proj.bias gets zeros)
+    ddp = torch.nn.parallel.DistributedDataParallel(m.train())
+    Xr, Er, gr = (X, E, g) if rank == 0 else (X.flip(0) * 0.9, E.flip(0) * 0.9, -g)
+    out = ddp(Xr, Er, gr, "video")
+    out.square().mean().backward()
+    grads = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+    ref = grads.clone()
+    dist.broadcast(ref, 0)
+    same = float((grads - ref).abs().max())
+    missing = [k for k, p in m.named_parameters() if p.grad is None]
+    if rank == 0:
+        results.put((same, missing, float(grads.abs().sum())))
+    dist.destroy_process_group()
+
+
+def test_ddp_training_world2():
+    """DistributedDataParallel over the training path, two ranks with different videos: the reducer sees a gradient for
+    every parameter (no find_unused_parameters) and both ranks end with the same averaged gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    same, missing, total = q.get()
+    assert same == 0.0 and missing == [] and total > 0.0
