@@ -98,3 +98,86 @@ def test_live_reference_clip_scale(use_guide):
         want = m.eval()(X, E, g, case.modal, nl)
         got = orc.forward(X, E, g, case.modal, nl)
     assert O.rel_err(got, want) <= 2e-6
+
+
+def _random_type_strings(n, seed=0):
+    """Seeded samples of the type-string mini-language (projector.py:231-304), incl. junk the reference ignores."""
+    import random
+    rng = random.Random(seed)
+    modes = ["direct", "coarse", "fine", "off"]
+    out = []
+    for _ in range(n):
+        parts = []
+        if rng.random() < 0.8:
+            loc = "local" + rng.choice(["43", "22", "412", "13", "23", "41"])
+            if rng.random() < 0.5:
+                loc += "_adapt" + "".join(rng.sample("qkvg", rng.randint(0, 4))) + rng.choice(["", "x", "_", "qz"])
+            if rng.random() < 0.3:
+                loc += "guide" + rng.choice(modes)
+            parts.append(loc)
+        if rng.random() < 0.8 or not parts:
+            glo = "global" + rng.choice(["32", "8", "16", "1", "64"])
+            if rng.random() < 0.4:
+                glo += "_adaptg"
+            if rng.random() < 0.3:
+                glo += "guide" + rng.choice(modes)
+            parts.append(glo)
+        if rng.random() < 0.3:
+            rng.shuffle(parts)
+        s = "_".join(parts) + rng.choice(["", "", "_coarse", "_fine", "_v2", "_anyres"])
+        out.append((s, rng.choice([None, "off", "direct", "coarse", "fine"])))
+    return out
+
+
+@pytest.mark.parametrize("ptype,use_guide", _random_type_strings(48))
+def test_factory_grammar_fuzz_against_reference(ptype, use_guide):
+    """The product factory builds the same modules (parameter names and shapes, guide modes, kernel sizes) as the
+    reference's build_vision_projector for random type strings — or fails with the same exception type."""
+    import hicom_b200
+    from util import Cfg
+    ref = load_reference()
+    mk = lambda: Cfg(mm_projector_type=ptype, use_guide=use_guide, hidden_size=64, max_num_frames=2)
+    try:
+        want = ref.build_vision_projector(mk())
+    except Exception as exc:  # noqa: BLE001 — whatever the reference raises is the contract
+        with pytest.raises(type(exc)):
+            hicom_b200.build_vision_projector(mk())
+        return
+    got = hicom_b200.build_vision_projector(mk())
+    assert {k: tuple(v.shape) for k, v in got.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in want.state_dict().items()}
+    for name in ("local_compressor", "global_compressor"):
+        a, b = getattr(got, name), getattr(want, name)
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.use_guide == b.use_guide
+    if got.local_compressor is not None:
+        assert (got.local_compressor.temporal_kernel_size, got.local_compressor.spatial_kernel_size) == \
+               (want.local_compressor.temporal_kernel_size, want.local_compressor.spatial_kernel_size)
+    if got.global_compressor is not None:
+        assert got.global_compressor.query.shape == want.global_compressor.query.shape
+
+
+@pytest.mark.parametrize("name", ["none_T8", "direct_T8", "coarse_T8", "fine_T8", "adaptkv_coarse_T8", "adaptqkvg_coarse_T4"])
+def test_oracle_autograd_equals_reference_autograd(name):
+    """The training-path tests compare the product's gradients with PyTorch autograd through the ORACLE; this pins that
+    yardstick to autograd through the reference module itself (what train.py:704-738 actually optimises)."""
+    from oracle.cases import CASES_BY_NAME
+    ref = load_reference()
+    case = CASES_BY_NAME[name]
+    sd, X, E, g, nl = materialise(case)
+    m = ref.build_vision_projector(cfg_for(case))
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    out = m(X, E, g, case.modal, nl)
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    (out * probe).sum().backward()
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    got = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf).forward(X, E, g, case.modal, nl)
+    (got * probe).sum().backward()
+    for k, p in m.named_parameters():
+        a, b = leaf[k].grad, p.grad
+        if b is None or float(b.abs().max()) <= 1e-6:
+            assert a is None or float(a.abs().max()) <= 1e-6, k
+        else:
+            assert O.rel_err(a, b) <= 1e-5, (k, O.rel_err(a, b))
