@@ -19,12 +19,13 @@ def _key(feat, embed, guide, modal):
             None if guide is None else tuple(guide.shape))
 
 
-@torch.no_grad()
 def compress_samples(projector, frames_features: Sequence, frames_embeds: Optional[Sequence],
                      guide_embeds: Optional[Sequence], modalities: Sequence[str], image_newline=None,
                      min_group: int = 2) -> List[torch.Tensor]:
     """``frames_features[i]`` is a (T,H,W,d) tensor or an any-res dict, ``frames_embeds[i]`` / ``guide_embeds[i]`` the
-    matching embeds (the sequences themselves may be None, hicom_arch.py:169-170).  Returns ``[tokens_i]``."""
+    matching embeds (the sequences themselves may be None, hicom_arch.py:169-170).  Returns ``[tokens_i]``.
+    Grad mode is the caller's: under ``torch.no_grad()`` the inference kernels run, with grad enabled (the same loop is
+    the forward of a training step, train.py) the tokens carry an autograd graph (``hicom_b200/autograd.py``)."""
     n = len(frames_features)
     out: List[Optional[torch.Tensor]] = [None] * n
     groups = defaultdict(list)

@@ -66,7 +66,9 @@ def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, 
     """One long video cut by frames: ``frames_feature`` (B,Ts,H,W,d) is THIS rank's block starting at global
     frame ``t0``.  Returns (local tokens of this block (B, Nw_block, Dh) | None, global tokens (B,Q,Dh) | None).
     Concatenating the local blocks in rank order and appending the global tokens reproduces
-    ``forward_batched`` on the whole video (newline layouts other than flat/no_token are not sharded)."""
+    ``forward_batched`` on the whole video (newline layouts other than flat/no_token are not sharded).
+    Inference only (decorated ``no_grad``): the exchange of partials between ranks is not differentiated — training
+    shards by video, where every rank runs the ordinary ``forward`` / ``forward_batched`` under DDP."""
     X = frames_feature
     B, Ts, H, W, d = X.shape
     lc, gc = projector.local_compressor, projector.global_compressor

@@ -184,3 +184,39 @@ def test_producer_head_gradients(monkeypatch):
     (SH.image_embeds(leaf, h, side=4) * probe).sum().backward()
     for k, p in m.named_parameters():
         assert O.rel_err(p.grad, leaf[k].grad) <= 2e-4, k
+
+
+def test_batched_caller_and_anyres_dict_under_autograd(monkeypatch):
+    """compress_samples (the replacement of the loop of hicom_arch.py:167-178, which is also the forward of a training
+    step) keeps the autograd graph: a mixed batch — grouped videos, an odd-length video, an any-res image dict with the
+    newline layouts — gives the gradients of the reference-style per-sample loop through the oracle."""
+    from hicom_b200 import autograd as ag
+    from hicom_b200.caller import compress_samples
+    case = CASES_BY_NAME["image_T1_newline"]
+    sd, _, _, _, nl = materialise(case)
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, sd)
+    mk = lambda T, s: O.synth_inputs(T, 6, 6, "vec", seed=s)
+    v = [mk(8, 1), mk(8, 2), mk(4, 3)]
+    gen = torch.Generator().manual_seed(9)
+    rnd = lambda *s: 0.5 * torch.randn(*s, generator=gen)
+    img, img_e = {"base": rnd(6, 6, 1152), "patch": rnd(12, 6, 1152)}, {"base": rnd(6, 6, 1152), "patch": rnd(12, 6, 1152)}
+    feats, embeds = [v[0][0], img, v[1][0], v[2][0]], [v[0][1], img_e, v[1][1], v[2][1]]
+    guides, modal = [v[0][2], v[1][2], v[1][2], v[2][2]], ["video", "image", "video", "video"]
+    nl_leaf = nl.clone().requires_grad_(True)
+    got = compress_samples(m, feats, embeds, guides, modal, nl_leaf)
+    probes = [torch.randn(t.shape, generator=torch.Generator().manual_seed(i)) for i, t in enumerate(got)]
+    sum((t * p).sum() for t, p in zip(got, probes)).backward()
+    leaf = {k: w.clone().requires_grad_(True) for k, w in sd.items()}
+    nl2 = nl.clone().requires_grad_(True)
+    orc = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf)
+    want = [orc.forward(f, e, g, md, nl2) for f, e, g, md in zip(feats, embeds, guides, modal)]
+    sum((t * p).sum() for t, p in zip(want, probes)).backward()
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and O.rel_err(a.detach(), b.detach()) <= 2e-5
+    for k, p in m.named_parameters():
+        if float(leaf[k].grad.abs().max()) <= 1e-6:
+            continue
+        assert O.rel_err(p.grad, leaf[k].grad) <= 2e-4, k
+    assert O.rel_err(nl_leaf.grad, nl2.grad) <= 1e-5

@@ -221,8 +221,8 @@ def test_batched_caller_matches_per_sample_loop(built_library):
     guides = [v[0][2], v[1][2], v[1][2], v[2][2], v[3][2]]
     modal = ["video", "image", "video", "video", "video"]
     nl = nl.cuda()
-    got = compress_samples(m, feats, embeds, guides, modal, nl)
     with torch.no_grad():
+        got = compress_samples(m, feats, embeds, guides, modal, nl)
         want = [m(f, e, g, md, nl) for f, e, g, md in zip(feats, embeds, guides, modal)]
     assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in want]
     for a, b in zip(got, want):
