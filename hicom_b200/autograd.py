@@ -103,8 +103,15 @@ class LinearFn(Function):
         return dA, dW, db, dR, None, None
 
 
+def _as(p, ref: torch.Tensor):
+    """Parameter ``p`` in the dtype of the activations ``ref``.  fp32 master weights under bf16 activations (HF Trainer
+    with ``--bf16`` and no DeepSpeed bf16 engine: ``torch.autocast`` semantics) are cast per use, as autocast does for
+    ``F.linear``; the cast is an autograd op, so the gradient arrives in the parameter's own dtype."""
+    return p if (p is None or p.dtype == ref.dtype) else p.to(ref.dtype)
+
+
 def linear(A, W, bias=None, residual=None, act=ops.ACT_NONE, out_fp32=False):
-    return LinearFn.apply(A, W, bias, residual, act, out_fp32)
+    return LinearFn.apply(A, _as(W, A), _as(bias, A), _as(residual, A), act, out_fp32)
 
 
 def mlp(seq: nn.Sequential, x: torch.Tensor, out_fp32: bool = False):
@@ -403,7 +410,7 @@ def _mix(x, proj, norm, alpha):
     if not _is_param(alpha):
         return x
     y = mlp(proj, x) if isinstance(proj, nn.Sequential) else linear(x, proj.weight, proj.bias)
-    return MixLayerNormFn.apply(x, y, norm.weight, norm.bias, alpha)
+    return MixLayerNormFn.apply(x, y, _as(norm.weight, x), _as(norm.bias, x), alpha)
 
 
 def _prepared_guide(inj, G):
@@ -424,14 +431,15 @@ def _inject(inj, mode, rows, G):
         return g.unsqueeze(1).expand(B, n, d)                              # autograd sums over the rows
     if mode == "coarse":                                                   # :369-372
         film = mlp(inj.coarse_proj, g, out_fp32=True)
-        return FilmLayerNormFn.apply(rows.contiguous(), film, inj.coarse_norm.weight, inj.coarse_norm.bias, n)
+        return FilmLayerNormFn.apply(rows.contiguous(), film, _as(inj.coarse_norm.weight, rows),
+                                     _as(inj.coarse_norm.bias, rows), n)
     mha = inj.fine_proj                                                    # fine, :374-397
     q = linear(rows, mha.q_proj.weight, mha.q_proj.bias)
     k = linear(g, mha.k_proj.weight, mha.k_proj.bias)
     v = linear(g, mha.v_proj.weight, mha.v_proj.bias)
     a = GuideAttendFn.apply(q, k, v, mha.num_heads, mha.scale)
     a = linear(a, mha.out_proj.weight, mha.out_proj.bias)
-    return AddLayerNormFn.apply(rows.contiguous(), a, inj.fine_norm.weight, inj.fine_norm.bias)
+    return AddLayerNormFn.apply(rows.contiguous(), a, _as(inj.fine_norm.weight, rows), _as(inj.fine_norm.bias, rows))
 
 
 def _local_tokens(proj, X, E, G, modal, image_newline, is_anyres):
@@ -491,9 +499,11 @@ def _global_tokens(proj, X, G, splits=None, t0=0):
         Qg = _inject(gc.guide_injector, gc.use_guide, rows, G)                      # projector.py:642
     nrows = Qg.shape[1]
     q = linear(Qg, attn.q_proj.weight, attn.q_proj.bias)                            # projector.py:180
-    qfold = FoldQueryFn.apply(q, attn.k_proj.weight, attn.k_proj.bias, attn.num_heads, attn.scale)  # :181 + :197
+    qfold = FoldQueryFn.apply(q, _as(attn.k_proj.weight, q), _as(attn.k_proj.bias, q), attn.num_heads,
+                              attn.scale)                                           # :181 + :197 folded
     pooled = GlobalPoolFn.apply(X, qfold, gc, t0, splits)                           # :197-215
-    a = ValueProjFn.apply(pooled, attn.v_proj.weight, attn.v_proj.bias, nrows, attn.num_heads)  # :182, :223-224
+    a = ValueProjFn.apply(pooled, _as(attn.v_proj.weight, pooled), _as(attn.v_proj.bias, pooled), nrows,
+                          attn.num_heads)                                           # :182, :223-224
     x = linear(a, attn.out_proj.weight, attn.out_proj.bias, Qg)                     # :226 + residual of :646
     tokens = mlp(gc.readout, x)                                                     # (B, nrows, Dh)
     if nrows != nq:

@@ -82,7 +82,7 @@ class SiglipHeadEmbed(nn.Module):
             if not ag.ENABLED:
                 _require_no_grad(self, h)
             ops._need_cuda(h)
-            y = ag.LayerNormFn.apply(h, self.layernorm.weight, self.layernorm.bias)
+            y = ag.LayerNormFn.apply(h, ag._as(self.layernorm.weight, h), ag._as(self.layernorm.bias, h))
             y = ag.linear(y, self.mlp.fc1.weight, self.mlp.fc1.bias, None, self.act)
             y = ag.linear(y, self.mlp.fc2.weight, self.mlp.fc2.bias, h)
             return y.view(b, side, side, d)

@@ -20,8 +20,15 @@ def _act(x, act):
     return F.gelu(x) if act == ACT_GELU else (F.gelu(x, approximate="tanh") if act == ACT_GELU_TANH else x)
 
 
+def _same_dtype(*ts):
+    """The kernels take ONE storage dtype per call (ops._check_linear & co. raise otherwise): the stand-ins insist too."""
+    dts = {t.dtype for t in ts if t is not None}
+    assert len(dts) <= 1, f"mixed dtypes reach a kernel: {dts}"
+
+
 def linear(A, W, bias, residual, act, out_fp32, impl):
     calls.append(("linear", tuple(A.shape), tuple(W.shape), act))
+    _same_dtype(A, W, bias, residual)
     y = _act(F.linear(A.float(), W.float(), None if bias is None else bias.float()), act)
     if residual is not None:
         y = y + residual.float().reshape(y.shape)
@@ -58,6 +65,7 @@ def softmax_backward(S, dP, lse, delta, out_bf16):
 
 
 def global_fold_query(q, Wk, heads, alpha):
+    _same_dtype(q, Wk)
     B, Q, d = q.shape
     hd = d // heads
     qf = torch.einsum("bihc,hck->bhik", q.float().view(B, Q, heads, hd), Wk.float().view(heads, hd, d)) * alpha
@@ -97,6 +105,7 @@ def softmax_merge(m, l, o, out_bf16):
 
 
 def global_value_proj(pooled, Wv, bv, Q, heads):
+    _same_dtype(pooled, Wv, bv)
     B, J, d = pooled.shape
     hd = d // heads
     a = torch.einsum("bhik,hck->bihc", pooled.float().view(B, heads, Q, d), Wv.float().view(heads, hd, d))
@@ -114,6 +123,8 @@ def grid_pool(X, kt, ks):
 
 
 def film_layernorm(x, film, ln_w, ln_b, rows_per_group):
+    _same_dtype(x, ln_w, ln_b)
+    assert film.dtype == torch.float32
     d = x.shape[-1]
     rows = x.reshape(-1, d).float()
     g = torch.arange(rows.shape[0]) // rows_per_group
@@ -170,6 +181,7 @@ def local_attend_backward(K, V, Q, dO, kt, ks, logit_scale, k_l2norm, need_q, ne
 
 
 def mix_layernorm(x, y, ln_w, ln_b, alpha):
+    _same_dtype(x, y, ln_w, ln_b, alpha)
     a = alpha.float()
     ln = F.layer_norm(y.float(), (y.shape[-1],), ln_w.float(), ln_b.float(), 1e-6)
     return ((1 - a) * x.float() + a * ln).to(x.dtype)
@@ -185,10 +197,12 @@ def mix_layernorm_backward(x, y, ln_w, ln_b, alpha, dout, need_dx):
 
 
 def add_layernorm(a, b, ln_w, ln_b):
+    _same_dtype(a, b, ln_w, ln_b)
     return F.layer_norm(a.float() + b.float(), (a.shape[-1],), ln_w.float(), ln_b.float(), 1e-6).to(a.dtype)
 
 
 def guide_attend(q, k, v, heads, scale):
+    _same_dtype(q, k, v)
     B, n, d = q.shape
     hd = d // heads
     sp = lambda t: t.float().view(B, t.shape[1], heads, hd).transpose(1, 2)
@@ -197,6 +211,7 @@ def guide_attend(q, k, v, heads, scale):
 
 
 def layernorm(x, w, b):
+    _same_dtype(x, w, b)
     return F.layer_norm(x.float(), (x.shape[-1],), w.float(), b.float(), 1e-6).to(x.dtype)
 
 

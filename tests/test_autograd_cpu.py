@@ -220,3 +220,37 @@ def test_batched_caller_and_anyres_dict_under_autograd(monkeypatch):
             continue
         assert O.rel_err(p.grad, leaf[k].grad) <= 2e-4, k
     assert O.rel_err(nl_leaf.grad, nl2.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["coarse_T4", "adaptqkvg_fine_T8"])
+def test_fp32_master_weights_with_bf16_activations(name, monkeypatch):
+    """HF Trainer with --bf16 and no DeepSpeed bf16 engine keeps fp32 master weights and feeds bf16 activations
+    (torch.autocast semantics): parameters are cast per use, every kernel still sees one dtype, gradients come back fp32."""
+    from hicom_b200 import autograd as ag
+    case = CASES_BY_NAME[name]
+    sd, X, E, g, _ = materialise(case)
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, sd)                                        # fp32 parameters
+    out = m(X.bfloat16(), E.bfloat16(), g.bfloat16(), case.modal)
+    assert out.dtype == torch.bfloat16
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    (out.float() * probe).sum().backward()
+    _, want, _ = _oracle_grads(case, sd, X.bfloat16().float(), E.bfloat16().float(), g.bfloat16().float(), None, probe)
+    for k, p in m.named_parameters():
+        assert p.grad is not None and p.grad.dtype == torch.float32, k
+        if float(want[k].abs().max()) > 1e-6:
+            assert O.cosine(p.grad, want[k]) >= 0.99, (k, O.cosine(p.grad, want[k]))
+
+
+def test_producer_fp32_master_weights_with_bf16_activations(monkeypatch):
+    from hicom_b200 import autograd as ag
+    from hicom_b200.producer import SiglipHeadEmbed
+    from oracle import siglip_head as SH
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = SiglipHeadEmbed(128, 256)
+    m.load_state_dict(SH.synth_head_state(3, hidden=128, inter=256), strict=True)
+    out = m(SH.synth_hidden(2, 16, seed=2, hidden=128).bfloat16())
+    out.float().sum().backward()
+    assert out.dtype == torch.bfloat16 and all(p.grad is not None and p.grad.dtype == torch.float32 for p in m.parameters())
