@@ -2,8 +2,9 @@
 
 Each op validates its tensors, allocates the result with torch's caching allocator, and passes raw
 device pointers plus the CURRENT CUDA stream to ``libhicom_b200.so`` — nothing here computes.  The ops
-are registered as ``torch.ops.hicom_b200.*`` (forward only: no autograd formula is registered, so a
-backward through them raises instead of silently dropping gradients).  There is no CPU or PyTorch
+are registered as ``torch.ops.hicom_b200.*`` (no autograd formula is registered on the ops themselves: gradients are
+the business of ``hicom_b200/autograd.py``, which wraps them in ``torch.autograd.Function``s and composes their
+backward from the backward blocks at the end of this file).  There is no CPU or PyTorch
 fallback: CPU tensors raise, a missing library raises.
 """
 from __future__ import annotations

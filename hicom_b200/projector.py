@@ -120,9 +120,9 @@ def _mix(x, proj, norm, alpha):
 
 
 def _require_no_grad(module, *tensors):
-    """The kernels are forward-only.  Fail loudly instead of silently returning tensors cut off from autograd
-    (SURVEY §8b): run under ``torch.no_grad()`` / ``torch.inference_mode()`` (as ``mm_infer`` does,
-    hicom/__init__.py:107) or freeze the projector."""
+    """With the training path (hicom_b200/autograd.py) switched off the kernels are forward-only: fail loudly instead
+    of silently returning tensors cut off from autograd — run under ``torch.no_grad()`` /
+    ``torch.inference_mode()`` (as ``mm_infer`` does, hicom/__init__.py:107) or freeze the projector."""
     if _grad_needed(module, *tensors):
         raise RuntimeError(
             "hicom_b200 compressor kernels are forward-only: call under torch.no_grad()/torch.inference_mode(), "
