@@ -254,3 +254,28 @@ def test_producer_fp32_master_weights_with_bf16_activations(monkeypatch):
     out = m(SH.synth_hidden(2, 16, seed=2, hidden=128).bfloat16())
     out.float().sum().backward()
     assert out.dtype == torch.bfloat16 and all(p.grad is not None and p.grad.dtype == torch.float32 for p in m.parameters())
+
+
+def test_partially_frozen_projector_skips_unneeded_backward(monkeypatch):
+    """Only the readouts trainable (everything else frozen): gradients reach exactly those parameters and the attention
+    backward blocks are never launched (needs_input_grad prunes them)."""
+    from hicom_b200 import autograd as ag
+    case = CASES_BY_NAME["coarse_T4"]
+    sd, X, E, g, _ = materialise(case)
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, sd)
+    for k, p in m.named_parameters():
+        p.requires_grad_(".readout." in k)
+    out = m(X, E, g, "video")
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    cpu_ops.calls.clear()
+    (out * probe).sum().backward()
+    _, want, _ = _oracle_grads(case, sd, X, E, g, None, probe)
+    for k, p in m.named_parameters():
+        if ".readout." in k:
+            assert O.rel_err(p.grad, want[k]) <= 2e-4, k
+        else:
+            assert p.grad is None, k
+    kinds = {c[0] for c in cpu_ops.calls}
+    assert not kinds & {"softmax_backward", "local_attend_backward", "film_layernorm_backward", "global_attend_partial"}
