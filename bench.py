@@ -178,6 +178,39 @@ def cpu_reference(hidden, T, videos, steps, warmup):
     return videos * T / sec, sec * 1e3, cores
 
 
+def cpu_next_rows(hidden, T):
+    """Host-core baselines beside the 'next' rows (bounded samples, fp32, all cores; the oracle as the reference port):
+    the producer on 8 frames and one training step (forward + backward through autograd) on one video."""
+    from oracle import hicom_oracle as O
+    from oracle import siglip_head as SH
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    out = {}
+    sd = SH.synth_head_state(0)
+    h = SH.synth_hidden(8, H * W, seed=1)
+    with torch.no_grad():
+        SH.image_embeds(sd, h, side=H)
+        t0 = time.perf_counter()
+        SH.image_embeds(sd, h, side=H)
+        sec = time.perf_counter() - t0
+    out["producer"] = {"value": 8 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
+                       "sample": "8 frames x 1 step, fp32, torch CPU restatement of encoder.py:284-286"}
+    leaf = {k: v.clone().requires_grad_(True) for k, v in O.synth_state_dict(PTYPE, USE_GUIDE, hidden, seed=0).items()}
+    orc = O.OracleProjector(PTYPE, USE_GUIDE, "flat", "one_token", leaf)
+    X, E, g = O.synth_inputs(T, H, W, O.guide_kind_for(USE_GUIDE), seed=1234)
+    secs = []
+    for it in range(2):
+        for v in leaf.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        orc.forward(X, E, g, "video").square().mean().backward()
+        secs.append(time.perf_counter() - t0)
+    out["train_step"] = {"value": T / secs[-1], "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"1 video of {T} frames, second of 2 steps, fp32, PyTorch autograd through the CPU "
+                                   "oracle port of projector.py:676-708"}
+    return out
+
+
 def gpu_eager_reference(hidden, T, videos, device, steps=5, warmup=2):
     """frames/s of the reference algorithm as plain torch ops in eager PyTorch/cuBLAS ON THE SAME B200 (bf16, per-video
     loop like hicom_arch.py:167-178) — BASELINE.md §5 'Baseline B', the existing-Blackwell bar.  Oracle code, reported
@@ -495,6 +528,13 @@ def run_ours(args):
             next_rows = measure_next_rows(hidden, T, B, device)
         except Exception as exc:  # reported, never fatal
             next_rows = {"unavailable": repr(exc)[:200]}
+        try:
+            cpu_rows = cpu_next_rows(hidden, min(T, 16))
+            for k, v in cpu_rows.items():
+                if isinstance(next_rows.get(k), dict):
+                    next_rows[k]["cpu_baseline"] = v
+        except Exception as exc:  # reported, never fatal
+            next_rows["cpu_baseline_unavailable"] = repr(exc)[:200]
 
     line = {
         "metric": "frames/s through the HICom compressor", "value": value, "unit": "frames/s",
