@@ -140,12 +140,14 @@ def test_bf16_parameter_gradients_have_parameter_dtype(monkeypatch):
         assert O.cosine(got, want[k]) >= 0.99, (k, O.cosine(got, want[k]))
 
 
-@pytest.mark.parametrize("name", ["direct_T8", "coarse_T8", "coarse_nondiv_7x8", "video_one_token"])
+@pytest.mark.parametrize("name", ["direct_T8", "coarse_T8", "coarse_nondiv_7x8", "video_one_token", "adaptkv_direct_T8",
+                                  "adaptqkvg_fine_T8"])
 def test_stage3_gradients_reach_frames_embed_and_guide(name, monkeypatch):
     """Stage 3 of the release recipe tunes vision_model_head and guide_encoder (train.py:717-726): frames_embed (the
     local keys) and the instruction embedding then require gradients."""
     from hicom_b200 import autograd as ag
-    case = CASES_BY_NAME[name]
+    case = (dataclasses.replace(CASES_BY_NAME["adaptkv_coarse_T8"], use_guide="direct")  # the second release recipe
+            if name == "adaptkv_direct_T8" else CASES_BY_NAME[name])
     sd, X, E, g, nl = materialise(case)
     cpu_ops.install(monkeypatch)
     monkeypatch.setattr(ag, "ENABLED", True)
@@ -162,7 +164,7 @@ def test_stage3_gradients_reach_frames_embed_and_guide(name, monkeypatch):
     for k, p in m.named_parameters():
         if leaf[k].grad is not None and float(leaf[k].grad.abs().max()) > 1e-6:
             assert O.rel_err(p.grad, leaf[k].grad) <= 2e-4, k
-    assert ("local_attend_backward", True, True, False) in cpu_ops.calls
+    assert any(c[0] == "local_attend_backward" and c[1] and c[2] for c in cpu_ops.calls)
 
 
 def test_producer_head_gradients(monkeypatch):
