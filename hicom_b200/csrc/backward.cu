@@ -452,6 +452,19 @@ static int try_gemm_tc(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, in
   if (nb > 1 && ((nb1 > 1 && (sAb1 % 8 || sBb1 % 8)) || (nb2 > 1 && (sAb2 % 8 || sBb2 % 8)))) return -1;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -1;
   const size_t csz = c_dtype == HICOM_F32 ? 4 : 2;
+  // EXPERIMENTAL, off unless HICOM_GEMM_TC_BATCH=1 (written without a GPU at hand, to be validated next): all batch
+  // entries of a TN problem in ONE launch through the kernel's batch axis (per-video dqfold = dSᵀ·x' has only 15
+  // tiles, so B launches leave most SMs idle)
+  static const bool batch_tn = [] { const char* e = getenv("HICOM_GEMM_TC_BATCH"); return e && e[0] == '1'; }();
+  if (batch_tn && mode == 2 && nb1 == 1 && nb2 > 1 && sCb2 % ldc == 0 && sAb2 > 0 && sBb2 > 0) {
+    TcLinearParams t{};
+    t.A = A; t.W = B; t.C = C; t.bias = nullptr; t.R = nullptr; t.ldr = 0;
+    t.lda = lda; t.ldw = ldw; t.ldc = ldc; t.M = M; t.N = N; t.K = K;
+    t.act = HICOM_ACT_NONE; t.out_dtype = c_dtype; t.rows_per_group = 1 << 30; t.group_stride_rows = 0;
+    t.alpha = 1.0f; t.w_is_kn = 1; t.a_is_km = 1;
+    t.batch = nb2; t.a_batch_stride = sAb2; t.w_batch_stride = sBb2; t.c_batch_rows = sCb2 / ldc;
+    return launch_tc_linear(t, stream);
+  }
   for (int b1 = 0; b1 < nb1; ++b1)
     for (int b2 = 0; b2 < nb2; ++b2) {
       TcLinearParams t{};

@@ -1070,13 +1070,14 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
                   "tcgen05 linear: (K,M) activations are only built for fp32 C, (K,N) weights, no activation");
     const int nb = q.batch > 0 ? q.batch : 1;
     if (make_map(&ta, q.A, q.M, kext, nb, q.lda, q.a_batch_stride, 64)) return 1;
-    if (make_map(&tb, q.W, q.N, kext, 1, q.ldw, 0, 64)) return 1;
+    const bool w_batched = q.w_batch_stride != 0;
+    if (make_map(&tb, q.W, q.N, kext, w_batched ? nb : 1, q.ldw, q.w_batch_stride, 64)) return 1;
     Params pm{};
     pm.M = q.M; pm.N = q.N; pm.K = q.K; pm.k_chunk = q.K; pm.b_box_rows = 64;
     pm.C = q.C; pm.ldc = q.ldc; pm.out_dtype = q.out_dtype; pm.act = q.act; pm.alpha = 1.f;
     pm.rows_per_group = 1 << 30; pm.group_stride_rows = 0;
     pm.z_slices = q.z_slices > 0 ? q.z_slices : 1; pm.z_a_k = q.z_a_k; pm.z_b_k = q.z_b_k; pm.z_c_rows = q.z_c_rows;
-    pm.c_batch_rows = q.c_batch_rows; pm.b_shared = 1; pm.guard = q.guard;
+    pm.c_batch_rows = q.c_batch_rows; pm.b_shared = w_batched ? 0 : 1; pm.guard = q.guard;
     if (q.N <= 128) {  // the probability marginals: 128-column tiles leave room for a six-stage ring (bandwidth-bound)
       dim3 gm128((q.N + 127) / 128, (q.M + BM - 1) / BM, nb * pm.z_slices);
       return launch<128, true, true, EPI_LINEAR, 2>(ta, tb, pm, gm128, stream);

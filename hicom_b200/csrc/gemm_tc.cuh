@@ -17,6 +17,7 @@ struct TcLinearParams {
   int accumulate = 0;       // C += result (fp32 C, w_is_kn, no activation)
   int a_is_km = 0;          // A stored (K, M) row-major per batch entry (with w_is_kn): batched, K-sliced, fp32 C
   int batch = 0; long long a_batch_stride = 0, c_batch_rows = 0;
+  long long w_batch_stride = 0;  // a_is_km only: != 0 -> W has a batch axis too (dqfold[b] = dS[b]ᵀ·x'[b]); 0 -> shared
   const int* guard = nullptr;  // device flag: the launch is a no-op unless *guard != 0
 };
 

@@ -350,3 +350,14 @@ def test_simt_cross_check_of_the_backward_gemms(built_library):
                         "gemm_large_bf16_layouts or (training_step_gradients and bfloat16 and (coarse_27x27 or adaptkv))"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HICOM_GEMM_TC_BATCH") != "1",
+                    reason="experimental single-launch batched TN GEMM: run with HICOM_GEMM_TC_BATCH=1 to validate it")
+def test_gemm_tn_batched_single_launch(built_library):
+    from hicom_b200 import ops
+    A = _r(5, 2916, 288, seed=1, std=0.5, dtype=torch.bfloat16).cuda()      # stored (K, M) per batch entry
+    Bm = _r(5, 2916, 1152, seed=2, std=0.05, dtype=torch.bfloat16).cuda()
+    got = ops.gemm(A.transpose(1, 2), Bm, None, True, 1.0)
+    want = torch.matmul(A.float().cpu().transpose(1, 2), Bm.float().cpu())
+    assert O.rel_err(got.cpu(), want) <= 2e-3
