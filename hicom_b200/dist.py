@@ -13,6 +13,8 @@ Two ways the path shards, one process per GPU (torch.distributed, NCCL over NVLi
 """
 from __future__ import annotations
 
+import contextlib
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -73,16 +75,25 @@ def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, 
     B, Ts, H, W, d = X.shape
     lc, gc = projector.local_compressor, projector.global_compressor
     local_tokens = global_tokens = None
+    # EXPERIMENTAL, off unless HICOM_SHARD_OVERLAP=1 (written without a GPU at hand, to be validated next): run the
+    # local chain on the side stream, as forward_batched does, so that it overlaps the global chain and its all-gather
+    side = None
+    if lc is not None and gc is not None and X.is_cuda and os.environ.get("HICOM_SHARD_OVERLAP", "0") == "1":
+        from .projector import _side_stream
+        main = torch.cuda.current_stream(X.device)
+        side = _side_stream(X.device)
+        side.wait_stream(main)
     if lc is not None:
         if Ts % lc.temporal_kernel_size:
             raise ValueError("frame shard must be a multiple of the temporal kernel")
-        att = lc.attend(X, frames_embed, guide_embed, modal, projector.local_logit_scale,
-                        projector.local_logit_bias)
-        Dh = lc.readout[-1].out_features
-        local_tokens = torch.empty((B * att.shape[1], Dh), dtype=X.dtype, device=X.device)
-        from .projector import _mlp_into
-        _mlp_into(lc.readout, att, local_tokens, 0, att.shape[1], att.shape[1])
-        local_tokens = local_tokens.view(B, att.shape[1], Dh)
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            att = lc.attend(X, frames_embed, guide_embed, modal, projector.local_logit_scale,
+                            projector.local_logit_bias)
+            Dh = lc.readout[-1].out_features
+            local_tokens = torch.empty((B * att.shape[1], Dh), dtype=X.dtype, device=X.device)
+            from .projector import _mlp_into
+            _mlp_into(lc.readout, att, local_tokens, 0, att.shape[1], att.shape[1])
+            local_tokens = local_tokens.view(B, att.shape[1], Dh)
     if gc is not None:
         Qg = gc.injected_query(guide_embed, B, X.dtype)
         m, l, o = gc.partials(X, gc.fold(Qg, projector.global_logit_scale), t0=t0,
@@ -97,4 +108,7 @@ def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, 
         global_tokens = torch.empty((B * nq, Dh), dtype=X.dtype, device=X.device)
         gc.finish(Qg, m, l, o, global_tokens, 0, nq)
         global_tokens = global_tokens.view(B, nq, Dh)
+    if side is not None:
+        main.wait_stream(side)
+        local_tokens.record_stream(main)
     return local_tokens, global_tokens
