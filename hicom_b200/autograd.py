@@ -453,7 +453,8 @@ def _local_tokens(proj, X, E, G, modal, image_newline, is_anyres):
     mode = lc.use_guide
     adapting = any(_is_param(a) for a in (lc.q_alpha, lc.k_alpha, lc.v_alpha))
     upstream = (mode in ("coarse", "fine") or adapting
-                or (mode == "direct" and (G.requires_grad or _is_param(lc.guide_injector.guide_alpha)))
+                or (mode == "direct" and ((G is not None and G.requires_grad)
+                                          or _is_param(lc.guide_injector.guide_alpha)))
                 or (E is not None and E.requires_grad))
     if not upstream:
         # nothing trainable in front of the readout (query = pooled feature or the frozen instruction vector, keys and

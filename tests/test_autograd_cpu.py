@@ -281,3 +281,19 @@ def test_partially_frozen_projector_skips_unneeded_backward(monkeypatch):
             assert p.grad is None, k
     kinds = {c[0] for c in cpu_ops.calls}
     assert not kinds & {"softmax_backward", "local_attend_backward", "film_layernorm_backward", "global_attend_partial"}
+
+
+def test_reference_errors_survive_under_autograd(monkeypatch):
+    """Bad guide inputs raise the reference's exception types on the training path too (projector.py:350,362,386)."""
+    from hicom_b200 import autograd as ag
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    for name in ("direct_T8", "coarse_T8", "fine_T8"):
+        case = CASES_BY_NAME[name]
+        sd, X, E, g, _ = materialise(case)
+        m = _module(case, sd)
+        with pytest.raises(ValueError):
+            m(X, E, None, "video")                                  # guide missing
+        wrong = torch.randn(3, 1152) if g.dim() == 1 else torch.randn(1152)
+        with pytest.raises(ValueError):
+            m(X, E, wrong, "video")                                 # wrong guide rank
