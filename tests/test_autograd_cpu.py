@@ -31,6 +31,8 @@ def _oracle_grads(case, sd, X, E, g, nl, probe):
     nl_leaf = None if nl is None else nl.clone().requires_grad_(True)
     orc = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf)
     out = orc.forward(X, E, g, case.modal, nl_leaf)
+    if probe is None:                      # forward only (shape probing)
+        return out.detach(), {}, None
     (out * probe).sum().backward()
     grads = {k: v.grad for k, v in leaf.items()}
     return out.detach(), grads, (None if nl_leaf is None else nl_leaf.grad)
@@ -297,3 +299,53 @@ def test_reference_errors_survive_under_autograd(monkeypatch):
         wrong = torch.randn(3, 1152) if g.dim() == 1 else torch.randn(1152)
         with pytest.raises(ValueError):
             m(X, E, wrong, "video")                                 # wrong guide rank
+
+
+def _random_train_cases(n, seed=7):
+    import random
+    from oracle.cases import Case
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        T = rng.choice([1, 2, 4, 7, 8])
+        H, W = rng.choice([(6, 6), (7, 8), (5, 6), (9, 9)])
+        adapt = "".join(ch for ch in "qkvg" if rng.random() < 0.4)
+        ptype = rng.choice(["local43{a}_global8{g}", "local22{a}_global4{g}", "local43{a}", "global8{g}"]).format(
+            a=("_adapt" + adapt) if adapt else "", g="_adaptg" if rng.random() < 0.4 else "")
+        guide = rng.choice([None, "direct", "coarse", "fine"])
+        modal = "image" if (T == 1 and rng.random() < 0.5) else "video"
+        merge, nlpos = rng.choice([("flat", "one_token"), ("spatial_unpad", "grid"), ("spatial_unpad", "frame"),
+                                   ("spatial_unpad", "one_token"), ("spatial_unpad", "no_token")])
+        out.append(Case(f"fuzz{i}_{ptype}_{guide}_T{T}_{H}x{W}_{modal}_{nlpos}", ptype, guide, T, H, W, 64, "float32", modal,
+                        merge, nlpos, merge != "flat", wseed=10 + i, xseed=20 + i))
+    return out
+
+
+@pytest.mark.parametrize("case", _random_train_cases(16), ids=lambda c: c.name)
+def test_training_path_fuzz_against_reference_autograd(case, monkeypatch):
+    """Seeded random configurations (grids, frame counts, guide modes, adapters, newline layouts, image modal): outputs
+    and every parameter gradient equal PyTorch autograd through the oracle; shapes the reference cannot stack raise the
+    same RuntimeError on both sides."""
+    from hicom_b200 import autograd as ag
+    sd, X, E, g, nl = materialise(case)
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, sd)
+    probe_seed = torch.Generator().manual_seed(3)
+    try:
+        want_out, want, _ = _oracle_grads(case, sd, X, E, g, nl, None)
+    except RuntimeError:
+        with pytest.raises(RuntimeError):
+            m(X, E, g, case.modal, nl)
+        return
+    out = m(X, E, g, case.modal, nl)
+    assert out.shape == want_out.shape and O.rel_err(out.detach(), want_out) <= 2e-5
+    probe = torch.randn(out.shape, generator=probe_seed)
+    (out * probe).sum().backward()
+    _, want, _ = _oracle_grads(case, sd, X, E, g, nl, probe)
+    for k, p in m.named_parameters():
+        w = want[k]
+        if w is None or float(w.abs().max()) <= 1e-6:
+            assert p.grad is None or float(p.grad.abs().max()) <= 1e-6, k
+        else:
+            assert p.grad is not None and O.rel_err(p.grad, w) <= 3e-4, (k, O.rel_err(p.grad, w))
