@@ -24,12 +24,21 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (hidden, T, per-GPU batch, description)
-    "c2": (3584, 16, 32, "c2: Qwen2.5-7B width 3584, 16 frames x 729 x 1152, bf16, batch 32 per GPU"),
-    "c3": (3584, 64, 8, "c3: width 3584, 64 frames, bf16, batch 64 video-parallel over 8 GPUs (8 per GPU)"),
-    "c5": (1536, 32, 64, "c5: Qwen2.5-1.5B width 1536, 32 frames, bf16, batch 512 over 8 GPUs (64 per GPU)"),
-    "c4": (3584, 512, 1, "c4: width 3584, one 512-frame video, frame-sharded over the GPUs (split-softmax merge)"),
+    # name: (hidden, T, batch, "weak" = batch per GPU / "strong" = TOTAL batch split over the GPUs of the run, description)
+    "c2": (3584, 16, 32, "weak", "c2: Qwen2.5-7B width 3584, 16 frames x 729 x 1152, bf16, batch 32 per GPU"),
+    "c3": (3584, 64, 64, "strong", "c3: width 3584, 64 frames, bf16, batch 64 in total, video-parallel over the GPUs"),
+    "c5": (1536, 32, 512, "strong", "c5: Qwen2.5-1.5B width 1536, 32 frames, bf16, batch 512 in total over the GPUs"),
+    "c4": (3584, 512, 1, "strong", "c4: width 3584, one 512-frame video, frame-sharded over the GPUs (split-softmax merge)"),
 }
+
+
+def workload(name, world):
+    hidden, T, batch, scaling, desc = WORKLOADS[name]
+    if scaling == "strong" and name != "c4":
+        if batch % world:
+            raise SystemExit(f"{name}: batch {batch} does not split over {world} GPUs")
+        batch //= world
+    return hidden, T, batch, scaling, desc
 PTYPE, USE_GUIDE = "local43_global32", "coarse"  # headline mode
 H = W = 27
 D = 1152
@@ -61,12 +70,15 @@ def peaks():
 def work_per_video(hidden, T):
     N = T * H * W
     Nw = (T // 4) * 81
-    J = Q * HEADS
+    # score columns actually evaluated: `direct` replaces all 32 queries by the instruction vector (projector.py:367-368),
+    # so ONE query per video is scored and pooled (9 head columns) and its token is replicated
+    J = HEADS if USE_GUIDE == "direct" else Q * HEADS
     return {
         "N": N, "Nw": Nw, "tokens_out": Nw + Q,
         # reference formulation (K/V projected for every token) — for context only
         "flops_reference": 4 * N * D * D + 4 * Q * N * D + 4 * N * D + 2 * Nw * (D * hidden + hidden * hidden)
                            + 4 * Q * D * D + 2 * Q * (D * hidden + hidden * hidden),
+        "J": J,
         # what this implementation executes on the tensor pipe (reassociated global path)
         "flops_scores": 2 * N * J * D, "flops_pool": 2 * N * J * D,
         "flops_local_readout": 2 * Nw * (D * hidden + hidden * hidden),
@@ -246,7 +258,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    hidden, T, B, desc = WORKLOADS[args.workload]
+    hidden, T, B, scaling, desc = workload(args.workload, max(1, args.gpus))
     videos = 2 if T <= 16 else 1
     if args.workload == "c4":
         T, videos = 64, 1  # bounded sample: one 64-frame shard of the 512-frame video
@@ -257,7 +269,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "frames/s through the HICom compressor", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "projector_type": PTYPE, "use_guide": USE_GUIDE},
         "tokens_per_s": fps / T * w["tokens_out"],
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
@@ -280,9 +292,33 @@ def build_projector(hidden, device):
 
 
 def synth_batch(B, T, device, seed):
+    """(X, E, G) ~ N(0, 0.5^2) in bf16, generated video by video so that the fp32 temporaries of a
+    512-video batch never exist at once."""
     g = torch.Generator(device=device).manual_seed(seed)
-    mk = lambda *s: (0.5 * torch.randn(*s, generator=g, device=device, dtype=torch.float32)).to(torch.bfloat16)
-    return mk(B, T, H, W, D), mk(B, T, H, W, D), mk(B, D)
+    X = torch.empty((B, T, H, W, D), dtype=torch.bfloat16, device=device)
+    E = torch.empty_like(X)
+    for b in range(B):
+        X[b] = 0.5 * torch.randn(T, H, W, D, generator=g, device=device, dtype=torch.float32)
+        E[b] = 0.5 * torch.randn(T, H, W, D, generator=g, device=device, dtype=torch.float32)
+    G = (0.5 * torch.randn(B, D, generator=g, device=device, dtype=torch.float32)).to(torch.bfloat16)
+    return X, E, G
+
+
+def oracle_parity(proj, X, E, G, tokens, video=0, t0=0):
+    """Compare the tokens of ONE video of the timed output with the fp32 oracle (the reference algorithm on the CPU) on
+    the same bf16-rounded weights and inputs: SURVEY §8c's bf16 gate (cos >= 0.999, max|a-b|/max|b| <= 1e-2).
+    The oracle is the checker here, never the thing measured."""
+    from oracle import hicom_oracle as O
+    sd = {k: v.detach().float().cpu() for k, v in proj.state_dict().items()}
+    orc = O.OracleProjector(PTYPE, USE_GUIDE, "flat", "one_token", sd)
+    f = lambda t: None if t is None else t[video].float().cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        truth = orc.forward(f(X), f(E), f(G), "video")
+    got = tokens[video].float().cpu()
+    return {"video": video, "rel_err": O.rel_err(got, truth), "cos": O.cosine(got, truth),
+            "tokens": list(got.shape), "against": "fp32 CPU oracle of projector.py:676-708 on the bf16-rounded weights/inputs",
+            "gate": "rel_err <= 1e-2 and cos >= 0.999"}
 
 
 def _timed_ms(fn, warmup, iters):
@@ -329,6 +365,90 @@ def measure_next_rows(hidden, T, B, device):
     return out
 
 
+def sustained_block(step, frames_per_step, exec_flops_per_step, device_index, seconds=3.0):
+    """>= `seconds` of back-to-back steps (CUDA-graph replays) with the clocks sampled: what the compressor sustains
+    once the burst clocks are gone, against the SUSTAINED bf16 peak of MEASURED_PEAKS.json."""
+    pk = peaks()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    step()
+    b.record()
+    torch.cuda.synchronize()
+    n = max(10, int(seconds * 1e3 / max(a.elapsed_time(b), 1e-3)) + 1)
+    with ClockSampler(device_index) as clk:
+        a.record()
+        for _ in range(n):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    tf = exec_flops_per_step / (ms * 1e-3) / 1e12
+    return {"seconds": a.elapsed_time(b) / 1e3, "steps": n, "ms_per_step": ms, "frames_per_s": frames_per_step / (ms * 1e-3),
+            "executed_tflops": tf, "frac_of_sustained_bf16_peak": tf / pk["tflops_sustained"],
+            "frac_of_burst_bf16_peak": tf / pk["tflops_burst"], "peak_source": pk["source"], "clocks": clk.summary()}
+
+
+def c4_block(proj, device, world, rank, steps=20):
+    """The frame-sharded long video (BASELINE config 4: one 512-frame video cut by frames over the GPUs of this run,
+    split-softmax merge of the global partials) measured beside the headline so that the scaling record carries it:
+    ms per video at N GPUs, the same video on ONE GPU (rank 0, unsharded) in the same run, the speed-up, and the
+    sharded tokens compared with the unsharded forward's."""
+    import torch.distributed as dist
+    from hicom_b200 import dist as hdist
+    from hicom_b200.graph import GraphedCompressor
+    T = 512
+    Ts = T // world
+    X, E, G = synth_batch(1, T, device, 4242)  # same seed on every rank: every rank holds the whole video
+    t0 = rank * Ts
+    Xs, Es = X[:, t0:t0 + Ts].contiguous(), E[:, t0:t0 + Ts].contiguous()
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / n], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    with torch.no_grad():
+        whole = GraphedCompressor(proj, X, E, G, "video")  # every rank can run the unsharded video (1.7 GB of inputs)
+        ms_one = timed(whole.replay, steps)
+        ref = whole.replay().clone()
+        out = {"frames": T, "ms_one_gpu": ms_one, "frames_per_s_one_gpu": T / (ms_one * 1e-3)}
+        if rank == 0:
+            out["parity_one_gpu"] = oracle_parity(proj, X, E, G, ref)
+        del whole
+        if world > 1:
+            sharded = GraphedCompressor(proj, Xs, Es, G, "video", frame_shard_t0=t0)
+            ms_n = timed(sharded.replay, steps)
+            loc, glob = sharded.replay()
+            nw = loc.shape[1]
+            want_loc, want_glob = ref[:, rank * nw:(rank + 1) * nw].float(), ref[:, -glob.shape[1]:].float()
+            scale = ref.float().abs().max()
+            err = torch.stack([(loc.float() - want_loc).abs().max() / scale, (glob.float() - want_glob).abs().max() / scale])
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+            out.update({"n_gpus": world, "frames_per_rank": Ts, "ms": ms_n, "frames_per_s": T / (ms_n * 1e-3),
+                        "speedup_vs_1": ms_one / ms_n, "kernels_per_replay": sharded.kernels_per_replay,
+                        "parity_vs_unsharded": {"local_rel_err": float(err[0]), "global_rel_err": float(err[1]),
+                                                "gate": "<= 8e-3 of max|tokens| (bf16 rounding of the merged partials)"}})
+            del sharded
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from hicom_b200 import ops
@@ -341,7 +461,7 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    hidden, T, B, desc = WORKLOADS[args.workload]
+    hidden, T, B, scaling, desc = workload(args.workload, world)
     frame_sharded = args.workload == "c4"
     if frame_sharded:
         from hicom_b200 import dist as hdist
@@ -356,9 +476,14 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     proj = build_projector(hidden, device)
-    X, E, G = synth_batch(B, T_local, device, 1234 + rank)
-    if frame_sharded:  # every rank must see the same instruction vector
-        G = synth_batch(1, 4, device, 99)[2]
+    if frame_sharded:  # every rank sees the same video and instruction vector, and takes its block of frames
+        Xf, Ef, G = synth_batch(B, T, device, 1234)
+        X = Xf[:, rank * T_local:(rank + 1) * T_local].contiguous()
+        E = Ef[:, rank * T_local:(rank + 1) * T_local].contiguous()
+        if world > 1:
+            del Xf, Ef
+    else:
+        X, E, G = synth_batch(B, T_local, device, 1234 + rank)
     if USE_GUIDE is None:  # stage-1 mode: no instruction, keys = features (frames_embed is None, encoder.py:288-290)
         E = G = None
 
@@ -373,7 +498,8 @@ def run_ours(args):
     if not args.no_graph:
         from hicom_b200.graph import GraphedCompressor
         with torch.no_grad():
-            graphed = GraphedCompressor(proj, X, E, G, "video", frame_shard_t0=rank * T_local if frame_sharded else None)
+            graphed = GraphedCompressor(proj, X, E, G, "video", frame_shard_t0=rank * T_local if frame_sharded else None,
+                                        adopt_inputs=True)
         X, E, G = graphed.frames_feature, graphed.frames_embed, graphed.guide_embed
 
     def step():
@@ -384,6 +510,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    w = work_per_video(hidden, T)
+    videos_per_step = 1 if frame_sharded else B * world
+    frames_per_step = (T if frame_sharded else B * T * world)
+    exec_flops = videos_per_step * (w["flops_scores"] + w["flops_pool"] + w["flops_local_readout"])
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             out = step()
@@ -403,7 +533,8 @@ def run_ours(args):
             # into the events), same inputs, still inside the clock-sampled region
             import hicom_b200.projector as _proj
             op_steps = max(3, min(args.steps, 10))
-            overlap, _proj.OVERLAP_STREAMS = _proj.OVERLAP_STREAMS, False
+            saved = _proj.OVERLAP_STREAMS, _proj.SM_SPLIT
+            _proj.OVERLAP_STREAMS, _proj.SM_SPLIT = False, 0
             eager_step()
             with ops.OpTimer() as timer:
                 for _ in range(op_steps):
@@ -413,34 +544,55 @@ def run_ours(args):
             with ops.KernelTimer() as ktimer:
                 for _ in range(op_steps):
                     eager_step()
-            _proj.OVERLAP_STREAMS = overlap
+            _proj.OVERLAP_STREAMS, _proj.SM_SPLIT = saved
             barrier()
         op_times = timer.summary()
         if frame_sharded:
-            out = out[1]
+            out = torch.cat([out[0], out[1]], dim=1) if world == 1 else out[1]
     ms_t = torch.tensor([ms_total], device=device)
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_step = float(ms_t) / args.steps
-    frames_per_step = (T if frame_sharded else B * T * world)
     value = frames_per_step / (ms_step * 1e-3)
-    w = work_per_video(hidden, T)
-    videos_per_step = 1 if frame_sharded else B * world
+
+    # ---- parity of the timed output with the oracle (rank 0; the c4 shard is checked inside c4_block at N > 1) ----
+    parity = None
+    if rank == 0 and not args.no_parity and (world == 1 or not frame_sharded):
+        try:
+            parity = oracle_parity(proj, X, E, G, out)
+        except Exception as exc:  # reported, never fatal
+            parity = {"unavailable": repr(exc)[:200]}
+
+    # ---- what the compressor sustains over seconds (rank-local replays; max over ranks) ---------------------
+    sustained = None
+    if not args.no_sustained and graphed is not None:
+        with torch.no_grad():
+            barrier()
+            sustained = sustained_block(step, frames_per_step / world if not frame_sharded else frames_per_step,
+                                        exec_flops / world, local_rank, seconds=args.sustain_seconds)
+            barrier()
+        if world > 1:
+            t = torch.tensor([sustained["ms_per_step"]], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sustained["ms_per_step_max_over_ranks"] = float(t)
+            sustained["frames_per_s_all_gpus"] = frames_per_step / (float(t) * 1e-3)
 
     # ---- end-to-end through the public host API (rank-local; copies inside the timed region) -------
     e2e = None
     if not frame_sharded:
         from hicom_b200.pipeline import host_affinity
         n_tok = out.shape[1]
-        with host_affinity(device):  # pinned buffers on the GPU's NUMA node
-            Xh, Eh, Gh = [None if t is None else t.cpu().pin_memory() for t in (X, E, G)]
-            out_h = torch.empty((B, n_tok, hidden), dtype=torch.bfloat16).pin_memory()
+        Be = min(B, 32)  # bounded host batch (c5 at N=1 would pin 55 GB): e2e is a per-video rate, PCIe-bound
+        with host_affinity(device) as numa:  # pinned buffers on the GPU's NUMA node
+            Xh, Eh, Gh = [None if t is None else t[:Be].cpu().pin_memory() for t in (X, E, G)]
+            out_h = torch.empty((Be, n_tok, hidden), dtype=torch.bfloat16).pin_memory()
             # raw pinned host->device rate of this box, so the e2e number can be read against its PCIe roofline
             torch.cuda.synchronize()
             cs, ce = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
             cs.record()
             for _ in range(3):
-                X.copy_(Xh, non_blocking=True)
+                X[:Be].copy_(Xh, non_blocking=True)
             ce.record()
             torch.cuda.synchronize()
             h2d_gbs = 3 * Xh.numel() * 2 / (cs.elapsed_time(ce) * 1e-3) / 1e9
@@ -448,7 +600,6 @@ def run_ours(args):
             compress_from_host(proj, Xh, Eh, Gh, "video", out=out_h, device=device)
         barrier()
         e_steps = max(2, min(args.steps, 10))
-        t0 = time.perf_counter()
         es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         es.record()
         for _ in range(e_steps):
@@ -456,13 +607,29 @@ def run_ours(args):
         ee.record()
         barrier()
         e_ms = torch.tensor([es.elapsed_time(ee) / e_steps], device=device)
+        rates = torch.tensor([h2d_gbs], device=device)
         if world > 1:
             dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * T * world / (float(e_ms) * 1e-3), "unit": "frames/s",
+            gathered = [torch.zeros_like(rates) for _ in range(world)]
+            dist.all_gather(gathered, rates)
+            rates = torch.cat(gathered)
+        e2e = {"value": Be * T * world / (float(e_ms) * 1e-3), "unit": "frames/s",
                "h2d_bytes_per_step": int(sum(t.numel() * 2 for t in (Xh, Eh, Gh) if t is not None)) * world,
                "d2h_bytes_per_step": int(out_h.numel() * 2) * world, "ms_per_step": float(e_ms),
+               "videos_per_gpu_per_step": Be,
                "pinned_h2d_gbs": round(h2d_gbs, 1),
+               "pinned_h2d_gbs_per_rank": [round(float(r), 1) for r in rates],  # measured concurrently on every rank
+               "host_numa": numa,
                "api": "hicom_b200.pipeline.compress_from_host (pinned host buffers, persistent device staging, 2-stream chunked overlap)"}
+        del Xh, Eh, out_h
+
+    # ---- the frame-sharded long video beside the headline (scaling record) --------------------------------
+    c4 = None
+    if not frame_sharded and not args.no_c4 and hidden == 3584:
+        try:
+            c4 = c4_block(proj, device, world, rank)
+        except Exception as exc:  # reported, never fatal
+            c4 = {"unavailable": repr(exc)[:300]}
 
     launch_mode = "cuda-graph replay" if graphed is not None else "eager"
     graphed = None
@@ -493,11 +660,12 @@ def run_ours(args):
         peak = pk["tflops_sustained"]
         roof.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak)
     roof["peak_source"] = pk["source"] + (" (sustained bf16)" if kind != "hbm" else " (copy)")
-    roof["traffic"] = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if args.workload == "c2" and USE_GUIDE == "coarse" and os.path.exists(tpath):  # DRAM bytes per launch, committed ncu capture
-        roof["traffic"] = json.load(open(tpath)).get(dname.split()[0])
-    exec_flops = videos_per_step * (w["flops_scores"] + w["flops_pool"] + w["flops_local_readout"])
+    roof["traffic"], roof["traffic_source"] = measured_traffic(args.workload, dname)
+    step_tf = exec_flops / (ms_step * 1e-3) / 1e12
+    roof["whole_step"] = {"executed_tflops": step_tf, "frac_of_burst_bf16_peak": step_tf / pk["tflops_burst"],
+                          "frac_of_sustained_bf16_peak": step_tf / pk["tflops_sustained"],
+                          "algorithmic_hbm_gb": videos_per_step * (w["bytes_in"] + w["bytes_out"]) / 1e9,
+                          "dram_gb_measured": measured_traffic(args.workload, "step")[0]}
     ops_table = {k: {"calls": c, "ms_per_step": ms / op_steps} for k, (c, ms) in
                  sorted(op_times.items(), key=lambda kv: -kv[1][1])}
     kernels_table = {k: {"launches": c, "ms_per_step": ms / op_steps} for k, (c, ms) in
@@ -523,7 +691,7 @@ def run_ours(args):
             gpu_eager = {"unavailable": repr(exc)[:200]}
 
     next_rows = None
-    if world == 1 and not args.no_cpu_baseline and not frame_sharded:
+    if world == 1 and not args.no_cpu_baseline and not frame_sharded and args.workload == "c2":
         try:
             next_rows = measure_next_rows(hidden, T, B, device)
         except Exception as exc:  # reported, never fatal
@@ -539,19 +707,22 @@ def run_ours(args):
     line = {
         "metric": "frames/s through the HICom compressor", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "strong" if frame_sharded else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": desc, "projector_type": PTYPE, "use_guide": USE_GUIDE,
                    "launch": launch_mode, "per_gpu_batch": B, "frames_per_video": T, "sharding": "frame" if frame_sharded else "video",
-                   "l2": f"inputs are {2 * B * w['N'] * D * 2 / 1e9:.2f} GB per GPU per step (> 126 MB L2), "
+                   "l2": f"inputs are {2 * B * T_local * H * W * D * 2 / 1e9:.2f} GB per GPU per step (> 126 MB L2), "
                          "re-read from HBM every step"},
         "tokens_per_s": value / T * w["tokens_out"],
-        "executed_tflops": exec_flops / (ms_step * 1e-3) / 1e12,
+        "executed_tflops": step_tf,
         "reference_equivalent_tflops": videos_per_step * w["flops_reference"] / (ms_step * 1e-3) / 1e12,
         "clocks": clk.summary(),
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": roof,
+        "parity": parity,
+        "sustained": sustained,
+        "c4": c4,
         "cpu_baseline": cpu,
         "gpu_eager_baseline": gpu_eager,
         "next_rows": next_rows,
@@ -562,6 +733,31 @@ def run_ours(args):
     if world > 1:
         sys.stdout.flush()
         os._exit(0)
+
+
+def measured_traffic(workload_name, key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu --set full capture of THIS
+    build: profiles/r02_traffic.json records the digest of the kernel sources it was captured from, and a stale capture
+    (any csrc file changed since) is reported as null rather than as a number."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(path):
+        return None, "no capture committed for this build"
+    rec = json.load(open(path))
+    if rec.get("csrc_digest") != csrc_digest():
+        return None, f"stale capture (kernels changed since {rec.get('csrc_digest', '?')[:12]})"
+    table = rec.get(workload_name + ":" + (USE_GUIDE or "none"), {})
+    name = key.split()[0]
+    return table.get(name), f"ncu --set full capture, {rec.get('captured', '?')}"
+
+
+def csrc_digest():
+    import hashlib
+    h = hashlib.sha256()
+    base = os.path.join(ROOT, "hicom_b200", "csrc")
+    for f in sorted(os.listdir(base)):
+        with open(os.path.join(base, f), "rb") as fh:
+            h.update(f.encode() + fh.read())
+    return h.hexdigest()
 
 
 def main():
@@ -576,8 +772,16 @@ def main():
                     help="guide mode (headline: coarse; direct = what the released checkpoint runs; none = stage 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed output")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s sustained block")
+    ap.add_argument("--no-c4", action="store_true", help="skip the frame-sharded long-video block beside the headline")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0)
+    ap.add_argument("--digest", action="store_true", help="print the digest of the kernel sources and exit")
     args = ap.parse_args()
     USE_GUIDE = None if args.use_guide == "none" else args.use_guide
+    if args.digest:
+        print(csrc_digest())
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -19,6 +19,7 @@ PROTOTYPES = {
     "hicom_kernel_timing_enable": (c_int, [c_int]),
     "hicom_kernel_timing_collect": (c_size_t, [ctypes.c_char_p, c_size_t]),
     "hicom_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+    "hicom_set_sm_limit": (c_int, [c_int]),
     "hicom_grid_pool": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "hicom_local_attend": (c_int, [c_void_p] * 8 + [c_int] * 8 + [c_float, c_int, c_int, c_void_p]),
     "hicom_linear": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,

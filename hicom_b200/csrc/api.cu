@@ -76,6 +76,19 @@ static GemmParams plain_gemm() {
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static thread_local int g_sm_limit = 0;
+int sm_budget() {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  return (g_sm_limit > 0 && g_sm_limit < num_sms) ? g_sm_limit : num_sms;
+}
+bool sm_limited() { return g_sm_limit > 0 && sm_budget() == g_sm_limit; }
+
 }  // namespace hicom
 
 using namespace hicom;
@@ -117,6 +130,12 @@ extern "C" size_t hicom_kernel_timing_collect(char* buf, size_t cap) {
     buf[n] = 0;
   }
   return out.size() + 1;
+}
+
+extern "C" int hicom_set_sm_limit(int sms) {
+  const int old = g_sm_limit;
+  g_sm_limit = sms > 0 ? (sms < 2 ? 2 : sms & ~1) : 0;
+  return old;
 }
 
 extern "C" int hicom_device_info(int* sm_count, int* cc_major, int* cc_minor) {

@@ -423,18 +423,13 @@ using namespace hicom;
 //   NT  A (M,K) K-major, B given as (N,K) K-major   S = x'·qfoldᵀ, dP = x'·dpooledᵀ            -> plain linear
 //   NN  A (M,K) K-major, B (K,N) row-major          dA = dpre·W                                 -> MN-major B (w_is_kn)
 //   TN  A stored (K,M),  B (K,N) row-major, fp32 C  dW = dpreᵀ·A, dqfold = dSᵀ·x'               -> MN-major A and B
-// Returns -1 when the problem stays on the SIMT kernel.  HICOM_GEMM_TC=0 keeps everything on SIMT (cross-check).
-static int gemm_tc_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("HICOM_GEMM_TC"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on;
-}
+// Returns -1 when the problem stays on the SIMT kernel.
 
 static int try_gemm_tc(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, int64_t sAb2, const void* B, int64_t sBk,
                        int64_t sBn, int64_t sBb1, int64_t sBb2, void* C, int64_t ldc, int64_t sCb1, int64_t sCb2, int M,
                        int N, int K, int nb1, int nb2, float alpha, int a_dtype, int b_dtype, int c_dtype,
                        cudaStream_t stream) {
-  if (!gemm_tc_enabled() || a_dtype != HICOM_BF16 || b_dtype != HICOM_BF16) return -1;
+  if (a_dtype != HICOM_BF16 || b_dtype != HICOM_BF16) return -1;
   if (M < 2 || N < 2 || K < 16 || (long long)M * N * K < (1ll << 24)) return -1;  // small: launch-bound either way
   const long long nb = (long long)nb1 * nb2;
   if (nb > 4096) return -1;  // one launch per batch entry (per video): beyond this the batched SIMT grid is the better deal
@@ -452,11 +447,9 @@ static int try_gemm_tc(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, in
   if (nb > 1 && ((nb1 > 1 && (sAb1 % 8 || sBb1 % 8)) || (nb2 > 1 && (sAb2 % 8 || sBb2 % 8)))) return -1;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -1;
   const size_t csz = c_dtype == HICOM_F32 ? 4 : 2;
-  // EXPERIMENTAL, off unless HICOM_GEMM_TC_BATCH=1 (written without a GPU at hand, to be validated next): all batch
-  // entries of a TN problem in ONE launch through the kernel's batch axis (per-video dqfold = dSᵀ·x' has only 15
-  // tiles, so B launches leave most SMs idle)
-  static const bool batch_tn = [] { const char* e = getenv("HICOM_GEMM_TC_BATCH"); return e && e[0] == '1'; }();
-  if (batch_tn && mode == 2 && nb1 == 1 && nb2 > 1 && sCb2 % ldc == 0 && sAb2 > 0 && sBb2 > 0) {
+  // all batch entries of a TN problem in ONE launch through the kernel's batch axis (per-video dqfold = dSᵀ·x' has
+  // only 15 tiles, so B launches leave most SMs idle)
+  if (mode == 2 && nb1 == 1 && nb2 > 1 && sCb2 % ldc == 0 && sAb2 > 0 && sBb2 > 0) {
     TcLinearParams t{};
     t.A = A; t.W = B; t.C = C; t.bias = nullptr; t.R = nullptr; t.ldr = 0;
     t.lda = lda; t.ldw = ldw; t.ldc = ldc; t.M = M; t.N = N; t.K = K;

@@ -26,6 +26,10 @@ struct KernelTimer {
   ~KernelTimer() { if (on) kernel_timing_end(s); }
 };
 
+// SMs the calling thread's launches may fill (hicom_set_sm_limit; whole device when no limit is set)
+int sm_budget();
+bool sm_limited();  // a limit below the device's SM count is in force
+
 #define HICOM_REQUIRE(cond, ...)        \
   do {                                  \
     if (!(cond)) {                      \

@@ -13,21 +13,14 @@
 // Uses:
 //   EPI_LINEAR  C = act(A·Wᵀ + bias) + R                 nn.Linear stages / readouts   (projector.py:307-312)
 //   EPI_MAX     column max of S = qfold·X'ᵀ               sampled / exact stabiliser    (projector.py:197,213)
-//   EPI_PROB2   P2 = exp(S - stab), tokens on M           global scores -> probabilities (default pipeline)
-//   EPI_PROB    P = exp(S - stab), score columns on M     same, older pipeline (HICOM_GLOBAL_V3=0)
+//   EPI_PROB2   P2 = exp(S - stab), tokens on M           global scores -> probabilities
 //   EPI_POOL    O = [X ; tables]ᵀ·[P ; marginals]         global P·V in reassociated form (projector.py:215)
-// Environment switches (read once per process; defaults are the fast paths, the others are kept as cross-checks and
-// exercised by child-process tests): HICOM_CTA2=0 single-CTA tiles only; HICOM_PROB_HALVES=0 one 288-column pair tile
-// instead of two 144-column halves; HICOM_GLOBAL_V3=0 the older global pipeline.
 #include <cuda.h>
 #include <stdlib.h>
 
 #include "gemm_tc.cuh"
 
 namespace hicom {
-int launch_posadd(const void* X, void* Y, const float* pt, const float* ph, const float* pw, int B, int T_,
-                  int H, int W, int d, int dtype, cudaStream_t stream);
-
 namespace tc {
 
 constexpr int BM = 128;  // UMMA M (rows of the accumulator = TMEM lanes)
@@ -41,7 +34,7 @@ __host__ __device__ constexpr int epi_warps(int epi, int flags = 0) {
 }
 __host__ __device__ constexpr int num_threads(int epi, int flags = 0) { return 64 + 32 * epi_warps(epi, flags); }
 
-enum { EPI_LINEAR = 0, EPI_MAX = 1, EPI_PROB = 2, EPI_POOL = 3, EPI_PROB2 = 4 };
+enum { EPI_LINEAR = 0, EPI_MAX = 1, EPI_POOL = 3, EPI_PROB2 = 4 };
 
 struct Params {
   int M, N, K;       // valid rows of A / rows of B / reduction length (per batch)
@@ -56,24 +49,19 @@ struct Params {
   int z_a_k, z_b_k;                //     A / B reduction coordinates start at z*z_a_k / z*z_b_k
   long long z_c_rows;              //     and output rows are shifted by z*z_c_rows,
   int z_c_cols;                    //     output columns by z*z_c_cols
-  // EPI_MAX / EPI_PROB / EPI_POOL
-  float* mg; float* lg;            // (B, J) running TRUE max of the scores / sum of probabilities
-  const float* stab;               // (B, J) softmax stabiliser used by EPI_PROB (any value near the max is exact)
+  // EPI_MAX / EPI_POOL
+  float* mg;                       // (B, J) running max of the scores seen by EPI_MAX
   int tiles_x, tiles_y, tiles_z;   // tile space walked by the persistent CTAs (filled by launch())
   int n_tile_stride;               // EPI_MAX sampling: this launch visits N tiles 0, stride, 2*stride, ...
   const int* guard;                // if non-null: the whole kernel is a no-op unless *guard != 0
-  __nv_bfloat16* Pt; long long pt_ld;  // (B, J, pt_ld) transposed probabilities
   float* o; int splits;            // (B, splits, J, d) pooled partials
   // position embedding folded in algebraically (no x' = x + PE tensor):
-  int k_ext_blocks;                // EPI_MAX/PROB: extra K blocks taken from the second map pair (spatial PE term)
+  int k_ext_blocks;                // EPI_MAX/PROB2/POOL: extra K blocks taken from the second / third map pair
   int HW, T;                       // tokens per frame, frames
   long long c_batch_rows;          // EPI_LINEAR: output rows are shifted by batch*c_batch_rows (batched GEMMs)
   int b_shared;                    // B operand has no batch axis (coordinate 0 for every batch entry)
   __nv_bfloat16* P2; long long p2_ld;  // EPI_PROB2: probabilities (B, tokens, p2_ld), token-major
-  const float* peq_t; long long peq_ld;  // (T, B*J) time term of the scores: pos_t[t]·qfold[b,j]
-  const __nv_bfloat16* tqm; long long tqm_ld;  // if set: the same term as (B*J, tqm_ld) bf16 rows (EPI_MAX, default pipeline)
-  float* margT; int margT_ld;      // (B*J, margT_ld) sum of probabilities per frame (EPI_PROB accumulates)
-
+  const __nv_bfloat16* tqm; long long tqm_ld;  // (B*J, tqm_ld) bf16 rows: time term pos_t[t]·qfold[b,j] of the scores (EPI_MAX)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -351,7 +339,7 @@ __device__ __forceinline__ TileInfo decode_tile(const Params& p, int tile, int p
   int k_end = t.k_begin + p.k_chunk;
   if (k_end > p.K) k_end = p.K;
   t.nkb_main = k_end > t.k_begin ? (k_end - t.k_begin + BK - 1) / BK : 0;
-  t.nkb = t.nkb_main + ((EPI == EPI_MAX || EPI == EPI_PROB || EPI == EPI_PROB2 || (EPI == EPI_POOL && t.split == 0))
+  t.nkb = t.nkb_main + ((EPI == EPI_MAX || EPI == EPI_PROB2 || (EPI == EPI_POOL && t.split == 0))
                             ? p.k_ext_blocks : 0);
   return t;
 }
@@ -769,14 +757,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     } else if (EPI == EPI_MAX && t.m_tile * BM + q * 32 >= p.M) {
       // every row of this warp is padding (J = 288 fills 2.25 M tiles): nothing to read, just release the buffer
-    } else if (EPI == EPI_PROB && t.m_tile * BM + q * 32 >= p.M) {
-      // same for the probability pass
     } else if (EPI == EPI_MAX) {
       // rows = score columns j (M = J), columns = tokens of this tile
       const bool row_ok = row < p.M;
       const size_t col = (size_t)batch * p.M + (row_ok ? row : 0);
-      const float* peq = p.peq_t != nullptr ? p.peq_t + col : nullptr;
-      const __nv_bfloat16* tqr = p.tqm != nullptr ? p.tqm + col * p.tqm_ld : nullptr;
+      const __nv_bfloat16* tqr = p.tqm + col * p.tqm_ld;
       float mx = -INFINITY;
       for (int c = half; c < BN / 32; c += CSTEP) {
         const int t0 = n_tile * BN + c * 32;
@@ -785,101 +770,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // time term of the position embedding: a 32-token chunk touches at most two frames (HW >= 32)
         const int f0 = t0 / p.HW;
         const int nb = (f0 + 1) * p.HW - t0;
-        float pt0, pt1;
-        if (p.tqm != nullptr) {
-          pt0 = __bfloat162float(tqr[f0]);
-          pt1 = (f0 + 1 < p.T) ? __bfloat162float(tqr[f0 + 1]) : 0.f;
-        } else {
-          pt0 = peq[(size_t)f0 * p.peq_ld];
-          pt1 = (f0 + 1 < p.T) ? peq[(size_t)(f0 + 1) * p.peq_ld] : 0.f;
-        }
+        const float pt0 = __bfloat162float(tqr[f0]);
+        const float pt1 = (f0 + 1 < p.T) ? __bfloat162float(tqr[f0 + 1]) : 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (t0 + i < p.N) mx = fmaxf(mx, v[i] + (i < nb ? pt0 : pt1));
       }
       if (row_ok) atomic_max_float(p.mg + (size_t)batch * p.M + row, mx);
-    } else if (EPI == EPI_PROB) {
-      const bool row_ok = row < p.M;
-      const size_t col = (size_t)batch * p.M + (row_ok ? row : 0);
-      const float pre = row_ok ? p.stab[col] * kLog2e : 0.f;
-      const float* peq = p.peq_t + col;
-      float* mrow = p.margT + col * p.margT_ld;
-      float sum = 0.f, mx = -INFINITY, fsum = 0.f;
-      int fcur = -1;
-      __nv_bfloat16* prow = p.Pt + col * p.pt_ld + (size_t)n_tile * BN;
-      for (int c = half; c < BN / 32; c += CSTEP) {
-        const int t0 = n_tile * BN + c * 32;
-        const bool any = t0 < p.N;  // warp-uniform
-        uint32_t pk[16];
-        float s0 = 0.f, s1 = 0.f;
-        int f0 = 0, nb = 32;
-        if (any) {
-          tmem_ld32(taddr + c * 32, v);
-          f0 = t0 / p.HW;
-          nb = (f0 + 1) * p.HW - t0;
-        }
-        if (any && nb >= 32 && t0 + 32 <= p.N) {
-          // fast path (warp-uniform): all 32 tokens valid and inside one frame
-          const float pt0 = peq[(size_t)f0 * p.peq_ld];
-          const float pb = fmaf(pt0, kLog2e, -pre);  // (x + pt0) * log2e - stab * log2e
-          float cm = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            cm = fmaxf(cm, fmaxf(v[i], v[i + 1]));
-            const float a = ex2_approx(fmaf(v[i], kLog2e, pb));
-            const float b = ex2_approx(fmaf(v[i + 1], kLog2e, pb));
-            s0 += a + b;
-            pk[i / 2] = pack_bf16(a, b);
-          }
-          mx = fmaxf(mx, cm + pt0);  // true max of the scores, for the stabiliser check
-        } else if (any) {
-          const float pt0 = peq[(size_t)f0 * p.peq_ld];
-          const float pt1 = (f0 + 1 < p.T) ? peq[(size_t)(f0 + 1) * p.peq_ld] : 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float a = 0.f, b = 0.f;
-            if (t0 + i < p.N) {
-              const float x = v[i] + (i < nb ? pt0 : pt1);
-              a = ex2_approx(fmaf(x, kLog2e, -pre));
-              mx = fmaxf(mx, x);
-            }
-            if (t0 + i + 1 < p.N) {
-              const float x = v[i + 1] + (i + 1 < nb ? pt0 : pt1);
-              b = ex2_approx(fmaf(x, kLog2e, -pre));
-              mx = fmaxf(mx, x);
-            }
-            if (i < nb) s0 += a; else s1 += a;
-            if (i + 1 < nb) s0 += b; else s1 += b;
-            pk[i / 2] = pack_bf16(a, b);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
-        }
-        sum += s0 + s1;
-        if (row_ok && any) {
-          // per-frame probability mass (time marginals): flush when the frame changes
-          if (f0 != fcur) {
-            if (fcur >= 0 && fcur < p.T) atomicAdd(mrow + fcur, fsum);
-            fcur = f0; fsum = 0.f;
-          }
-          fsum += s0;
-          if (nb < 32) {
-            if (fcur < p.T) atomicAdd(mrow + fcur, fsum);
-            fcur = f0 + 1; fsum = s1;
-          }
-        }
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(prow + c * 32);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-        }
-      }
-      if (row_ok) {
-        if (fcur >= 0 && fcur < p.T) atomicAdd(mrow + fcur, fsum);
-        atomicAdd(p.lg + col, sum);
-        atomic_max_float(p.mg + col, mx);
-      }
     } else {  // EPI_POOL: rows = channels d (M), columns = score columns j (N = J)
       float* obase = p.o + (((size_t)batch * p.splits + split) * p.N) * p.M + row;
       for (int c = half; c < (BN + 31) / 32; c += CSTEP) {
@@ -909,40 +806,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// small helpers for the global pipeline
-// ---------------------------------------------------------------------------------------------
-__global__ void init_stats_kernel(float* mg, float* lg, int n, int* flag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { mg[i] = -INFINITY; lg[i] = 0.f; }
-  if (i == 0) *flag = 0;
-}
-// Stabiliser from the sampled max: stab = sampled max + margin.  exp(S - stab) then stays far from both ends of the
-// bf16/fp32 exponent range unless some unsampled score exceeds the sampled max by ~80 nats (checked afterwards).
-constexpr float kStabMargin = 20.f;   // nats
-constexpr float kStabLimit = 60.f;    // true max - stab above this triggers the exact-max fallback
-__global__ void make_stab_kernel(const float* mg, float* stab, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) stab[i] = mg[i] + kStabMargin;
-}
-__global__ void check_stab_kernel(const float* mg, const float* stab, int n, int* flag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && (mg[i] - stab[i] > kStabLimit || !(mg[i] - stab[i] > -1e30f))) atomicExch(flag, 1);
-}
-// fallback only: stabiliser := true max, sums reset
-__global__ void repair_stab_kernel(const float* mg, float* stab, float* lg, int n, const int* flag) {
-  if (*flag == 0) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { stab[i] = mg[i]; lg[i] = 0.f; }
-}
-// m[b,s,j] = stabiliser for every split; l[b,0,j] = lg[b,j], 0 for the other splits (they share the stabiliser).
-__global__ void spread_stats_kernel(const float* stab, const float* lg, float* m, float* l, int B, int S, int J) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * S * J) return;
-  const int j = i % J, s = (i / J) % S, b = i / (J * S);
-  m[i] = stab[b * J + j];
-  l[i] = s == 0 ? lg[b * J + j] : 0.f;
-}
+constexpr float kStabMargin = 20.f;   // nats added to the sampled max: exp(S - stab) stays far from both ends of the range
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -996,13 +860,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     HICOM_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = sm_budget();
   Params pp = p;
   // pair mode: grid.y counts M tiles; two of them (one per CTA of a pair) make one scheduled tile
   pp.tiles_x = (int)grid.x; pp.tiles_y = CTA2 ? (int)(grid.y + 1) / 2 : (int)grid.y; pp.tiles_z = (int)grid.z;
@@ -1012,7 +870,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   const unsigned ctas = CTA2 ? 2u * (unsigned)(total < num_sms / 2 ? total : num_sms / 2)
                              : (unsigned)(total < num_sms ? total : num_sms);
   char label[96];
-  static const char* names[] = {"tc_linear", "tc_scores_max", "tc_scores_prob", "tc_pool", "tc_scores_prob2"};
+  static const char* names[] = {"tc_linear", "tc_scores_max", "", "tc_pool", "tc_scores_prob2"};
   snprintf(label, sizeof(label), "%s%s%s M=%d N=%d K=%d tiles=%lld%s", names[EPI],
            (FLAGS & 1) ? "+gelu" : ((FLAGS & 8) ? "+gelu_tanh" : ""),
            CTA2 ? "/pair" : "", p.M, p.N, p.K, total, p.guard ? " guarded" : "");
@@ -1034,13 +892,6 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   char what[160];
   snprintf(what, sizeof(what), "tc_gemm_kernel<%d,%d,%d> %s", BN, (int)A_MN, (int)B_MN, label);
   return check_launch(what);
-}
-
-static bool pair_mode_enabled() {
-  static int on = -1;
-  // default on; HICOM_CTA2=0 keeps every GEMM on single-CTA tiles (cross-check, tested in a child process)
-  if (on < 0) { const char* e = getenv("HICOM_CTA2"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on == 1;
 }
 
 }  // namespace tc
@@ -1125,7 +976,7 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
     }
   }
   // large plain K-major GEMMs: CTA pairs (cta_group::2), each CTA stages half of the weight tile
-  if (pair_mode_enabled() && !q.w_is_kn && q.z_slices == 0 && q.diag_heads == 0 &&
+  if (!q.w_is_kn && q.z_slices == 0 && q.diag_heads == 0 &&
       (long long)grid.x * grid.y >= 296) {
     CUtensorMap tb128;
     if (make_map(&tb128, q.W, kext, q.N, 1, q.ldw, 0, 128)) return 1;
@@ -1158,7 +1009,6 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 constexpr int kKe = 64;  // spatial indicator columns (H + W <= 64): one extra K block
-constexpr int kSpatialSlices = 2;  // the marginal GEMM splits its token range in two (tile z axis) to fill the SMs
 
 bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W) {
   (void)T;
@@ -1167,105 +1017,8 @@ bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W) 
   return dtype == HICOM_BF16 && d % 128 == 0 && J >= 1 && J <= 288 && H * W >= 32 && H + W <= kKe;
 }
 
-struct GlobalWs {
-  size_t pt, mg, lg, stab, flag, pe_t, pe2, ind, peq_s, peq_t, margT, marg, total;
-  long long pt_ld;
-  int Tk, ke2;
-};
-static GlobalWs global_ws(int B, int T, int H, int W, int d, int J, int splits) {
-  (void)splits;
-  const size_t N = (size_t)T * H * W;
-  GlobalWs w;
-  w.pt_ld = (long long)((N + 255) / 256) * 256;
-  w.Tk = (T + 7) / 8 * 8;
-  w.ke2 = kSpatialSlices * kKe + (T + 63) / 64 * 64;  // [spatial 64 x slices | time, padded to whole K blocks]
-  size_t off = 0;
-  auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return o; };
-  w.pt = take((size_t)B * J * w.pt_ld * 2);
-  w.mg = take((size_t)B * J * 4);
-  w.lg = take((size_t)B * J * 4);
-  w.stab = take((size_t)B * J * 4);
-  w.flag = take(256);
-  w.pe_t = take((size_t)w.Tk * d * 2);            // pos_t rounded to bf16, zero rows up to Tk (score time term)
-  w.pe2 = take((size_t)w.ke2 * d * 2);            // [pos_h ; pos_w ; 0 | pos_t ; 0] bf16: spatial + time tables
-  w.ind = take(N * kKe * 2);                      // one-hot (token -> h, H + w) bf16
-  w.peq_s = take((size_t)B * J * kKe * 2);        // qfold · pe_sᵀ  (bf16, K-major rows j)
-  w.peq_t = take((size_t)T * B * J * 4);          // pe_t · qfoldᵀ  (fp32, (T, B*J))
-  w.margT = take((size_t)B * J * w.Tk * 4);       // probability mass per frame (fp32 atomics)
-  w.marg = take((size_t)B * J * w.ke2 * 2);       // [spatial marginals | time marginals] bf16, K-major rows j
-  w.total = off;
-  return w;
-}
-
-struct GlobalWs3;
-static size_t global_ws3_total(int B, int T, int H, int W, int d, int J, int splits);
-static bool global_v3_enabled() {
-  static int on = -1;
-  // default: the v3 pipeline; HICOM_GLOBAL_V3=0 selects the older column-major-probability pipeline (kept as a cross-check)
-  if (on < 0) { const char* e = getenv("HICOM_GLOBAL_V3"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on == 1;
-}
-
-size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits) {
-  return global_v3_enabled() ? global_ws3_total(B, T, H, W, d, J, splits) : global_ws(B, T, H, W, d, J, splits).total;
-}
-
-namespace tc {
-// bf16 copies of the per-axis tables: pe_t (Tk x d, rows >= T zero) and pe_s = [pos_h ; pos_w ; 0] (64 x d)
-__global__ void build_pe_kernel(const float* pt, const float* ph, const float* pw, __nv_bfloat16* pe_t,
-                                __nv_bfloat16* pe2, int T, int Tk, int ke2, int H, int W, int d) {
-  const int r = blockIdx.x;  // 0..Tk-1 -> pe_t rows; Tk..Tk+ke2-1 -> pe2 rows ([pos_h ; pos_w ; 0 | pos_t ; 0])
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    if (r < Tk) {
-      pe_t[(size_t)r * d + c] = __float2bfloat16_rn(r < T ? pt[(size_t)r * d + c] : 0.f);
-    } else {
-      const int s = r - Tk;
-      const int ss = s % kKe;  // the spatial table is repeated once per marginal slice
-      float v = 0.f;
-      if (s < kSpatialSlices * kKe) {
-        if (ss < H) v = ph[(size_t)ss * d + c];
-        else if (ss < H + W) v = pw[(size_t)(ss - H) * d + c];
-      } else if (s - kSpatialSlices * kKe < T) {
-        v = pt[(size_t)(s - kSpatialSlices * kKe) * d + c];
-      }
-      pe2[(size_t)s * d + c] = __float2bfloat16_rn(v);
-    }
-  }
-}
-// ind[n][c] = 1 for c == h(n) and c == H + w(n)
-__global__ void build_ind_kernel(__nv_bfloat16* ind, long long N, int H, int W) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * kKe) return;
-  const long long n = i / kKe;
-  const int c = (int)(i % kKe);
-  const int w = (int)(n % W), h = (int)((n / W) % H);
-  ind[i] = __float2bfloat16_rn((c == h || c == H + w) ? 1.f : 0.f);
-}
-__global__ void zero_f32_kernel(float* p, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 0.f;
-}
-// time marginals (rows x Tk fp32) -> columns [col0, col0 + tcols) of the bf16 marginal matrix (rows x ld); columns past
-// Tk are zero.  `flag` non-null: only when *flag != 0 (fallback re-run).
-__global__ void pack_margT_kernel(const float* src, int Tk, __nv_bfloat16* dst, int ld, int col0, int tcols,
-                                  long long rows, const int* flag) {
-  if (flag != nullptr && *flag == 0) return;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * tcols) return;
-  const long long r = i / tcols;
-  const int c = (int)(i % tcols);
-  dst[r * ld + col0 + c] = __float2bfloat16_rn(c < Tk ? src[r * Tk + c] : 0.f);
-}
-// fallback only: stabiliser := true max, sums and time marginals reset
-__global__ void repair_margT_kernel(float* margT, long long n, const int* flag) {
-  if (*flag == 0) return;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) margT[i] = 0.f;
-}
-}  // namespace tc
-
 // =================================================================================================
-// v3 pipeline: token-major probabilities, no padded MMA rows, no atomics, marginals from one GEMM
+// global pipeline: token-major probabilities, no padded MMA rows, no atomics, marginals from one GEMM
 // =================================================================================================
 struct GlobalWs3 {
   size_t p2, mg, lsum, stab, flag, pe2, ind, qt, margf, marg, total;
@@ -1309,7 +1062,7 @@ static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits
   return w;
 }
 
-static size_t global_ws3_total(int B, int T, int H, int W, int d, int J, int splits) {
+size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits) {
   return global_ws3(B, T, H, W, d, J, splits).total;
 }
 
@@ -1421,7 +1174,7 @@ __global__ void spread3_kernel(const float* stab, const float* lsum, float* m, f
 }
 }  // namespace tc
 
-static int launch_tc_global_v3(const void* X, const void* Kscore, const float* pos_t, const float* pos_h,
+int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, const float* pos_h,
                                const float* pos_w,
                                const void* qfold, float* m, float* l, float* o, int B, int T, int H, int W, int d, int J,
                                int splits, void* workspace, cudaStream_t stream) {
@@ -1451,7 +1204,7 @@ static int launch_tc_global_v3(const void* X, const void* Kscore, const float* p
 
   // 0. indicator matrix, position tables, statistics: one launch
   // the probability pass runs on CTA pairs (256-token tiles) when enabled
-  const bool pair = pair_mode_enabled() && J > 64;  // H*W >= 32 (tc_global_selected): 256 tokens span <= 9 frames
+  const bool pair = J > 64;  // H*W >= 32 (tc_global_selected): 256 tokens span <= 9 frames
   {
     const unsigned nb_ind = blocks((long long)N * (w.ild / 8));
     prep3_kernel<<<nb_ind + (unsigned)w.ke2 + blocks(BJ), 256, 0, stream>>>(
@@ -1529,8 +1282,7 @@ static int launch_tc_global_v3(const void* X, const void* Kscore, const float* p
     make_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, stab, qt, w.ke2, (int)BJ, margin, guard);
     if (check_launch("make_stab3_kernel")) return 1;
     Params p1 = pp; p1.guard = guard;
-    static const bool halves = [] { const char* e = getenv("HICOM_PROB_HALVES"); return !(e && e[0] == '0'); }();
-    if (pair && halves && J == 288) {
+    if (pair && J == 288) {
       // two 144-column N tiles per 256-token pair tile: accumulators double-buffered, the token tile is fetched twice
       if (launch<144, false, false, EPI_PROB2, 0, true>(tx128, tqj72, p1, dim3(2, gprob.y, gprob.z), stream, &ti0,
                                                         &tqej72, &ti1, &ttq72)) return 1;
@@ -1577,140 +1329,6 @@ static int launch_tc_global_v3(const void* X, const void* Kscore, const float* p
   }
   spread3_kernel<<<blocks(BJ * splits), 256, 0, stream>>>(stab, lsum, m, l, B, splits, J);
   return check_launch("spread3_kernel");
-}
-
-int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, const float* pos_h, const float* pos_w,
-                     const void* qfold,
-                     float* m, float* l, float* o, int B, int T, int H, int W, int d, int J, int splits,
-                     void* workspace, cudaStream_t stream) {
-  using namespace tc;
-  if (global_v3_enabled())
-    return launch_tc_global_v3(X, Kscore, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace,
-                               stream);
-  HICOM_REQUIRE(Kscore == nullptr, "global_attend_partial_keys needs the default global pipeline (HICOM_GLOBAL_V3 != 0)");
-  const int N = T * H * W;
-  const GlobalWs w = global_ws(B, T, H, W, d, J, splits);
-  char* ws = static_cast<char*>(workspace);
-  __nv_bfloat16* Pt = reinterpret_cast<__nv_bfloat16*>(ws + w.pt);
-  float* mg = reinterpret_cast<float*>(ws + w.mg);
-  float* lg = reinterpret_cast<float*>(ws + w.lg);
-  float* stab = reinterpret_cast<float*>(ws + w.stab);
-  int* flag = reinterpret_cast<int*>(ws + w.flag);
-  __nv_bfloat16* pe_t = reinterpret_cast<__nv_bfloat16*>(ws + w.pe_t);
-  __nv_bfloat16* pe2 = reinterpret_cast<__nv_bfloat16*>(ws + w.pe2);
-  __nv_bfloat16* ind = reinterpret_cast<__nv_bfloat16*>(ws + w.ind);
-  __nv_bfloat16* peq_s = reinterpret_cast<__nv_bfloat16*>(ws + w.peq_s);
-  float* peq_t = reinterpret_cast<float*>(ws + w.peq_t);
-  float* margT = reinterpret_cast<float*>(ws + w.margT);
-  __nv_bfloat16* marg = reinterpret_cast<__nv_bfloat16*>(ws + w.marg);
-  const long long BJ = (long long)B * J;
-  const int tcols = w.ke2 - kSpatialSlices * kKe;
-
-  // 0. tables.  PE is separable, PE[t,h,w] = pos_t[t] + pos_h[h] + pos_w[w], so no x' = x + PE tensor is needed:
-  //      S = x·qfold + pos_t[t]·qfold + (pos_h[h] + pos_w[w])·qfold      time term: added in the score epilogue;
-  //                                                                     spatial term: one extra K block against `ind`
-  //      O = sum_n p_n x_n + sum_c marg[c] · pe2[c]                      marg = probability mass per (h | w | t):
-  //                                                                     extra K blocks of the pooling GEMM
-  build_pe_kernel<<<w.Tk + w.ke2, 256, 0, stream>>>(pos_t, pos_h, pos_w, pe_t, pe2, T, w.Tk, w.ke2, H, W, d);
-  if (check_launch("build_pe_kernel")) return 1;
-  build_ind_kernel<<<(unsigned)(((long long)N * kKe + 255) / 256), 256, 0, stream>>>(ind, N, H, W);
-  if (check_launch("build_ind_kernel")) return 1;
-  init_stats_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, lg, (int)BJ, flag);
-  if (check_launch("init_stats_kernel")) return 1;
-  zero_f32_kernel<<<(unsigned)((BJ * w.Tk + 255) / 256), 256, 0, stream>>>(margT, BJ * w.Tk);
-  if (check_launch("zero_f32_kernel")) return 1;
-  {  // peq_s (B*J, 64) bf16 = qfold · pe_sᵀ (pe_s = first 64 rows of pe2);  peq_t (T, B*J) fp32 = pe_t · qfoldᵀ
-    TcLinearParams a{};
-    a.A = qfold; a.W = pe2; a.C = peq_s; a.lda = d; a.ldw = d; a.ldc = kKe; a.M = (int)BJ; a.N = kKe; a.K = d;
-    a.act = HICOM_ACT_NONE; a.out_dtype = HICOM_BF16; a.rows_per_group = 1 << 30;
-    if (launch_tc_linear(a, stream)) return 1;
-    TcLinearParams b{};
-    b.A = pe_t; b.W = qfold; b.C = peq_t; b.lda = d; b.ldw = d; b.ldc = BJ; b.M = T; b.N = (int)BJ; b.K = d;
-    b.act = HICOM_ACT_NONE; b.out_dtype = HICOM_F32; b.rows_per_group = 1 << 30;
-    if (launch_tc_linear(b, stream)) return 1;
-  }
-
-  // scores: S[b] (J x N) = [qfold[b] | peq_s[b]] · [X[b] | ind]ᵀ  — A rows j, B rows = tokens
-  CUtensorMap tq, tx, tq2, tind;
-  if (make_map(&tq, qfold, d, J, B, d, (uint64_t)J * d, BM)) return 1;
-  if (make_map(&tx, X, d, N, B, d, (uint64_t)N * d, 256)) return 1;
-  if (make_map(&tq2, peq_s, kKe, J, B, kKe, (uint64_t)J * kKe, BM)) return 1;
-  if (make_map(&tind, ind, kKe, N, 1, kKe, 0, 256)) return 1;
-  Params p{};
-  p.M = J; p.N = N; p.K = d; p.k_chunk = d; p.b_box_rows = 256;
-  p.mg = mg; p.lg = lg; p.stab = stab; p.Pt = Pt; p.pt_ld = w.pt_ld;
-  p.k_ext_blocks = kKe / BK; p.HW = H * W; p.T = T; p.peq_t = peq_t; p.peq_ld = BJ;
-  p.margT = margT; p.margT_ld = w.Tk;
-  const int n_tiles = (N + 255) / 256;
-  const int m_tiles = (J + BM - 1) / BM;
-
-  // spatial marginals: marg[:, 0:64] (B*J x 64) = Pt (B*J x tokens) · ind (tokens x 64)
-  TcLinearParams ms{};
-  ms.A = Pt; ms.W = ind; ms.C = marg; ms.lda = w.pt_ld; ms.ldw = kKe; ms.ldc = w.ke2;
-  const int kslice = ((N + kSpatialSlices - 1) / kSpatialSlices + BK - 1) / BK * BK;  // tokens per slice
-  ms.M = (int)BJ; ms.N = kKe; ms.K = kslice; ms.act = HICOM_ACT_NONE; ms.out_dtype = HICOM_BF16;
-  ms.rows_per_group = 1 << 30; ms.w_is_kn = 1;
-  ms.z_slices = kSpatialSlices; ms.z_a_k = kslice; ms.z_b_k = kslice; ms.z_c_cols = kKe; ms.k_total = N;
-
-  // pooling: O[b,s] (d x J) = [X[b, tokens of s] ; pe2]ᵀ · [P ; marg]  — the table/marginal K blocks ride on split 0
-  CUtensorMap txa, tp, tpe, tmg;
-  if (make_map(&txa, X, d, N, B, d, (uint64_t)N * d, 64)) return 1;
-  // J <= 64 (e.g. `direct` mode: one distinct query per video -> 9 columns) uses the narrow 128x64 pooling tile, which is
-  // bound by streaming X instead of by MMAs on padding columns
-  const bool narrow = J <= 64;
-  const uint32_t pool_box = narrow ? 64 : 96;
-  if (make_map(&tp, Pt, w.pt_ld, J, B, w.pt_ld, (uint64_t)J * w.pt_ld, pool_box)) return 1;
-  if (make_map(&tpe, pe2, d, w.ke2, 1, d, 0, 64)) return 1;
-  if (make_map(&tmg, marg, w.ke2, J, B, w.ke2, (uint64_t)J * w.ke2, pool_box)) return 1;
-  Params g{};
-  g.M = d; g.N = J; g.K = N;
-  int chunk = (N + splits - 1) / splits;
-  chunk = (chunk + BK - 1) / BK * BK;
-  g.k_chunk = chunk; g.b_box_rows = (int)pool_box;
-  g.o = o; g.splits = splits; g.k_ext_blocks = w.ke2 / BK;
-  dim3 gp(splits, d / BM, B);
-  const unsigned pack_blocks = (unsigned)((BJ * tcols + 255) / 256);
-
-  // 1. sampled max (a few evenly spaced token tiles) -> stabiliser.  The softmax is invariant to the stabiliser;
-  //    it only has to keep exp() inside the exponent range, so the full max pass is not needed.
-  {
-    Params ps = p;
-    const int n_sample = n_tiles < 4 ? n_tiles : 4;
-    ps.n_tile_stride = n_tiles / n_sample;
-    dim3 gsample(n_sample, m_tiles, B);
-    if (launch<256, false, false, EPI_MAX>(tq, tx, ps, gsample, stream, &tq2, &tind)) return 1;
-    make_stab_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, stab, (int)BJ);
-    if (check_launch("make_stab_kernel")) return 1;
-  }
-  // 2. single full pass: P = exp(S - stab) (bf16, transposed), row sums, time marginals, TRUE max for the check
-  dim3 gs(n_tiles, m_tiles, B);
-  if (launch<256, false, false, EPI_PROB>(tq, tx, p, gs, stream, &tq2, &tind)) return 1;
-  check_stab_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, stab, (int)BJ, flag);
-  if (check_launch("check_stab_kernel")) return 1;
-  // 3. marginals, then pooling with the position terms folded in as K blocks
-  if (launch_tc_linear(ms, stream)) return 1;
-  pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kSpatialSlices * kKe, tcols, BJ, nullptr);
-  if (check_launch("pack_margT_kernel")) return 1;
-  if (narrow ? launch<64, true, false, EPI_POOL>(txa, tp, g, gp, stream, &tpe, &tmg)
-             : launch<288, true, false, EPI_POOL>(txa, tp, g, gp, stream, &tpe, &tmg)) return 1;
-  // 4. guarded exact fallback (no-ops unless some score beat the sampled max by > 80 nats): redo 2-3 with the true max
-  {
-    repair_stab_kernel<<<(unsigned)((BJ + 255) / 256), 256, 0, stream>>>(mg, stab, lg, (int)BJ, flag);
-    if (check_launch("repair_stab_kernel")) return 1;
-    repair_margT_kernel<<<(unsigned)((BJ * w.Tk + 255) / 256), 256, 0, stream>>>(margT, BJ * w.Tk, flag);
-    if (check_launch("repair_margT_kernel")) return 1;
-    Params pf = p; pf.guard = flag;
-    Params gf = g; gf.guard = flag;
-    TcLinearParams msf = ms; msf.guard = flag;
-    if (launch<256, false, false, EPI_PROB>(tq, tx, pf, gs, stream, &tq2, &tind)) return 1;
-    if (launch_tc_linear(msf, stream)) return 1;
-    pack_margT_kernel<<<pack_blocks, 256, 0, stream>>>(margT, w.Tk, marg, w.ke2, kSpatialSlices * kKe, tcols, BJ, flag);
-    if (check_launch("pack_margT_kernel")) return 1;
-    if (narrow ? launch<64, true, false, EPI_POOL>(txa, tp, gf, gp, stream, &tpe, &tmg)
-               : launch<288, true, false, EPI_POOL>(txa, tp, gf, gp, stream, &tpe, &tmg)) return 1;
-  }
-  spread_stats_kernel<<<(unsigned)((BJ * splits + 255) / 256), 256, 0, stream>>>(stab, lg, m, l, B, splits, J);
-  return check_launch("spread_stats_kernel");
 }
 
 }  // namespace hicom

@@ -240,8 +240,11 @@ __device__ __forceinline__ void la_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-template <typename T, int CPL, int RM>
-__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1) local_attend_v2_kernel(const LocalParams p) {
+// WPB = 8: two CTAs per SM (bf16).  WPB = 16: ONE CTA per SM holding the same 16 rings (all of the SM's shared memory),
+// launched as clusters of two so that a grid limited to n SMs (hicom_set_sm_limit) occupies n/2 whole SM pairs and the
+// tensor-core kernels running beside it keep the remaining pairs for their cta_group::2 tiles.
+template <typename T, int CPL, int RM, int WPB>
+__global__ void __launch_bounds__(WPB * 32, (sizeof(T) == 2 && WPB == 8) ? 2 : 1) local_attend_v2_kernel(const LocalParams p) {
   extern __shared__ __align__(128) uint8_t la_smem[];
   constexpr int ROWB = CPL * 128 * (int)sizeof(T);
   constexpr int SLOTB = 2 * ROWB;
@@ -423,31 +426,36 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 2 : 1) local_attend_v2_k
   }
 }
 
-template <typename T, int CPL>
-static int launch_local_v2(const LocalParams& p, cudaStream_t stream) {
+template <typename T, int CPL, int WPB>
+static int launch_local_v2(const LocalParams& p, cudaStream_t stream, bool pairs) {
   constexpr int RM = sizeof(T) == 2 ? 3 : 2;  // members in flight per warp
-  constexpr int WPB = 8;
   constexpr size_t smem = (size_t)WPB * RM * 2 * CPL * 128 * sizeof(T) + WPB * RM * 8;
   static bool configured = false;
-  auto kern = local_attend_v2_kernel<T, CPL, RM>;
+  auto kern = local_attend_v2_kernel<T, CPL, RM, WPB>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HICOM_REQUIRE(e == cudaSuccess, "local_attend: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
   const long long total = (long long)p.wt.count * p.wh.count * p.ww.count * p.B;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  const int num_sms = sm_budget();
   long long blocks = (total + WPB - 1) / WPB;
-  const long long resident = (long long)num_sms * (sizeof(T) == 2 ? 2 : 1);
+  const long long resident = (long long)num_sms * ((sizeof(T) == 2 && WPB == 8) ? 2 : 1);
   if (blocks > resident) blocks = resident;  // persistent warps: the ring stays primed across windows
   KernelTimer timer("local_attend_v2", stream);
-  kern<<<(unsigned)blocks, WPB * 32, smem, stream>>>(p);
+  if (pairs) {
+    blocks = (blocks + 1) & ~1ll;  // whole clusters; a surplus CTA finds no window and exits
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(WPB * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    HICOM_REQUIRE(e == cudaSuccess, "cudaLaunchKernelEx(local_attend_v2): %s", cudaGetErrorString(e));
+  } else {
+    kern<<<(unsigned)blocks, WPB * 32, smem, stream>>>(p);
+  }
   return check_launch("local_attend_v2_kernel");
 }
 
@@ -459,14 +467,14 @@ static int launch_local(const LocalParams& p, cudaStream_t stream) {
   long long blocks = (total + warps_per_block - 1) / warps_per_block;
   if (blocks > (1 << 20)) blocks = 1 << 20;
   const int cpl = p.d / 128;
-  static int use_v1 = -1;
-  if (use_v1 < 0) { const char* e = getenv("HICOM_LOCAL_V1"); use_v1 = (e && e[0] == '1') ? 1 : 0; }
   const bool aligned = (((uintptr_t)p.K | (uintptr_t)p.V) & 15) == 0;
-  if (!p.pool_only && !use_v1 && aligned) {
+  if (!p.pool_only && aligned) {
+    // under an SM limit (the tensor-bound chain runs beside this kernel): one 16-warp CTA per SM, whole SM pairs
+    if (sizeof(T) == 2 && sm_limited() && cpl == 9) return launch_local_v2<T, 9, 16>(p, stream, true);
     switch (cpl) {
-      case 9: return launch_local_v2<T, 9>(p, stream);
-      case 6: return launch_local_v2<T, 6>(p, stream);
-      case 8: return launch_local_v2<T, 8>(p, stream);
+      case 9: return launch_local_v2<T, 9, 8>(p, stream, false);
+      case 6: return launch_local_v2<T, 6, 8>(p, stream, false);
+      case 8: return launch_local_v2<T, 8, 8>(p, stream, false);
       default: break;
     }
   }

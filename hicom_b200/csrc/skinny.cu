@@ -104,12 +104,10 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const SkinnyParams p
   }
 }
 
-static int kSkinnyMaxRows = 8;  // beyond this the 128-row tensor tile is faster (measured); HICOM_SKINNY_MAX overrides
+constexpr int kSkinnyMaxRows = 8;  // beyond this the 128-row tensor tile is faster (measured)
 
 bool skinny_supported(int in_dtype, int M, int N, int K, long long lda, long long ldw, const void* A, const void* W) {
   (void)N;
-  static bool init = false;
-  if (!init) { const char* e = getenv("HICOM_SKINNY_MAX"); if (e) kSkinnyMaxRows = atoi(e); init = true; }
   const size_t es = in_dtype == HICOM_BF16 ? 2 : 4;
   const int e16 = 16 / (int)es;
   if (M < 1 || M > kSkinnyMaxRows) return false;

@@ -21,6 +21,9 @@ import torch
 import torch.distributed as dist
 
 
+SHARD_OVERLAP = True
+
+
 def video_shard(num_videos: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous [begin, end) block of videos for ``rank`` (sizes differ by at most one)."""
     base, extra = divmod(num_videos, world)
@@ -75,10 +78,9 @@ def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, 
     B, Ts, H, W, d = X.shape
     lc, gc = projector.local_compressor, projector.global_compressor
     local_tokens = global_tokens = None
-    # EXPERIMENTAL, off unless HICOM_SHARD_OVERLAP=1 (written without a GPU at hand, to be validated next): run the
-    # local chain on the side stream, as forward_batched does, so that it overlaps the global chain and its all-gather
+    # the local chain runs on the side stream, as in forward_batched, so that it overlaps the global chain and its exchange
     side = None
-    if lc is not None and gc is not None and X.is_cuda and os.environ.get("HICOM_SHARD_OVERLAP", "0") == "1":
+    if lc is not None and gc is not None and X.is_cuda and SHARD_OVERLAP:
         from .projector import _side_stream
         main = torch.cuda.current_stream(X.device)
         side = _side_stream(X.device)

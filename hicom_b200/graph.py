@@ -16,13 +16,16 @@ import torch
 class GraphedCompressor:
     def __init__(self, projector, frames_feature: torch.Tensor, frames_embed: Optional[torch.Tensor],
                  guide_embed: Optional[torch.Tensor], modal: str = "video", frame_shard_t0: Optional[int] = None,
-                 group=None, warmup: int = 3, image_newline: Optional[torch.Tensor] = None):
+                 group=None, warmup: int = 3, image_newline: Optional[torch.Tensor] = None, adopt_inputs: bool = False):
+        """``adopt_inputs``: use the given tensors themselves as the static input buffers instead of cloning them (a
+        512-video batch is 55 GB; the caller then refills them in place between replays)."""
         self.projector = projector
         self.modal = modal
         self.image_newline = image_newline  # read in place at replay (a parameter of the parent model)
-        self.frames_feature = frames_feature.clone()
-        self.frames_embed = None if frames_embed is None else frames_embed.clone()
-        self.guide_embed = None if guide_embed is None else guide_embed.clone()
+        keep = (lambda t: t) if adopt_inputs else (lambda t: t.clone())
+        self.frames_feature = keep(frames_feature)
+        self.frames_embed = None if frames_embed is None else keep(frames_embed)
+        self.guide_embed = None if guide_embed is None else keep(guide_embed)
         self._t0 = frame_shard_t0
         self._group = group
         dev = frames_feature.device

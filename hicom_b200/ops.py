@@ -578,6 +578,27 @@ def _impl_mix_layernorm_backward(x: Tensor, y: Tensor, ln_w: Tensor, ln_b: Tenso
     return dx, dy, dw, db, da
 
 
+def set_sm_limit(sms: int) -> int:
+    """Kernels enqueued by this thread from now on size their persistent grids for at most ``sms`` SMs (0 = whole
+    device).  Returns the previous limit.  Used to run the HBM-bound local chain and the tensor-bound global chain side
+    by side on disjoint SM sets (``projector.SM_SPLIT``)."""
+    return int(_cabi.load().hicom_set_sm_limit(int(sms)))
+
+
+class sm_limit:
+    """``with ops.sm_limit(n): ...`` — scoped ``set_sm_limit``."""
+
+    def __init__(self, sms: int):
+        self.sms = int(sms)
+
+    def __enter__(self):
+        self.old = set_sm_limit(self.sms)
+        return self
+
+    def __exit__(self, *exc):
+        set_sm_limit(self.old)
+
+
 def kernel_launch_count() -> int:
     """Kernels enqueued by libhicom_b200 since load (bench.py's ``gpu_launches``)."""
     return int(_cabi.load().hicom_kernel_launch_count())
@@ -656,6 +677,17 @@ class _Timed:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
             _ACTIVE_TIMER.records.append((self.name, self.start, end))
+
+
+_SM_COUNT = {}
+
+
+def sm_count(device=None) -> int:
+    """SMs of ``device`` (cached)."""
+    key = str(device)
+    if key not in _SM_COUNT:
+        _SM_COUNT[key] = device_info(device)[0]
+    return _SM_COUNT[key]
 
 
 def device_info(device=None):

@@ -13,14 +13,35 @@ from typing import Optional
 import torch
 
 
+def _numa_nodes_of(cpus):
+    """NUMA nodes (sysfs) that own the given CPU ids; [] when sysfs does not say."""
+    nodes = set()
+    base = "/sys/devices/system/node"
+    try:
+        for name in os.listdir(base):
+            if not name.startswith("node") or not name[4:].isdigit():
+                continue
+            for part in open(os.path.join(base, name, "cpulist")).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                if part and any(int(lo) <= c <= int(hi or lo) for c in cpus):
+                    nodes.add(int(name[4:]))
+    except Exception:
+        return []
+    return sorted(nodes)
+
+
 @contextlib.contextmanager
 def host_affinity(device=None):
     """Pin the calling thread to the CPUs NVML reports as local to ``device`` for the duration of the block.
 
     Pinned host buffers allocated inside land on the GPU's NUMA node; a buffer on the far socket can cut the
-    host->device rate by 2-3x.  Best effort: without NVML, or when the container's cpuset forbids it, nothing changes.
+    host->device rate by 2-3x.  Yields a report ``{"pinned": bool, "cpus": n, "numa_nodes": [...], "reason": ...}``:
+    without NVML, or when the container's cpuset forbids the call, nothing changes and the report says why —
+    ``HICOM_REQUIRE_NUMA=1`` turns that into an error.
     """
     old = None
+    report = {"pinned": False, "cpus": len(os.sched_getaffinity(0)), "numa_nodes": _numa_nodes_of(os.sched_getaffinity(0)),
+              "reason": None}
     try:
         import pynvml
         index = torch.device(device if device is not None else torch.cuda.current_device()).index or 0
@@ -30,10 +51,15 @@ def host_affinity(device=None):
         pynvml.nvmlInit()
         old = os.sched_getaffinity(0)
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
-    except Exception:
+        now = os.sched_getaffinity(0)
+        report.update(pinned=True, cpus=len(now), numa_nodes=_numa_nodes_of(now))
+    except Exception as exc:
         old = None
+        report["reason"] = repr(exc)[:160]
+        if os.environ.get("HICOM_REQUIRE_NUMA", "0") == "1":
+            raise RuntimeError(f"host_affinity: cannot pin to the CPUs local to {device}: {exc!r}") from exc
     try:
-        yield
+        yield report
     finally:
         if old is not None:
             try:

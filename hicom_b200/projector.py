@@ -36,7 +36,10 @@ __all__ = [
 ]
 
 _IMPL = ops.IMPL_AUTO
-OVERLAP_STREAMS = os.environ.get("HICOM_OVERLAP_STREAMS", "1") == "1"
+OVERLAP_STREAMS = True  # local chain on a side stream beside the global chain (bench.py's per-op timing pass turns it off)
+# SMs given to the HBM-bound local window attention while the tensor-bound global attention runs beside it on the
+# remaining SMs (0 = both kernels are sized for the whole device and the hardware time-slices them).
+SM_SPLIT = int(os.environ.get("HICOM_SM_SPLIT", "0"))
 _SIDE_STREAMS = {}
 
 
@@ -117,6 +120,27 @@ def _mix(x, proj, norm, alpha):
     y = _run_mlp(proj, x) if isinstance(proj, nn.Sequential) else ops.linear(
         x, proj.weight, proj.bias, None, ops.ACT_NONE, False, _IMPL)
     return ops.mix_layernorm(x, y, norm.weight, norm.bias, alpha.to(x.dtype))
+
+
+_EXP_CACHE = {}
+
+
+def _exp_scalar(logit_scale) -> float:
+    """exp(logit_scale) as a Python float for the local kernel's scalar argument.  A tensor needs one device->host read:
+    it is done once per value (keyed by storage and version counter), never under stream capture — a capture that
+    meets an unseen scale fails loudly instead of baking a stale number into the graph."""
+    if not isinstance(logit_scale, torch.Tensor):
+        return float(math.exp(logit_scale))
+    key = (logit_scale.data_ptr(), logit_scale._version, logit_scale.device)
+    val = _EXP_CACHE.get(key)
+    if val is None:
+        if logit_scale.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("hicom_b200: local logit_scale must be read once outside CUDA-graph capture "
+                               "(run one eager forward first)")
+        if len(_EXP_CACHE) > 64:
+            _EXP_CACHE.clear()
+        val = _EXP_CACHE[key] = float(logit_scale.detach().float().exp())
+    return val
 
 
 def _require_no_grad(module, *tensors):
@@ -327,14 +351,19 @@ class LocalCompressor(nn.Module):
         B, T, H, W, d = X.shape
         k_l2norm = False
         if E is not None and logit_scale is not None:  # projector.py:527-529
-            k_l2norm = True
             guide = guide / guide.norm(p=2, dim=-1, keepdim=True)
+            if isinstance(self.k_alpha, torch.Tensor):
+                # the reference normalises frames_embed BEFORE the key adapter (:528, then :533):
+                # key = (1-a)·norm(E) + a·LN(k_proj(norm(E))) — normalising the mixed rows in the kernel would be norm(mix(E))
+                E = ops.l2norm_rows(E)
+            else:
+                k_l2norm = True  # no adapter: the kernel normalises each key row as it reads it
         K = X if E is None else E  # :532
         K = _mix(K, self.k_proj, self.k_norm, self.k_alpha)  # :533 (no-op kernel-free when not adapting)
         V = _mix(X, self.v_proj, self.v_norm, self.v_alpha)  # :534
         tk, _ = self.output_grid(T, H, W, modal)
         sk = self.spatial_kernel_size
-        scale = float(torch.as_tensor(logit_scale).exp()) if logit_scale is not None else 1.0 / math.sqrt(self.qk_dim)
+        scale = _exp_scalar(logit_scale) if logit_scale is not None else 1.0 / math.sqrt(self.qk_dim)
 
         mode = self.use_guide
         adapt_q = isinstance(self.q_alpha, torch.Tensor)
@@ -401,16 +430,17 @@ class GlobalCompressor(nn.Module):
 
     def _adjust_pos_cache(self, tgt_sizes, device):
         """Grow-on-demand like projector.py:609-621."""
-        grown = False
         for i in range(3):
             if tgt_sizes[i] > self.max_size[i]:
                 self.max_size[i] = tgt_sizes[i]
-                grown = True
-        key = str(device)
-        if grown or key not in self._pos_cache:
-            self._pos_cache[key] = tuple(
+        device = torch.device(device)
+        index = device.index if device.index is not None or device.type != "cuda" else torch.cuda.current_device()
+        key = (device.type, index)
+        tabs = self._pos_cache.get(key)
+        if tabs is None or any(t.shape[0] < n for t, n in zip(tabs, self.max_size)):  # stale entry of another device
+            tabs = self._pos_cache[key] = tuple(
                 torch.from_numpy(_axis_table(n, self.embed_dim)).float().to(device) for n in self.max_size)
-        return self._pos_cache[key]
+        return tabs
 
     def pos_tables(self, t0, T, H, W, device):
         pt, ph, pw = self._adjust_pos_cache((t0 + T, H, W), device)
@@ -686,13 +716,17 @@ class HIComProjector(nn.Module):
             main = torch.cuda.current_stream(X.device)
             side = _side_stream(X.device)
             side.wait_stream(main)
+        split = SM_SPLIT if (side is not None and X.dtype == torch.bfloat16 and B * T * H * W >= 65536) else 0
         if lc is not None:
             with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
-                att = lc.attend(X, frames_embed, guide_embed, modal, self.local_logit_scale, self.local_logit_bias)
+                with ops.sm_limit(split):
+                    att = lc.attend(X, frames_embed, guide_embed, modal, self.local_logit_scale, self.local_logit_bias)
                 self._emit_local(att, grid, plan, image_newline, out, n_base, stride)
         if gc is not None:
             Qg = gc.injected_query(guide_embed, B, X.dtype)
-            m, l, o = gc.partials(X, gc.fold(Qg, self.global_logit_scale), logit_scale=self.global_logit_scale)
+            qfold = gc.fold(Qg, self.global_logit_scale)
+            with ops.sm_limit(ops.sm_count(X.device) - split if split else 0):
+                m, l, o = gc.partials(X, qfold, logit_scale=self.global_logit_scale)
             gc.finish(Qg, m, l, o, out, n_base + n_local, stride)
         if side is not None:
             main.wait_stream(side)
@@ -718,7 +752,10 @@ class HIComProjector(nn.Module):
         sig = lambda t: None if t is None else (tuple(t.shape), t.dtype, t.device)
         key = (sig(frames_feature), sig(frames_embed), sig(guide_embed), modal,
                None if image_newline is None else image_newline.data_ptr(),
-               tuple(p.data_ptr() for p in self.parameters()))
+               tuple(p.data_ptr() for p in self.parameters()),
+               tuple(None if t is None else (t.data_ptr(), t._version) for t in
+                     (self.local_logit_scale, self.local_logit_bias, self.global_logit_scale, self.global_logit_bias)
+                     if t is None or isinstance(t, torch.Tensor)))
         g = cache.get(key)
         if g is None:
             from .graph import GraphedCompressor

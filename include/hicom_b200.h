@@ -47,6 +47,12 @@ int hicom_kernel_timing_enable(int on);
 size_t hicom_kernel_timing_collect(char* buf, size_t cap);
 /* Fills SM count / compute capability of the current device; fails if it is not sm_100. */
 int hicom_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* SM partitioning: kernels enqueued by the calling thread after this call size their persistent grids for at most
+ * `sms` SMs (rounded down to whole SM pairs; 0 = the whole device).  The compressor's HBM-bound chain (local window
+ * attention) and its tensor-bound chain (global scores / pooling GEMMs) have no reference counterpart to cite: the
+ * reference runs them back to back (projector.py:691,700); here they run side by side on disjoint SM sets of one GPU.
+ * Returns the previous limit. */
+int hicom_set_sm_limit(int sms);
 
 /* ---- local compressor -------------------------------------------------------------------
  * hicom_grid_pool: the trilinear grid pooling `F.interpolate(..., mode='trilinear')`

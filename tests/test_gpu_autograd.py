@@ -54,7 +54,7 @@ def test_gemm_strided_views(da, db, mode, built_library):
 @pytest.mark.parametrize("layout", ["NT", "NN", "TN"])
 @pytest.mark.parametrize("M,N,K,batch", [(2916, 288, 1152, 2), (700, 1152, 3584, 1), (1152, 4304, 648, 1), (288, 1152, 2916, 3)])
 def test_gemm_large_bf16_layouts(layout, M, N, K, batch, built_library):
-    """The three operand layouts of the backward's big bf16 contractions (tcgen05 path when HICOM_GEMM_TC is on, SIMT
+    """The three operand layouts of the backward's big bf16 contractions (tcgen05 path for large problems, SIMT
     otherwise — same contract): NT S = x'·qfoldᵀ, NN dA = dY·W, TN dW = dYᵀ·A with fp32 output; ragged M/N/K tiles."""
     from hicom_b200 import ops
     A = _r(batch, M, K, seed=1, std=0.5, dtype=torch.bfloat16)
@@ -335,25 +335,6 @@ def test_producer_head_gradients(dtype, built_library, autograd_on):
             assert O.cosine(got, leaf[k].grad) >= 0.99, k
 
 
-def test_simt_cross_check_of_the_backward_gemms(built_library):
-    """HICOM_GEMM_TC=0 keeps every backward contraction on the SIMT GEMM (read once per process): run the layout tests
-    and two whole-step gradient checks in a child process."""
-    import os
-    import subprocess
-    import sys
-    if os.environ.get("HICOM_GEMM_TC") == "0":
-        pytest.skip("already the SIMT configuration")
-    here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, HICOM_GEMM_TC="0")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_autograd.py"), "-q", "-x", "-m", "gpu",
-                        "-p", "no:cacheprovider", "-k",
-                        "gemm_large_bf16_layouts or (training_step_gradients and bfloat16 and (coarse_27x27 or adaptkv))"],
-                       env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-
-
-@pytest.mark.skipif(__import__("os").environ.get("HICOM_GEMM_TC_BATCH") != "1",
-                    reason="experimental single-launch batched TN GEMM: run with HICOM_GEMM_TC_BATCH=1 to validate it")
 def test_gemm_tn_batched_single_launch(built_library):
     from hicom_b200 import ops
     A = _r(5, 2916, 288, seed=1, std=0.5, dtype=torch.bfloat16).cuda()      # stored (K, M) per batch entry

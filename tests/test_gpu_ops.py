@@ -266,35 +266,6 @@ def test_global_partial_long_video(T, H, W, splits, built_library):
     assert O.rel_err(got[0], want) <= 8e-3
 
 
-def test_global_v2_pipeline_still_matches(built_library):
-    """HICOM_GLOBAL_V3=0 selects the older global pipeline (read once per process): run its op tests in a child."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, HICOM_GLOBAL_V3="0")
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_ops.py"), "-q", "-x", "-m", "gpu",
-                        "-k", "global_partial and not v2_pipeline", "-p", "no:cacheprovider"],
-                       env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "passed" in r.stdout
-
-
-def test_single_cta_tiles_still_match(built_library):
-    """HICOM_CTA2=0 turns the CTA-pair (cta_group::2) variants off (read once per process): run the GEMM-heavy op tests
-    on single-CTA tiles in a child."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, HICOM_CTA2="0")
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_ops.py"), "-q", "-x", "-m", "gpu",
-                        "-k", "(linear or global_partial) and not pipeline and not single_cta", "-p",
-                        "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "passed" in r.stdout
-
-
 @pytest.mark.parametrize("M,N,K,act", [(40000, 512, 256, 0), (10300, 3584, 1152, 1), (38000, 300, 64, 0)])
 def test_linear_cta_pairs_large(M, N, K, act, built_library):
     """Large plain GEMMs run on CTA pairs (M = 256 per MMA, half of the weight tile per CTA): odd M-tile counts, ragged

@@ -273,10 +273,12 @@ def test_clip_l_tower_dims(guide, dtype, built_library):
         assert O.cosine(got, want) >= 0.999 and O.rel_err(got, want) <= 1e-2
 
 
-@pytest.mark.parametrize("name", ["coarse_T8", "direct_T8", "fine_T8", "bf16_coarse_T8"])
+@pytest.mark.parametrize("name", ["coarse_T8", "direct_T8", "fine_T8", "bf16_coarse_T8", "adaptkv_coarse_T8",
+                                  "adaptqkvg_coarse_T4", "adaptqkvg_fine_T8"])
 def test_local_clip_scale(name, built_library):
     """use_clip_scale='local' (projector.py:527-529, 547-549): L2-normalised keys and guide, exp(logit_scale) logits.
-    The SigLIP scalars are set on the module directly (the reference pulls them from the hub, :661-663)."""
+    The SigLIP scalars are set on the module directly (the reference pulls them from the hub, :661-663).  With the key
+    adapter (adaptk) the reference normalises frames_embed BEFORE the adapter mix (:528 then :533)."""
     case = CASES_BY_NAME[name]
     sd, X, E, g, nl = materialise(case)
     m = cuda_module_for(case, sd)

@@ -79,10 +79,10 @@ def test_live_reference_clip_l_dims(use_guide):
     assert O.rel_err(got, want) <= 2e-6
 
 
-@pytest.mark.parametrize("use_guide", ["coarse", "direct", "fine"])
+@pytest.mark.parametrize("use_guide", ["coarse", "direct", "fine", "adaptkv_coarse", "adaptqkvg_fine"])
 def test_live_reference_clip_scale(use_guide):
     """use_clip_scale='local,global' (projector.py:527-529, 547-549, 184-188) with the SigLIP scalars passed in
-    (the hub weights are unavailable offline)."""
+    (the hub weights are unavailable offline); the adapter cases pin the order normalise -> key adapter (:528, :533)."""
     from oracle.cases import CASES_BY_NAME
     ref = load_reference()
     case = CASES_BY_NAME[f"{use_guide}_T8"]
