@@ -75,11 +75,12 @@ def _impl_grid_pool(X: Tensor, kt: int, ks: int) -> Tensor:
     return out
 
 
-def _impl_local_attend(K: Tensor, V: Tensor, P: Tensor, q_aux: Optional[Tensor], film: Optional[Tensor],
-                 ln_w: Optional[Tensor], ln_b: Optional[Tensor], kt: int, ks: int, qmode: int,
-                 logit_scale: float, k_l2norm: bool) -> Tensor:
-    """Fused pool -> inject -> window softmax -> A·V — projector.py:536-558.  Returns (B,Nw,d)."""
-    dev = _need_cuda(K, V, P, q_aux, film, ln_w, ln_b)
+def _impl_local_attend_into(K: Tensor, V: Tensor, P: Tensor, q_aux: Optional[Tensor], film: Optional[Tensor],
+                            ln_w: Optional[Tensor], ln_b: Optional[Tensor], kt: int, ks: int, qmode: int,
+                            logit_scale: float, k_l2norm: bool, out: Tensor) -> None:
+    """Fused pool -> inject -> window softmax -> A·V — projector.py:536-558 — written into ``out`` (B,Nw,d), which may
+    be a leading-dim slice of a larger buffer (the forward computes the batch in two halves)."""
+    dev = _need_cuda(K, V, P, q_aux, film, ln_w, ln_b, out)
     same_kv = K.data_ptr() == V.data_ptr()
     same_pv = P.data_ptr() == V.data_ptr()
     V = V.contiguous()
@@ -103,12 +104,22 @@ def _impl_local_attend(K: Tensor, V: Tensor, P: Tensor, q_aux: Optional[Tensor],
         raise ValueError("local_attend: Q_VECTOR needs q_aux (B,d)")
     if qmode == Q_EXPLICIT and (q_aux is None or q_aux.shape != (B, nw, d)):
         raise ValueError(f"local_attend: Q_EXPLICIT needs q_aux (B,{nw},{d})")
-    out = torch.empty((B, nw, d), dtype=V.dtype, device=dev)
+    if out.shape != (B, nw, d) or out.dtype != V.dtype or not out.is_contiguous():
+        raise ValueError(f"local_attend: out must be a contiguous (B,{nw},{d}) tensor in the feature dtype")
     with torch.cuda.device(dev):
         rc = _cabi.load().hicom_local_attend(_ptr(K), _ptr(V), _ptr(P), _ptr(q_aux), _ptr(film), _ptr(ln_w),
                                              _ptr(ln_b), _ptr(out), B, T, H, W, d, kt, ks, qmode,
                                              float(logit_scale), int(k_l2norm), _dt(V), _stream(dev))
     _cabi.check(rc, "hicom_local_attend")
+
+
+def _impl_local_attend(K: Tensor, V: Tensor, P: Tensor, q_aux: Optional[Tensor], film: Optional[Tensor],
+                       ln_w: Optional[Tensor], ln_b: Optional[Tensor], kt: int, ks: int, qmode: int,
+                       logit_scale: float, k_l2norm: bool) -> Tensor:
+    """Fused pool -> inject -> window softmax -> A·V — projector.py:536-558.  Returns (B,Nw,d)."""
+    B, T, H, W, d = V.shape
+    out = torch.empty((B, num_windows(T, H, W, kt, ks), d), dtype=V.dtype, device=V.device)
+    _impl_local_attend_into(K, V, P, q_aux, film, ln_w, ln_b, kt, ks, qmode, logit_scale, k_l2norm, out)
     return out
 
 
@@ -742,6 +753,7 @@ def _rows(t):
 _lin_label = lambda A, W, *a: f"linear M={_rows(A)} N={W.shape[0]} K={W.shape[1]}"
 grid_pool = _wrap("grid_pool", _impl_grid_pool, (), lambda *a: "grid_pool")
 local_attend = _wrap("local_attend", _impl_local_attend, (), lambda *a: "local_attend")
+local_attend_into = _wrap("local_attend_into", _impl_local_attend_into, ("out",), lambda *a: "local_attend")
 linear = _wrap("linear", _impl_linear, (), _lin_label)
 linear_into = _wrap("linear_into", _impl_linear_into, ("out",), _lin_label)
 layernorm = _wrap("layernorm", _impl_layernorm, (), lambda *a: "layernorm")

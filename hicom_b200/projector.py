@@ -39,7 +39,7 @@ _IMPL = ops.IMPL_AUTO
 OVERLAP_STREAMS = True  # local chain on a side stream beside the global chain (bench.py's per-op timing pass turns it off)
 # SMs given to the HBM-bound local window attention while the tensor-bound global attention runs beside it on the
 # remaining SMs (0 = both kernels are sized for the whole device and the hardware time-slices them).
-SM_SPLIT = int(os.environ.get("HICOM_SM_SPLIT", "0"))
+SM_SPLIT = int(os.environ.get("HICOM_SM_SPLIT", "48"))
 _SIDE_STREAMS = {}
 
 
@@ -346,8 +346,9 @@ class LocalCompressor(nn.Module):
         sk = self.spatial_kernel_size
         return tk, (math.ceil(t / tk), math.ceil(h / sk), math.ceil(w / sk))
 
-    def attend(self, X, E, guide, modal, logit_scale=None, logit_bias=None):
-        """Batched projector.py:524-558: X,E (B,T,H,W,d) -> attended (B,Nw,d) before the readout."""
+    def attend(self, X, E, guide, modal, logit_scale=None, logit_bias=None, out=None):
+        """Batched projector.py:524-558: X,E (B,T,H,W,d) -> attended (B,Nw,d) before the readout (written into ``out``
+        when given: a leading-dim slice of a larger buffer)."""
         B, T, H, W, d = X.shape
         k_l2norm = False
         if E is not None and logit_scale is not None:  # projector.py:527-529
@@ -385,7 +386,10 @@ class LocalCompressor(nn.Module):
                 q0 = ops.grid_pool(X, tk, sk)
                 q0 = _mix(q0, self.q_proj, self.q_norm, self.q_alpha)  # :541
                 q_aux, qmode = inj(q0, guide), ops.Q_EXPLICIT
-        return ops.local_attend(K, V, X, q_aux, film, ln_w, ln_b, tk, sk, qmode, scale, k_l2norm)
+        if out is None:
+            return ops.local_attend(K, V, X, q_aux, film, ln_w, ln_b, tk, sk, qmode, scale, k_l2norm)
+        ops.local_attend_into(K, V, X, q_aux, film, ln_w, ln_b, tk, sk, qmode, scale, k_l2norm, out)
+        return out
 
     def forward(self, frames_feature, frames_embed, guide_embed, modal, logit_scale, logit_bias):
         """Reference signature (projector.py:524): one video, returns (t1,h1,w1,Dh)."""
@@ -716,7 +720,11 @@ class HIComProjector(nn.Module):
             main = torch.cuda.current_stream(X.device)
             side = _side_stream(X.device)
             side.wait_stream(main)
-        split = SM_SPLIT if (side is not None and X.dtype == torch.bfloat16 and B * T * H * W >= 65536) else 0
+        big = side is not None and X.dtype == torch.bfloat16 and B >= 4 and B * T * H * W >= 65536
+        # Large batches: the window attention is HBM-bound — on 48 SMs it needs 30 SM-ms instead of the 47 it holds on
+        # all 148 while waiting for HBM — so it gets `SM_SPLIT` SMs (whole SM pairs) and the tensor-bound global chain
+        # the rest, side by side (measured: c2 -4 %, c3 / c5 -0.2..2 %; profiles/r02_sm_split.md).
+        split = SM_SPLIT if big else 0
         if lc is not None:
             with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
                 with ops.sm_limit(split):

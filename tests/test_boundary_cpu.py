@@ -149,3 +149,21 @@ def test_splice_rows_per_sample_offsets():
         splice_rows(out, tokens, [0, 9, 3])
     with pytest.raises(ValueError, match="do not match"):
         splice_rows(out, tokens, [0, 1])
+
+
+def test_batch_view_is_zero_copy_for_split_views():
+    """caller.batch_view: consecutive `split` views of one tower output (hicom_arch.py:162-164) become one strided view;
+    scattered tensors fall back to a stacked copy with the same values."""
+    from hicom_b200.caller import batch_view
+    big = torch.randn(5 * 4, 3, 3, 8)
+    parts = big.split([4] * 5, 0)
+    v = batch_view(parts)
+    assert v.data_ptr() == big.data_ptr() and v.shape == (5, 4, 3, 3, 8) and torch.equal(v, torch.stack(parts))
+    v2 = batch_view([parts[1], parts[3]])  # constant pitch: still a view
+    assert v2.data_ptr() == parts[1].data_ptr() and torch.equal(v2, torch.stack([parts[1], parts[3]]))
+    for scattered in ([parts[3], parts[1]], [parts[0], parts[1], parts[3]], [parts[0], parts[1].clone()]):
+        v3 = batch_view(scattered)
+        assert torch.equal(v3, torch.stack(scattered)) and v3.data_ptr() != scattered[0].data_ptr()
+    g = torch.randn(5, 8)
+    assert batch_view([g[i] for i in range(5)]).data_ptr() == g.data_ptr()
+    assert batch_view([g[2]]).shape == (1, 8)

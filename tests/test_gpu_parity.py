@@ -229,6 +229,37 @@ def test_batched_caller_matches_per_sample_loop(built_library):
         assert O.rel_err(a.cpu(), b.cpu()) <= 1e-5
 
 
+def test_batched_caller_views_the_tower_output_in_place(built_library, monkeypatch):
+    """hicom_arch.py:162-164: the per-sample tensors are `split` views of ONE tower output.  compress_samples must hand
+    forward_batched a batch VIEW of that allocation (no 27 MB-per-video stack copy) and still equal the loop."""
+    from hicom_b200.caller import compress_samples
+    case = CASES_BY_NAME["bf16_coarse_T8"]
+    sd, _, _, _, _ = materialise(case)
+    m = cuda_module_for(case, sd)
+    B, T = 4, case.T
+    gen = torch.Generator().manual_seed(21)
+    tower_x = (0.5 * torch.randn(B * T, case.H, case.W, 1152, generator=gen)).to(torch.bfloat16).cuda()
+    tower_e = (0.5 * torch.randn(B * T, case.H, case.W, 1152, generator=gen)).to(torch.bfloat16).cuda()
+    guides_t = (0.5 * torch.randn(B, 1152, generator=gen)).to(torch.bfloat16).cuda()
+    feats, embeds = tower_x.split([T] * B, dim=0), tower_e.split([T] * B, dim=0)
+    guides = [guides_t[i] for i in range(B)]
+    seen = {}
+    real = m.forward_batched
+
+    def spy(X, E, G, *a, **k):
+        seen["ptrs"] = (X.data_ptr(), E.data_ptr(), G.data_ptr())
+        return real(X, E, G, *a, **k)
+
+    monkeypatch.setattr(m, "forward_batched", spy)
+    with torch.no_grad():
+        got = compress_samples(m, feats, embeds, guides, ["video"] * B)
+        assert seen["ptrs"] == (tower_x.data_ptr(), tower_e.data_ptr(), guides_t.data_ptr())  # views, not copies
+        monkeypatch.undo()
+        want = [m(feats[i], embeds[i], guides[i], "video") for i in range(B)]
+    for a, b in zip(got, want):
+        assert O.rel_err(a.float().cpu(), b.float().cpu()) <= 1e-2
+
+
 @pytest.mark.parametrize("name", ["coarse_T8", "direct_T8", "fine_T8", "image_T1_newline"])
 def test_fp16_inference_dtype(name, built_library):
     """The reference's inference path is fp16 (model/__init__.py:44; mm_infer casts inputs to fp16): fp16 weights and

@@ -1,7 +1,7 @@
 #!/bin/bash
 # sweep HICOM_SM_SPLIT over the headline workloads (graph replay, no extras)
-for wl in c2 c3 c5; do
-  for L in 0 32 40 48 56; do
+for wl in $WLS; do
+  for L in $SPLITS; do
     HICOM_SM_SPLIT=$L python bench.py --workload $wl --steps 10 --no-cpu-baseline --no-parity --no-sustained --no-c4 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
