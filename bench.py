@@ -282,25 +282,28 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+DTYPE = torch.bfloat16  # --dtype fp16 switches the timed arm to the reference's inference dtype (model/__init__.py:44)
+
+
 def build_projector(hidden, device):
     import hicom_b200
     torch.manual_seed(0)
     m = hicom_b200.build_vision_projector(Cfg(hidden))
     with torch.no_grad():
         m.global_compressor.query.normal_(0, 0.02)  # zero-init in the reference (projector.py:583)
-    return m.to(torch.bfloat16).to(device).eval()
+    return m.to(DTYPE).to(device).eval()
 
 
 def synth_batch(B, T, device, seed):
     """(X, E, G) ~ N(0, 0.5^2) in bf16, generated video by video so that the fp32 temporaries of a
     512-video batch never exist at once."""
     g = torch.Generator(device=device).manual_seed(seed)
-    X = torch.empty((B, T, H, W, D), dtype=torch.bfloat16, device=device)
+    X = torch.empty((B, T, H, W, D), dtype=DTYPE, device=device)
     E = torch.empty_like(X)
     for b in range(B):
         X[b] = 0.5 * torch.randn(T, H, W, D, generator=g, device=device, dtype=torch.float32)
         E[b] = 0.5 * torch.randn(T, H, W, D, generator=g, device=device, dtype=torch.float32)
-    G = (0.5 * torch.randn(B, D, generator=g, device=device, dtype=torch.float32)).to(torch.bfloat16)
+    G = (0.5 * torch.randn(B, D, generator=g, device=device, dtype=torch.float32)).to(DTYPE)
     return X, E, G
 
 
@@ -317,7 +320,7 @@ def oracle_parity(proj, X, E, G, tokens, video=0, t0=0):
         truth = orc.forward(f(X), f(E), f(G), "video")
     got = tokens[video].float().cpu()
     return {"video": video, "rel_err": O.rel_err(got, truth), "cos": O.cosine(got, truth),
-            "tokens": list(got.shape), "against": "fp32 CPU oracle of projector.py:676-708 on the bf16-rounded weights/inputs",
+            "tokens": list(got.shape), "against": "fp32 CPU oracle of projector.py:676-708 on the 16-bit-rounded weights/inputs",
             "gate": "rel_err <= 1e-2 and cos >= 0.999"}
 
 
@@ -585,7 +588,7 @@ def run_ours(args):
         Be = min(B, 32)  # bounded host batch (c5 at N=1 would pin 55 GB): e2e is a per-video rate, PCIe-bound
         with host_affinity(device) as numa:  # pinned buffers on the GPU's NUMA node
             Xh, Eh, Gh = [None if t is None else t[:Be].cpu().pin_memory() for t in (X, E, G)]
-            out_h = torch.empty((Be, n_tok, hidden), dtype=torch.bfloat16).pin_memory()
+            out_h = torch.empty((Be, n_tok, hidden), dtype=DTYPE).pin_memory()
             # raw pinned host->device rate of this box, so the e2e number can be read against its PCIe roofline
             torch.cuda.synchronize()
             cs, ce = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -708,7 +711,7 @@ def run_ours(args):
         "metric": "frames/s through the HICom compressor", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "dtype": "fp16" if DTYPE == torch.float16 else "bf16", "data": "synthetic",
         "config": {"workload": desc, "projector_type": PTYPE, "use_guide": USE_GUIDE,
                    "launch": launch_mode, "per_gpu_batch": B, "frames_per_video": T, "sharding": "frame" if frame_sharded else "video",
                    "l2": f"inputs are {2 * B * T_local * H * W * D * 2 / 1e9:.2f} GB per GPU per step (> 126 MB L2), "
@@ -761,7 +764,7 @@ def csrc_digest():
 
 
 def main():
-    global USE_GUIDE
+    global USE_GUIDE, DTYPE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -770,6 +773,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--use-guide", default=USE_GUIDE, choices=["coarse", "direct", "none"],
                     help="guide mode (headline: coarse; direct = what the released checkpoint runs; none = stage 1)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="storage dtype of the timed arm (fp16 = the reference's inference dtype; tcgen05 kind::f16 either way)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed output")
@@ -779,6 +784,7 @@ def main():
     ap.add_argument("--digest", action="store_true", help="print the digest of the kernel sources and exit")
     args = ap.parse_args()
     USE_GUIDE = None if args.use_guide == "none" else args.use_guide
+    DTYPE = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     if args.digest:
         print(csrc_digest())
         return

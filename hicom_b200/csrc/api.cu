@@ -178,6 +178,7 @@ extern "C" int hicom_linear(const void* A, int64_t lda, const void* W, int64_t l
     t.A = A; t.W = W; t.bias = bias; t.R = R; t.C = C;
     t.lda = lda; t.ldw = ldw; t.ldr = ldr; t.ldc = ldc; t.M = M; t.N = N; t.K = K; t.act = act;
     t.out_dtype = out_dtype; t.rows_per_group = rows_per_group; t.group_stride_rows = group_stride_rows;
+    t.a_f16 = t.w_f16 = in_dtype == HICOM_F16;
     return launch_tc_linear(t, as_stream(stream));
   }
   GemmParams g = plain_gemm();
@@ -192,6 +193,8 @@ extern "C" int hicom_linear(const void* A, int64_t lda, const void* W, int64_t l
   if (in_dtype == HICOM_BF16 && out_dtype == HICOM_BF16) return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(g, s);
   if (in_dtype == HICOM_BF16 && out_dtype == HICOM_F32) return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, float>(g, s);
   if (in_dtype == HICOM_F32 && out_dtype == HICOM_BF16) return launch_gemm_simt<float, float, __nv_bfloat16>(g, s);
+  if (in_dtype == HICOM_F16 && out_dtype == HICOM_F16) return launch_gemm_simt<__half, __half, __half>(g, s);
+  if (in_dtype == HICOM_F16 && out_dtype == HICOM_F32) return launch_gemm_simt<__half, __half, float>(g, s);
   set_error("linear: bad dtype codes %d/%d", in_dtype, out_dtype);
   return 1;
 }
@@ -202,13 +205,15 @@ extern "C" int hicom_global_fold_query(const void* q, const void* Wk, void* qfol
   HICOM_REQUIRE(B >= 0 && Q > 0 && heads > 0 && d % heads == 0, "global_fold_query: bad shape");
   if (B == 0) return 0;
   const int hd = d / heads;
-  if (dtype == HICOM_BF16 && hd % 64 == 0 && d % 8 == 0 && !((uintptr_t)q & 15) && !((uintptr_t)Wk & 15)) {
+  if ((dtype == HICOM_BF16 || dtype == HICOM_F16) && hd % 64 == 0 && d % 8 == 0 && !((uintptr_t)q & 15) &&
+      !((uintptr_t)Wk & 15)) {
     // one tcgen05 launch, blockIdx.z = head: A = q (B*Q, d) K-slice of the head, B operand = Wk (k rows, n
     // contiguous -> MN-major), rows (b,i) land at qfold row b*J + h*Q + i
     TcLinearParams t{};
     t.A = q; t.W = Wk; t.C = qfold;
     t.lda = d; t.ldw = d; t.ldc = d; t.M = B * Q; t.N = d; t.K = hd; t.act = HICOM_ACT_NONE;
-    t.out_dtype = HICOM_BF16; t.rows_per_group = Q; t.group_stride_rows = (long long)heads * Q;
+    t.out_dtype = dtype; t.a_f16 = t.w_f16 = dtype == HICOM_F16;
+    t.rows_per_group = Q; t.group_stride_rows = (long long)heads * Q;
     t.alpha = alpha; t.w_is_kn = 1;
     t.z_slices = heads; t.z_a_k = hd; t.z_b_k = hd; t.z_c_rows = Q;
     return launch_tc_linear(t, as_stream(stream));
@@ -223,6 +228,7 @@ extern "C" int hicom_global_fold_query(const void* q, const void* Wk, void* qfol
   cudaStream_t s = as_stream(stream);
   if (dtype == HICOM_F32) return launch_gemm_simt<float, float, float>(g, s);
   if (dtype == HICOM_BF16) return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(g, s);
+  if (dtype == HICOM_F16) return launch_gemm_simt<__half, __half, __half>(g, s);
   set_error("global_fold_query: bad dtype %d", dtype);
   return 1;
 }
@@ -233,13 +239,15 @@ extern "C" int hicom_global_value_proj(const void* pooled, const void* Wv, const
   HICOM_REQUIRE(B >= 0 && Q > 0 && heads > 0 && d % heads == 0, "global_value_proj: bad shape");
   if (B == 0) return 0;
   const int hd = d / heads;
-  if (dtype == HICOM_BF16 && hd % 32 == 0 && d % 8 == 0 && !((uintptr_t)pooled & 15) && !((uintptr_t)Wv & 15)) {
+  if ((dtype == HICOM_BF16 || dtype == HICOM_F16) && hd % 32 == 0 && d % 8 == 0 && !((uintptr_t)pooled & 15) &&
+      !((uintptr_t)Wv & 15)) {
     // one dense tcgen05 GEMM (B*J, d) x Wvᵀ whose epilogue keeps only the diagonal head blocks: the 9x redundant
     // flops (tens of GFLOP) are cheaper than nine launch-bound per-head GEMMs.
     TcLinearParams t{};
     t.A = pooled; t.W = Wv; t.bias = bv; t.C = attn;
     t.lda = d; t.ldw = d; t.ldc = d; t.M = B * heads * Q; t.N = d; t.K = d; t.act = HICOM_ACT_NONE;
-    t.out_dtype = HICOM_BF16; t.rows_per_group = 1 << 30; t.group_stride_rows = 0;
+    t.out_dtype = dtype; t.a_f16 = t.w_f16 = dtype == HICOM_F16;
+    t.rows_per_group = 1 << 30; t.group_stride_rows = 0;
     t.diag_heads = heads; t.diag_rows = Q; t.diag_cols = hd;
     return launch_tc_linear(t, as_stream(stream));
   }
@@ -254,6 +262,7 @@ extern "C" int hicom_global_value_proj(const void* pooled, const void* Wv, const
   cudaStream_t s = as_stream(stream);
   if (dtype == HICOM_F32) return launch_gemm_simt<float, float, float>(g, s);
   if (dtype == HICOM_BF16) return launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(g, s);
+  if (dtype == HICOM_F16) return launch_gemm_simt<__half, __half, __half>(g, s);
   set_error("global_value_proj: bad dtype %d", dtype);
   return 1;
 }
@@ -261,7 +270,7 @@ extern "C" int hicom_global_value_proj(const void* pooled, const void* Wv, const
 // ---- global attention partials --------------------------------------------------------------------
 // SIMT pipeline (fp32 mode, and the cross-check for the tensor path):
 //   posadd -> S = X'·qfoldᵀ (fp32) -> per-split column softmax stats, P in place -> O = Pᵀ·X' per split.
-static size_t elem_size(int dtype) { return dtype == HICOM_BF16 ? 2 : 4; }
+static size_t elem_size(int dtype) { return dtype == HICOM_F32 ? 4 : 2; }
 
 extern "C" size_t hicom_global_attend_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits,
                                                       int dtype, int impl) {
@@ -281,7 +290,7 @@ static int global_attend_partial_impl(const void* X, const void* Kscore, const f
   HICOM_REQUIRE(pos_t && pos_h && pos_w, "global_attend_partial: position tables required");
   HICOM_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && d > 0 && d % 128 == 0 && J > 0 && splits > 0,
                 "global_attend_partial: bad shape");
-  HICOM_REQUIRE(dtype == HICOM_F32 || dtype == HICOM_BF16, "global_attend_partial: bad dtype %d", dtype);
+  HICOM_REQUIRE(dtype == HICOM_F32 || dtype == HICOM_BF16 || dtype == HICOM_F16, "global_attend_partial: bad dtype %d", dtype);
   HICOM_REQUIRE(workspace_bytes >= hicom_global_attend_workspace_bytes(B, T, H, W, d, J, splits, dtype, impl),
                 "global_attend_partial: workspace too small");
   HICOM_REQUIRE(((uintptr_t)workspace & 255) == 0, "global_attend_partial: workspace must be 256-byte aligned");
@@ -291,7 +300,8 @@ static int global_attend_partial_impl(const void* X, const void* Kscore, const f
   if (impl == HICOM_IMPL_TCGEN05)
     HICOM_REQUIRE(tc_global_selected(dtype, impl, d, J, T, H, W), "global_attend_partial: tcgen05 path needs bf16, d%%128==0");
   if (tc_global_selected(dtype, impl, d, J, T, H, W))
-    return launch_tc_global(X, Kscore, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace, s);
+    return launch_tc_global(X, Kscore, pos_t, pos_h, pos_w, qfold, m, l, o, B, T, H, W, d, J, splits, workspace, s,
+                            dtype == HICOM_F16);
 
   const int rows_per_split = (N + splits - 1) / splits;
   char* ws = static_cast<char*>(workspace);
@@ -306,7 +316,9 @@ static int global_attend_partial_impl(const void* X, const void* Kscore, const f
     g.sBk = 1; g.sBn = d; g.sBb1 = (long long)J * d;
     g.ldc = J; g.sCb1 = (long long)N * J;
     g.nb1 = B; g.nb2 = 1;
-    int rc = dtype == HICOM_F32 ? launch_gemm_simt<float, float, float>(g, s) : launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, float>(g, s);
+    int rc = dtype == HICOM_F32 ? launch_gemm_simt<float, float, float>(g, s)
+             : dtype == HICOM_F16 ? launch_gemm_simt<__half, __half, float>(g, s)
+                                  : launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, float>(g, s);
     if (rc) return rc;
   }
   if (launch_col_softmax(S, m, l, B, N, J, splits, rows_per_split, s)) return 1;
@@ -319,7 +331,9 @@ static int global_attend_partial_impl(const void* X, const void* Kscore, const f
     g.sBk = d; g.sBn = 1; g.sBb1 = (long long)N * d; g.sBb2 = (long long)rows_per_split * d;
     g.ldc = d; g.sCb1 = (long long)splits * J * d; g.sCb2 = (long long)J * d;
     g.nb1 = B; g.nb2 = splits;
-    int rc = dtype == HICOM_F32 ? launch_gemm_simt<float, float, float>(g, s) : launch_gemm_simt<float, __nv_bfloat16, float>(g, s);
+    int rc = dtype == HICOM_F32 ? launch_gemm_simt<float, float, float>(g, s)
+             : dtype == HICOM_F16 ? launch_gemm_simt<float, __half, float>(g, s)
+                                  : launch_gemm_simt<float, __nv_bfloat16, float>(g, s);
     if (rc) return rc;
   }
   return 0;

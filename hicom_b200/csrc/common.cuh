@@ -1,6 +1,7 @@
 // Shared helpers for the hicom_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -86,6 +87,30 @@ struct Vec4<__nv_bfloat16> {
   }
 };
 
+template <>
+struct Vec4<__half> {
+  using raw = uint2;
+  static __device__ __forceinline__ void unpack(uint2 r, float (&v)[4]) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[4]) {
+    unpack(*reinterpret_cast<const uint2*>(p), v);
+  }
+  static __device__ __forceinline__ void load_stream(const __half* p, float (&v)[4]) {
+    unpack(__ldcs(reinterpret_cast<const uint2*>(p)), v);
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[4]) {
+    __half2 a = __floats2half2_rn(v[0], v[1]);
+    __half2 b = __floats2half2_rn(v[2], v[3]);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+};
+
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>
@@ -93,8 +118,13 @@ __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
 template <typename T>
 __device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <>
 __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
@@ -124,7 +154,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLnEps = 1e-6f;  // projector.py:318,403,565
 
-// dispatch a lambda-like macro over the two storage types
+// dispatch a lambda-like macro over the three storage types
 #define HICOM_DISPATCH_DTYPE(dtype, T, ...)                 \
   do {                                                      \
     if ((dtype) == HICOM_F32) {                             \
@@ -132,6 +162,9 @@ constexpr float kLnEps = 1e-6f;  // projector.py:318,403,565
       __VA_ARGS__;                                          \
     } else if ((dtype) == HICOM_BF16) {                     \
       using T = __nv_bfloat16;                              \
+      __VA_ARGS__;                                          \
+    } else if ((dtype) == HICOM_F16) {                      \
+      using T = __half;                                     \
       __VA_ARGS__;                                          \
     } else {                                                \
       ::hicom::set_error("unknown dtype code %d", (dtype)); \

@@ -117,5 +117,8 @@ template int launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(const
 template int launch_gemm_simt<__nv_bfloat16, __nv_bfloat16, float>(const GemmParams&, cudaStream_t);
 template int launch_gemm_simt<float, float, __nv_bfloat16>(const GemmParams&, cudaStream_t);
 template int launch_gemm_simt<float, __nv_bfloat16, float>(const GemmParams&, cudaStream_t);
+template int launch_gemm_simt<__half, __half, __half>(const GemmParams&, cudaStream_t);
+template int launch_gemm_simt<__half, __half, float>(const GemmParams&, cudaStream_t);
+template int launch_gemm_simt<float, __half, float>(const GemmParams&, cudaStream_t);
 
 }  // namespace hicom

@@ -41,7 +41,7 @@ struct Params {
   int k_chunk;       // K range per blockIdx.x for EPI_POOL (multiple of BK); else K
   int b_box_rows;    // rows per TMA box of the B tile
   // EPI_LINEAR
-  const __nv_bfloat16* bias; const __nv_bfloat16* R; long long ldr;
+  const uint16_t* bias; const uint16_t* R; long long ldr;   // 16-bit rows in A's format
   void* C; long long ldc; int out_dtype; int act; int rows_per_group; long long group_stride_rows;
   float alpha;                     // accumulator scale applied before the bias
   int diag_heads, diag_rows, diag_cols;  // >0: row r=(g,h,i) keeps only columns of head h, written to row g*diag_rows+i
@@ -62,6 +62,11 @@ struct Params {
   int b_shared;                    // B operand has no batch axis (coordinate 0 for every batch entry)
   __nv_bfloat16* P2; long long p2_ld;  // EPI_PROB2: probabilities (B, tokens, p2_ld), token-major
   const __nv_bfloat16* tqm; long long tqm_ld;  // (B*J, tqm_ld) bf16 rows: time term pos_t[t]·qfold[b,j] of the scores (EPI_MAX)
+  // operand formats of the MAIN K blocks (extension blocks are always the library's own bf16 tables): 1 = fp16.
+  // bias and R are stored like A; out_dtype says how C is stored.
+  int a_f16, b_f16;
+  int ext_f16;                     // format of BOTH operands of the extension K blocks (A and B of one MMA must agree)
+  int p2_f16;                      // EPI_PROB2 stores fp16 probabilities; EPI_MAX reads fp16 time terms (tqm)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -275,6 +280,28 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// two 16-bit elements -> fp32 (bf16: a shift; fp16: one cvt) and back; `f16` is warp-uniform
+__device__ __forceinline__ void unpack2(uint32_t w, bool f16, float& lo, float& hi) {
+  if (f16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x; hi = f.y;
+  } else {
+    lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool f16) { return f16 ? pack_f16(a, b) : pack_bf16(a, b); }
+__device__ __forceinline__ float ld16(const uint16_t* p, bool f16) {
+  const uint16_t v = *p;
+  return f16 ? __half2float(__ushort_as_half(v)) : __uint_as_float((uint32_t)v << 16);
+}
+__device__ __forceinline__ uint16_t cvt16(float v, bool f16) {
+  return f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 
 // Epilogue store coalescing.  After tcgen05.ld each lane owns one output row: 32 bf16 columns = four 16-byte pieces
@@ -492,7 +519,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (pair_rank == 0) {
         constexpr int NI = BN > 256 ? BN / 2 : BN;          // columns per instruction
         constexpr int HALF = NI / 2;                        // B rows per CTA per instruction
-        constexpr uint32_t idesc = make_idesc(NI, false, false, 2 * BM);
+        constexpr uint32_t idesc_bf = make_idesc(NI, false, false, 2 * BM);
+        // fp16 operands: clear the format field (1 = bf16, 0 = fp16) of A (bit 7) / B (bit 10) for the main K blocks
+        const uint32_t idesc_io = idesc_bf & ~((p.a_f16 ? 1u << 7 : 0u) | (p.b_f16 ? 1u << 10 : 0u));
+        const uint32_t idesc_ext = p.ext_f16 ? (idesc_bf & ~((1u << 7) | (1u << 10))) : idesc_bf;
         uint32_t it = 0, tcount = 0;
         for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
           const TileInfo t = decode_tile<EPI>(p, tile, pair_rank);
@@ -508,6 +538,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
             const uint32_t sb = sa + C::A_BYTES;
+            const uint32_t idesc = kb < t.nkb_main ? idesc_io : idesc_ext;  // extension blocks: the library's own tables
             if (elect_one()) {
 #pragma unroll
               for (int kk = 0; kk < BK / UK; ++kk) {
@@ -549,8 +580,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sb = sa + C::A_BYTES;
           // the pooling GEMM's extension blocks carry a K-major B (marginals) next to an MN-major main B (probabilities)
           const bool b_mn_now = B_MN && !(EPI == EPI_POOL && kb >= t.nkb_main);
-          const uint32_t idesc_main = b_mn_now ? idesc_main_mn : idesc_main_k;
-          const uint32_t idesc_tail = b_mn_now ? idesc_tail_mn : idesc_tail_k;
+          // fp16 operands: clear the format field (1 = bf16, 0 = fp16) of A (bit 7) / B (bit 10); the two operands of one
+          // instruction must have the same format (a mixed pair is an illegal instruction on sm_100a), main and
+          // extension blocks may differ
+          const uint32_t fmt = kb < t.nkb_main ? ~((p.a_f16 ? 1u << 7 : 0u) | (p.b_f16 ? 1u << 10 : 0u))
+                                               : (p.ext_f16 ? ~((1u << 7) | (1u << 10)) : ~0u);
+          const uint32_t idesc_main = (b_mn_now ? idesc_main_mn : idesc_main_k) & fmt;
+          const uint32_t idesc_tail = (b_mn_now ? idesc_tail_mn : idesc_tail_k) & fmt;
           if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk) {
@@ -610,6 +646,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       orow += (long long)zslice * p.z_c_rows + (long long)batch * p.c_batch_rows;
       const bool has_bias = p.bias != nullptr, has_res = p.R != nullptr;
+      const bool in16 = p.a_f16 != 0, out16 = p.out_dtype == HICOM_F16;  // fp16 instead of bf16 (warp-uniform)
       const int n_chunks = (p.N - n_tile * BN + 31) / 32 < BN / 32 ? (p.N - n_tile * BN + 31) / 32 : BN / 32;
       // coalesced bf16 stores (transpose_pieces): warp-uniform conditions only, the shuffles need every lane
       const bool tr_ok = !kOutF32 && p.diag_heads == 0 && p.ldc % 8 == 0 && (zslice * p.z_c_cols) % 8 == 0 &&
@@ -636,7 +673,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
           if (has_bias) {
-            const __nv_bfloat16* bp = p.bias + n0;
+            const uint16_t* bp = p.bias + n0;
             if (full && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -644,14 +681,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  v[g * 8 + 2 * e] += __uint_as_float(w[e] << 16);
-                  v[g * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                  float lo, hi;
+                  unpack2(w[e], in16, lo, hi);
+                  v[g * 8 + 2 * e] += lo;
+                  v[g * 8 + 2 * e + 1] += hi;
                 }
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < nvalid) v[i] += __bfloat162float(bp[i]);
+                if (i < nvalid) v[i] += ld16(bp + i, in16);
             }
           }
           if (kGelu) {
@@ -663,7 +702,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fast(v[i]);
           }
           if (has_res && row_ok) {
-            const __nv_bfloat16* rp = p.R + (long long)row * p.ldr + n0;
+            const uint16_t* rp = p.R + (long long)row * p.ldr + n0;
             if (full && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -671,43 +710,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  v[g * 8 + 2 * e] += __uint_as_float(w[e] << 16);
-                  v[g * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                  float lo, hi;
+                  unpack2(w[e], in16, lo, hi);
+                  v[g * 8 + 2 * e] += lo;
+                  v[g * 8 + 2 * e + 1] += hi;
                 }
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < nvalid) v[i] += __bfloat162float(rp[i]);
+                if (i < nvalid) v[i] += ld16(rp + i, in16);
             }
           }
           if (tr) {
             uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) pk[i / 2] = pack_bf16(v[i], v[i + 1]);
+            for (int i = 0; i < 32; i += 2) pk[i / 2] = pack2(v[i], v[i + 1], out16);
             transpose_pieces(pk, lane);
-            __nv_bfloat16* cb = static_cast<__nv_bfloat16*>(p.C) + n0 + zslice * p.z_c_cols + (lane >> 3) * 8;
+            uint16_t* cb = static_cast<uint16_t*>(p.C) + n0 + zslice * p.z_c_cols + (lane >> 3) * 8;
 #pragma unroll
             for (int s2 = 0; s2 < 4; ++s2)
               if (ok_s[s2])
                 *reinterpret_cast<uint4*>(cb + orow_s[s2] * p.ldc) =
                     make_uint4(pk[s2 * 4], pk[s2 * 4 + 1], pk[s2 * 4 + 2], pk[s2 * 4 + 3]);
           } else if (!kOutF32) {
-            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.C) + orow * p.ldc + n0 + zslice * p.z_c_cols;
+            uint16_t* dst = static_cast<uint16_t*>(p.C) + orow * p.ldc + n0 + zslice * p.z_c_cols;
             if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 uint4 pk;
-                pk.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                pk.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                pk.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                pk.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                pk.x = pack2(v[g * 8 + 0], v[g * 8 + 1], out16);
+                pk.y = pack2(v[g * 8 + 2], v[g * 8 + 3], out16);
+                pk.z = pack2(v[g * 8 + 4], v[g * 8 + 5], out16);
+                pk.w = pack2(v[g * 8 + 6], v[g * 8 + 7], out16);
                 reinterpret_cast<uint4*>(dst)[g] = pk;
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < nvalid) dst[i] = __float2bfloat16_rn(v[i]);
+                if (i < nvalid) dst[i] = cvt16(v[i], out16);
             }
           } else {
             float* dst = static_cast<float*>(p.C) + orow * p.ldc + n0 + zslice * p.z_c_cols;
@@ -747,7 +788,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld32(taddr + c * 32, v);
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) pk[i / 2] = pack_bf16(ex2_approx(v[i] * kLog2e), ex2_approx(v[i + 1] * kLog2e));
+        for (int i = 0; i < 32; i += 2)
+          pk[i / 2] = pack2(ex2_approx(v[i] * kLog2e), ex2_approx(v[i + 1] * kLog2e), p.p2_f16 != 0);
         transpose_pieces(pk, lane);
 #pragma unroll
         for (int s2 = 0; s2 < 4; ++s2)
@@ -761,7 +803,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // rows = score columns j (M = J), columns = tokens of this tile
       const bool row_ok = row < p.M;
       const size_t col = (size_t)batch * p.M + (row_ok ? row : 0);
-      const __nv_bfloat16* tqr = p.tqm + col * p.tqm_ld;
+      const uint16_t* tqr = reinterpret_cast<const uint16_t*>(p.tqm) + col * p.tqm_ld;
+      const bool tq16 = p.p2_f16 != 0;
       float mx = -INFINITY;
       for (int c = half; c < BN / 32; c += CSTEP) {
         const int t0 = n_tile * BN + c * 32;
@@ -770,8 +813,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // time term of the position embedding: a 32-token chunk touches at most two frames (HW >= 32)
         const int f0 = t0 / p.HW;
         const int nb = (f0 + 1) * p.HW - t0;
-        const float pt0 = __bfloat162float(tqr[f0]);
-        const float pt1 = (f0 + 1 < p.T) ? __bfloat162float(tqr[f0 + 1]) : 0.f;
+        const float pt0 = ld16(tqr + f0, tq16);
+        const float pt1 = (f0 + 1 < p.T) ? ld16(tqr + f0 + 1, tq16) : 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (t0 + i < p.N) mx = fmaxf(mx, v[i] + (i < nb ? pt0 : pt1));
@@ -832,7 +875,7 @@ static EncodeTiledFn get_encode() {
 // bf16 tensor viewed as (batch, rows, inner) with row pitch `ld` elements and batch pitch `batch_stride` elements;
 // box = (64 inner, box_rows, 1), SWIZZLE_128B, out-of-range elements read as zero.
 static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t ld,
-                    uint64_t batch_stride, uint32_t box_rows) {
+                    uint64_t batch_stride, uint32_t box_rows, bool f16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return 1;
   HICOM_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tcgen05 path: operand not 16-byte aligned");
@@ -841,7 +884,7 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   cuuint64_t strides[2] = {ld * 2, (batch_stride ? batch_stride : rows * ld) * 2};
   cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HICOM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
@@ -902,8 +945,8 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
 bool tc_linear_supported(int in_dtype, int out_dtype, int M, int N, int K, long long lda, long long ldw,
                          long long ldc, const void* A, const void* W, const void* C) {
   (void)ldc; (void)C; (void)N;
-  if (in_dtype != HICOM_BF16) return false;
-  if (out_dtype != HICOM_BF16 && out_dtype != HICOM_F32) return false;
+  if (in_dtype != HICOM_BF16 && in_dtype != HICOM_F16) return false;
+  if (out_dtype != in_dtype && out_dtype != HICOM_F32) return false;
   if (M <= 0 || K % 8 != 0 || lda % 8 != 0 || ldw % 8 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) return false;
   return true;
@@ -920,10 +963,11 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
     HICOM_REQUIRE(q.w_is_kn && q.out_dtype == HICOM_F32 && q.act == HICOM_ACT_NONE && !q.accumulate,
                   "tcgen05 linear: (K,M) activations are only built for fp32 C, (K,N) weights, no activation");
     const int nb = q.batch > 0 ? q.batch : 1;
-    if (make_map(&ta, q.A, q.M, kext, nb, q.lda, q.a_batch_stride, 64)) return 1;
+    if (make_map(&ta, q.A, q.M, kext, nb, q.lda, q.a_batch_stride, 64, q.a_f16)) return 1;
     const bool w_batched = q.w_batch_stride != 0;
-    if (make_map(&tb, q.W, q.N, kext, w_batched ? nb : 1, q.ldw, q.w_batch_stride, 64)) return 1;
+    if (make_map(&tb, q.W, q.N, kext, w_batched ? nb : 1, q.ldw, q.w_batch_stride, 64, q.w_f16)) return 1;
     Params pm{};
+    pm.a_f16 = q.a_f16; pm.b_f16 = q.w_f16;
     pm.M = q.M; pm.N = q.N; pm.K = q.K; pm.k_chunk = q.K; pm.b_box_rows = 64;
     pm.C = q.C; pm.ldc = q.ldc; pm.out_dtype = q.out_dtype; pm.act = q.act; pm.alpha = 1.f;
     pm.rows_per_group = 1 << 30; pm.group_stride_rows = 0;
@@ -936,19 +980,20 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
     dim3 gm((q.N + 255) / 256, (q.M + BM - 1) / BM, nb * pm.z_slices);
     return launch<256, true, true, EPI_LINEAR, 2>(ta, tb, pm, gm, stream);
   }
-  if (make_map(&ta, q.A, kext, q.M, 1, q.lda, 0, BM)) return 1;
+  if (make_map(&ta, q.A, kext, q.M, 1, q.lda, 0, BM, q.a_f16)) return 1;
   if (q.w_is_kn) {  // W given as (K, N) row-major: MN-major B operand, boxes of 64 n x 64 k
-    if (make_map(&tb, q.W, q.N, kext, 1, q.ldw, 0, 64)) return 1;
+    if (make_map(&tb, q.W, q.N, kext, 1, q.ldw, 0, 64, q.w_f16)) return 1;
   } else {
-    if (make_map(&tb, q.W, kext, q.N, 1, q.ldw, 0, 256)) return 1;
+    if (make_map(&tb, q.W, kext, q.N, 1, q.ldw, 0, 256, q.w_f16)) return 1;
   }
   Params p{};
+  p.a_f16 = q.a_f16; p.b_f16 = q.w_f16;
   p.alpha = q.alpha; p.diag_heads = q.diag_heads; p.diag_rows = q.diag_rows; p.diag_cols = q.diag_cols;
   p.z_slices = q.z_slices; p.z_a_k = q.z_a_k; p.z_b_k = q.z_b_k; p.z_c_rows = q.z_c_rows; p.z_c_cols = q.z_c_cols;
   p.guard = q.guard;
   p.M = q.M; p.N = q.N; p.K = q.K; p.k_chunk = q.K; p.b_box_rows = 256;
-  p.bias = static_cast<const __nv_bfloat16*>(q.bias);
-  p.R = static_cast<const __nv_bfloat16*>(q.R); p.ldr = q.ldr;
+  p.bias = static_cast<const uint16_t*>(q.bias);
+  p.R = static_cast<const uint16_t*>(q.R); p.ldr = q.ldr;
   p.C = q.C; p.ldc = q.ldc; p.out_dtype = q.out_dtype; p.act = q.act;
   p.rows_per_group = q.rows_per_group; p.group_stride_rows = q.group_stride_rows;
   dim3 grid((q.N + 255) / 256, (q.M + BM - 1) / BM, q.z_slices > 0 ? q.z_slices : 1);
@@ -959,12 +1004,12 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   }
   const int flags = (q.act == HICOM_ACT_GELU ? 1 : 0) | (q.out_dtype == HICOM_F32 ? 2 : 0) |
                     (q.act == HICOM_ACT_GELU_TANH ? 8 : 0);
-  HICOM_REQUIRE(q.act != HICOM_ACT_GELU_TANH || (!q.w_is_kn && q.out_dtype == HICOM_BF16),
-                "tcgen05 linear: the tanh GELU is only built for bf16 C and (N,K) weights");
+  HICOM_REQUIRE(q.act != HICOM_ACT_GELU_TANH || (!q.w_is_kn && q.out_dtype != HICOM_F32),
+                "tcgen05 linear: the tanh GELU is only built for 16-bit C and (N,K) weights");
   // small problems: 128x64 tiles spread over 4x more CTAs with an 8-deep ring (latency-bound otherwise)
   if (!q.w_is_kn && q.z_slices == 0 && (long long)grid.x * grid.y < 74 && q.N >= 64) {
     CUtensorMap tb64;
-    if (make_map(&tb64, q.W, kext, q.N, 1, q.ldw, 0, 64)) return 1;
+    if (make_map(&tb64, q.W, kext, q.N, 1, q.ldw, 0, 64, q.w_f16)) return 1;
     p.b_box_rows = 64;
     dim3 g64((q.N + 63) / 64, grid.y, 1);
     switch (flags) {
@@ -979,7 +1024,7 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   if (!q.w_is_kn && q.z_slices == 0 && q.diag_heads == 0 &&
       (long long)grid.x * grid.y >= 296) {
     CUtensorMap tb128;
-    if (make_map(&tb128, q.W, kext, q.N, 1, q.ldw, 0, 128)) return 1;
+    if (make_map(&tb128, q.W, kext, q.N, 1, q.ldw, 0, 128, q.w_f16)) return 1;
     switch (flags) {
       case 0: return launch<256, false, false, EPI_LINEAR, 0, true>(ta, tb128, p, grid, stream);
       case 1: return launch<256, false, false, EPI_LINEAR, 1, true>(ta, tb128, p, grid, stream);
@@ -1014,14 +1059,15 @@ bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W) 
   (void)T;
   if (impl == HICOM_IMPL_SIMT) return false;
   // the algebraic position-embedding path needs: chunks of 32 tokens spanning <= 2 frames, H + W indicator columns
-  return dtype == HICOM_BF16 && d % 128 == 0 && J >= 1 && J <= 288 && H * W >= 32 && H + W <= kKe;
+  return (dtype == HICOM_BF16 || dtype == HICOM_F16) && d % 128 == 0 && J >= 1 && J <= 288 && H * W >= 32 &&
+         H + W <= kKe;
 }
 
 // =================================================================================================
 // global pipeline: token-major probabilities, no padded MMA rows, no atomics, marginals from one GEMM
 // =================================================================================================
 struct GlobalWs3 {
-  size_t p2, mg, lsum, stab, flag, pe2, ind, qt, margf, marg, total;
+  size_t p2, mg, lsum, stab, flag, pe2, pe2h, ind, qt, margf, marg, total;
   long long pld, ild;
   int ke2, mslices, kslice;
 };
@@ -1054,6 +1100,7 @@ static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits
   w.stab = take((size_t)B * J * 4);
   w.flag = take(256);
   w.pe2 = take((size_t)w.ke2 * d * 2);
+  w.pe2h = take((size_t)w.ke2 * d * 2);           // fp16 copy of the table (fp16 callers only)
   w.ind = take(N * w.ild * 2);
   w.qt = take((size_t)B * J * w.ke2 * 2);         // qfold · pe2ᵀ = [spatial term, col 63 = -stabiliser | time term per frame]
   w.margf = take((size_t)B * w.mslices * J * 2 * kKe * 4);
@@ -1071,7 +1118,7 @@ namespace tc {
 //            n's score tile: 128 tokens, or the 256 of a CTA pair) ], 3 x 64 columns; a base is the first frame of the range rounded down to a multiple of
 //            8 (the same 16-byte-aligned coordinate the TMA producer uses).  One thread writes 8 columns (16 bytes).
 __device__ __forceinline__ void build_ind3_row(__nv_bfloat16* ind, long long i, int N, int H, int W, int kslice,
-                                               int rel_tile) {
+                                               int rel_tile, uint32_t one) {
   constexpr int G = 3 * kKe / 8;
   if (i >= (long long)N * G) return;
   const int n = (int)(i / G), g = (int)(i % G);
@@ -1085,8 +1132,8 @@ __device__ __forceinline__ void build_ind3_row(__nv_bfloat16* ind, long long i, 
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int c = g * 8 + 2 * q;
-    const uint32_t lo = (c == hot0 || c == hot1 || c == hot2) ? 0x3f80u : 0u;
-    const uint32_t hi = (c + 1 == hot0 || c + 1 == hot1 || c + 1 == hot2) ? 0x3f80u : 0u;
+    const uint32_t lo = (c == hot0 || c == hot1 || c == hot2) ? one : 0u;
+    const uint32_t hi = (c + 1 == hot0 || c + 1 == hot1 || c + 1 == hot2) ? one : 0u;
     v[q] = lo | (hi << 16);
   }
   *reinterpret_cast<uint4*>(ind + (size_t)n * (3 * kKe) + g * 8) = make_uint4(v[0], v[1], v[2], v[3]);
@@ -1098,12 +1145,15 @@ __global__ void zero_bf16_kernel(__nv_bfloat16* p, long long n) {
 // ONE launch prepares everything that does not depend on the scores: blocks [0, nb_ind) the indicator matrix, the next
 // ke2 blocks the bf16 table pe2 = [pos_h ; pos_w ; 0 (row 63 multiplies the ones column) | pos_t ; 0] (ke2 x d), the rest
 // reset the running max / denominators / fallback flag.
+// f16: the indicator is written as fp16 ones and a second, fp16 copy of the table (pe2h) is kept for the table GEMM
+// against fp16 folded queries; pe2 itself stays bf16 (it meets the bf16 marginals in the pooling GEMM)
 __global__ void prep3_kernel(__nv_bfloat16* ind, int N, int H, int W, int kslice, int rel_tile, unsigned nb_ind,
-                             const float* pt, const float* ph, const float* pw, __nv_bfloat16* pe2, int T, int ke2, int d,
-                             float* mg, float* lsum, int n_stats, int* flag) {
+                             const float* pt, const float* ph, const float* pw, __nv_bfloat16* pe2, __half* pe2h, int T,
+                             int ke2, int d, float* mg, float* lsum, int n_stats, int* flag) {
   const unsigned bid = blockIdx.x;
   if (bid < nb_ind) {
-    build_ind3_row(ind, (long long)bid * blockDim.x + threadIdx.x, N, H, W, kslice, rel_tile);
+    build_ind3_row(ind, (long long)bid * blockDim.x + threadIdx.x, N, H, W, kslice, rel_tile,
+                   pe2h != nullptr ? 0x3c00u : 0x3f80u);
   } else if (bid < nb_ind + (unsigned)ke2) {
     const int s = (int)(bid - nb_ind);
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -1112,6 +1162,7 @@ __global__ void prep3_kernel(__nv_bfloat16* ind, int N, int H, int W, int kslice
       else if (s < H + W) v = pw[(size_t)(s - H) * d + c];
       else if (s >= kKe && s - kKe < T) v = pt[(size_t)(s - kKe) * d + c];
       pe2[(size_t)s * d + c] = __float2bfloat16_rn(v);
+      if (pe2h != nullptr) pe2h[(size_t)s * d + c] = __float2half_rn(v);
     }
   } else {
     const int i = (int)(bid - nb_ind - (unsigned)ke2) * blockDim.x + threadIdx.x;
@@ -1122,13 +1173,20 @@ __global__ void prep3_kernel(__nv_bfloat16* ind, int N, int H, int W, int kslice
 // stabiliser = bf16(max + margin): it rides into the GEMM as the extension row -stab against the ones column, so the
 // value reported to the merge must be the rounded one that was actually applied
 __global__ void make_stab3_kernel(const float* mg, float* stab, __nv_bfloat16* qt, int ld, int n, float margin,
-                                  const int* flag) {
+                                  const int* flag, int f16) {
   if (flag != nullptr && *flag == 0) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const __nv_bfloat16 sb = __float2bfloat16_rn(mg[i] + margin);
-  stab[i] = __bfloat162float(sb);
-  qt[(size_t)i * ld + kKe - 1] = __float2bfloat16_rn(-__bfloat162float(sb));
+  uint16_t* q16 = reinterpret_cast<uint16_t*>(qt) + (size_t)i * ld + kKe - 1;
+  if (f16) {
+    const __half sb = __float2half_rn(mg[i] + margin);
+    stab[i] = __half2float(sb);
+    *q16 = __half_as_ushort(__hneg(sb));
+  } else {
+    const __nv_bfloat16 sb = __float2bfloat16_rn(mg[i] + margin);
+    stab[i] = __bfloat162float(sb);
+    *q16 = __bfloat16_as_ushort(__float2bfloat16_rn(-__bfloat162float(sb)));
+  }
 }
 // exact re-run only: forget the sampled max and remove the previous stabiliser (column 63 of qt) so the max pass sees
 // the raw scores again
@@ -1177,7 +1235,11 @@ __global__ void spread3_kernel(const float* stab, const float* lsum, float* m, f
 int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, const float* pos_h,
                                const float* pos_w,
                                const void* qfold, float* m, float* l, float* o, int B, int T, int H, int W, int d, int J,
-                               int splits, void* workspace, cudaStream_t stream) {
+                               int splits, void* workspace, cudaStream_t stream, bool f16) {
+  // f16: X, Kscore and qfold are fp16.  Both operands of one MMA must share a format, so the tables that meet them
+  // become fp16 as well: the indicator, the score extensions qt, the probabilities P2 (stabiliser margin chosen for
+  // fp16's range, below) and a second copy of the position table for the table GEMM; the marginals and the table of
+  // the pooling GEMM's extension blocks stay bf16 (sums of probabilities exceed fp16's range)
   using namespace tc;
   const int N = T * H * W;
   const GlobalWs3 w = global_ws3(B, T, H, W, d, J, splits);
@@ -1188,6 +1250,7 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
   float* stab = reinterpret_cast<float*>(ws + w.stab);
   int* flag = reinterpret_cast<int*>(ws + w.flag);
   __nv_bfloat16* pe2 = reinterpret_cast<__nv_bfloat16*>(ws + w.pe2);
+  __half* pe2h = f16 ? reinterpret_cast<__half*>(ws + w.pe2h) : nullptr;
   __nv_bfloat16* ind = reinterpret_cast<__nv_bfloat16*>(ws + w.ind);
   // qt (B*J, ke2): columns 0..63 = spatial position term of every score column (63 = -stabiliser, against the ones
   // column of `ind`), columns 64.. = time term per frame; `qext` and `tq` are views of it
@@ -1208,7 +1271,8 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
   {
     const unsigned nb_ind = blocks((long long)N * (w.ild / 8));
     prep3_kernel<<<nb_ind + (unsigned)w.ke2 + blocks(BJ), 256, 0, stream>>>(
-        ind, N, H, W, w.kslice, pair ? 2 * BM : BM, nb_ind, pos_t, pos_h, pos_w, pe2, T, w.ke2, d, mg, lsum, (int)BJ, flag);
+        ind, N, H, W, w.kslice, pair ? 2 * BM : BM, nb_ind, pos_t, pos_h, pos_w, pe2, pe2h, T, w.ke2, d, mg, lsum, (int)BJ,
+        flag);
     if (check_launch("prep3_kernel")) return 1;
   }
   if (Kscore != nullptr) {  // the caller's keys already carry their position terms: no score-side tables
@@ -1216,41 +1280,45 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
     if (check_launch("zero_bf16_kernel")) return 1;
   } else {  // qt = qfold · pe2ᵀ: [pos_h·q | pos_w·q | 0 ... | pos_t[0]·q, pos_t[1]·q, ...] in one GEMM
     TcLinearParams a{};
-    a.A = qfold; a.W = pe2; a.C = qt; a.lda = d; a.ldw = d; a.ldc = w.ke2; a.M = (int)BJ; a.N = w.ke2; a.K = d;
-    a.act = HICOM_ACT_NONE; a.out_dtype = HICOM_BF16; a.rows_per_group = 1 << 30;
+    a.A = qfold; a.W = f16 ? static_cast<const void*>(pe2h) : pe2; a.C = qt; a.lda = d; a.ldw = d; a.ldc = w.ke2;
+    a.M = (int)BJ; a.N = w.ke2; a.K = d;
+    a.act = HICOM_ACT_NONE; a.out_dtype = f16 ? HICOM_F16 : HICOM_BF16; a.rows_per_group = 1 << 30;
+    a.a_f16 = a.w_f16 = f16;
     if (launch_tc_linear(a, stream)) return 1;
   }
 
   // ---- sampled / exact max pass (rows = score columns, as in v2) -------------------------------------------------
   CUtensorMap tq128, tx256, tqe128, tind256;
-  if (make_map(&tq128, qfold, d, J, B, d, (uint64_t)J * d, BM)) return 1;
+  if (make_map(&tq128, qfold, d, J, B, d, (uint64_t)J * d, BM, f16)) return 1;
   const void* Xs = Kscore != nullptr ? Kscore : X;  // score operand of the max / probability passes
-  if (make_map(&tx256, Xs, d, N, B, d, (uint64_t)N * d, 256)) return 1;
-  if (make_map(&tqe128, qext, kKe, J, B, qld, (uint64_t)J * qld, BM)) return 1;
-  if (make_map(&tind256, ind, kKe, N, 1, w.ild, 0, 256)) return 1;
+  if (make_map(&tx256, Xs, d, N, B, d, (uint64_t)N * d, 256, f16)) return 1;
+  if (make_map(&tqe128, qext, kKe, J, B, qld, (uint64_t)J * qld, BM, f16)) return 1;
+  if (make_map(&tind256, ind, kKe, N, 1, w.ild, 0, 256, f16)) return 1;
   Params pmx{};
   pmx.M = J; pmx.N = N; pmx.K = d; pmx.k_chunk = d; pmx.b_box_rows = 256;
+  pmx.a_f16 = pmx.b_f16 = pmx.ext_f16 = pmx.p2_f16 = f16;
   pmx.mg = mg; pmx.k_ext_blocks = 1; pmx.HW = H * W; pmx.T = T; pmx.tqm = tq; pmx.tqm_ld = (long long)qld;
   const int n_tiles256 = (N + 255) / 256;
   const int mj_tiles = (J + BM - 1) / BM;
 
   // ---- probabilities: P2[b] (tokens x J) = exp([X | ind0 | indrel] · [qfold | qext | tq(f0..)]ᵀ) --------------------
   CUtensorMap tx128, tqj, ti0, ti1, tqej, ttq;
-  if (make_map(&tx128, Xs, d, N, B, d, (uint64_t)N * d, BM)) return 1;
-  if (make_map(&tqj, qfold, d, J, B, d, (uint64_t)J * d, jbox)) return 1;
-  if (make_map(&ti0, ind, kKe, N, 1, w.ild, 0, BM)) return 1;
-  if (make_map(&ti1, ind + 2 * kKe, kKe, N, 1, w.ild, 0, BM)) return 1;
-  if (make_map(&tqej, qext, kKe, J, B, qld, (uint64_t)J * qld, jbox)) return 1;
+  if (make_map(&tx128, Xs, d, N, B, d, (uint64_t)N * d, BM, f16)) return 1;
+  if (make_map(&tqj, qfold, d, J, B, d, (uint64_t)J * d, jbox, f16)) return 1;
+  if (make_map(&ti0, ind, kKe, N, 1, w.ild, 0, BM, f16)) return 1;
+  if (make_map(&ti1, ind + 2 * kKe, kKe, N, 1, w.ild, 0, BM, f16)) return 1;
+  if (make_map(&tqej, qext, kKe, J, B, qld, (uint64_t)J * qld, jbox, f16)) return 1;
   // frames past T read as zero (zero rows of pe2 up to the padded extent, TMA zero fill beyond it)
-  if (make_map(&ttq, tq, tcols, J, B, qld, (uint64_t)J * qld, jbox)) return 1;
+  if (make_map(&ttq, tq, tcols, J, B, qld, (uint64_t)J * qld, jbox, f16)) return 1;
   CUtensorMap tqj72, tqej72, ttq72;  // pair mode: each CTA stages 72 of the 144 rows of an MMA instruction's B operand
   if (pair) {
-    if (make_map(&tqj72, qfold, d, J, B, d, (uint64_t)J * d, 72)) return 1;
-    if (make_map(&tqej72, qext, kKe, J, B, qld, (uint64_t)J * qld, 72)) return 1;
-    if (make_map(&ttq72, tq, tcols, J, B, qld, (uint64_t)J * qld, 72)) return 1;
+    if (make_map(&tqj72, qfold, d, J, B, d, (uint64_t)J * d, 72, f16)) return 1;
+    if (make_map(&tqej72, qext, kKe, J, B, qld, (uint64_t)J * qld, 72, f16)) return 1;
+    if (make_map(&ttq72, tq, tcols, J, B, qld, (uint64_t)J * qld, 72, f16)) return 1;
   }
   Params pp{};
   pp.M = N; pp.N = J; pp.K = d; pp.k_chunk = d; pp.b_box_rows = (int)jbox;
+  pp.a_f16 = pp.b_f16 = pp.ext_f16 = pp.p2_f16 = f16;
   pp.k_ext_blocks = 2; pp.HW = H * W; pp.T = T; pp.P2 = P2; pp.p2_ld = w.pld;
   dim3 gprob(1, (N + BM - 1) / BM, B);
 
@@ -1259,14 +1327,14 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
   const int kslice = w.kslice;
   mm.A = P2; mm.W = ind; mm.C = margf; mm.lda = w.pld; mm.ldw = w.ild; mm.ldc = 2 * kKe;
   mm.M = J; mm.N = 2 * kKe; mm.K = kslice; mm.k_total = N; mm.act = HICOM_ACT_NONE; mm.out_dtype = HICOM_F32;
-  mm.rows_per_group = 1 << 30; mm.w_is_kn = 1; mm.a_is_km = 1;
+  mm.rows_per_group = 1 << 30; mm.w_is_kn = 1; mm.a_is_km = 1; mm.a_f16 = mm.w_f16 = f16;
   mm.batch = B; mm.a_batch_stride = (long long)N * w.pld; mm.c_batch_rows = (long long)w.mslices * J;
   mm.z_slices = w.mslices; mm.z_a_k = kslice; mm.z_b_k = kslice; mm.z_c_rows = J;
 
   // ---- pooling: O[b,s] (d x J) = [X[b, tokens of s] ; pe2]ᵀ · [P2 ; marg] ------------------------------------------------
   CUtensorMap txa, tp2, tpe, tmg;
-  if (make_map(&txa, X, d, N, B, d, (uint64_t)N * d, 64)) return 1;
-  if (make_map(&tp2, P2, w.pld, N, B, w.pld, (uint64_t)N * w.pld, 64)) return 1;
+  if (make_map(&txa, X, d, N, B, d, (uint64_t)N * d, 64, f16)) return 1;
+  if (make_map(&tp2, P2, w.pld, N, B, w.pld, (uint64_t)N * w.pld, 64, f16)) return 1;
   if (make_map(&tpe, pe2, d, w.ke2, 1, d, 0, 64)) return 1;
   if (make_map(&tmg, marg, w.ke2, J, B, w.ke2, (uint64_t)J * w.ke2, jbox)) return 1;
   Params g{};
@@ -1274,12 +1342,13 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
   int chunk = (N + splits - 1) / splits;
   chunk = (chunk + BK - 1) / BK * BK;
   g.k_chunk = chunk; g.b_box_rows = (int)jbox;
+  g.a_f16 = g.b_f16 = f16;  // main blocks: X and P2 in the caller's format; extension blocks: bf16 table x bf16 marginals
   g.o = o; g.splits = splits; g.k_ext_blocks = w.ke2 / BK;
   dim3 gp(splits, d / BM, B);
 
   auto run = [&](const int* guard, float margin) -> int {
     // stabiliser -> probabilities -> marginals -> pooling (the exact re-run passes guard = flag)
-    make_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, stab, qt, w.ke2, (int)BJ, margin, guard);
+    make_stab3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, stab, qt, w.ke2, (int)BJ, margin, guard, (int)f16);
     if (check_launch("make_stab3_kernel")) return 1;
     Params p1 = pp; p1.guard = guard;
     if (pair && J == 288) {
@@ -1317,7 +1386,9 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
     if (launch<256, false, false, EPI_MAX>(tq128, tx256, ps, dim3(n_sample, mj_tiles, B), stream, &tqe128, &tind256))
       return 1;
   }
-  if (run(nullptr, kStabMargin)) return 1;
+  // fp16 probabilities: exp(S - stab) must stay below 65504 = e^11.09 and keep ~10 nats of normal range below the
+  // largest score, so the sampled max sits 6 nats ABOVE the stabiliser (overflow -> inf denominator -> exact re-run)
+  if (run(nullptr, f16 ? -6.f : kStabMargin)) return 1;
   // 3. guarded exact fallback: the denominator check in marg_reduce raised the flag -> exact max over all tiles, margin 0
   {
     reset_for_exact3_kernel<<<blocks(BJ), 256, 0, stream>>>(mg, qt, w.ke2, (int)BJ, flag);

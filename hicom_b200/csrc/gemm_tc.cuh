@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / TMA tensor-core paths (bf16 in, fp32 accumulate).
+// tcgen05 / TMEM / TMA tensor-core paths (bf16 or fp16 in, fp32 accumulate).
 #pragma once
 #include "common.cuh"
 
@@ -19,6 +19,8 @@ struct TcLinearParams {
   int batch = 0; long long a_batch_stride = 0, c_batch_rows = 0;
   long long w_batch_stride = 0;  // a_is_km only: != 0 -> W has a batch axis too (dqfold[b] = dS[b]ᵀ·x'[b]); 0 -> shared
   const int* guard = nullptr;  // device flag: the launch is a no-op unless *guard != 0
+  // 16-bit operand formats: 0 = bf16, 1 = fp16 (tcgen05.mma.kind::f16 takes either, per operand).  bias and R follow A.
+  int a_f16 = 0, w_f16 = 0;
 };
 
 bool tc_linear_supported(int in_dtype, int out_dtype, int M, int N, int K, long long lda, long long ldw,
@@ -29,6 +31,6 @@ bool tc_global_selected(int dtype, int impl, int d, int J, int T, int H, int W);
 size_t tc_global_workspace_bytes(int B, int T, int H, int W, int d, int J, int splits);
 int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, const float* pos_h, const float* pos_w,
                      const void* qfold, float* m, float* l, float* o, int B, int T, int H, int W, int d, int J,
-                     int splits, void* workspace, cudaStream_t stream);
+                     int splits, void* workspace, cudaStream_t stream, bool f16 = false);
 
 }  // namespace hicom

@@ -19,6 +19,7 @@ struct SkinnyParams {
 template <typename T> struct Elems16;  // elements per 16-byte load
 template <> struct Elems16<float> { static constexpr int n = 4; };
 template <> struct Elems16<__nv_bfloat16> { static constexpr int n = 8; };
+template <> struct Elems16<__half> { static constexpr int n = 8; };
 
 template <typename T>
 __device__ __forceinline__ void load16(const T* p, float (&v)[Elems16<T>::n]);
@@ -35,6 +36,18 @@ __device__ __forceinline__ void load16<__nv_bfloat16>(const __nv_bfloat16* p, fl
   for (int e = 0; e < 4; ++e) {
     v[2 * e] = __uint_as_float(w[e] << 16);
     v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+
+template <>
+__device__ __forceinline__ void load16<__half>(const __half* p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
   }
 }
 
@@ -108,7 +121,7 @@ constexpr int kSkinnyMaxRows = 8;  // beyond this the 128-row tensor tile is fas
 
 bool skinny_supported(int in_dtype, int M, int N, int K, long long lda, long long ldw, const void* A, const void* W) {
   (void)N;
-  const size_t es = in_dtype == HICOM_BF16 ? 2 : 4;
+  const size_t es = in_dtype == HICOM_F32 ? 4 : 2;
   const int e16 = 16 / (int)es;
   if (M < 1 || M > kSkinnyMaxRows) return false;
   if (K % e16 || lda % e16 || ldw % e16) return false;
@@ -151,6 +164,8 @@ int launch_skinny(const SkinnyParams& p, int in_dtype, int out_dtype, cudaStream
   if (in_dtype == HICOM_BF16 && out_dtype == HICOM_BF16) return launch_skinny_t<__nv_bfloat16, __nv_bfloat16>(p, stream);
   if (in_dtype == HICOM_BF16 && out_dtype == HICOM_F32) return launch_skinny_t<__nv_bfloat16, float>(p, stream);
   if (in_dtype == HICOM_F32 && out_dtype == HICOM_F32) return launch_skinny_t<float, float>(p, stream);
+  if (in_dtype == HICOM_F16 && out_dtype == HICOM_F16) return launch_skinny_t<__half, __half>(p, stream);
+  if (in_dtype == HICOM_F16 && out_dtype == HICOM_F32) return launch_skinny_t<__half, float>(p, stream);
   set_error("skinny_linear: unsupported dtype combination %d/%d", in_dtype, out_dtype);
   return 1;
 }

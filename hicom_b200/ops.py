@@ -20,14 +20,15 @@ from . import _cabi
 from ._cabi import ACT_GELU, ACT_GELU_TANH, ACT_NONE, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05  # noqa: F401 (re-exported)
 from ._cabi import Q_EXPLICIT, Q_FILM_LN, Q_POOLED, Q_VECTOR  # noqa: F401
 
-_DT = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+_DT = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16, torch.float16: _cabi.F16}
+_CODE_DT = {v: k for k, v in _DT.items()}
 
 
 def _dt(t: Tensor) -> int:
     try:
         return _DT[t.dtype]
     except KeyError:
-        raise TypeError(f"hicom_b200 supports float32 and bfloat16 tensors, got {t.dtype}") from None
+        raise TypeError(f"hicom_b200 supports float32, bfloat16 and float16 tensors, got {t.dtype}") from None
 
 
 def _need_cuda(*ts: Optional[Tensor]):
@@ -374,14 +375,21 @@ def _impl_l2norm_rows(X: Tensor) -> Tensor:
     return out
 
 
-def _impl_softmax_merge(m: Tensor, l: Tensor, o: Tensor, out_bf16: bool) -> Tensor:
-    """Combine (m,l,o) partials over dim 1 (token splits and/or frame shards) -> pooled (B,J,d)."""
+def out_code(dtype: torch.dtype) -> int:
+    """dtype code of a 16-bit model dtype (1 = bf16, 2 = fp16), 0 (fp32 output) otherwise — the `out_bf16` argument of
+    softmax_merge (a bool in the first ABI: True == 1 == bf16)."""
+    return _DT[dtype] if dtype in (torch.bfloat16, torch.float16) else 0
+
+
+def _impl_softmax_merge(m: Tensor, l: Tensor, o: Tensor, out_bf16: int) -> Tensor:
+    """Combine (m,l,o) partials over dim 1 (token splits and/or frame shards) -> pooled (B,J,d); ``out_bf16``: 0/False
+    fp32, 1/True bf16, 2 fp16 (`out_code`)."""
     dev = _need_cuda(m, l, o)
     m, l, o = m.contiguous(), l.contiguous(), o.contiguous()
     B, P, J, d = o.shape
     if m.shape != (B, P, J) or l.shape != (B, P, J) or o.dtype != torch.float32:
         raise ValueError("softmax_merge: shape mismatch")
-    odt = torch.bfloat16 if out_bf16 else torch.float32
+    odt = _CODE_DT[int(out_bf16)]
     out = torch.empty((B, J, d), dtype=odt, device=dev)
     with torch.cuda.device(dev):
         rc = _cabi.load().hicom_softmax_merge(_ptr(m), _ptr(l), _ptr(o), B, P, J, d, _ptr(out), _DT[odt],

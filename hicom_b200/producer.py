@@ -70,8 +70,8 @@ class SiglipHeadEmbed(nn.Module):
         h = last_hidden_state
         if h.dim() != 3:
             raise ValueError(f"expected last_hidden_state (b, tokens, d), got {tuple(h.shape)}")
-        if h.dtype not in (torch.float32, torch.bfloat16):
-            raise TypeError(f"hicom_b200 supports float32 and bfloat16 tensors, got {h.dtype}")
+        if h.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise TypeError(f"hicom_b200 supports float32, bfloat16 and float16 tensors, got {h.dtype}")
         b, n, d = h.shape
         side = num_patches_per_side if num_patches_per_side is not None else int(round(n ** 0.5))
         if side * side != n:

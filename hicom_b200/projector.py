@@ -487,7 +487,7 @@ class GlobalCompressor(nn.Module):
         """merge -> v_proj -> out_proj + residual -> readout, written into rows of ``out`` (projector.py:215-226,646)."""
         attn = self.attn_layer
         nq, nrows = self.query.shape[0], Qg.shape[1]
-        pooled = ops.softmax_merge(m, l, o, Qg.dtype == torch.bfloat16)
+        pooled = ops.softmax_merge(m, l, o, ops.out_code(Qg.dtype))
         a = ops.global_value_proj(pooled, attn.v_proj.weight, attn.v_proj.bias, nrows, attn.num_heads)
         x = ops.linear(a, attn.out_proj.weight, attn.out_proj.bias, Qg, ops.ACT_NONE, False, _IMPL)
         _mlp_into(self.readout, x, out, row_offset, nrows, group_stride)
@@ -561,24 +561,6 @@ class HIComProjector(nn.Module):
         self.global_compressor = global_compressor
         assert local_compressor is not None or global_compressor is not None, \
             "At least one compressor should be provided."
-
-    def _fp32_shadow(self):
-        """fp32 copy of this projector for fp16 callers, rebuilt when a parameter changes.  Kept out of
-        ``_modules`` so it never shows up in ``state_dict()``."""
-        key = tuple((p.data_ptr(), p._version, p.dtype) for p in self.parameters())
-        cached = self.__dict__.get("_shadow")
-        if cached is None or cached[0] != key:
-            import copy
-            self.__dict__.pop("_shadow", None)
-            saved = {k: self.__dict__.pop(k) for k in ("_graphs", "_graphs_max") if k in self.__dict__}
-            try:  # captured graphs are not copyable and belong to this module's parameters
-                clone = copy.deepcopy(self)
-            finally:
-                self.__dict__.update(saved)
-            clone.float()
-            clone.eval()
-            self.__dict__["_shadow"] = (key, clone)
-        return self.__dict__["_shadow"][1]
 
     # -- layout (mm_utils.py:92-140) -------------------------------------------------------------
     def _layout(self):
@@ -660,6 +642,14 @@ class HIComProjector(nn.Module):
             if tokens is not None:
                 splice_rows(out, tokens.detach() if not torch.is_grad_enabled() else tokens, out_row_offset)
             return tokens
+        if (X.dtype == torch.float16 and not self.training and torch.is_grad_enabled()
+                and not any(torch.is_tensor(t) and t.requires_grad for t in (X, frames_embed, guide_embed, base))):
+            # fp16 is the reference's INFERENCE dtype (model/__init__.py:44).  An eval-mode call outside no_grad whose
+            # only grad-requiring tensors are the module's own parameters is inference too: run it as such (the
+            # training path is bf16 / fp32 like the release recipes) instead of rejecting the dtype.
+            with torch.no_grad():
+                return self.forward_batched(X, frames_embed, guide_embed, modal, image_newline, is_anyres=is_anyres,
+                                            base=base, with_global=with_global, out=out, out_row_offset=out_row_offset)
         if _grad_needed(self, X, frames_embed, guide_embed, image_newline, base):
             from . import autograd as _ag
             if not _ag.ENABLED:
@@ -670,18 +660,6 @@ class HIComProjector(nn.Module):
                                              is_anyres=is_anyres, base=base, with_global=with_global)
         if not X.is_cuda:
             raise RuntimeError("hicom_b200 ops run on CUDA tensors only (no CPU fallback)")
-        if X.dtype == torch.float16:
-            # The reference's inference path runs in fp16 (model/__init__.py:44, hicom/__init__.py:68, projector.py:53).
-            # fp16 has no kernel family of its own yet: evaluate on an fp32 shadow of the weights (fp32 is an exact
-            # superset of fp16, fp32 CUDA kernels) and round the tokens back once.
-            f32 = lambda t: None if t is None else t.float()
-            shadow = self._fp32_shadow()
-            res = shadow.forward_batched(X.float(), f32(frames_embed), f32(guide_embed), modal, f32(image_newline),
-                                         is_anyres=is_anyres, base=f32(base), with_global=with_global)
-            if res is None or out is None:
-                return None if res is None else res.to(torch.float16)
-            out[:, out_row_offset:out_row_offset + res.shape[1]] = res.to(out.dtype)
-            return out[:, out_row_offset:out_row_offset + res.shape[1]]
         B, T, H, W, d = X.shape
         lc = self.local_compressor
         gc = self.global_compressor if with_global else None
@@ -720,7 +698,7 @@ class HIComProjector(nn.Module):
             main = torch.cuda.current_stream(X.device)
             side = _side_stream(X.device)
             side.wait_stream(main)
-        big = side is not None and X.dtype == torch.bfloat16 and B >= 4 and B * T * H * W >= 65536
+        big = side is not None and X.dtype in (torch.bfloat16, torch.float16) and B >= 4 and B * T * H * W >= 65536
         # Large batches: the window attention is HBM-bound — on 48 SMs it needs 30 SM-ms instead of the 47 it holds on
         # all 148 while waiting for HBM — so it gets `SM_SPLIT` SMs (whole SM pairs) and the tensor-bound global chain
         # the rest, side by side (measured: c2 -4 %, c3 / c5 -0.2..2 %; profiles/r02_sm_split.md).
@@ -781,7 +759,7 @@ class HIComProjector(nn.Module):
 
     def forward(self, frames_feature, frames_embed, guide_embed, modal, image_newline=None):
         if ("_graphs" in self.__dict__ and torch.is_tensor(frames_feature) and frames_feature.is_cuda
-                and frames_feature.dtype in (torch.float32, torch.bfloat16) and not torch.is_grad_enabled()
+                and frames_feature.dtype in (torch.float32, torch.bfloat16, torch.float16) and not torch.is_grad_enabled()
                 and not torch.cuda.is_current_stream_capturing()):
             return self._graphed_forward(frames_feature, frames_embed, guide_embed, modal, image_newline)
         g = None if guide_embed is None else guide_embed.unsqueeze(0)

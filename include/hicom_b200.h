@@ -9,8 +9,9 @@
  * `void*`; nothing here synchronises the device.  Functions return 0 on success and a non-zero
  * code otherwise — `hicom_last_error()` then holds a message (thread-local).  Nothing aborts.
  *
- * dtype codes: HICOM_F32 tensors are float, HICOM_BF16 tensors are __nv_bfloat16; accumulation is
- * always fp32, softmax statistics are fp32.
+ * dtype codes: HICOM_F32 tensors are float, HICOM_BF16 tensors are __nv_bfloat16, HICOM_F16 tensors are __half
+ * (the reference's inference dtype, hicom/model/__init__.py:44; forward entry points only — the backward blocks take
+ * F32 / BF16); accumulation is always fp32, softmax statistics are fp32.
  */
 #ifndef HICOM_B200_H
 #define HICOM_B200_H
@@ -24,7 +25,7 @@ extern "C" {
 
 #define HICOM_ABI_VERSION 1
 
-enum { HICOM_F32 = 0, HICOM_BF16 = 1 };
+enum { HICOM_F32 = 0, HICOM_BF16 = 1, HICOM_F16 = 2 };
 /* GELU = exact erf form (nn.GELU(), projector.py:310); GELU_TANH = the tanh form ("gelu_pytorch_tanh") of the SigLIP
  * pooling-head MLP that produces frames_embed (encoder.py:284-285) */
 enum { HICOM_ACT_NONE = 0, HICOM_ACT_GELU = 1, HICOM_ACT_GELU_TANH = 2 };

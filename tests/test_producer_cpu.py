@@ -63,7 +63,7 @@ def test_no_cpu_fallback_and_bad_inputs():
         with pytest.raises(ValueError):
             m(torch.zeros(1, 5, 128))                    # 5 tokens are not a square grid
         with pytest.raises(TypeError):
-            m(torch.zeros(1, 4, 128, dtype=torch.float16))
+            m(torch.zeros(1, 4, 128, dtype=torch.float64))       # fp32 / bf16 / fp16 are the storage types
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 4, 128))                        # autograd on: the training path, same refusal of CPU tensors
     from hicom_b200 import autograd as ag
