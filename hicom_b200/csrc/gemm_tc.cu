@@ -91,13 +91,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Every wait is bounded: a protocol error must surface as a launch failure (trap), never as a hung device.
+constexpr long long kWaitCycles = 8000000000ll;  // ~4 s at 2 GHz, orders of magnitude beyond any legitimate wait
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWaitCycles) __trap();
   }
 }
 // producer-side wait: the ring is STAGES deep, so back off instead of stealing issue slots from the epilogue warps
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (clock64() - t0 > kWaitCycles) __trap();
+  }
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
