@@ -663,12 +663,16 @@ def run_ours(args):
         peak = pk["tflops_sustained"]
         roof.update(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak)
     roof["peak_source"] = pk["source"] + (" (sustained bf16)" if kind != "hbm" else " (copy)")
-    roof["traffic"], roof["traffic_source"] = measured_traffic(args.workload, dname)
+    k_bytes, step_bytes, t_src = ((None, None, "skipped (--no-traffic or N > 1)") if args.no_traffic or world > 1
+                                  else live_traffic(args, dname))
+    roof["traffic"], roof["traffic_source"] = k_bytes, t_src
+    if k_bytes:
+        roof["traffic_over_algorithmic"] = k_bytes / amount if kind == "hbm" else None
     step_tf = exec_flops / (ms_step * 1e-3) / 1e12
     roof["whole_step"] = {"executed_tflops": step_tf, "frac_of_burst_bf16_peak": step_tf / pk["tflops_burst"],
                           "frac_of_sustained_bf16_peak": step_tf / pk["tflops_sustained"],
                           "algorithmic_hbm_gb": videos_per_step * (w["bytes_in"] + w["bytes_out"]) / 1e9,
-                          "dram_gb_measured": measured_traffic(args.workload, "step")[0]}
+                          "dram_gb_measured": None if step_bytes is None else step_bytes / 1e9}
     ops_table = {k: {"calls": c, "ms_per_step": ms / op_steps} for k, (c, ms) in
                  sorted(op_times.items(), key=lambda kv: -kv[1][1])}
     kernels_table = {k: {"launches": c, "ms_per_step": ms / op_steps} for k, (c, ms) in
@@ -738,19 +742,86 @@ def run_ours(args):
         os._exit(0)
 
 
-def measured_traffic(workload_name, key):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu --set full capture of THIS
-    build: profiles/r02_traffic.json records the digest of the kernel sources it was captured from, and a stale capture
-    (any csrc file changed since) is reported as null rather than as a number."""
-    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
-    if not os.path.exists(path):
-        return None, "no capture committed for this build"
-    rec = json.load(open(path))
-    if rec.get("csrc_digest") != csrc_digest():
-        return None, f"stale capture (kernels changed since {rec.get('csrc_digest', '?')[:12]})"
-    table = rec.get(workload_name + ":" + (USE_GUIDE or "none"), {})
-    name = key.split()[0]
-    return table.get(name), f"ncu --set full capture, {rec.get('captured', '?')}"
+def traffic_child(args):
+    """Child of `live_traffic`, run UNDER ncu: two warm eager steps, then ONE eager step (one stream, no SM split)
+    bracketed by cudaProfilerStart/Stop so that only its kernels are measured.  Prints nothing the parent needs."""
+    from __graft_entry__ import build
+    import hicom_b200.projector as _proj
+    build()
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    hidden, T, B, _, _ = workload(args.workload, 1)
+    proj = build_projector(hidden, device)
+    X, E, G = synth_batch(B, T, device, 1234)
+    if USE_GUIDE is None:
+        E = G = None
+    _proj.OVERLAP_STREAMS, _proj.SM_SPLIT = False, 0
+    with torch.no_grad():
+        for _ in range(2):
+            proj.forward_batched(X, E, G, "video")
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        proj.forward_batched(X, E, G, "video")
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+
+
+_EPI_OF_LABEL = {"tc_linear": 0, "tc_scores_max": 1, "tc_pool": 3, "tc_scores_prob2": 4}
+
+
+def live_traffic(args, dominant_label):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel's launch and of the whole step,
+    measured NOW: this build, this workload, one eager step of a child process under
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none`.
+    Returns (kernel_bytes | None, step_bytes | None, source string)."""
+    import csv
+    import re
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, None, "ncu not found on this box"
+    fd, log = tempfile.mkstemp(suffix=".csv")
+    os.close(fd)
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
+           "--profile-from-start", "off", "--print-units", "base", "--csv", "--log-file", log,
+           sys.executable, os.path.abspath(__file__), "--traffic-child", "--workload", args.workload,
+           "--use-guide", args.use_guide, "--dtype", args.dtype]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+        if r.returncode != 0:
+            return None, None, f"ncu child failed (rc {r.returncode}): {(r.stderr or r.stdout).strip()[-160:]}"
+        rows = [row for row in csv.reader(l for l in open(log) if l.startswith('"'))]
+    except Exception as exc:
+        return None, None, f"ncu child: {exc!r}"[:200]
+    finally:
+        pass
+    if not rows:
+        return None, None, "ncu wrote no kernel rows"
+    head = rows[0]
+    ci = {name: head.index(name) for name in ("ID", "Kernel Name", "Metric Name", "Metric Value")}
+    launches = {}
+    for row in rows[1:]:
+        try:
+            e = launches.setdefault(row[ci["ID"]], {"name": row[ci["Kernel Name"]]})
+            e[row[ci["Metric Name"]]] = float(row[ci["Metric Value"]].replace(",", ""))
+        except (ValueError, IndexError):
+            continue
+    os.unlink(log)
+    byt = lambda e: e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0)
+    step = sum(byt(e) for e in launches.values())
+    head_label = dominant_label.split()[0].split("/")[0].split("+")[0]
+    if head_label.startswith("local_attend"):
+        cand = [e for e in launches.values() if "local_attend" in e["name"]]
+    else:
+        epi = _EPI_OF_LABEL.get(head_label)
+        pat = re.compile(r"tc_gemm_kernel<\(int\)\d+, \(bool\)[01], \(bool\)[01], \(int\)%s," % epi)
+        cand = [e for e in launches.values() if epi is not None and pat.search(e["name"])]
+    if not cand:
+        return None, step, f"ncu child: no launch matched {head_label!r} among {len(launches)} kernels"
+    top = max(cand, key=lambda e: e.get("gpu__time_duration.sum", 0.0))  # the longest launch of that kernel family
+    return byt(top), step, (f"measured in this run: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of one eager "
+                            f"step in a child process ({len(launches)} kernels profiled)")
 
 
 def csrc_digest():
@@ -776,6 +847,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"],
                     help="storage dtype of the timed arm (fp16 = the reference's inference dtype; tcgen05 kind::f16 either way)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the live DRAM-traffic measurement (an ncu child process)")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed output")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s sustained block")
@@ -787,6 +860,9 @@ def main():
     DTYPE = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     if args.digest:
         print(csrc_digest())
+        return
+    if args.traffic_child:
+        traffic_child(args)
         return
     if args.impl == "reference":
         run_reference(args)
