@@ -36,6 +36,8 @@ PROTOTYPES = {
     "hicom_posadd": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "hicom_l2norm_rows": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p]),
     "hicom_softmax_merge": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_int, c_void_p]),
+    "hicom_softmax_merge_lse": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_int, c_void_p, c_void_p]),
+    "hicom_shard_combine": (c_int, [c_void_p] + [ctypes.c_longlong] * 3 + [c_int] * 5 + [c_void_p, c_int, c_void_p]),
     "hicom_softmax_reduce": (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p] * 4),
     "hicom_global_value_proj": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "hicom_gemm": (c_int, [c_void_p] + [c_int64] * 4 + [c_void_p] + [c_int64] * 4 + [c_void_p] + [c_int64] * 3 +

@@ -240,6 +240,8 @@ __global__ void __launch_bounds__(128) softmax_merge_kernel(const float* __restr
     m_out[(size_t)b * J + j] = M;
     l_out[(size_t)b * J + j] = L;
   }
+  // normalising merge with m_out set: also emit the log-sum-exp of the column (what a frame shard sends to its peers)
+  if (!PARTIAL && m_out != nullptr && threadIdx.x == 0) m_out[(size_t)b * J + j] = M + logf(L);
   const float invL = PARTIAL ? 1.f : 1.f / L;
   for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -360,6 +362,67 @@ extern "C" int hicom_softmax_merge(const float* m, const float* l, const float* 
   HICOM_DISPATCH_DTYPE(out_dtype, E, (softmax_merge_kernel<E, false><<<grid, 128, 0, as_stream(stream)>>>(
       m, l, o, static_cast<E*>(pooled), nullptr, nullptr, P, J, d)));
   return check_launch("softmax_merge_kernel");
+}
+
+extern "C" int hicom_softmax_merge_lse(const float* m, const float* l, const float* o, int B, int P, int J, int d,
+                                       void* pooled, int out_dtype, float* lse, void* stream) {
+  HICOM_REQUIRE(m && l && o && pooled && lse, "softmax_merge_lse: null pointer");
+  HICOM_REQUIRE(B >= 0 && P > 0 && J > 0 && d > 0 && d % 4 == 0 && B <= 65535, "softmax_merge_lse: bad shape");
+  if (B == 0) return 0;
+  dim3 grid(J, B);
+  HICOM_DISPATCH_DTYPE(out_dtype, E, (softmax_merge_kernel<E, false><<<grid, 128, 0, as_stream(stream)>>>(
+      m, l, o, static_cast<E*>(pooled), lse, nullptr, P, J, d)));
+  return check_launch("softmax_merge_lse_kernel");
+}
+
+// Frame shards: rank r holds attn_r (B, Q, d) — its own normalised attention output after the value projection (linear
+// per head, so it commutes with the merge) — and lse_r (B, heads*Q).  out[b,i,h*hd+c] = sum_r w_r attn_r[b,i,h*hd+c],
+// w_r = softmax over r of lse_r[b, h*Q+i].
+template <typename T>
+__global__ void __launch_bounds__(128) shard_combine_kernel(const uint8_t* __restrict__ msgs, size_t rank_stride,
+                                                            size_t video_stride, size_t lse_offset, int R, int Q, int d,
+                                                            int heads, T* __restrict__ out) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int hd = d / heads;
+  for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+    const int h = c / hd;  // hd % 4 == 0: the four channels share a head
+    float M = -INFINITY;
+    for (int r = 0; r < R; ++r) {
+      const float* lse = reinterpret_cast<const float*>(msgs + r * rank_stride + b * video_stride + lse_offset);
+      M = fmaxf(M, lse[h * Q + i]);
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, L = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const uint8_t* base = msgs + r * rank_stride + b * video_stride;
+      const float w = exp2f((reinterpret_cast<const float*>(base + lse_offset)[h * Q + i] - M) * kLog2e);
+      float v[4];
+      Vec4<T>::load(reinterpret_cast<const T*>(base) + (size_t)i * d + c, v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = fmaf(w, v[e], acc[e]);
+      L += w;
+    }
+    const float inv = 1.f / L;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] *= inv;
+    Vec4<T>::store(out + ((size_t)b * Q + i) * d + c, acc);
+  }
+}
+
+extern "C" int hicom_shard_combine(const void* msgs, long long rank_stride_bytes, long long video_stride_bytes,
+                                   long long lse_offset_bytes, int R, int B, int Q, int d, int heads, void* out,
+                                   int dtype, void* stream) {
+  HICOM_REQUIRE(msgs && out, "shard_combine: null pointer");
+  HICOM_REQUIRE(R > 0 && B >= 0 && Q > 0 && heads > 0 && d % heads == 0 && (d / heads) % 4 == 0 && B <= 65535,
+                "shard_combine: bad shape");
+  HICOM_REQUIRE(lse_offset_bytes % 4 == 0 && video_stride_bytes % 16 == 0 && rank_stride_bytes % 16 == 0 &&
+                ((uintptr_t)msgs & 15) == 0, "shard_combine: message not 16-byte aligned");
+  HICOM_REQUIRE(dtype != HICOM_F32 || lse_offset_bytes >= (long long)Q * d * 4, "shard_combine: lse overlaps the rows");
+  if (B == 0) return 0;
+  dim3 grid(Q, B);
+  HICOM_DISPATCH_DTYPE(dtype, E, (shard_combine_kernel<E><<<grid, 128, 0, as_stream(stream)>>>(
+      static_cast<const uint8_t*>(msgs), (size_t)rank_stride_bytes, (size_t)video_stride_bytes,
+      (size_t)lse_offset_bytes, R, Q, d, heads, static_cast<E*>(out))));
+  return check_launch("shard_combine_kernel");
 }
 
 extern "C" int hicom_softmax_reduce(const float* m, const float* l, const float* o, int B, int P, int J, int d,

@@ -7,9 +7,11 @@ Two ways the path shards, one process per GPU (torch.distributed, NCCL over NVLi
 * by FRAME for one long video — rank r holds frames [t0, t0+Ts), Ts % temporal_kernel == 0.
   Local path: windows never cross a 4-frame boundary and the grid-pool taps stay inside the window,
   so there is no halo and no communication.  Global path: every rank computes split-softmax partials
-  (m, l, o) over its frames (position rows offset by t0), ONE all-gather exchanges them
-  (J*(d+2) fp32 per split), and every rank merges them with ``softmax_merge`` and finishes the 32 query
-  rows (replicated — cheaper than a second exchange).
+  (m, l, o) over its frames (position rows offset by t0), normalises them on its own and applies the
+  per-head value projection (linear, so it commutes with the merge); ONE all-gather exchanges the
+  resulting 32 x d attention rows + the log-sum-exps of the scores (75 KB per video; the raw fp32
+  partial would be 1.3 MB), and every rank combines them with softmax weights of the log-sum-exps
+  (``ops.shard_combine``) and finishes the 32 query rows (replicated — cheaper than a second exchange).
 """
 from __future__ import annotations
 
@@ -65,6 +67,14 @@ def gather_partials(m: torch.Tensor, l: torch.Tensor, o: torch.Tensor, group=Non
     return unpack_partials(out)
 
 
+def gather_messages(msg: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather every rank's (B, nbytes) frame-shard message -> (world, B, nbytes), rank-major."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(msg.shape), dtype=msg.dtype, device=msg.device)
+    dist.all_gather_into_tensor(out.view(world * msg.shape[0], msg.shape[1]), msg.contiguous(), group=group)
+    return out
+
+
 @torch.no_grad()
 def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, t0: int, group=None,
                           modal: str = "video"):
@@ -100,15 +110,22 @@ def forward_frame_sharded(projector, frames_feature, frames_embed, guide_embed, 
         Qg = gc.injected_query(guide_embed, B, X.dtype)
         m, l, o = gc.partials(X, gc.fold(Qg, projector.global_logit_scale), t0=t0,
                               logit_scale=projector.global_logit_scale)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            from . import ops
-            if m.shape[1] > 1:  # reduce this rank's token splits first: one J*(d+2) fp32 message per video
-                m, l, o = ops.softmax_reduce(m, l, o)
-            m, l, o = gather_partials(m, l, o, group)
         Dh = gc.readout[-1].out_features
         nq = gc.query.shape[0]  # Qg may hold one row per video (direct mode); finish() replicates it
         global_tokens = torch.empty((B * nq, Dh), dtype=X.dtype, device=X.device)
-        gc.finish(Qg, m, l, o, global_tokens, 0, nq)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            from . import ops
+            if X.dtype == torch.float32:  # fp32 mode: exchange the raw partials (exact to fp32 rounding)
+                if m.shape[1] > 1:  # reduce this rank's token splits first: one J*(d+2) fp32 message per video
+                    m, l, o = ops.softmax_reduce(m, l, o)
+                m, l, o = gather_partials(m, l, o, group)
+                gc.finish(Qg, m, l, o, global_tokens, 0, nq)
+            else:
+                msgs = gather_messages(gc.shard_message(Qg, m, l, o), group)
+                a = ops.shard_combine(msgs, Qg.shape[1], d, gc.attn_layer.num_heads, X.dtype)
+                gc.finish_attended(Qg, a, global_tokens, 0, nq)
+        else:
+            gc.finish(Qg, m, l, o, global_tokens, 0, nq)
         global_tokens = global_tokens.view(B, nq, Dh)
     if side is not None:
         main.wait_stream(side)

@@ -398,6 +398,51 @@ def _impl_softmax_merge(m: Tensor, l: Tensor, o: Tensor, out_bf16: int) -> Tenso
     return out
 
 
+def _impl_softmax_merge_lse(m: Tensor, l: Tensor, o: Tensor, out_bf16: int,
+                            lse_out: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """softmax_merge that also returns lse (B,J) fp32 = log sum_n exp(score) over the tokens of these partials
+    (written into ``lse_out`` when given: a contiguous (B,J) fp32 view, e.g. the tail of a frame-shard message)."""
+    dev = _need_cuda(m, l, o, lse_out)
+    m, l, o = m.contiguous(), l.contiguous(), o.contiguous()
+    B, P, J, d = o.shape
+    if m.shape != (B, P, J) or l.shape != (B, P, J) or o.dtype != torch.float32:
+        raise ValueError("softmax_merge_lse: shape mismatch")
+    out = torch.empty((B, J, d), dtype=_CODE_DT[int(out_bf16)], device=dev)
+    if lse_out is not None and (lse_out.shape != (B, J) or lse_out.dtype != torch.float32 or not lse_out.is_contiguous()):
+        raise ValueError("softmax_merge_lse: lse_out must be a contiguous (B,J) fp32 tensor")
+    lse = torch.empty((B, J), dtype=torch.float32, device=dev) if lse_out is None else lse_out
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_softmax_merge_lse(_ptr(m), _ptr(l), _ptr(o), B, P, J, d, _ptr(out), _dt(out),
+                                                  _ptr(lse), _stream(dev))
+    _cabi.check(rc, "hicom_softmax_merge_lse")
+    return out, lse
+
+
+def shard_message_layout(Q: int, d: int, heads: int, dtype: torch.dtype) -> Tuple[int, int]:
+    """(bytes per video, byte offset of the lse block) of the frame-shard message [attn (Q,d) | lse (heads*Q) fp32]."""
+    rows = Q * d * torch.empty((), dtype=dtype).element_size()
+    lse_off = -(-rows // 16) * 16
+    return -(-(lse_off + heads * Q * 4) // 16) * 16, lse_off
+
+
+def _impl_shard_combine(msgs: Tensor, Q: int, d: int, heads: int, dtype: torch.dtype) -> Tensor:
+    """msgs (R, B, nbytes) uint8, the gathered frame-shard messages -> attn (B, Q, d): the ranks' attention rows combined
+    with softmax weights of their log-sum-exps (hicom_shard_combine)."""
+    dev = _need_cuda(msgs)
+    if msgs.dtype != torch.uint8 or msgs.dim() != 3 or not msgs.is_contiguous():
+        raise ValueError("shard_combine: msgs must be a contiguous (R, B, nbytes) uint8 tensor")
+    R, B, nbytes = msgs.shape
+    need, lse_off = shard_message_layout(Q, d, heads, dtype)
+    if nbytes != need:
+        raise ValueError(f"shard_combine: message of {nbytes} bytes, expected {need}")
+    out = torch.empty((B, Q, d), dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_shard_combine(_ptr(msgs), B * nbytes, nbytes, lse_off, R, B, Q, d, heads, _ptr(out),
+                                              _DT[dtype], _stream(dev))
+    _cabi.check(rc, "hicom_shard_combine")
+    return out
+
+
 def _impl_softmax_reduce(m: Tensor, l: Tensor, o: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     """Reduce the P partials along dim 1 to ONE un-normalised partial (m,l,o) with P=1 — done by every rank before
     the frame-shard exchange so the message does not grow with the number of token splits."""
@@ -414,6 +459,24 @@ def _impl_softmax_reduce(m: Tensor, l: Tensor, o: Tensor) -> Tuple[Tensor, Tenso
                                                _stream(dev))
     _cabi.check(rc, "hicom_softmax_reduce")
     return mo, lo, oo
+
+
+def global_value_proj_into(pooled: Tensor, Wv: Tensor, bv: Optional[Tensor], Q: int, heads: int, out: Tensor) -> Tensor:
+    """global_value_proj written into ``out`` (B, Q, d), a contiguous view (e.g. the row block of a frame-shard message)."""
+    dev = _need_cuda(pooled, Wv, bv, out)
+    pooled, Wv = pooled.contiguous(), Wv.contiguous()
+    B, J, d = pooled.shape
+    if J != Q * heads or out.shape != (B, Q, d) or out.dtype != pooled.dtype or out.stride(-1) != 1 \
+            or out.stride(1) != d:
+        raise ValueError("global_value_proj_into: bad shapes")
+    if B > 1 and out.stride(0) != Q * d:  # the kernel writes one dense (B*Q, d) block: go through a temporary
+        out.copy_(_impl_global_value_proj(pooled, Wv, bv, Q, heads))
+        return out
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_global_value_proj(_ptr(pooled), _ptr(Wv), _ptr(_c(bv)), _ptr(out), B, Q, d, heads,
+                                                  _dt(pooled), _stream(dev))
+    _cabi.check(rc, "hicom_global_value_proj")
+    return out
 
 
 def _impl_global_value_proj(pooled: Tensor, Wv: Tensor, bv: Optional[Tensor], Q: int, heads: int) -> Tensor:
@@ -778,6 +841,8 @@ posadd = _wrap("posadd", _impl_posadd, (), lambda *a: "posadd")
 l2norm_rows = _wrap("l2norm_rows", _impl_l2norm_rows, (), lambda *a: "l2norm_rows")
 softmax_merge = _wrap("softmax_merge", _impl_softmax_merge, (), lambda *a: "softmax_merge")
 softmax_reduce = _wrap("softmax_reduce", _impl_softmax_reduce, (), lambda *a: "softmax_reduce")
+softmax_merge_lse = _impl_softmax_merge_lse  # optional output view: called directly
+shard_combine = _impl_shard_combine  # takes a torch.dtype: called directly
 global_value_proj = _wrap("global_value_proj", _impl_global_value_proj, (), lambda *a: "global_value_proj")
 # backward blocks are called directly (``gemm`` writes into strided views, which torch.library cannot describe)
 gemm, act_backward, softmax_backward, colsum = _impl_gemm, _impl_act_backward, _impl_softmax_backward, _impl_colsum

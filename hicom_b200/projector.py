@@ -486,9 +486,35 @@ class GlobalCompressor(nn.Module):
     def finish(self, Qg, m, l, o, out, row_offset, group_stride):
         """merge -> v_proj -> out_proj + residual -> readout, written into rows of ``out`` (projector.py:215-226,646)."""
         attn = self.attn_layer
-        nq, nrows = self.query.shape[0], Qg.shape[1]
         pooled = ops.softmax_merge(m, l, o, ops.out_code(Qg.dtype))
-        a = ops.global_value_proj(pooled, attn.v_proj.weight, attn.v_proj.bias, nrows, attn.num_heads)
+        a = ops.global_value_proj(pooled, attn.v_proj.weight, attn.v_proj.bias, Qg.shape[1], attn.num_heads)
+        self.finish_attended(Qg, a, out, row_offset, group_stride)
+
+    def shard_message(self, Qg, m, l, o):
+        """This rank's message of a frame-sharded video: (B, nbytes) uint8 = [its own normalised attention rows after the
+        value projection (B, rows, d) | the log-sum-exp of its scores (B, heads*rows) fp32].  The per-head value
+        projection is linear, so it commutes with the softmax merge across ranks (`ops.shard_combine`): 75 KB per video
+        instead of the 1.3 MB fp32 partial."""
+        attn = self.attn_layer
+        B, nrows, d = Qg.shape
+        if Qg.dtype == torch.float32:
+            raise NotImplementedError("frame sharding exchanges 16-bit attention rows (bf16 / fp16 models)")
+        nbytes, lse_off = ops.shard_message_layout(nrows, d, attn.num_heads, Qg.dtype)
+        msg = torch.empty((B, nbytes), dtype=torch.uint8, device=Qg.device)
+        J = m.shape[-1]
+        lse_view = msg[:, lse_off:lse_off + J * 4].view(torch.float32)
+        pooled, lse = ops.softmax_merge_lse(m, l, o, ops.out_code(Qg.dtype), lse_view if B == 1 else None)
+        if B > 1:
+            lse_view.copy_(lse)
+        rows = msg[:, :nrows * d * Qg.element_size()].view(Qg.dtype).view(B, nrows, d)
+        ops.global_value_proj_into(pooled, attn.v_proj.weight, attn.v_proj.bias, nrows, attn.num_heads, rows)
+        return msg
+
+    def finish_attended(self, Qg, a, out, row_offset, group_stride):
+        """out_proj + residual -> readout of attention rows ``a`` (B, rows, d), written into rows of ``out``
+        (projector.py:226,646)."""
+        attn = self.attn_layer
+        nq, nrows = self.query.shape[0], Qg.shape[1]
         x = ops.linear(a, attn.out_proj.weight, attn.out_proj.bias, Qg, ops.ACT_NONE, False, _IMPL)
         _mlp_into(self.readout, x, out, row_offset, nrows, group_stride)
         if nrows != nq:  # direct mode: one distinct query per video -> replicate its token (projector.py:367-368)

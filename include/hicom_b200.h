@@ -192,6 +192,23 @@ int hicom_softmax_merge(const float* m, const float* l, const float* o, int B, i
 int hicom_softmax_reduce(const float* m, const float* l, const float* o, int B, int P, int J, int d,
                          float* m_out, float* l_out, float* o_out, void* stream);
 
+/* hicom_softmax_merge_lse: hicom_softmax_merge that also returns lse (B,J) = M + log L, the log-sum-exp of every
+ *   (video, column) over the tokens this call saw — what a frame shard sends to its peers beside its attention rows.
+ */
+int hicom_softmax_merge_lse(const float* m, const float* l, const float* o, int B, int P, int J, int d,
+                            void* pooled, int out_dtype, float* lse, void* stream);
+
+/* hicom_shard_combine: frame shards of one long video.  Every rank r contributes one message per video:
+ *   [ attn_r (Q, d) in `dtype` | ... | lse_r (heads*Q) fp32 at byte lse_offset ], its own normalised attention output
+ *   AFTER the per-head value projection (linear, so it commutes with the softmax merge; projector.py:215,223-224) and
+ *   the log-sum-exp of its scores.  `msgs` holds the R gathered messages: rank r, video b at
+ *   msgs + r*rank_stride + b*video_stride.   out[b,i,h*hd+c] = sum_r softmax_r(lse_r[b,h*Q+i]) * attn_r[b,i,h*hd+c].
+ *   The message is Q*d 16-bit values + heads*Q floats (75 KB for 32 x 1152) instead of the J*(d+2) fp32 partial (1.3 MB).
+ */
+int hicom_shard_combine(const void* msgs, long long rank_stride_bytes, long long video_stride_bytes,
+                        long long lse_offset_bytes, int R, int B, int Q, int d, int heads, void* out, int dtype,
+                        void* stream);
+
 /* hicom_global_value_proj: attn[b,i,h*hd+c] = sum_k Wv[h*hd+c,k] * pooled[b,h*Q+i,k] + bv[h*hd+c]
  *   (v_proj :182 applied after the pooling, and the head merge :223-224).
  */

@@ -108,6 +108,19 @@ def test_c4_width3584_T512_long_video(built_library):
         sharded = torch.cat([torch.cat(local, 1)[0], glob], 0)
     assert O.rel_err(sharded.float().cpu(), got[0].float().cpu()) <= 8e-3
     _check(case, sd, vids, sharded.unsqueeze(0), (0,))
+    # the exchange the ranks actually use for 16-bit models: each shard's own normalised attention rows after the value
+    # projection + the log-sum-exp of its scores (75 KB), combined with softmax weights (ops.shard_combine)
+    with torch.no_grad():
+        msgs = []
+        for r in range(8):
+            Xs = X[:, 64 * r:64 * (r + 1)].contiguous()
+            msgs.append(gc.shard_message(Qg, *gc.partials(Xs, qf, t0=64 * r)))
+        msgs = torch.stack(msgs, 0)
+        assert msgs.shape[2] == 32 * 1152 * 2 + 288 * 4
+        a = ops.shard_combine(msgs, 32, 1152, gc.attn_layer.num_heads, X.dtype)
+        glob2 = torch.empty(32, 3584, dtype=X.dtype, device="cuda")
+        gc.finish_attended(Qg, a, glob2, 0, 0)
+    assert O.rel_err(glob2.float().cpu(), got[0, -32:].float().cpu()) <= 8e-3
 
 
 def test_c2_fp16_native(built_library):
