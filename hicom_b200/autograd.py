@@ -148,15 +148,15 @@ class FoldQueryFn(Function):
         dqf = dqfold.contiguous().view(B, heads, Q, d)                      # [b, h, i, k]
         dq = dWk = None
         if ctx.needs_input_grad[0]:
-            dq = torch.empty_like(q)
-            wk_t = Wk.view(heads, hd, d).transpose(1, 2)                    # [h, k, c]
-            dq_view = dq.view(B, Q, heads, hd).permute(0, 2, 1, 3)          # [b, h, i, c]
-            if dqf.dtype != wk_t.dtype:
-                dqf_op, wk_t = dqf.float(), wk_t.float()
-                tmp = ops.gemm(dqf_op, wk_t, None, True, alpha)
-                dq_view.copy_(tmp)
+            if dqf.dtype == Wk.dtype:
+                # dq[b, i, head h] = alpha * Wk[head h rows] · dqfold[b, h*Q+i]: the value projection's formula with Wk in
+                # Wv's place -- one dense tensor-core GEMM whose epilogue keeps the diagonal head blocks
+                dq = ops.global_value_proj(dqf.view(B, heads * Q, d), Wk, None, Q, heads).mul_(alpha).to(q.dtype)
             else:
-                ops.gemm(dqf, wk_t, dq_view, False, alpha)
+                dq = torch.empty_like(q)
+                wk_t = Wk.view(heads, hd, d).transpose(1, 2).float()        # [h, k, c]
+                dq_view = dq.view(B, Q, heads, hd).permute(0, 2, 1, 3)      # [b, h, i, c]
+                dq_view.copy_(ops.gemm(dqf.float(), wk_t, None, True, alpha))
         if ctx.needs_input_grad[1]:
             q_h = q.contiguous().view(B * Q, heads, hd).permute(1, 2, 0)    # [h, c, (b,i)]
             dqf_h = dqf.permute(1, 0, 2, 3).reshape(heads, B * Q, d)        # [h, (b,i), k]  (small copy)
@@ -186,11 +186,13 @@ class ValueProjFn(Function):
         da = dattn.contiguous()
         dpooled = dWv = dbv = None
         if ctx.needs_input_grad[0]:
-            da_h = da.view(B, Q, heads, hd).permute(0, 2, 1, 3)             # [b, h, i, c]
-            wv_h = Wv.view(heads, hd, d)                                    # [h, c, k]
-            if da_h.dtype != wv_h.dtype:
-                da_h, wv_h = da_h.float(), wv_h.float()
-            dpooled = ops.gemm(da_h, wv_h, None, False, 1.0).reshape(B, J, d).to(pooled.dtype)
+            if da.dtype == Wv.dtype:
+                # dpooled[b, h*Q+i, :] = da[b, i, head h] · Wv[head h rows, :]: the query fold's formula with Wv in Wk's place
+                dpooled = ops.global_fold_query(da, Wv, heads, 1.0).to(pooled.dtype)
+            else:
+                da_h = da.view(B, Q, heads, hd).permute(0, 2, 1, 3).float()  # [b, h, i, c]
+                wv_h = Wv.view(heads, hd, d).float()                         # [h, c, k]
+                dpooled = ops.gemm(da_h, wv_h, None, False, 1.0).reshape(B, J, d).to(pooled.dtype)
         if ctx.needs_input_grad[1]:
             da_t = da.view(B * Q, heads, hd).permute(1, 2, 0)               # [h, c, (b,i)]
             p_h = pooled.view(B, heads, Q, d).permute(1, 0, 2, 3).reshape(heads, B * Q, d)

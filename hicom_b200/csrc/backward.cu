@@ -458,6 +458,20 @@ static int try_gemm_tc(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, in
     t.batch = nb2; t.a_batch_stride = sAb2; t.w_batch_stride = sBb2; t.c_batch_rows = sCb2 / ldc;
     return launch_tc_linear(t, stream);
   }
+  // all batch entries of an NT problem in ONE launch (S[b] = x'[b]·qfold[b]ᵀ, dP[b] = x'[b]·dpooled[b]ᵀ per video):
+  // the kernel's batch axis walks A, C and (when it has a batch stride) B
+  if (mode == 0 && nb > 1 && (nb1 == 1 || nb2 == 1)) {
+    const long long sa = nb1 == 1 ? sAb2 : sAb1, sb = nb1 == 1 ? sBb2 : sBb1, sc = nb1 == 1 ? sCb2 : sCb1;
+    if (sa > 0 && sb >= 0 && sc > 0 && sc % ldc == 0) {
+      TcLinearParams t{};
+      t.A = A; t.W = B; t.C = C; t.bias = nullptr; t.R = nullptr; t.ldr = 0;
+      t.lda = lda; t.ldw = ldw; t.ldc = ldc; t.M = M; t.N = N; t.K = K;
+      t.act = HICOM_ACT_NONE; t.out_dtype = c_dtype; t.rows_per_group = 1 << 30; t.group_stride_rows = 0;
+      t.alpha = alpha;
+      t.batch = (int)nb; t.a_batch_stride = sa; t.w_batch_stride = sb; t.c_batch_rows = sc / ldc;
+      return launch_tc_linear(t, stream);
+    }
+  }
   for (int b1 = 0; b1 < nb1; ++b1)
     for (int b2 = 0; b2 < nb2; ++b2) {
       TcLinearParams t{};
@@ -474,6 +488,77 @@ static int try_gemm_tc(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, in
   return 0;
 }
 
+// ---- skinny NN: C (M <= 8 rows, fp32) = alpha * A (M x K) · B (K x N, n contiguous) -----------------------------------
+// The input gradient of a linear layer evaluated on a handful of rows (dA = dpre·W of the per-video FiLM MLPs): on the
+// generic SIMT tiles it is N/64 blocks walking the whole K range (latency-bound, ~290 us at 8 x 2304 x 2304).  Here
+// every block streams a K range of B with coalesced 8/16-byte loads, keeps the M x 4 partial sums of its four columns
+// in registers and adds them to C with fp32 atomics (C is zeroed first).
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) skinny_nn_kernel(const TA* __restrict__ A, long long sAm, long long sAk,
+                                                        const TB* __restrict__ B, long long sBk, float* __restrict__ C,
+                                                        long long ldc, int M, int N, int K, int kc, float alpha) {
+  __shared__ float As[8][64];
+  const int n = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int k0 = blockIdx.y * kc, k1 = min(K, k0 + kc);
+  float acc[8][4];
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[m][e] = 0.f;
+  for (int kb = k0; kb < k1; kb += 64) {
+    const int kn = min(64, k1 - kb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 64; i += 256) {
+      const int m = i >> 6, k = i & 63;
+      As[m][k] = (m < M && k < kn) ? to_f32<TA>(A[m * sAm + (long long)(kb + k) * sAk]) : 0.f;
+    }
+    __syncthreads();
+    if (n < N) {
+#pragma unroll 4
+      for (int k = 0; k < kn; ++k) {
+        float b[4];
+        Vec4<TB>::load(B + (long long)(kb + k) * sBk + n, b);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const float a = As[m][k];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[m][e] = fmaf(a, b[e], acc[m][e]);
+        }
+      }
+    }
+  }
+  if (n < N)
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(C + m * ldc + n + e, alpha * acc[m][e]);
+}
+
+// -1: not this kernel's problem
+static int try_skinny_nn(const void* A, int64_t sAm, int64_t sAk, const void* B, int64_t sBk, int64_t sBn, void* C,
+                         int64_t ldc, int M, int N, int K, int nb, float alpha, int a_dtype, int b_dtype, int c_dtype,
+                         cudaStream_t s) {
+  if (nb != 1 || M < 1 || M > 8 || c_dtype != HICOM_F32 || sBn != 1 || N % 4 || sBk % 4 || K < 256) return -1;
+  if ((a_dtype != HICOM_F32 && a_dtype != HICOM_BF16) || (b_dtype != HICOM_F32 && b_dtype != HICOM_BF16)) return -1;
+  if (reinterpret_cast<uintptr_t>(B) & 15) return -1;
+  const int gx = (N + 1023) / 1024;
+  int gy = 296 / gx;                       // about two blocks per SM
+  int kc = ((K + gy - 1) / gy + 7) / 8 * 8;
+  if (kc < 32) kc = 32;
+  gy = (K + kc - 1) / kc;
+  cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, s);
+  HICOM_REQUIRE(e == cudaSuccess, "gemm (skinny): memset: %s", cudaGetErrorString(e));
+  dim3 grid(gx, gy);
+#define HICOM_SKINNY_NN(TA, TB)                                                                                     \
+  skinny_nn_kernel<TA, TB><<<grid, 256, 0, s>>>(static_cast<const TA*>(A), sAm, sAk, static_cast<const TB*>(B), sBk, \
+                                                 static_cast<float*>(C), ldc, M, N, K, kc, alpha)
+  if (a_dtype == HICOM_F32 && b_dtype == HICOM_BF16) HICOM_SKINNY_NN(float, __nv_bfloat16);
+  else if (a_dtype == HICOM_BF16 && b_dtype == HICOM_BF16) HICOM_SKINNY_NN(__nv_bfloat16, __nv_bfloat16);
+  else if (a_dtype == HICOM_F32 && b_dtype == HICOM_F32) HICOM_SKINNY_NN(float, float);
+  else HICOM_SKINNY_NN(__nv_bfloat16, float);
+#undef HICOM_SKINNY_NN
+  return check_launch("skinny_nn_kernel");
+}
+
 extern "C" int hicom_gemm(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1, int64_t sAb2, const void* B,
                           int64_t sBk, int64_t sBn, int64_t sBb1, int64_t sBb2, void* C, int64_t ldc, int64_t sCb1,
                           int64_t sCb2, int M, int N, int K, int nb1, int nb2, float alpha, int a_dtype, int b_dtype,
@@ -483,6 +568,11 @@ extern "C" int hicom_gemm(const void* A, int64_t sAm, int64_t sAk, int64_t sAb1,
                 nb1, nb2);
   HICOM_REQUIRE(ldc >= N, "gemm: ldc too small");
   if (M == 0 || N == 0 || nb1 * nb2 == 0) return 0;
+  {
+    const int rc = try_skinny_nn(A, sAm, sAk, B, sBk, sBn, C, ldc, M, N, K, nb1 * nb2, alpha, a_dtype, b_dtype, c_dtype,
+                                 as_stream(stream));
+    if (rc >= 0) return rc;
+  }
   {
     const int rc = try_gemm_tc(A, sAm, sAk, sAb1, sAb2, B, sBk, sBn, sBb1, sBb2, C, ldc, sCb1, sCb2, M, N, K, nb1, nb2,
                                alpha, a_dtype, b_dtype, c_dtype, as_stream(stream));

@@ -467,7 +467,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_3d_pair(sa, &tmA, bar, k0 + t.zslice * p.z_a_k, t.m_tile * BM, t.batch);
 #pragma unroll
               for (int i = 0; i < NINST; ++i)
-                tma_load_3d_pair(sb + i * HALF * 128, &tmB, bar, k0 + t.zslice * p.z_b_k, brow + i * 2 * HALF, t.batch);
+                tma_load_3d_pair(sb + i * HALF * 128, &tmB, bar, k0 + t.zslice * p.z_b_k, brow + i * 2 * HALF,
+                                 p.b_shared ? 0 : t.batch);
             }
           } else {
           // MN-major B arrives as whole 64-wide blocks; K-major B as BN rows
@@ -513,7 +514,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                           k0 + t.zslice * p.z_b_k, p.b_shared ? 0 : t.batch);
           } else {
             for (int r = 0; r < BN; r += p.b_box_rows)
-              tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0 + t.zslice * p.z_b_k, t.n_tile * BN + r, t.batch);
+              tma_load_3d(sb + r * 128, &tmB, &full_bar[s], k0 + t.zslice * p.z_b_k, t.n_tile * BN + r,
+                          p.b_shared ? 0 : t.batch);
           }
           }  // !CTA2
           }
@@ -990,14 +992,20 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
     dim3 gm((q.N + 255) / 256, (q.M + BM - 1) / BM, nb * pm.z_slices);
     return launch<256, true, true, EPI_LINEAR, 2>(ta, tb, pm, gm, stream);
   }
-  if (make_map(&ta, q.A, kext, q.M, 1, q.lda, 0, BM, q.a_f16)) return 1;
+  // batch > 1 (plain (N,K) weights only): blockIdx.z walks batch entries of A, of C (rows shifted by c_batch_rows) and,
+  // when w_batch_stride != 0, of W -- the per-video score GEMMs of the attention backward in one launch
+  const int nbat = (q.batch > 1 && !q.w_is_kn && q.z_slices == 0) ? q.batch : 1;
+  HICOM_REQUIRE(q.batch <= 1 || nbat == q.batch, "tcgen05 linear: batched launches need (N,K) weights and no K slices");
+  const bool w_bat = nbat > 1 && q.w_batch_stride != 0;
+  if (make_map(&ta, q.A, kext, q.M, nbat, q.lda, nbat > 1 ? q.a_batch_stride : 0, BM, q.a_f16)) return 1;
   if (q.w_is_kn) {  // W given as (K, N) row-major: MN-major B operand, boxes of 64 n x 64 k
     if (make_map(&tb, q.W, q.N, kext, 1, q.ldw, 0, 64, q.w_f16)) return 1;
   } else {
-    if (make_map(&tb, q.W, kext, q.N, 1, q.ldw, 0, 256, q.w_f16)) return 1;
+    if (make_map(&tb, q.W, kext, q.N, w_bat ? nbat : 1, q.ldw, w_bat ? q.w_batch_stride : 0, 256, q.w_f16)) return 1;
   }
   Params p{};
   p.a_f16 = q.a_f16; p.b_f16 = q.w_f16;
+  p.b_shared = w_bat ? 0 : 1; p.c_batch_rows = nbat > 1 ? q.c_batch_rows : 0;
   p.alpha = q.alpha; p.diag_heads = q.diag_heads; p.diag_rows = q.diag_rows; p.diag_cols = q.diag_cols;
   p.z_slices = q.z_slices; p.z_a_k = q.z_a_k; p.z_b_k = q.z_b_k; p.z_c_rows = q.z_c_rows; p.z_c_cols = q.z_c_cols;
   p.guard = q.guard;
@@ -1006,7 +1014,7 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   p.R = static_cast<const uint16_t*>(q.R); p.ldr = q.ldr;
   p.C = q.C; p.ldc = q.ldc; p.out_dtype = q.out_dtype; p.act = q.act;
   p.rows_per_group = q.rows_per_group; p.group_stride_rows = q.group_stride_rows;
-  dim3 grid((q.N + 255) / 256, (q.M + BM - 1) / BM, q.z_slices > 0 ? q.z_slices : 1);
+  dim3 grid((q.N + 255) / 256, (q.M + BM - 1) / BM, q.z_slices > 0 ? q.z_slices : nbat);
   if (q.accumulate) {
     HICOM_REQUIRE(q.w_is_kn && q.out_dtype == HICOM_F32 && q.act == HICOM_ACT_NONE,
                   "tcgen05 linear: accumulate is only built for fp32 C, (K,N) weights, no activation");
@@ -1017,11 +1025,11 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   HICOM_REQUIRE(q.act != HICOM_ACT_GELU_TANH || (!q.w_is_kn && q.out_dtype != HICOM_F32),
                 "tcgen05 linear: the tanh GELU is only built for 16-bit C and (N,K) weights");
   // small problems: 128x64 tiles spread over 4x more CTAs with an 8-deep ring (latency-bound otherwise)
-  if (!q.w_is_kn && q.z_slices == 0 && (long long)grid.x * grid.y < 74 && q.N >= 64) {
+  if (!q.w_is_kn && q.z_slices == 0 && (long long)grid.x * grid.y * nbat < 74 && q.N >= 64) {
     CUtensorMap tb64;
-    if (make_map(&tb64, q.W, kext, q.N, 1, q.ldw, 0, 64, q.w_f16)) return 1;
+    if (make_map(&tb64, q.W, kext, q.N, w_bat ? nbat : 1, q.ldw, w_bat ? q.w_batch_stride : 0, 64, q.w_f16)) return 1;
     p.b_box_rows = 64;
-    dim3 g64((q.N + 63) / 64, grid.y, 1);
+    dim3 g64((q.N + 63) / 64, grid.y, nbat);
     switch (flags) {
       case 0: return launch<64, false, false, EPI_LINEAR, 0>(ta, tb64, p, g64, stream);
       case 1: return launch<64, false, false, EPI_LINEAR, 1>(ta, tb64, p, g64, stream);
@@ -1032,9 +1040,9 @@ int launch_tc_linear(const TcLinearParams& q, cudaStream_t stream) {
   }
   // large plain K-major GEMMs: CTA pairs (cta_group::2), each CTA stages half of the weight tile
   if (!q.w_is_kn && q.z_slices == 0 && q.diag_heads == 0 &&
-      (long long)grid.x * grid.y >= 296) {
+      (long long)grid.x * grid.y * nbat >= 296) {
     CUtensorMap tb128;
-    if (make_map(&tb128, q.W, kext, q.N, 1, q.ldw, 0, 128, q.w_f16)) return 1;
+    if (make_map(&tb128, q.W, kext, q.N, w_bat ? nbat : 1, q.ldw, w_bat ? q.w_batch_stride : 0, 128, q.w_f16)) return 1;
     switch (flags) {
       case 0: return launch<256, false, false, EPI_LINEAR, 0, true>(ta, tb128, p, grid, stream);
       case 1: return launch<256, false, false, EPI_LINEAR, 1, true>(ta, tb128, p, grid, stream);
