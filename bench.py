@@ -361,10 +361,26 @@ def measure_next_rows(hidden, T, B, device):
         m.zero_grad(set_to_none=True)
         m.forward_batched(X, E, G, "video").float().square().mean().backward()
 
+    # graph-captured forward + backward first (it must be built before the module's first eager backward)
+    ms_graph = None
+    try:
+        from hicom_b200.graph import graphed_training_forward
+        fn = graphed_training_forward(m, X, E, G, "video")
+        args = tuple(t for t in (X, E, G) if t is not None)
+
+        def gstep():
+            m.zero_grad(set_to_none=True)
+            fn(*args).float().square().mean().backward()
+
+        ms_graph = _timed_ms(gstep, 3, 10)
+    except Exception as exc:  # reported, never fatal
+        ms_graph = repr(exc)[:160]
     ms = _timed_ms(step, 2, 5)
     out["train_step"] = {"what": "forward + backward of the projector (parameter gradients, hicom_b200.autograd)",
                          "videos": Bt, "frames": Bt * T, "use_guide": USE_GUIDE, "ms": ms,
-                         "frames_per_s": Bt * T / ms * 1e3}
+                         "frames_per_s": Bt * T / ms * 1e3,
+                         "ms_cuda_graphs": ms_graph,
+                         "frames_per_s_cuda_graphs": Bt * T / ms_graph * 1e3 if isinstance(ms_graph, float) else None}
     return out
 
 

@@ -342,3 +342,56 @@ def test_gemm_tn_batched_single_launch(built_library):
     got = ops.gemm(A.transpose(1, 2), Bm, None, True, 1.0)
     want = torch.matmul(A.float().cpu().transpose(1, 2), Bm.float().cpu())
     assert O.rel_err(got.cpu(), want) <= 2e-3
+
+
+def test_gemm_nt_batched_single_launch(built_library):
+    """S[b] = x'[b]·qfold[b]ᵀ per video: every batch entry of a K-major x K-major contraction in ONE tcgen05 launch
+    (the kernel's batch axis walks A, B and C), ragged M tiles included."""
+    from hicom_b200 import ops
+    A = _r(3, 1000, 1152, seed=3, std=0.5, dtype=torch.bfloat16).cuda()
+    Bm = _r(3, 288, 1152, seed=4, std=0.05, dtype=torch.bfloat16).cuda()
+    n0 = ops.kernel_launch_count()
+    got = ops.gemm(A, Bm.transpose(1, 2), None, True, 1.0)
+    assert ops.kernel_launch_count() - n0 == 1
+    want = torch.matmul(A.float().cpu(), Bm.float().cpu().transpose(1, 2))
+    assert got.shape == (3, 1000, 288) and O.rel_err(got.cpu(), want) <= 2e-3
+
+
+@pytest.mark.parametrize("adt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(8, 2304, 2304), (1, 1152, 2304), (5, 1028, 300)])
+def test_gemm_skinny_nn(M, N, K, adt, built_library):
+    """dA = dpre·W on a handful of rows (the per-video FiLM MLPs): the streaming skinny kernel (fp32 atomics into a
+    zeroed C) against fp32 torch."""
+    from hicom_b200 import ops
+    A = _r(M, K, seed=5, std=0.5, dtype=adt).cuda()
+    W = _r(K, N, seed=6, std=0.05, dtype=torch.bfloat16).cuda()
+    got = ops.gemm(A, W, None, True, 0.5)
+    want = 0.5 * torch.matmul(A.float().cpu(), W.float().cpu())
+    assert got.dtype == torch.float32 and O.rel_err(got.cpu(), want) <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["coarse", "direct"])
+def test_graphed_training_step_matches_eager(mode, built_library, autograd_on):
+    """forward + backward captured in CUDA graphs (hicom_b200.graph.graphed_training_forward): same tokens and the same
+    parameter gradients as the eager training path, over two replays with different inputs."""
+    import copy
+    from hicom_b200.graph import graphed_training_forward
+    case = dataclasses.replace(CASES_BY_NAME[f"{mode}_T8"], dtype="bfloat16")
+    sd, X, E, g, nl = materialise(case)
+    m = _train_module(case, sd)
+    ref = copy.deepcopy(m)
+    Xc, Ec, gc = X.cuda(), E.cuda(), g.cuda()
+    fn = graphed_training_forward(m, Xc.unsqueeze(0), Ec.unsqueeze(0), gc.unsqueeze(0), case.modal)
+    for scale in (1.0, 0.7):
+        xs, es, gs = (Xc * scale).unsqueeze(0), (Ec * scale).unsqueeze(0), (gc * scale).unsqueeze(0)
+        m.zero_grad(set_to_none=True)
+        out = fn(xs, es, gs)
+        out.float().square().mean().backward()
+        ref.zero_grad(set_to_none=True)
+        want = ref.forward_batched(xs, es, gs, case.modal)
+        want.float().square().mean().backward()
+        assert O.rel_err(out.float().cpu(), want.float().cpu()) <= 1e-2
+        for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+            assert (p.grad is None) == (q.grad is None), k
+            if p.grad is not None and float(q.grad.float().abs().max()) > 0:
+                assert O.cosine(p.grad.float().cpu(), q.grad.float().cpu()) >= 0.999, k
