@@ -31,13 +31,13 @@ def _numa_nodes_of(cpus):
 
 
 @contextlib.contextmanager
-def host_affinity(device=None):
+def host_affinity(device=None, require: bool = False):
     """Pin the calling thread to the CPUs NVML reports as local to ``device`` for the duration of the block.
 
     Pinned host buffers allocated inside land on the GPU's NUMA node; a buffer on the far socket can cut the
     host->device rate by 2-3x.  Yields a report ``{"pinned": bool, "cpus": n, "numa_nodes": [...], "reason": ...}``:
     without NVML, or when the container's cpuset forbids the call, nothing changes and the report says why —
-    ``HICOM_REQUIRE_NUMA=1`` turns that into an error.
+    ``require=True`` turns that into an error.
     """
     old = None
     report = {"pinned": False, "cpus": len(os.sched_getaffinity(0)), "numa_nodes": _numa_nodes_of(os.sched_getaffinity(0)),
@@ -56,7 +56,7 @@ def host_affinity(device=None):
     except Exception as exc:
         old = None
         report["reason"] = repr(exc)[:160]
-        if os.environ.get("HICOM_REQUIRE_NUMA", "0") == "1":
+        if require:
             raise RuntimeError(f"host_affinity: cannot pin to the CPUs local to {device}: {exc!r}") from exc
     try:
         yield report
