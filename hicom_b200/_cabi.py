@@ -45,6 +45,8 @@ PROTOTYPES = {
     "hicom_colsum": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "hicom_act_backward": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "hicom_softmax_backward": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_int, c_void_p]),
+    "hicom_grid_pool_backward": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "hicom_l2norm_rows_backward": (c_int, [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_int, c_void_p]),
     "hicom_local_attend_backward": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_float, c_int, c_int, c_void_p]),
     "hicom_film_layernorm_backward": (c_int, [c_void_p] * 8 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "hicom_mix_layernorm_backward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_void_p]),

@@ -204,14 +204,13 @@ class ValueProjFn(Function):
 
 class GlobalPoolFn(Function):
     """pooled[b, j, :] = sum_n softmax_n(x'_n · qfold[b, j]) x'_n,  x' = X + pos_embed  (split-softmax kernels + merge).
-    X comes from the frozen tower: the only differentiable input is ``qfold``."""
+    Differentiable in ``qfold`` and — when the SigLIP body is tuned (train.py:712-715) — in ``X``:
+    dx'_n = sum_j P[n,j] dpooled[j] + sum_j dS[n,j] qfold[j]."""
 
     @staticmethod
     def forward(ctx, X, qfold, gc, t0, splits):
         m, l, o = gc.partials(X, qfold, t0, splits)
-        pooled = ops.softmax_merge(m, l, o, X.dtype == torch.bfloat16)
-        mo, lo, _ = ops.softmax_reduce(m, l, o)
-        lse = mo[:, 0] + torch.log(lo[:, 0])                                # (B, J) fp32
+        pooled, lse = ops.softmax_merge_lse(m, l, o, ops.out_code(X.dtype))  # lse (B, J) fp32
         ctx.save_for_backward(X, qfold, pooled, lse)
         ctx.gc, ctx.t0 = gc, t0
         return pooled
@@ -219,7 +218,8 @@ class GlobalPoolFn(Function):
     @staticmethod
     def backward(ctx, dpooled):
         X, qfold, pooled, lse = ctx.saved_tensors
-        if not ctx.needs_input_grad[1]:
+        need_x, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_x or need_q):
             return None, None, None, None, None
         B, T, H, W, d = X.shape
         N = T * H * W
@@ -229,9 +229,59 @@ class GlobalPoolFn(Function):
         S = ops.gemm(Xp, qfold.transpose(1, 2), None, True, 1.0)            # (B, N, J) fp32 scores
         dP = ops.gemm(Xp, dpl.transpose(1, 2), None, True, 1.0)             # (B, N, J) fp32
         delta = (pooled.float() * dpl.float()).sum(-1)                      # (B, J)
+        P = None
+        if need_x:  # the probabilities themselves (softmax_backward overwrites nothing, but S is consumed below)
+            P = torch.exp(S - lse[:, None, :]).to(X.dtype)
         dS = ops.softmax_backward(S, dP, lse, delta, X.dtype == torch.bfloat16)
-        dqfold = _gemm_to(dS.transpose(1, 2), Xp, qfold.dtype)              # (B, J, d)
-        return None, dqfold, None, None, None
+        dqfold = _gemm_to(dS.transpose(1, 2), Xp, qfold.dtype) if need_q else None   # (B, J, d)
+        dX = None
+        if need_x:
+            dX = ops.gemm(P, dpl, None, True, 1.0)                                  # (B, N, d) fp32
+            dX += ops.gemm(dS.to(X.dtype), qfold, None, True, 1.0)
+            dX = dX.view(X.shape).to(X.dtype)
+        return dX, dqfold, None, None, None
+
+
+class GlobalPoolKeysFn(Function):
+    """use_clip_scale (projector.py:184-188): pooled[b, j, :] = sum_n softmax_n(kn_n · qs[b, j]) x'_n with EXPLICIT
+    normalised keys ``Kn`` (B,T,H,W,d) and score columns ``qs`` (B,J,d) = exp(logit_scale) x the normalised query masked
+    to its head's channels.  Differentiable in Kn (-> k_proj), qs (-> q_proj, logit_scale) and X."""
+
+    @staticmethod
+    def forward(ctx, X, Kn, qs, gc, t0, splits):
+        B, T, H, W, d = X.shape
+        pt, ph, pw = gc.pos_tables(t0, T, H, W, X.device)
+        if splits is None:
+            from .projector import default_splits
+            splits = default_splits(B, T * H * W, d)
+        m, l, o = ops.global_attend_partial_keys(X, Kn, pt, ph, pw, qs, splits, _impl())
+        pooled, lse = ops.softmax_merge_lse(m, l, o, ops.out_code(X.dtype))
+        ctx.save_for_backward(X, Kn, qs, pooled, lse)
+        ctx.gc, ctx.t0 = gc, t0
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        X, Kn, qs, pooled, lse = ctx.saved_tensors
+        need_x, need_k, need_q = ctx.needs_input_grad[:3]
+        if not (need_x or need_k or need_q):
+            return None, None, None, None, None, None
+        B, T, H, W, d = X.shape
+        N = T * H * W
+        pt, ph, pw = ctx.gc.pos_tables(ctx.t0, T, H, W, X.device)
+        Xp = ops.posadd(X, pt, ph, pw).view(B, N, d)
+        Kf = Kn.contiguous().view(B, N, d)
+        dpl = dpooled.contiguous().to(X.dtype)
+        S = ops.gemm(Kf, qs.transpose(1, 2), None, True, 1.0)               # (B, N, J) fp32
+        dP = ops.gemm(Xp, dpl.transpose(1, 2), None, True, 1.0)
+        delta = (pooled.float() * dpl.float()).sum(-1)
+        P = torch.exp(S - lse[:, None, :]).to(X.dtype) if need_x else None
+        dS = ops.softmax_backward(S, dP, lse, delta, X.dtype == torch.bfloat16)
+        dSc = dS.to(X.dtype)
+        dqs = _gemm_to(dS.transpose(1, 2), Kf, qs.dtype) if need_q else None
+        dKn = ops.gemm(dSc, qs, None, True, 1.0).view(X.shape).to(Kn.dtype) if need_k else None
+        dX = ops.gemm(P, dpl, None, True, 1.0).view(X.shape).to(X.dtype) if need_x else None
+        return dX, dKn, dqs, None, None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -257,15 +307,47 @@ class FilmLayerNormFn(Function):
                 db.to(ctx.b_dtype) if ctx.needs_input_grad[3] else None, None)
 
 
+class GridPoolFn(Function):
+    """Trilinear grid pooling of frames_feature (projector.py:539-540), differentiable in X (only needed when the SigLIP
+    body is tuned, train.py:712-715)."""
+
+    @staticmethod
+    def forward(ctx, X, kt, ks):
+        ctx.geom = (X.shape, X.dtype, kt, ks)
+        return ops.grid_pool(X, kt, ks)
+
+    @staticmethod
+    def backward(ctx, dq):
+        (B, T, H, W, d), dtype, kt, ks = ctx.geom
+        return ops.grid_pool_backward(dq.contiguous().to(dtype), T, H, W, kt, ks).to(dtype), None, None
+
+
+class L2NormFn(Function):
+    """x / |x| over the last dim (use_clip_scale, projector.py:184-188,527-529)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.l2norm_rows(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.l2norm_rows_backward(x, dy.contiguous().to(x.dtype))
+
+
 class LocalAttendFn(Function):
     """Window attention on explicit query rows (ops.local_attend, Q_EXPLICIT); differentiable in the query rows, the
     keys (``frames_embed`` / the key adapter's output) and the values (only behind a trainable value adapter — plain
     values are ``frames_feature`` of the frozen SigLIP body)."""
 
     @staticmethod
-    def forward(ctx, K, V, Qrows, kt, ks, scale, k_l2norm):
+    def forward(ctx, K, V, Qrows, kt, ks, scale, k_l2norm, logit_scale=None):
+        """``logit_scale`` (0-dim tensor, use_clip_scale): scores = exp(logit_scale) * q·k (projector.py:549); ``scale`` is
+        its value as a float.  d/d(logit_scale) = sum over windows of q·dq (dq already carries the factor)."""
         ctx.save_for_backward(K, V, Qrows)
         ctx.geom = (kt, ks, scale, k_l2norm)
+        ctx.ls_meta = None if logit_scale is None else (logit_scale.shape, logit_scale.dtype)
         return ops.local_attend(K, V, V, Qrows, None, None, None, kt, ks, ops.Q_EXPLICIT, scale, k_l2norm)
 
     @staticmethod
@@ -273,13 +355,19 @@ class LocalAttendFn(Function):
         K, V, Qrows = ctx.saved_tensors
         kt, ks, scale, k_l2norm = ctx.geom
         need_k, need_v, need_q = ctx.needs_input_grad[:3]
-        dQ = dK = dV = None
-        if need_q or need_k or need_v:
+        need_ls = len(ctx.needs_input_grad) > 7 and ctx.needs_input_grad[7] and ctx.ls_meta is not None
+        dQ = dK = dV = dls = None
+        if need_q or need_k or need_v or need_ls:
             dQ, dK, dV = ops.local_attend_backward(K, V, Qrows, dO.contiguous().to(Qrows.dtype), kt, ks, scale,
-                                                   k_l2norm, need_q, need_k, need_v)
+                                                   k_l2norm, need_q or need_ls, need_k, need_v)
             dK = None if dK is None else dK.to(K.dtype)
             dV = None if dV is None else dV.to(V.dtype)
-        return dK, dV, dQ, None, None, None, None
+            if need_ls:
+                shape, dtype = ctx.ls_meta
+                dls = (Qrows.float() * dQ.float()).sum().reshape(shape).to(dtype)
+            if not need_q:
+                dQ = None
+        return dK, dV, dQ, None, None, None, None, dls
 
 
 class LayerNormFn(Function):
@@ -394,14 +482,8 @@ def _is_param(x) -> bool:
 
 
 def check_supported(proj, X, E, G) -> None:
-    if X.requires_grad:
-        raise NotImplementedError(
-            "hicom_b200.autograd: frames_feature requires grad — gradients into the SigLIP body (mm_tunable_parts "
-            "'pure_vision_model', train.py:712-715) are not built; the release recipe keeps it frozen (encoder.py:235)")
     if X.dtype not in (torch.float32, torch.bfloat16):
         raise NotImplementedError(f"hicom_b200.autograd: dtype {X.dtype} (train in fp32 or bf16)")
-    if proj.local_logit_scale is not None or proj.global_logit_scale is not None:
-        raise NotImplementedError("hicom_b200.autograd: use_clip_scale is not differentiable yet")
     for comp in (proj.local_compressor, proj.global_compressor):
         if comp is not None and comp.use_guide not in (None, "off", "direct", "coarse", "fine"):
             raise NotImplementedError  # projector.py:350
@@ -453,8 +535,10 @@ def _local_tokens(proj, X, E, G, modal, image_newline, is_anyres):
     if plan != "plain" and image_newline is None:
         raise ValueError("this mm_newline_position needs image_newline")
     mode = lc.use_guide
+    ls, lb = proj.local_logit_scale, proj.local_logit_bias                        # use_clip_scale 'local' (:667-668)
+    ls_grad = torch.is_tensor(ls) and ls.requires_grad
     adapting = any(_is_param(a) for a in (lc.q_alpha, lc.k_alpha, lc.v_alpha))
-    upstream = (mode in ("coarse", "fine") or adapting
+    upstream = (mode in ("coarse", "fine") or adapting or ls_grad or X.requires_grad
                 or (mode == "direct" and ((G is not None and G.requires_grad)
                                           or _is_param(lc.guide_injector.guide_alpha)))
                 or (E is not None and E.requires_grad))
@@ -462,18 +546,31 @@ def _local_tokens(proj, X, E, G, modal, image_newline, is_anyres):
         # nothing trainable in front of the readout (query = pooled feature or the frozen instruction vector, keys and
         # values from frozen towers): the fused inference kernel, as a constant
         with torch.no_grad():
-            att = lc.attend(X, E, G, modal, None, None)
+            att = lc.attend(X, E, G, modal, ls, lb)
     else:
+        if E is not None and ls is not None:                                       # :527-529
+            E = L2NormFn.apply(E)
+            if G is not None:
+                G = G / G.norm(p=2, dim=-1, keepdim=True)
         K = _mix(X if E is None else E, lc.k_proj, lc.k_norm, lc.k_alpha)          # projector.py:532-533
         V = _mix(X, lc.v_proj, lc.v_norm, lc.v_alpha)                              # :534
         if mode == "direct":
             rows = torch.empty((B, ops.num_windows(T, H, W, tk, sk), d), dtype=X.dtype, device=X.device)  # shape only
         else:
-            with torch.no_grad():
-                rows = ops.grid_pool(X, tk, sk)                                    # :539-540 (no parameter)
+            if X.requires_grad:                                                    # SigLIP body tuned (train.py:712-715)
+                rows = GridPoolFn.apply(X, tk, sk)
+            else:
+                with torch.no_grad():
+                    rows = ops.grid_pool(X, tk, sk)                                # :539-540 (no parameter)
             rows = _mix(rows, lc.q_proj, lc.q_norm, lc.q_alpha)                    # :541
         rows = _inject(lc.guide_injector, mode, rows, G)                           # :542
-        att = LocalAttendFn.apply(K, V, rows, tk, sk, 1.0 / math.sqrt(lc.qk_dim), False)   # :544-558
+        if ls is None:
+            att = LocalAttendFn.apply(K, V, rows, tk, sk, 1.0 / math.sqrt(lc.qk_dim), False)   # :544-558
+        else:                                                                      # :548-549, logit_bias cancels
+            from .projector import _exp_scalar
+            att = LocalAttendFn.apply(K, V, rows.contiguous(), tk, sk, _exp_scalar(ls), False, ls if ls_grad else None)
+            if torch.is_tensor(lb) and lb.requires_grad:  # softmax ignores the bias: an exact zero gradient, not None
+                att = att + (lb * 0).to(att.dtype)
     tokens = mlp(lc.readout, att)                                                  # (B, Nw, Dh), projector.py:559
     Dh = tokens.shape[-1]
     t1, h1, w1 = grid
@@ -489,6 +586,17 @@ def _local_tokens(proj, X, E, G, modal, image_newline, is_anyres):
     return blk.reshape(B, n_local, Dh)
 
 
+def _masked_heads(qn: torch.Tensor, heads: int) -> torch.Tensor:
+    """(B, Q, d) -> (B, heads*Q, d): score column (h, i) keeps head h's channels of query i, zeros elsewhere
+    (differentiable: a product with a constant block mask)."""
+    B, Q, d = qn.shape
+    hd = d // heads
+    mask = torch.zeros((heads, 1, heads, 1), dtype=qn.dtype, device=qn.device)
+    ar = torch.arange(heads, device=qn.device)
+    mask[ar, 0, ar, 0] = 1
+    return (qn.view(B, 1, Q, heads, hd) * mask.view(1, heads, 1, heads, 1)).reshape(B, heads * Q, d)
+
+
 def _global_tokens(proj, X, G, splits=None, t0=0):
     gc = proj.global_compressor
     attn = gc.attn_layer
@@ -502,9 +610,29 @@ def _global_tokens(proj, X, G, splits=None, t0=0):
         Qg = _inject(gc.guide_injector, gc.use_guide, rows, G)                      # projector.py:642
     nrows = Qg.shape[1]
     q = linear(Qg, attn.q_proj.weight, attn.q_proj.bias)                            # projector.py:180
-    qfold = FoldQueryFn.apply(q, _as(attn.k_proj.weight, q), _as(attn.k_proj.bias, q), attn.num_heads,
-                              attn.scale)                                           # :181 + :197 folded
-    pooled = GlobalPoolFn.apply(X, qfold, gc, t0, splits)                           # :197-215
+    ls, lb = proj.global_logit_scale, proj.global_logit_bias                        # use_clip_scale 'global' (:669-670)
+    if ls is None:
+        qfold = FoldQueryFn.apply(q, _as(attn.k_proj.weight, q), _as(attn.k_proj.bias, q), attn.num_heads,
+                                  attn.scale)                                       # :181 + :197 folded
+        pooled = GlobalPoolFn.apply(X, qfold, gc, t0, splits)                       # :197-215
+    else:
+        # :184-188 — queries and keys L2-normalised over all d channels before the head split: the key norm cannot be
+        # folded into the queries, so the keys are explicit: k = k_proj(x + pos_embed)
+        heads, hd = attn.num_heads, d // attn.num_heads
+        B_, T, H, W, _ = X.shape
+        pt, ph, pw = gc.pos_tables(t0, T, H, W, X.device)
+        if X.requires_grad:  # differentiable x' = x + pos_embed (:636-640)
+            Xp = X + (pt[None, :, None, None, :] + ph[None, None, :, None, :] + pw[None, None, None, :, :]).to(X.dtype)
+        else:
+            with torch.no_grad():
+                Xp = ops.posadd(X, pt, ph, pw)
+        Kn = L2NormFn.apply(linear(Xp.view(B_, T * H * W, d), attn.k_proj.weight, attn.k_proj.bias)).view(X.shape)
+        scale = torch.as_tensor(ls, device=q.device).exp().to(q.dtype)
+        qn = L2NormFn.apply(q) * scale
+        qs = _masked_heads(qn, heads)
+        pooled = GlobalPoolKeysFn.apply(X, Kn, qs, gc, t0, splits)
+        if torch.is_tensor(lb) and lb.requires_grad:  # the bias shifts every score of a row equally: exact zero gradient
+            pooled = pooled + (lb * 0).to(pooled.dtype)
     a = ValueProjFn.apply(pooled, _as(attn.v_proj.weight, pooled), _as(attn.v_proj.bias, pooled), nrows,
                           attn.num_heads)                                           # :182, :223-224
     x = linear(a, attn.out_proj.weight, attn.out_proj.bias, Qg)                     # :226 + residual of :646

@@ -700,6 +700,101 @@ extern "C" int hicom_local_attend_backward(const void* Ksrc, const void* Vsrc, c
                                                                 logit_scale, k_l2norm, as_stream(stream))));
 }
 
+// ---- grid pooling backward (projector.py:539-540; gradients into frames_feature, mm_tunable_parts 'pure_vision_model') --
+// dX[b, tap] += w_tap * dQ[b, window] over the <= 8 trilinear taps of upsample_trilinear3d (align_corners=False).
+// One warp per window, lanes over channels; fp32 atomics (neighbouring windows share taps); dX is zeroed by the caller.
+template <typename T>
+__global__ void __launch_bounds__(256) grid_pool_backward_kernel(const T* __restrict__ dQ, float* __restrict__ dX,
+                                                                 long long total, int T_, int H, int W, int d, int t1n,
+                                                                 int h1n, int w1n) {
+  const int lane = threadIdx.x & 31;
+  const long long wi = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wi >= total) return;
+  const long long nwin = (long long)t1n * h1n * w1n;
+  const int b = (int)(wi / nwin), r = (int)(wi % nwin);
+  const int t1 = r / (h1n * w1n), h1 = (r / w1n) % h1n, w1 = r % w1n;
+  const Tap tt = linear_tap(t1, T_, t1n), th = linear_tap(h1, H, h1n), tw = linear_tap(w1, W, w1n);
+  const int ti[2] = {tt.i0, tt.i1}; const float twt[2] = {tt.w0, tt.w1};
+  const int hi[2] = {th.i0, th.i1}; const float hwt[2] = {th.w0, th.w1};
+  const int wj[2] = {tw.i0, tw.i1}; const float wwt[2] = {tw.w0, tw.w1};
+  const T* q = dQ + wi * d;
+  float* base = dX + (size_t)b * T_ * H * W * d;
+  for (int c = lane * 4; c < d; c += 128) {
+    float g[4];
+    Vec4<T>::load(q + c, g);
+    for (int a = 0; a < 2; ++a) {
+      if (twt[a] == 0.f) continue;
+      for (int bb = 0; bb < 2; ++bb) {
+        if (hwt[bb] == 0.f) continue;
+        for (int cc = 0; cc < 2; ++cc) {
+          if (wwt[cc] == 0.f) continue;
+          const float wgt = twt[a] * (hwt[bb] * wwt[cc]);
+          float* dst = base + ((size_t)(ti[a] * H + hi[bb]) * W + wj[cc]) * d + c;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) atomicAdd(dst + e, wgt * g[e]);
+        }
+      }
+    }
+  }
+}
+
+extern "C" int hicom_grid_pool_backward(const void* dQ, float* dX, int B, int T, int H, int W, int d, int kt, int ks,
+                                        int dtype, void* stream) {
+  HICOM_REQUIRE(dQ && dX, "grid_pool_backward: null pointer");
+  HICOM_REQUIRE(B >= 0 && T > 0 && H > 0 && W > 0 && d > 0 && d % 4 == 0 && kt > 0 && ks > 0, "grid_pool_backward: bad shape");
+  const int t1n = ceil_div(T, kt), h1n = ceil_div(H, ks), w1n = ceil_div(W, ks);
+  const long long total = (long long)B * t1n * h1n * w1n;
+  if (total == 0) return 0;
+  const long long blocks = (total + 7) / 8;
+  HICOM_REQUIRE(blocks < (1ll << 31), "grid_pool_backward: too many windows");
+  HICOM_DISPATCH_DTYPE(dtype, E, (grid_pool_backward_kernel<E><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      static_cast<const E*>(dQ), dX, total, T, H, W, d, t1n, h1n, w1n)));
+  return check_launch("grid_pool_backward_kernel");
+}
+
+// ---- L2 row normalisation backward (use_clip_scale, projector.py:184-188,527-529): y = x / |x|,
+//      dx = (dy - y (y·dy)) / |x|.  One warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256) l2norm_rows_backward_kernel(const T* __restrict__ X, const T* __restrict__ dY,
+                                                                   T* __restrict__ dX, long long rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* x = X + row * d;
+  const T* g = dY + row * d;
+  float ss = 0.f, dot = 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    float v[4], u[4];
+    Vec4<T>::load(x + c, v);
+    Vec4<T>::load(g + c, u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { ss = fmaf(v[e], v[e], ss); dot = fmaf(v[e], u[e], dot); }
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float inv = rsqrtf(ss), k = dot / ss;
+  for (int c = lane * 4; c < d; c += 128) {
+    float v[4], u[4];
+    Vec4<T>::load(x + c, v);
+    Vec4<T>::load(g + c, u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) u[e] = (u[e] - v[e] * k) * inv;
+    Vec4<T>::store(dX + row * d + c, u);
+  }
+}
+
+extern "C" int hicom_l2norm_rows_backward(const void* X, const void* dY, void* dX, long long rows, int d, int dtype,
+                                          void* stream) {
+  HICOM_REQUIRE(X && dY && dX, "l2norm_rows_backward: null pointer");
+  HICOM_REQUIRE(rows >= 0 && d > 0 && d % 4 == 0, "l2norm_rows_backward: bad shape");
+  if (rows == 0) return 0;
+  const long long blocks = (rows + 7) / 8;
+  HICOM_REQUIRE(blocks < (1ll << 31), "l2norm_rows_backward: too many rows");
+  HICOM_DISPATCH_DTYPE(dtype, E, (l2norm_rows_backward_kernel<E><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+      static_cast<const E*>(X), static_cast<const E*>(dY), static_cast<E*>(dX), rows, d)));
+  return check_launch("l2norm_rows_backward_kernel");
+}
+
 template <typename T>
 static int launch_film_ln_bwd(const void* x, const float* film, const void* w, const void* dy, void* dx, float* dfilm,
                               float* dw, float* dbias, long long rows, int d, int rows_per_group, cudaStream_t s) {

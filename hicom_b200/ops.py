@@ -615,6 +615,35 @@ def _impl_local_attend_backward(K: Tensor, V: Tensor, Q: Tensor, dO: Tensor, kt:
     return dQ, dK, dV
 
 
+def _impl_grid_pool_backward(dQ: Tensor, T: int, H: int, W: int, kt: int, ks: int) -> Tensor:
+    """Backward of grid_pool: dQ (B,Nw,d) -> dX (B,T,H,W,d) fp32 (gradients into frames_feature)."""
+    dev = _need_cuda(dQ)
+    dQ = dQ.contiguous()
+    B, nw, d = dQ.shape
+    if nw != num_windows(T, H, W, kt, ks):
+        raise ValueError("grid_pool_backward: dQ does not match the window grid")
+    dX = torch.zeros((B, T, H, W, d), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_grid_pool_backward(_ptr(dQ), _ptr(dX), B, T, H, W, d, kt, ks, _dt(dQ), _stream(dev))
+    _cabi.check(rc, "hicom_grid_pool_backward")
+    return dX
+
+
+def _impl_l2norm_rows_backward(X: Tensor, dY: Tensor) -> Tensor:
+    """Backward of l2norm_rows: dX = (dY - Y (Y·dY)) / |X| per row of the last dim."""
+    dev = _need_cuda(X, dY)
+    X, dY = X.contiguous(), dY.contiguous()
+    if dY.shape != X.shape or dY.dtype != X.dtype:
+        raise ValueError("l2norm_rows_backward: operands differ")
+    d = X.shape[-1]
+    dX = torch.empty_like(X)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_l2norm_rows_backward(_ptr(X), _ptr(dY), _ptr(dX), X.numel() // d, d, _dt(X),
+                                                     _stream(dev))
+    _cabi.check(rc, "hicom_l2norm_rows_backward")
+    return dX
+
+
 def _impl_film_layernorm_backward(x: Tensor, film: Tensor, ln_w: Tensor, dy: Tensor, rows_per_group: int,
                                   need_dx: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Backward of film_layernorm: returns (dx | empty, dfilm (G,2d) fp32, dw (d) fp32, dbias (d) fp32)."""
@@ -847,5 +876,6 @@ global_value_proj = _wrap("global_value_proj", _impl_global_value_proj, (), lamb
 # backward blocks are called directly (``gemm`` writes into strided views, which torch.library cannot describe)
 gemm, act_backward, softmax_backward, colsum = _impl_gemm, _impl_act_backward, _impl_softmax_backward, _impl_colsum
 local_attend_backward = _impl_local_attend_backward
+grid_pool_backward, l2norm_rows_backward = _impl_grid_pool_backward, _impl_l2norm_rows_backward
 film_layernorm_backward = _impl_film_layernorm_backward
 mix_layernorm_backward = _impl_mix_layernorm_backward

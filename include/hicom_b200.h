@@ -247,6 +247,16 @@ int hicom_act_backward(const void* pre, const void* dy, void* dx, int64_t n, int
 int hicom_softmax_backward(const float* S, const float* dP, const float* lse, const float* delta, void* dS, int B,
                            int64_t N, int J, int out_dtype, void* stream);
 
+/* hicom_grid_pool_backward: backward of hicom_grid_pool (the trilinear grid pooling of projector.py:539-540) —
+ *   dX (B,T,H,W,d) fp32 += taps^T dQ (B,Nw,d).  ACCUMULATED with atomics: zero dX first (or pass a buffer that already
+ *   holds other contributions to the gradient of frames_feature; train.py:712-715 'pure_vision_model'). */
+int hicom_grid_pool_backward(const void* dQ, float* dX, int B, int T, int H, int W, int d, int kt, int ks, int dtype,
+                             void* stream);
+
+/* hicom_l2norm_rows_backward: backward of hicom_l2norm_rows (use_clip_scale, projector.py:184-188,527-529):
+ *   dX = (dY - Y (Y·dY)) / |X| per row, Y = X / |X|; X, dY, dX (rows, d) in dtype. */
+int hicom_l2norm_rows_backward(const void* X, const void* dY, void* dX, long long rows, int d, int dtype, void* stream);
+
 /* hicom_local_attend_backward: gradients of hicom_local_attend's output (projector.py:546-553) with respect to
  *   dQ (B,Nw,d) in dtype   the query rows actually used by the forward (Q, same shape) — FiLM / instruction parameters;
  *   dK (B,T,H,W,d) fp32    the keys (frames_embed: stage 3 tunes the SigLIP head that produces it, train.py:717-721);

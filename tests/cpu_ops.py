@@ -104,6 +104,56 @@ def softmax_merge(m, l, o, out_bf16):
     return pooled.bfloat16() if out_bf16 else pooled
 
 
+def softmax_merge_lse(m, l, o, out_bf16, lse_out=None):
+    M, L, Osum = softmax_reduce(m, l, o)
+    pooled = (Osum / L[..., None])[:, 0]
+    lse = (M + torch.log(L))[:, 0]
+    if lse_out is not None:
+        lse_out.copy_(lse)
+    return (pooled.bfloat16() if out_bf16 else pooled), lse
+
+
+def out_code(dtype):
+    return 1 if dtype == torch.bfloat16 else (2 if dtype == torch.float16 else 0)
+
+
+def global_attend_partial_keys(X, Kscore, pt, ph, pw, qfold, splits, impl):
+    calls.append(("global_attend_partial_keys", splits))
+    B, T, H, W, d = X.shape
+    N = T * H * W
+    Xp = posadd(X, pt, ph, pw).float().view(B, N, d)
+    S = torch.matmul(Kscore.float().view(B, N, d), qfold.float().transpose(1, 2))
+    chunk = -(-N // splits)
+    ms, ls, os_ = [], [], []
+    for s in range(splits):
+        a, b = s * chunk, min(N, (s + 1) * chunk)
+        m = S[:, a:b].max(dim=1).values
+        p = torch.exp(S[:, a:b] - m[:, None, :])
+        ms.append(m); ls.append(p.sum(1)); os_.append(torch.einsum("bnj,bnd->bjd", p, Xp[:, a:b]))
+    return torch.stack(ms, 1), torch.stack(ls, 1), torch.stack(os_, 1)
+
+
+def l2norm_rows(X):
+    return (X.float() / X.float().norm(p=2, dim=-1, keepdim=True)).to(X.dtype)
+
+
+def l2norm_rows_backward(X, dY):
+    x, g = X.float(), dY.float()
+    n = x.norm(p=2, dim=-1, keepdim=True)
+    y = x / n
+    return ((g - y * (y * g).sum(-1, keepdim=True)) / n).to(X.dtype)
+
+
+def grid_pool_backward(dQ, T, H, W, kt, ks):
+    B, nw, d = dQ.shape
+    ds = (math.ceil(T / kt), math.ceil(H / ks), math.ceil(W / ks))
+    x = torch.zeros((B, d, T, H, W), dtype=torch.float32, requires_grad=True)
+    with torch.enable_grad():
+        q = F.interpolate(x, size=ds, mode="trilinear")
+        (gx,) = torch.autograd.grad(q, x, dQ.float().view(B, *ds, d).permute(0, 4, 1, 2, 3))
+    return gx.permute(0, 2, 3, 4, 1).contiguous()
+
+
 def global_value_proj(pooled, Wv, bv, Q, heads):
     _same_dtype(pooled, Wv, bv)
     B, J, d = pooled.shape
@@ -225,7 +275,8 @@ def _need_cuda(*ts):
 ALL = ["linear", "gemm", "colsum", "act_backward", "softmax_backward", "global_fold_query", "posadd", "global_attend_partial",
        "softmax_reduce", "softmax_merge", "global_value_proj", "grid_pool", "film_layernorm", "film_layernorm_backward",
        "local_attend", "local_attend_backward", "layernorm", "mix_layernorm", "mix_layernorm_backward", "add_layernorm",
-       "guide_attend", "_need_cuda"]
+       "guide_attend", "_need_cuda", "softmax_merge_lse", "out_code", "global_attend_partial_keys", "l2norm_rows",
+       "l2norm_rows_backward", "grid_pool_backward"]
 
 
 def install(monkeypatch):

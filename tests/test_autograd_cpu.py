@@ -110,11 +110,8 @@ def test_opt_in_and_unsupported_configs_fail_loudly(monkeypatch):
     with pytest.raises(RuntimeError, match="forward-only"):
         m(X, E, g, "video")
     monkeypatch.setattr(ag, "ENABLED", True)
-    m.local_logit_scale, m.local_logit_bias = torch.tensor(2.0), torch.tensor(-1.0)   # use_clip_scale='local'
-    with pytest.raises(NotImplementedError, match="use_clip_scale"):
-        m(X, E, g, "video")
-    with pytest.raises(NotImplementedError, match="frames_feature requires grad"):
-        _module(case, sd)(X.clone().requires_grad_(True), E, g, "video")
+    with pytest.raises(NotImplementedError, match="dtype"):
+        _module(case, sd).half()(X.half(), E.half(), g.half(), "video")   # fp16 is the inference dtype; train in bf16 / fp32
     # frozen projector under grad mode: nothing needs a graph -> the plain inference path (which refuses CPU tensors)
     m = _module(case, sd).requires_grad_(False)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
@@ -349,3 +346,79 @@ def test_training_path_fuzz_against_reference_autograd(case, monkeypatch):
             assert p.grad is None or float(p.grad.abs().max()) <= 1e-6, k
         else:
             assert p.grad is not None and O.rel_err(p.grad, w) <= 3e-4, (k, O.rel_err(p.grad, w))
+
+
+@pytest.mark.parametrize("name", ["none_T8", "direct_T8", "coarse_T8", "coarse_nondiv_7x8", "fine_T8", "adaptqkvg_coarse_T4",
+                                  "global_only_coarse_T8"])
+def test_gradients_into_frames_feature(name, monkeypatch):
+    """mm_tunable_parts 'pure_vision_model' (train.py:712-715): the SigLIP body is tuned, so frames_feature carries a
+    gradient — through the window values (and keys when frames_embed is None), the trilinear grid pooling of the query
+    and the global attention's pooled operand x' = x + pos_embed."""
+    from hicom_b200 import autograd as ag
+    case = CASES_BY_NAME[name]
+    sd, X, E, g, nl = materialise(case)
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, sd)
+    X1 = X.clone().requires_grad_(True)
+    out = m(X1, E, g, case.modal, nl)
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(8))
+    (out * probe).sum().backward()
+    X2 = X.clone().requires_grad_(True)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    want = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf).forward(X2, E, g, case.modal, nl)
+    (want * probe).sum().backward()
+    assert O.rel_err(out.detach(), want.detach()) <= 2e-5
+    assert X1.grad is not None and O.rel_err(X1.grad, X2.grad) <= 2e-4, O.rel_err(X1.grad, X2.grad)
+    for k, p in m.named_parameters():
+        if leaf[k].grad is not None and float(leaf[k].grad.abs().max()) > 1e-6:
+            assert O.rel_err(p.grad, leaf[k].grad) <= 2e-4, k
+
+
+@pytest.mark.parametrize("name,where", [("coarse_T8", "local"), ("coarse_T8", "global"), ("direct_T8", "local,global"),
+                                        ("none_T8", "global"), ("adaptkv_coarse_T8", "local,global"),
+                                        ("fine_T8", "local,global")])
+def test_clip_scale_is_differentiable(name, where, monkeypatch):
+    """use_clip_scale (projector.py:184-188,527-529,548-549) with mm_tunable_parts 'attn_scale' (train.py:729-732):
+    logit_scale / logit_bias are trainable parameters of the projector; gradients of every parameter, of both scalars
+    and of frames_embed against PyTorch autograd through the oracle."""
+    from hicom_b200 import autograd as ag
+    case = CASES_BY_NAME[name]
+    sd, X, E, g, nl = materialise(case)
+    cpu_ops.install(monkeypatch)
+    monkeypatch.setattr(ag, "ENABLED", True)
+    m = _module(case, sd)
+    scal = {}
+    for part in where.split(","):
+        ls, lb = torch.nn.Parameter(torch.tensor(1.3)), torch.nn.Parameter(torch.tensor(-0.7))
+        setattr(m, f"{part}_logit_scale", ls)
+        setattr(m, f"{part}_logit_bias", lb)
+        scal[part] = (ls, lb)
+    E1 = None if E is None else E.clone().requires_grad_(True)
+    out = m(X, E1, g, case.modal, nl)
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(9))
+    (out * probe).sum().backward()
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    orc = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf)
+    oscal = {}
+    for part in where.split(","):
+        oscal[part] = (torch.tensor(1.3, requires_grad=True), torch.tensor(-0.7, requires_grad=True))
+        setattr(orc, f"{part}_logit", oscal[part])
+    E2 = None if E is None else E.clone().requires_grad_(True)
+    want = orc.forward(X, E2, g, case.modal, nl)
+    (want * probe).sum().backward()
+    assert O.rel_err(out.detach(), want.detach()) <= 2e-5
+    for k, p in m.named_parameters():
+        if k.endswith(("logit_scale", "logit_bias")):
+            continue
+        w = leaf[k].grad
+        if w is None or float(w.abs().max()) <= 1e-6:
+            continue
+        assert p.grad is not None and O.rel_err(p.grad, w) <= 5e-4, (k, O.rel_err(p.grad, w))
+    for part, (ls, lb) in scal.items():
+        ols, olb = oscal[part]
+        if ols.grad is not None and float(ols.grad.abs()) > 1e-7:
+            assert ls.grad is not None and abs(float(ls.grad) - float(ols.grad)) <= 5e-4 * max(1.0, abs(float(ols.grad))), part
+        assert lb.grad is None or abs(float(lb.grad)) <= 1e-6       # the softmax cancels the bias
+    if E1 is not None and E2.grad is not None and E1.grad is not None:
+        assert O.rel_err(E1.grad, E2.grad) <= 5e-4

@@ -279,13 +279,9 @@ def test_switch_off_restores_forward_only(built_library):
             m(X.cuda(), E.cuda(), g.cuda(), "video")
     finally:
         ag.enable(old)
-    # what is not differentiable stays loud with the path on: use_clip_scale, gradients into frames_feature
-    m.local_logit_scale, m.local_logit_bias = torch.tensor(2.0, device="cuda"), torch.tensor(-1.0, device="cuda")
-    with pytest.raises(NotImplementedError, match="use_clip_scale"):
-        m(X.cuda(), E.cuda(), g.cuda(), "video")
-    m.local_logit_scale = m.local_logit_bias = None
-    with pytest.raises(NotImplementedError, match="frames_feature requires grad"):
-        m(X.cuda().requires_grad_(True), E.cuda(), g.cuda(), "video")
+    # what is not trainable stays loud with the path on: fp16 is the inference dtype (train in bf16 / fp32)
+    with pytest.raises(NotImplementedError, match="dtype"):
+        m.half()(X.cuda().half(), E.cuda().half(), g.cuda().half(), "video")
 
 
 @pytest.mark.parametrize("name,dtype", [("direct_T8", "float32"), ("coarse_nondiv_7x8", "float32"),
@@ -395,3 +391,95 @@ def test_graphed_training_step_matches_eager(mode, built_library, autograd_on):
             assert (p.grad is None) == (q.grad is None), k
             if p.grad is not None and float(q.grad.float().abs().max()) > 0:
                 assert O.cosine(p.grad.float().cpu(), q.grad.float().cpu()) >= 0.999, k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_grid_pool_and_l2norm_backward(dtype, built_library):
+    import cpu_ops
+    from hicom_b200 import ops
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for (B, T, H, W, d, kt, ks) in [(2, 8, 6, 6, 128, 4, 3), (1, 7, 7, 8, 256, 4, 3), (1, 1, 6, 6, 128, 1, 2)]:
+        nw = ops.num_windows(T, H, W, kt, ks)
+        dq = _r(B, nw, d, seed=11, dtype=dtype)
+        got = ops.grid_pool_backward(dq.cuda(), T, H, W, kt, ks)
+        want = cpu_ops.grid_pool_backward(dq, T, H, W, kt, ks)
+        assert got.dtype == torch.float32 and O.rel_err(got.cpu(), want) <= (1e-5 if dtype == torch.float32 else 1e-5)
+    x, dy = _r(37, 1152, seed=12, dtype=dtype), _r(37, 1152, seed=13, dtype=dtype)
+    got = ops.l2norm_rows_backward(x.cuda(), dy.cuda())
+    assert got.dtype == dtype and O.rel_err(got.float().cpu(), cpu_ops.l2norm_rows_backward(x.float(), dy.float())) <= tol
+
+
+@pytest.mark.parametrize("name,dtype", [("coarse_T8", "float32"), ("none_T8", "float32"), ("direct_T8", "bfloat16"),
+                                        ("coarse_nondiv_7x8", "float32")])
+def test_gradients_reach_frames_feature(name, dtype, built_library, autograd_on):
+    """'pure_vision_model' tuned (train.py:712-715): frames_feature carries a gradient, compared with PyTorch autograd
+    through the oracle."""
+    case = dataclasses.replace(CASES_BY_NAME[name], dtype=dtype)
+    sd, X, E, g, nl = materialise(case)
+    m = _train_module(case, sd)
+    dv = lambda t: None if t is None else t.cuda()
+    X1 = X.cuda().requires_grad_(True)
+    out = m(X1, dv(E), dv(g), case.modal, None)
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    (out.float() * probe.cuda()).sum().backward()
+    f = lambda t: None if t is None else t.float()
+    leaf = {k: v.float().clone().requires_grad_(True) for k, v in sd.items()}
+    X2 = X.float().clone().requires_grad_(True)
+    want = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf).forward(X2, f(E), f(g), case.modal, None)
+    (want * probe).sum().backward()
+    assert X1.grad is not None and X1.grad.dtype == X1.dtype
+    if dtype == "float32":
+        assert O.rel_err(X1.grad.cpu(), X2.grad) <= 1e-3, O.rel_err(X1.grad.cpu(), X2.grad)
+    else:
+        assert O.cosine(X1.grad.float().cpu(), X2.grad) >= 0.99
+
+
+@pytest.mark.parametrize("name,where,dtype", [("coarse_T8", "local,global", "float32"), ("direct_T8", "local,global", "bfloat16"),
+                                              ("adaptkv_coarse_T8", "local", "float32"), ("none_T8", "global", "float32")])
+def test_clip_scale_training_step(name, where, dtype, built_library, autograd_on):
+    """use_clip_scale with trainable logit_scale / logit_bias ('attn_scale', train.py:729-732): every gradient against
+    PyTorch autograd through the oracle."""
+    case = dataclasses.replace(CASES_BY_NAME[name], dtype=dtype)
+    sd, X, E, g, nl = materialise(case)
+    m = _train_module(case, sd)
+    scal = {}
+    for part in where.split(","):
+        ls = torch.nn.Parameter(torch.tensor(1.3, device="cuda"))
+        lb = torch.nn.Parameter(torch.tensor(-0.7, device="cuda"))
+        setattr(m, f"{part}_logit_scale", ls)
+        setattr(m, f"{part}_logit_bias", lb)
+        scal[part] = (ls, lb)
+    dv = lambda t: None if t is None else t.cuda()
+    out = m(dv(X), dv(E), dv(g), case.modal, None)
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(9))
+    (out.float() * probe.cuda()).sum().backward()
+    f = lambda t: None if t is None else t.float()
+    leaf = {k: v.float().clone().requires_grad_(True) for k, v in sd.items()}
+    orc = O.OracleProjector(case.ptype, case.use_guide, case.merge, case.nlpos, leaf)
+    oscal = {}
+    for part in where.split(","):
+        oscal[part] = (torch.tensor(1.3, requires_grad=True), torch.tensor(-0.7, requires_grad=True))
+        setattr(orc, f"{part}_logit", oscal[part])
+    want = orc.forward(f(X), f(E), f(g), case.modal, None)
+    (want * probe).sum().backward()
+    if dtype == "float32":
+        assert O.rel_err(out.detach().float().cpu(), want.detach()) <= 1e-4
+    for k, p in m.named_parameters():
+        if k.endswith(("logit_scale", "logit_bias")):
+            continue
+        w = leaf[k].grad
+        if w is None or float(w.abs().max()) <= 1e-6:
+            continue
+        assert p.grad is not None, k
+        if dtype == "float32":
+            assert O.rel_err(p.grad.cpu(), w) <= 2e-3, (k, O.rel_err(p.grad.cpu(), w))
+        else:
+            # the key bias of the normalised keys is a column sum over every token of gradients that nearly cancel (1e-5
+            # against 1e-2 for the weights): bf16 rounding of the per-token gradients is visible in it
+            assert O.cosine(p.grad.float().cpu(), w) >= (0.8 if k.endswith("attn_layer.k_proj.bias") else 0.99), k
+    for part, (ls, lb) in scal.items():
+        ols, _ = oscal[part]
+        if ols.grad is not None and abs(float(ols.grad)) > 1e-6:
+            tol = 2e-3 if dtype == "float32" else 5e-2
+            assert ls.grad is not None and abs(float(ls.grad) - float(ols.grad)) <= tol * max(1.0, abs(float(ols.grad))), \
+                (part, float(ls.grad), float(ols.grad))
