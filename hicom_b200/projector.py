@@ -644,6 +644,30 @@ class HIComProjector(nn.Module):
             block[:, :, :h1 * w1] = tokens.view(B, t1, h1 * w1, Dh)
             block[:, :, h1 * w1] = nl
 
+    # -- DeepSpeed ZeRO-3 (hicom_trainer.py:21-38, projector.py:604-605) ------------------------------------------
+    def register_zero3_parameters(self) -> int:
+        """Under ZeRO-3 every parameter is partitioned and only gathered around the ``forward`` of the sub-module that
+        owns it.  This module's kernels read the sub-modules' weights directly (``self.readout[0].weight`` is an
+        argument of a launch, ``self.readout[0]`` is never called), so the owners' hooks never fire: register every
+        parameter as an EXTERNAL parameter of this module (DeepSpeed's API for exactly that case) and it is gathered
+        around this module's forward and backward instead.  Call once after ``deepspeed.initialize`` (idempotent;
+        returns the number of partitioned parameters; a no-op without ZeRO-3)."""
+        params = [p for p in self.parameters() if hasattr(p, "ds_id")]
+        done = self.__dict__.setdefault("_zero3_registered", set())
+        todo = [p for p in params if id(p) not in done]
+        if todo:
+            from deepspeed import zero
+            for p in todo:
+                zero.register_external_parameter(self, p)
+                done.add(id(p))
+        return len(params)
+
+    def _check_zero3(self):
+        first = next(self.parameters(), None)
+        if first is not None and hasattr(first, "ds_id") and len(self.__dict__.get("_zero3_registered", ())) == 0:
+            raise RuntimeError("hicom_b200: the projector's parameters are ZeRO-3 partitioned; call "
+                               "projector.register_zero3_parameters() once after deepspeed.initialize (INTEGRATION.md)")
+
     # -- batched entry (additive; SURVEY §8b) ------------------------------------------------------
     def forward_batched(self, frames_feature, frames_embed, guide_embed, modal, image_newline=None,
                         is_anyres=False, base=None, with_global=True, out=None, out_row_offset=0):
@@ -660,6 +684,7 @@ class HIComProjector(nn.Module):
         X = frames_feature
         if X.dim() != 5:
             raise ValueError(f"forward_batched expects (B,T,H,W,d), got {tuple(X.shape)}")
+        self._check_zero3()
         if out is not None and not isinstance(out_row_offset, int):
             if out.dim() != 3 or not out.is_contiguous():
                 raise ValueError("out must be a contiguous (B, L, Dh) tensor")

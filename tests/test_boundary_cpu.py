@@ -167,3 +167,31 @@ def test_batch_view_is_zero_copy_for_split_views():
     g = torch.randn(5, 8)
     assert batch_view([g[i] for i in range(5)]).data_ptr() == g.data_ptr()
     assert batch_view([g[2]]).shape == (1, 8)
+
+
+def test_zero3_parameters_are_registered_as_external(monkeypatch):
+    """DeepSpeed ZeRO-3 (hicom_trainer.py:21-38): partitioned parameters (``ds_id``) read outside their owner's forward
+    must be registered with ``deepspeed.zero.register_external_parameter``.  DeepSpeed is not in this image: the call
+    pattern is checked against a stub of its API."""
+    import sys
+    import types
+    import hicom_b200
+    from util import Cfg
+    seen = []
+    zero = types.ModuleType("deepspeed.zero")
+    zero.register_external_parameter = lambda module, p: seen.append((module, p))
+    ds = types.ModuleType("deepspeed")
+    ds.zero = zero
+    monkeypatch.setitem(sys.modules, "deepspeed", ds)
+    monkeypatch.setitem(sys.modules, "deepspeed.zero", zero)
+    m = hicom_b200.build_vision_projector(Cfg(use_guide="coarse"))
+    assert m.register_zero3_parameters() == 0 and seen == []          # not partitioned: nothing to do
+    for i, p in enumerate(m.parameters()):
+        p.ds_id = i                                                    # what zero.Init / deepspeed.initialize adds
+    X = torch.zeros(1, 4, 6, 6, 1152)
+    with pytest.raises(RuntimeError, match="register_zero3_parameters"):
+        m.forward_batched(X, X, torch.zeros(1, 1152), "video")
+    n = m.register_zero3_parameters()
+    assert n == len(list(m.parameters())) == len(seen) and all(mod is m for mod, _ in seen)
+    assert {id(p) for _, p in seen} == {id(p) for p in m.parameters()}
+    assert m.register_zero3_parameters() == n and len(seen) == n       # idempotent
