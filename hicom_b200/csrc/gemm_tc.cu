@@ -472,7 +472,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
           // MN-major B arrives as whole 64-wide blocks; K-major B as BN rows
-          const bool b_mn_now = B_MN && !(EPI == EPI_POOL && ext);
+          constexpr bool b_mn_now = B_MN;
           mbar_expect_tx(&full_bar[s], C::A_BYTES + (b_mn_now ? C::B_BYTES : (uint32_t)BN * BK * 2));
           if (A_MN) {
             // A[m, k] stored (k rows, m contiguous): two 64-wide M blocks of (BK rows x 128 B)
@@ -502,9 +502,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (ke == 0) tma_load_3d(sb + r * 128, &tmB2, &full_bar[s], 0, t.n_tile * BN + r, t.batch);
               else tma_load_3d(sb + r * 128, &tmB3, &full_bar[s], f0, t.n_tile * BN + r, t.batch);
             }
-          } else if (ext && EPI == EPI_POOL) {  // probability marginals (J x ke2) of this video, K-major
-            for (int r = 0; r < BN; r += p.b_box_rows)
-              tma_load_3d(sb + r * 128, &tmB2, &full_bar[s], ke * BK, r, t.batch);
+          } else if (ext && EPI == EPI_POOL) {  // transposed probability marginals (ke2 x J) of this video, MN-major like P2
+            for (int r = 0; r < BN; r += 64)
+              tma_load_3d(sb + (r / 64) * (BK * 128), &tmB2, &full_bar[s], r, ke * BK, t.batch);
           } else if (ext) {
             tma_load_3d(sb, &tmB2, &full_bar[s], ke * BK, t.n_tile * BN, 0);  // (tokens x ke) indicator
           } else if (B_MN) {
@@ -590,8 +590,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
-          // the pooling GEMM's extension blocks carry a K-major B (marginals) next to an MN-major main B (probabilities)
-          const bool b_mn_now = B_MN && !(EPI == EPI_POOL && kb >= t.nkb_main);
+          constexpr bool b_mn_now = B_MN;
           // fp16 operands: clear the format field (1 = bf16, 0 = fp16) of A (bit 7) / B (bit 10); the two operands of one
           // instruction must have the same format (a mixed pair is an illegal instruction on sm_100a), main and
           // extension blocks may differ
@@ -1122,7 +1121,7 @@ static GlobalWs3 global_ws3(int B, int T, int H, int W, int d, int J, int splits
   w.ind = take(N * w.ild * 2);
   w.qt = take((size_t)B * J * w.ke2 * 2);         // qfold · pe2ᵀ = [spatial term, col 63 = -stabiliser | time term per frame]
   w.margf = take((size_t)B * w.mslices * J * 2 * kKe * 4);
-  w.marg = take((size_t)B * J * w.ke2 * 2);
+  w.marg = take((size_t)B * w.ke2 * w.pld * 2);   // transposed marginals (ke2 x pld per video)
   w.total = off;
   return w;
 }
@@ -1213,10 +1212,12 @@ __global__ void reset_for_exact3_kernel(float* mg, __nv_bfloat16* qt, int ld, in
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { mg[i] = -INFINITY; qt[(size_t)i * ld + kKe - 1] = __float2bfloat16_rn(0.f); }
 }
-// marg (B*J, ke2) bf16 = sum over K slices of margf; column 63 is the softmax denominator.  A denominator that is not a
-// positive finite number means exp() left the exponent range: raise the flag for the exact-max re-run.
+// margT (B, ke2, pld) bf16 = sum over K slices of margf, stored TRANSPOSED (indicator column c major, score column j
+// contiguous, padded to pld like P2) so that the pooling GEMM's extension blocks look exactly like its main blocks;
+// column 63 of margf is the softmax denominator.  A denominator that is not a positive finite number means exp() left
+// the exponent range: raise the flag for the exact-max re-run.
 __global__ void marg_reduce_kernel(const float* margf, __nv_bfloat16* marg, float* lsum, int B, int S, int J, int ke2,
-                                   int kslice, int hw, int* flag, int guarded) {
+                                   int pld, int kslice, int hw, int* flag, int guarded) {
   if (guarded && *flag == 0) return;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * J * ke2) return;
@@ -1235,7 +1236,7 @@ __global__ void marg_reduce_kernel(const float* margf, __nv_bfloat16* marg, floa
       if (rel >= 0 && rel < kKe) acc += src[s2 * sstride + kKe + rel];
     }
   }
-  marg[i] = __float2bfloat16_rn(acc);
+  marg[((size_t)b * ke2 + c) * pld + j] = __float2bfloat16_rn(acc);
   if (c == kKe - 1) {
     lsum[bj] = acc;
     if (!guarded && !(acc > 0.f && acc < 3.0e38f)) atomicExch(flag, 1);
@@ -1354,7 +1355,7 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
   if (make_map(&txa, X, d, N, B, d, (uint64_t)N * d, 64, f16)) return 1;
   if (make_map(&tp2, P2, w.pld, N, B, w.pld, (uint64_t)N * w.pld, 64, f16)) return 1;
   if (make_map(&tpe, pe2, d, w.ke2, 1, d, 0, 64)) return 1;
-  if (make_map(&tmg, marg, w.ke2, J, B, w.ke2, (uint64_t)J * w.ke2, jbox)) return 1;
+  if (make_map(&tmg, marg, w.pld, w.ke2, B, w.pld, (uint64_t)w.ke2 * w.pld, 64)) return 1;
   Params g{};
   g.M = d; g.N = J; g.K = N;
   int chunk = (N + splits - 1) / splits;
@@ -1381,8 +1382,8 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
                : launch<288, false, false, EPI_PROB2>(tx128, tqj, p1, gprob, stream, &ti0, &tqej, &ti1, &ttq)) return 1;
     TcLinearParams m1 = mm; m1.guard = guard;
     if (launch_tc_linear(m1, stream)) return 1;
-    marg_reduce_kernel<<<blocks(BJ * w.ke2), 256, 0, stream>>>(margf, marg, lsum, B, w.mslices, J, w.ke2, kslice,
-                                                               H * W, flag, guard != nullptr);
+    marg_reduce_kernel<<<blocks(BJ * w.ke2), 256, 0, stream>>>(margf, marg, lsum, B, w.mslices, J, w.ke2, (int)w.pld,
+                                                               kslice, H * W, flag, guard != nullptr);
     if (check_launch("marg_reduce_kernel")) return 1;
     Params g1 = g; g1.guard = guard;
     if (narrow ? launch<64, true, true, EPI_POOL>(txa, tp2, g1, gp, stream, &tpe, &tmg)
