@@ -362,7 +362,7 @@ def measure_next_rows(hidden, T, B, device):
         m.forward_batched(X, E, G, "video").float().square().mean().backward()
 
     # graph-captured forward + backward first (it must be built before the module's first eager backward)
-    ms_graph = None
+    ms_graph = fn = None
     try:
         from hicom_b200.graph import graphed_training_forward
         fn = graphed_training_forward(m, X, E, G, "video")
@@ -375,6 +375,8 @@ def measure_next_rows(hidden, T, B, device):
         ms_graph = _timed_ms(gstep, 3, 10)
     except Exception as exc:  # reported, never fatal
         ms_graph = repr(exc)[:160]
+    del fn
+    m = build_projector(hidden, device).train()  # a fresh module: the graphed one keeps its gradient accumulation on the capture stream
     ms = _timed_ms(step, 2, 5)
     out["train_step"] = {"what": "forward + backward of the projector (parameter gradients, hicom_b200.autograd)",
                          "videos": Bt, "frames": Bt * T, "use_guide": USE_GUIDE, "ms": ms,
