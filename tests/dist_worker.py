@@ -25,11 +25,13 @@ def main():
     from hicom_b200 import dist as hdist
     from hicom_b200.graph import GraphedCompressor
     worst = 0.0
-    for mode, hidden, T in (("coarse", 3584, 16 * world), ("direct", 896, 8 * world), (None, 896, 8 * world)):
-        case = Case(f"dist_{mode}", "local43_global32", mode, T, 27, 27, hidden, "bfloat16", wseed=3)
-        sd = O.synth_state_dict(case.ptype, mode, hidden, seed=3, dtype=torch.bfloat16)
+    for mode, hidden, T, dname in (("coarse", 3584, 16 * world, "bfloat16"), ("direct", 896, 8 * world, "bfloat16"),
+                                   (None, 896, 8 * world, "bfloat16"), ("coarse", 896, 8 * world, "float16")):
+        dt = getattr(torch, dname)
+        case = Case(f"dist_{mode}", "local43_global32", mode, T, 27, 27, hidden, dname, wseed=3)
+        sd = O.synth_state_dict(case.ptype, mode, hidden, seed=3, dtype=dt)
         m = cuda_module_for(case, sd, dev)
-        X, E, g = O.synth_inputs(T, 27, 27, O.guide_kind_for(mode), seed=77, dtype=torch.bfloat16)  # same on every rank
+        X, E, g = O.synth_inputs(T, 27, 27, O.guide_kind_for(mode), seed=77, dtype=dt)  # same on every rank
         dv = lambda t: None if t is None else t.unsqueeze(0).to(dev)
         X, E, g = dv(X), dv(E), dv(g)
         t0, t1 = hdist.frame_shard(T, world, rank)

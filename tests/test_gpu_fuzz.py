@@ -12,7 +12,7 @@ from util import Cfg, to_dev
 pytestmark = pytest.mark.gpu
 
 
-def _cases(n=28, seed=7):
+def _cases(n=28, seed=7, dtypes=("float32", "bfloat16")):
     rng = random.Random(seed)
     out = []
     while len(out) < n:
@@ -22,12 +22,13 @@ def _cases(n=28, seed=7):
         if T * H * W * B > 7000:
             continue
         out.append((T, H, W, B, rng.choice([None, "direct", "coarse", "fine"]), rng.choice([64, 128, 896]),
-                    rng.choice(["float32", "bfloat16"]), rng.choice(["local43_global32", "local43_global32",
+                    rng.choice(list(dtypes)), rng.choice(["local43_global32", "local43_global32",
                                                                      "local22_global8", "local43_global5"]), len(out)))
     return out
 
 
-@pytest.mark.parametrize("T,H,W,B,guide,hidden,dtype,ptype,idx", _cases(),
+# fp16 (the reference's inference dtype) gets its own seeded set so that the fp32 / bf16 case list stays what it was
+@pytest.mark.parametrize("T,H,W,B,guide,hidden,dtype,ptype,idx", _cases() + _cases(14, seed=11, dtypes=("float16",)),
                          ids=lambda v: str(v) if not isinstance(v, str) else v)
 def test_random_shapes_match_oracle(T, H, W, B, guide, hidden, dtype, ptype, idx, built_library):
     dt = getattr(torch, dtype)
@@ -56,5 +57,7 @@ def test_random_shapes_match_oracle(T, H, W, B, guide, hidden, dtype, ptype, idx
     assert got.shape == want.shape
     if dtype == "float32":
         assert O.rel_err(got, want) <= 1e-4
+    elif dtype == "float16":
+        assert O.cosine(got, want) >= 0.99999 and O.rel_err(got, want) <= 3e-3
     else:
         assert O.cosine(got, want) >= 0.999 and O.rel_err(got, want) <= 1e-2
