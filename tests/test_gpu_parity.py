@@ -272,10 +272,15 @@ def test_fp16_inference_dtype(name, built_library):
     with torch.inference_mode():
         out = m(to_dev(X), to_dev(E), to_dev(g), case.modal, to_dev(nl))
     assert out.dtype == torch.float16
-    assert set(m.state_dict().keys()) == set(sd.keys())  # the fp32 shadow never leaks into the state_dict
+    assert set(m.state_dict().keys()) == set(sd.keys())
     truth = truth_fp32(case)
     assert out.shape == truth.shape
     assert O.rel_err(out.float().cpu(), truth) <= 2e-3
+    # eval-mode inference OUTSIDE no_grad with (still trainable) fp16 parameters, as a caller of the reference may do: the
+    # same tokens, no autograd graph (fp16 is the inference dtype; the training path is bf16 / fp32)
+    assert any(p.requires_grad for p in m.parameters())
+    out2 = m(to_dev(X), to_dev(E), to_dev(g), case.modal, to_dev(nl))
+    assert not out2.requires_grad and torch.equal(out2, out)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
