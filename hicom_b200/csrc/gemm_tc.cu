@@ -1216,8 +1216,11 @@ __global__ void reset_for_exact3_kernel(float* mg, __nv_bfloat16* qt, int ld, in
 // contiguous, padded to pld like P2) so that the pooling GEMM's extension blocks look exactly like its main blocks;
 // column 63 of margf is the softmax denominator.  A denominator that is not a positive finite number means exp() left
 // the exponent range: raise the flag for the exact-max re-run.
+// The thread that owns the denominator also publishes the split-softmax statistics of its column: every token range of
+// the pooling GEMM shares the stabiliser as its max; the denominator goes with range 0.
 __global__ void marg_reduce_kernel(const float* margf, __nv_bfloat16* marg, float* lsum, int B, int S, int J, int ke2,
-                                   int pld, int kslice, int hw, int* flag, int guarded) {
+                                   int pld, int kslice, int hw, int* flag, int guarded, const float* stab, float* m_out,
+                                   float* l_out, int splits) {
   if (guarded && *flag == 0) return;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * J * ke2) return;
@@ -1240,14 +1243,12 @@ __global__ void marg_reduce_kernel(const float* margf, __nv_bfloat16* marg, floa
   if (c == kKe - 1) {
     lsum[bj] = acc;
     if (!guarded && !(acc > 0.f && acc < 3.0e38f)) atomicExch(flag, 1);
+    const float st = stab[bj];
+    for (int s2 = 0; s2 < splits; ++s2) {
+      m_out[((size_t)b * splits + s2) * J + j] = st;
+      l_out[((size_t)b * splits + s2) * J + j] = s2 == 0 ? acc : 0.f;
+    }
   }
-}
-__global__ void spread3_kernel(const float* stab, const float* lsum, float* m, float* l, int B, int S, int J) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * S * J) return;
-  const int j = i % J, s2 = (i / J) % S, b = i / (J * S);
-  m[i] = stab[b * J + j];
-  l[i] = s2 == 0 ? lsum[b * J + j] : 0.f;
 }
 }  // namespace tc
 
@@ -1383,7 +1384,7 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
     TcLinearParams m1 = mm; m1.guard = guard;
     if (launch_tc_linear(m1, stream)) return 1;
     marg_reduce_kernel<<<blocks(BJ * w.ke2), 256, 0, stream>>>(margf, marg, lsum, B, w.mslices, J, w.ke2, (int)w.pld,
-                                                               kslice, H * W, flag, guard != nullptr);
+                                                               kslice, H * W, flag, guard != nullptr, stab, m, l, splits);
     if (check_launch("marg_reduce_kernel")) return 1;
     Params g1 = g; g1.guard = guard;
     if (narrow ? launch<64, true, true, EPI_POOL>(txa, tp2, g1, gp, stream, &tpe, &tmg)
@@ -1417,8 +1418,7 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
       return 1;
     if (run(flag, 0.f)) return 1;
   }
-  spread3_kernel<<<blocks(BJ * splits), 256, 0, stream>>>(stab, lsum, m, l, B, splits, J);
-  return check_launch("spread3_kernel");
+  return 0;
 }
 
 }  // namespace hicom
