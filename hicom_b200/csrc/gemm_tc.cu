@@ -1218,35 +1218,58 @@ __global__ void reset_for_exact3_kernel(float* mg, __nv_bfloat16* qt, int ld, in
 // the exponent range: raise the flag for the exact-max re-run.
 // The thread that owns the denominator also publishes the split-softmax statistics of its column: every token range of
 // the pooling GEMM shares the stabiliser as its max; the denominator goes with range 0.
-__global__ void marg_reduce_kernel(const float* margf, __nv_bfloat16* marg, float* lsum, int B, int S, int J, int ke2,
-                                   int pld, int kslice, int hw, int* flag, int guarded, const float* stab, float* m_out,
-                                   float* l_out, int splits) {
+__global__ void __launch_bounds__(256) marg_reduce_kernel(const float* margf, __nv_bfloat16* marg, float* lsum, int B,
+                                                          int S, int J, int ke2, int pld, int kslice, int hw, int* flag,
+                                                          int guarded, const float* stab, float* m_out, float* l_out,
+                                                          int splits) {
+  // one block = a 32 (score columns j) x 32 (indicator columns c) tile of one video; thread (tx, ty) of 32 x 8 owns c =
+  // c0 + tx of the four rows j0 + ty + 8k: read with c fastest (margf rows are c-contiguous; the four rows' loads of a
+  // slice are independent), transpose through shared memory, write with j fastest (margT rows are j-contiguous); the
+  // statistics of the denominator column are published after the stores nobody waits for.  grid (J/32, ke2/32, B)
   if (guarded && *flag == 0) return;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * J * ke2) return;
-  const int c = (int)(i % ke2);
-  const long long bj = i / ke2;
-  const int j = (int)(bj % J), b = (int)(bj / J);
-  const float* src = margf + ((size_t)b * S * J + j) * (2 * kKe);
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
   const size_t sstride = (size_t)J * 2 * kKe;
-  float acc = 0.f;
-  if (c < kKe) {
-    for (int s2 = 0; s2 < S; ++s2) acc += src[s2 * sstride + c];
-  } else {  // frame c - 64: slices store it relative to their own base
+  const int c = c0 + tx;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < ke2) {
+    const float* src = margf + ((size_t)b * S * J + j0 + ty) * (2 * kKe);
     const int t = c - kKe;
     for (int s2 = 0; s2 < S; ++s2) {
-      const int rel = t - ((int)(((long long)s2 * kslice) / hw) & ~7);
-      if (rel >= 0 && rel < kKe) acc += src[s2 * sstride + kKe + rel];
+      int col = c;
+      if (c >= kKe) {  // frame c - 64: slices store it relative to their own base
+        const int rel = t - ((int)(((long long)s2 * kslice) / hw) & ~7);
+        col = (rel >= 0 && rel < kKe) ? kKe + rel : -1;
+      }
+      if (col >= 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (j0 + ty + 8 * k < J) acc[k] += src[s2 * sstride + (size_t)(8 * k) * (2 * kKe) + col];
+      }
     }
   }
-  marg[((size_t)b * ke2 + c) * pld + j] = __float2bfloat16_rn(acc);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tile[ty + 8 * k][tx] = acc[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int cc = c0 + ty + 8 * k, j = j0 + tx;
+    if (cc < ke2 && j < J) marg[((size_t)b * ke2 + cc) * pld + j] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
+  }
   if (c == kKe - 1) {
-    lsum[bj] = acc;
-    if (!guarded && !(acc > 0.f && acc < 3.0e38f)) atomicExch(flag, 1);
-    const float st = stab[bj];
-    for (int s2 = 0; s2 < splits; ++s2) {
-      m_out[((size_t)b * splits + s2) * J + j] = st;
-      l_out[((size_t)b * splits + s2) * J + j] = s2 == 0 ? acc : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = j0 + ty + 8 * k;
+      if (j >= J) continue;
+      const size_t bj = (size_t)b * J + j;
+      lsum[bj] = acc[k];
+      if (!guarded && !(acc[k] > 0.f && acc[k] < 3.0e38f)) atomicExch(flag, 1);
+      const float st = stab[bj];
+      for (int s2 = 0; s2 < splits; ++s2) {
+        m_out[((size_t)b * splits + s2) * J + j] = st;
+        l_out[((size_t)b * splits + s2) * J + j] = s2 == 0 ? acc[k] : 0.f;
+      }
     }
   }
 }
@@ -1383,8 +1406,8 @@ int launch_tc_global(const void* X, const void* Kscore, const float* pos_t, cons
                : launch<288, false, false, EPI_PROB2>(tx128, tqj, p1, gprob, stream, &ti0, &tqej, &ti1, &ttq)) return 1;
     TcLinearParams m1 = mm; m1.guard = guard;
     if (launch_tc_linear(m1, stream)) return 1;
-    marg_reduce_kernel<<<blocks(BJ * w.ke2), 256, 0, stream>>>(margf, marg, lsum, B, w.mslices, J, w.ke2, (int)w.pld,
-                                                               kslice, H * W, flag, guard != nullptr, stab, m, l, splits);
+    marg_reduce_kernel<<<dim3((J + 31) / 32, (w.ke2 + 31) / 32, B), 256, 0, stream>>>(
+        margf, marg, lsum, B, w.mslices, J, w.ke2, (int)w.pld, kslice, H * W, flag, guard != nullptr, stab, m, l, splits);
     if (check_launch("marg_reduce_kernel")) return 1;
     Params g1 = g; g1.guard = guard;
     if (narrow ? launch<64, true, true, EPI_POOL>(txa, tp2, g1, gp, stream, &tpe, &tmg)
