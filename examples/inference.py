@@ -27,3 +27,9 @@ with torch.inference_mode():
                                       frames_embed[None].expand(4, -1, -1, -1, -1).contiguous(),
                                       guide_embed[None].expand(4, -1).contiguous(), "video")
 print(tuple(tokens.shape), tuple(batch.shape), float((batch[0].float() - tokens.float()).abs().max()))
+
+# fp16 is the reference's own inference dtype (hicom/model/__init__.py:44): same call, native tcgen05 path
+p16 = projector.half()
+with torch.inference_mode():
+    t16 = p16(frames_feature.half(), frames_embed.half(), guide_embed.half(), "video")
+print("fp16", t16.dtype, float((t16.float() - tokens.float()).abs().max() / tokens.float().abs().max()))

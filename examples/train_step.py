@@ -34,3 +34,14 @@ loss.backward()
 opt.step()
 missing = [k for k, p in projector.named_parameters() if p.grad is None]
 print("loss", float(loss), "| parameters without a gradient:", missing, "| d(guide)", tuple(guide.grad.shape))
+
+# Fixed shapes: forward AND backward replayed from CUDA graphs (about 1.8x faster than the eager step, which is bound by
+# ~150 launches).  Build it on a module that has not run an eager backward yet.
+from hicom_b200.graph import graphed_training_forward  # noqa: E402
+proj2 = hicom_b200.build_vision_projector(config).to(torch.bfloat16).cuda().train()
+E2 = frames_embed.detach()
+step = graphed_training_forward(proj2, frames_feature, E2, guide.detach(), "video")
+out = step(frames_feature, E2, guide.detach())
+out.float().square().mean().backward()
+print("graphed step:", tuple(out.shape), "| parameters without a gradient:",
+      [k for k, p in proj2.named_parameters() if p.grad is None])
