@@ -16,8 +16,7 @@ Two ways the path shards, one process per GPU (torch.distributed, NCCL over NVLi
 from __future__ import annotations
 
 import contextlib
-import os
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist
