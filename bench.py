@@ -833,7 +833,9 @@ def live_traffic(args, dominant_label):
         cand = [e for e in launches.values() if "local_attend" in e["name"]]
     else:
         epi = _EPI_OF_LABEL.get(head_label)
-        pat = re.compile(r"tc_gemm_kernel<\(int\)\d+, \(bool\)[01], \(bool\)[01], \(int\)%s," % epi)
+        # ncu prints the template arguments as "<144, 0, 0, 4, 0, 1>" or "<(int)144, (bool)0, ...>" depending on the name base
+        pat = re.compile(r"tc_gemm_kernel<(?:\(int\))?\d+, (?:\(bool\))?(?:[01]|true|false), (?:\(bool\))?(?:[01]|true|false), "
+                         r"(?:\(int\))?%s," % epi)
         cand = [e for e in launches.values() if epi is not None and pat.search(e["name"])]
     if not cand:
         return None, step, f"ncu child: no launch matched {head_label!r} among {len(launches)} kernels"
