@@ -44,6 +44,7 @@ PROTOTYPES = {
                    [c_int] * 5 + [c_float] + [c_int] * 3 + [c_void_p]),
     "hicom_colsum": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "hicom_act_backward": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_int, c_int, c_void_p]),
+    "hicom_col_stats": (c_int, [c_void_p] * 3 + [c_int, ctypes.c_longlong, c_int, c_int, c_void_p]),
     "hicom_softmax_backward": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int, c_int, c_void_p]),
     "hicom_grid_pool_backward": (c_int, [c_void_p, c_void_p] + [c_int] * 8 + [c_void_p]),
     "hicom_l2norm_rows_backward": (c_int, [c_void_p] * 3 + [ctypes.c_longlong, c_int, c_int, c_void_p]),

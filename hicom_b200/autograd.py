@@ -227,6 +227,11 @@ class GlobalPoolFn(Function):
         Xp = ops.posadd(X, pt, ph, pw).view(B, N, d)                        # explicit x' (projector.py:636-640)
         dpl = dpooled.contiguous().to(X.dtype)
         S = ops.gemm(Xp, qfold.transpose(1, 2), None, True, 1.0)            # (B, N, J) fp32 scores
+        if X.dtype != torch.float32:
+            # the 16-bit forward applied the position terms in higher precision than this x' (rounded to 16 bits): take
+            # the log-sum-exp of the backward's OWN scores so that exp(S - lse) sums to one exactly (no systematic bias
+            # in dS, hence in the q_proj / k_proj / query / guide gradients)
+            lse = ops.col_logsumexp(S)
         dP = ops.gemm(Xp, dpl.transpose(1, 2), None, True, 1.0)             # (B, N, J) fp32
         delta = (pooled.float() * dpl.float()).sum(-1)                      # (B, J)
         P = None

@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(256) l2norm_rows_kernel(const T* __restrict__ 
 // m the max over the split's token range, l the sum of P.   (projector.py:213, per split)
 // grid (J/32, splits, B), block (32, 8).
 // ------------------------------------------------------------------------------------------------
+template <bool WRITE_P>
 __global__ void __launch_bounds__(256) col_softmax_kernel(float* __restrict__ S, float* __restrict__ m_out,
                                                           float* __restrict__ l_out, int N, int J, int splits,
                                                           int rows_per_split) {
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(256) col_softmax_kernel(float* __restrict__ S,
   if (j < J && mx > -INFINITY)
     for (int r = r0 + ry; r < r1; r += 8) {
       const float pv = exp2f((base[(size_t)r * J + j] - mx) * kLog2e);
-      base[(size_t)r * J + j] = pv;
+      if (WRITE_P) base[(size_t)r * J + j] = pv;
       sum += pv;
     }
   red[ry][cx] = sum;
@@ -211,9 +212,27 @@ int launch_col_softmax(float* S, float* m, float* l, int B, int N, int J, int sp
   if (B == 0) return 0;
   dim3 grid((J + 31) / 32, splits, B), block(32, 8);
   HICOM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "col_softmax: grid too large");
-  col_softmax_kernel<<<grid, block, 0, stream>>>(S, m, l, N, J, splits, rows_per_split);
+  col_softmax_kernel<true><<<grid, block, 0, stream>>>(S, m, l, N, J, splits, rows_per_split);
   return check_launch("col_softmax_kernel");
 }
+
+}  // namespace hicom
+
+// Column statistics of a score tensor WITHOUT touching it: per (video, token range, column) the max and the sum of
+// exp(S - max) — the attention backward takes the log-sum-exp of its own recomputed scores from them (hicom_col_stats).
+extern "C" int hicom_col_stats(const float* S, float* m, float* l, int B, long long N, int J, int splits, void* stream) {
+  using namespace hicom;
+  HICOM_REQUIRE(S && m && l, "col_stats: null pointer");
+  HICOM_REQUIRE(B >= 0 && N > 0 && J > 0 && splits > 0 && N < (1ll << 31), "col_stats: bad shape");
+  if (B == 0) return 0;
+  const int rows = (int)((N + splits - 1) / splits);
+  dim3 grid((J + 31) / 32, splits, B), block(32, 8);
+  HICOM_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "col_stats: grid too large");
+  col_softmax_kernel<false><<<grid, block, 0, as_stream(stream)>>>(const_cast<float*>(S), m, l, (int)N, J, splits, rows);
+  return check_launch("col_stats_kernel");
+}
+
+namespace hicom {
 
 // ------------------------------------------------------------------------------------------------
 // Split-softmax merge: one block per (video, column).

@@ -572,6 +572,22 @@ def _impl_act_backward(pre: Tensor, dy: Tensor, act: int) -> Tensor:
     return out
 
 
+def col_logsumexp(S: Tensor) -> Tensor:
+    """log sum_n exp(S[b, n, j]) of fp32 scores (B,N,J) -> (B,J), S untouched (hicom_col_stats over token ranges, then
+    a tiny combine)."""
+    dev = _need_cuda(S)
+    if S.dtype != torch.float32 or S.dim() != 3 or not S.is_contiguous():
+        raise ValueError("col_logsumexp: S must be a contiguous fp32 (B,N,J) tensor")
+    B, N, J = S.shape
+    splits = max(1, min(64, N // 256))
+    m = torch.empty((B, splits, J), dtype=torch.float32, device=dev)
+    l = torch.empty_like(m)
+    with torch.cuda.device(dev):
+        rc = _cabi.load().hicom_col_stats(_ptr(S), _ptr(m), _ptr(l), B, N, J, splits, _stream(dev))
+    _cabi.check(rc, "hicom_col_stats")
+    return torch.logsumexp(m + torch.log(l), dim=1)
+
+
 def _impl_softmax_backward(S: Tensor, dP: Tensor, lse: Tensor, delta: Tensor, out_bf16: bool) -> Tensor:
     """dS = exp(S - lse) * (dP - delta): S, dP (B,N,J) fp32, lse/delta (B,J) fp32 — softmax of projector.py:213."""
     dev = _need_cuda(S, dP, lse, delta)

@@ -240,6 +240,11 @@ int hicom_colsum(const void* x, int64_t ld, float* out, int64_t M, int N, int dt
 int hicom_act_backward(const void* pre, const void* dy, void* dx, int64_t n, int act, int pre_dtype, int dtype,
                        void* stream);
 
+/* hicom_col_stats: per (video, token range, column) max m and sum l of exp(S - m) of fp32 scores S (B,N,J), S untouched;
+ *   m, l (B, splits, J).  The attention backward derives the log-sum-exp of its OWN recomputed scores from them, so that
+ *   exp(S - lse) sums to one exactly whatever precision the forward applied the position terms in. */
+int hicom_col_stats(const float* S, float* m, float* l, int B, long long N, int J, int splits, void* stream);
+
 /* hicom_softmax_backward: backward of the column softmax of the global attention (projector.py:213) in the
  *   reassociated form: with P[b,n,j] = exp(S[b,n,j] - lse[b,j]) and pooled[b,j] = sum_n P x'_n,
  *     dS[b,n,j] = P[b,n,j] * (dP[b,n,j] - delta[b,j]),  dP = x'_n·dpooled[b,j],  delta[b,j] = pooled[b,j]·dpooled[b,j].

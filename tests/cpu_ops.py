@@ -133,6 +133,10 @@ def global_attend_partial_keys(X, Kscore, pt, ph, pw, qfold, splits, impl):
     return torch.stack(ms, 1), torch.stack(ls, 1), torch.stack(os_, 1)
 
 
+def col_logsumexp(S):
+    return torch.logsumexp(S, dim=1)
+
+
 def l2norm_rows(X):
     return (X.float() / X.float().norm(p=2, dim=-1, keepdim=True)).to(X.dtype)
 
@@ -276,7 +280,7 @@ ALL = ["linear", "gemm", "colsum", "act_backward", "softmax_backward", "global_f
        "softmax_reduce", "softmax_merge", "global_value_proj", "grid_pool", "film_layernorm", "film_layernorm_backward",
        "local_attend", "local_attend_backward", "layernorm", "mix_layernorm", "mix_layernorm_backward", "add_layernorm",
        "guide_attend", "_need_cuda", "softmax_merge_lse", "out_code", "global_attend_partial_keys", "l2norm_rows",
-       "l2norm_rows_backward", "grid_pool_backward"]
+       "l2norm_rows_backward", "grid_pool_backward", "col_logsumexp"]
 
 
 def install(monkeypatch):

@@ -483,3 +483,12 @@ def test_clip_scale_training_step(name, where, dtype, built_library, autograd_on
             tol = 2e-3 if dtype == "float32" else 5e-2
             assert ls.grad is not None and abs(float(ls.grad) - float(ols.grad)) <= tol * max(1.0, abs(float(ols.grad))), \
                 (part, float(ls.grad), float(ols.grad))
+
+
+def test_col_logsumexp(built_library):
+    from hicom_b200 import ops
+    S = _r(3, 5000, 288, seed=21, std=4.0)
+    S[1, 77, 5] = 90.0                                  # one dominant score
+    got = ops.col_logsumexp(S.cuda())
+    assert got.shape == (3, 288) and O.rel_err(got.cpu(), torch.logsumexp(S, dim=1)) <= 1e-6
+    assert torch.equal(S, S.clone())                    # input untouched (the kernel reads only)
